@@ -1,0 +1,141 @@
+/* roo_b200.h -- C ABI of the B200-native census / semi-global-matching engine.
+ *
+ * This is the drop-in boundary for the one hot path of arpg/Kangaroo this repository rebuilds
+ * (SURVEY.md section 8b).  The reference exposes that path as C++ free functions in namespace roo
+ * taking roo::Image / roo::Volume by value (include/kangaroo/cu_census.h:12-38,
+ * cu_semi_global_matching.h:10-12, cu_dense_stereo.h:13-47,81-85); those types have user-provided
+ * destructors, so a C ABI cannot take them directly.  Each entry point below names the reference
+ * function it replaces (paths relative to /root/reference); include/kangaroo_b200/roo.hpp
+ * re-creates the exact roo:: overloads on top of these, and INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - roo_image_t / roo_volume_t are binary-identical to roo::Image<T> / roo::Volume<T>
+ *    (Image.h:617-620, Volume.h:363-369): element (x,y,z) lives at
+ *    (char*)ptr + z*img_pitch + y*pitch + x*sizeof(T); any pitch is honoured (sub-views work).
+ *  - Every pointer is DEVICE memory on the current device unless a name says `host`.
+ *  - `stream` is a cudaStream_t passed as void*; NULL (the legacy default stream) reproduces the
+ *    reference's ordering.  All calls are asynchronous like the reference's launchers.
+ *  - Operators never allocate or free user-visible memory (reference: same).  roo_sgm() and the
+ *    engine use stream-ordered scratch from the CUDA memory pool.
+ *  - Return value: ROO_OK (0), a positive cudaError_t, or a negative roo_status code.  The reference
+ *    launchers return void and never check errors; roo.hpp ignores the code unless
+ *    ROO_B200_THROW is defined.
+ *  - There is no CPU fallback anywhere behind this header.
+ */
+#ifndef ROO_B200_H
+#define ROO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct roo_image_t { size_t pitch; void* ptr; size_t w; size_t h; } roo_image_t;
+typedef struct roo_volume_t { size_t pitch; void* ptr; size_t w; size_t h; size_t img_pitch; size_t d; } roo_volume_t;
+/* include/kangaroo/CostVolElem.h:10-19 */
+typedef struct roo_costvolelem_t { int32_t n; float sum; } roo_costvolelem_t;
+
+enum roo_status {
+    ROO_OK = 0,
+    ROO_ERR_INVALID_ARGUMENT = -1,
+    ROO_ERR_UNSUPPORTED = -2,     /* e.g. maxDisp > 256 or a non-integer disparity step sd */
+    ROO_ERR_OUT_OF_MEMORY = -3,
+    ROO_ERR_NO_DEVICE = -4
+};
+
+enum roo_window { ROO_WIN_9x7 = 0, ROO_WIN_11x11 = 1, ROO_WIN_16x16 = 2 };   /* -> 1 / 2 / 4 uint64 per pixel */
+enum roo_img_type { ROO_IMG_U8 = 0, ROO_IMG_F32 = 1 };
+/* ROO_POPC32_COMPAT reproduces the reference's 32-bit __popc on 64-bit words
+ * (hamming_distance.h:40-62: only the low 32 bits of every word are compared). */
+enum roo_popc_mode { ROO_POPC32_COMPAT = 0, ROO_POPC64 = 1 };
+enum roo_vol_type { ROO_VOL_U16 = 0, ROO_VOL_F32 = 1, ROO_VOL_I32 = 2, ROO_VOL_U32 = 3, ROO_VOL_U8 = 4, ROO_VOL_ELEM = 5 };
+enum roo_disp_type { ROO_DISP_I8 = 0, ROO_DISP_F32 = 1 };
+
+const char* roo_b200_version(void);
+const char* roo_status_string(int status);
+/* Number of kernels this library has launched in this process (all threads), for bench.py. */
+unsigned long long roo_launch_count(void);
+
+/* ---- granular operators: one per reference launcher -------------------------------------- */
+
+/* roo::Census x6 (cu_census.h:13-23; cu_census.cu:180-220).  census holds 1/2/4 uint64 per pixel. */
+int roo_census(const roo_image_t* census, const roo_image_t* img, int window, int in_type, void* stream);
+
+/* roo::CensusStereo (cu_census.h:33; cu_census.cu:226-266).  unsigned long descriptors -> char disparity. */
+int roo_census_stereo(const roo_image_t* disp_i8, const roo_image_t* left, const roo_image_t* right, int maxDisp,
+                      void* stream);
+
+/* roo::CensusStereoVolume<Tvol,T> (cu_census.h:36-38; cu_census.cu:272-314).
+ * words in {1,2,4}; vol_type in {ROO_VOL_U16, ROO_VOL_F32}; sd must be -1 or +1. */
+int roo_census_stereo_volume(const roo_volume_t* vol, const roo_image_t* left, const roo_image_t* right, int words,
+                             int vol_type, int maxDisp, float sd, int popc_mode, void* stream);
+
+/* roo::SemiGlobalMatching<TH,TC,Timg> (cu_semi_global_matching.h:10-12; .cu:21-89).
+ * volH float; volc_type in {ROO_VOL_F32, ROO_VOL_ELEM}; img_type in {ROO_IMG_U8, ROO_IMG_F32};
+ * 1 <= maxDisp <= 256.  dodiag = 0 is the reference (paths down, up, right, left in that order);
+ * dodiag = 1 adds the four diagonal paths (extension). */
+int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int volc_type, const roo_image_t* left, int img_type,
+            int maxDisp, float P1, float P2, int dohoriz, int dovert, int doreverse, int dodiag, void* stream);
+
+/* roo::CostVolMinimum<Tdisp,Tvol> (cu_dense_stereo.h:13-15; .cu:25-60); bounds-guarded. */
+int roo_costvol_minimum(const roo_image_t* disp, int disp_type, const roo_volume_t* vol, int vol_type,
+                        unsigned maxDisp, void* stream);
+
+/* roo::CostVolMinimum(Image<float>, Volume<CostVolElem>) (cu_dense_stereo.h:81-82; .cu:735-763). */
+int roo_costvol_minimum_elem(const roo_image_t* disp_f32, const roo_volume_t* vol_elem, void* stream);
+
+/* roo::CostVolMinimumSubpix (cu_dense_stereo.h:84-85; .cu:66-116); sd must be -1 or +1.
+ * Where the reference reads slice bestd+1 == vol.d (out of bounds) the integer disparity is kept. */
+int roo_costvol_minimum_subpix(const roo_image_t* disp_f32, const roo_volume_t* vol_f32, unsigned maxDisp, float sd,
+                               void* stream);
+
+/* roo::DenseStereoSubpixelRefine (cu_dense_stereo.h:45-47; .cu:580-627).  Pixels whose 5x5 windows
+ * leave the images (undefined in the reference) get NaN. */
+int roo_dense_stereo_subpixel_refine(const roo_image_t* out_f32, const roo_image_t* disp_u8,
+                                     const roo_image_t* left_u8, const roo_image_t* right_u8, void* stream);
+
+/* roo::LeftRightCheck (cu_dense_stereo.h:37-41; .cu:512-546); in place on dispL. */
+int roo_left_right_check_f32(const roo_image_t* dispL, const roo_image_t* dispR, float sd, float maxDiff, void* stream);
+int roo_left_right_check_i8(const roo_image_t* dispL, const roo_image_t* dispR, int sd, int maxDiff, void* stream);
+
+/* ---- fused engine: the whole per-frame path of applications/stereo2/main.cpp:375-454 ------- */
+
+typedef struct roo_engine roo_engine_t;
+
+typedef struct roo_pipeline_params_t {
+    int w, h;             /* image size (any; not limited to 1024 like the reference, Q4) */
+    int max_disp;         /* 1..256 */
+    int window;           /* enum roo_window */
+    int popc_mode;        /* enum roo_popc_mode */
+    float P1, P2;         /* stereo2/main.cpp:246-247 defaults: 0.01, 0.02 */
+    float img_scale;      /* adaptive-P2 intensity = u8 * img_scale; 1/255 matches main.cpp:376, 1 matches the uchar instantiation */
+    int dohoriz, dovert, doreverse, dodiag;
+    int subpix;           /* 0: CostVolMinimum<float,float>; 1: CostVolMinimumSubpix */
+    int lrcheck;          /* 1: right-reference WTA on the un-aggregated volume + both LeftRightChecks (main.cpp:385,432,451-454) */
+    float lr_maxdiff;
+    int max_batch;        /* stereo pairs in flight per call (scratch is sized for this many) */
+} roo_pipeline_params_t;
+
+int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t* params);
+int roo_engine_destroy(roo_engine_t* e);
+size_t roo_engine_scratch_bytes(const roo_engine_t* e);
+
+/* n_pairs tightly packed (h x w) uint8 images each side, device memory; disp: n_pairs x h x w float.
+ * Processes the pairs in groups of max_batch on `stream`. */
+int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const uint8_t* right, float* disp, int n_pairs,
+                          void* stream);
+/* Same with HOST buffers (pinned memory recommended): uploads, runs, downloads, and synchronises. */
+int roo_engine_run_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
+                        int n_pairs);
+/* Copies the aggregated volume of batch slot `slot` from the last run into a roo::Volume<float>
+ * (d >= max_disp slices are left untouched); for parity tests. */
+int roo_engine_export_volume(roo_engine_t* e, int slot, const roo_volume_t* volH, void* stream);
+/* Same for the census descriptors of the last run: side 0 = left, 1 = right. */
+int roo_engine_export_census(roo_engine_t* e, int slot, int side, const roo_image_t* census, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROO_B200_H */

@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy/ctypes front end of the CPU oracle (oracle/kangaroo_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package.  The product (kangaroo_b200/) never does.
+
+Arrays use numpy's C order: images are (H, W[, words]) and volumes are (D, H, W) -- the same
+"x fastest, then y, then d" order as roo::Image / roo::Volume (Image.h:617-620, Volume.h:363-369).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libkangaroo_oracle.so")
+
+WIN_9x7, WIN_11x11, WIN_16x16 = 0, 1, 2
+WORDS = {WIN_9x7: 1, WIN_11x11: 2, WIN_16x16: 4}
+IMG_U8, IMG_F32 = 0, 1
+POPC32_COMPAT, POPC64 = 0, 1
+VOL_U16, VOL_F32, VOL_I32, VOL_U32, VOL_U8, VOL_ELEM = 0, 1, 2, 3, 4, 5
+DISP_I8, DISP_F32 = 0, 1
+
+COSTVOLELEM = np.dtype([("n", np.int32), ("sum", np.float32)])  # CostVolElem.h:10-19
+
+_VOL_TYPES = {np.dtype(np.uint16): VOL_U16, np.dtype(np.float32): VOL_F32, np.dtype(np.int32): VOL_I32,
+              np.dtype(np.uint32): VOL_U32, np.dtype(np.uint8): VOL_U8, COSTVOLELEM: VOL_ELEM}
+
+
+class KoImage(C.Structure):
+    _fields_ = [("pitch", C.c_size_t), ("ptr", C.c_void_p), ("w", C.c_size_t), ("h", C.c_size_t)]
+
+
+class KoVolume(C.Structure):
+    _fields_ = [("pitch", C.c_size_t), ("ptr", C.c_void_p), ("w", C.c_size_t), ("h", C.c_size_t),
+                ("img_pitch", C.c_size_t), ("d", C.c_size_t)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc -O2 -fopenmp -ffp-contract=off). Building is not using."""
+    src = os.path.join(_HERE, "kangaroo_oracle.c")
+    hdr = os.path.join(_HERE, "kangaroo_oracle.h")
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        P = C.POINTER
+        L.ko_num_threads.restype = C.c_int
+        L.ko_census.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
+        L.ko_census_stereo.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_int]
+        L.ko_census_stereo_volume.argtypes = [P(KoVolume), P(KoImage), P(KoImage), C.c_int, C.c_int, C.c_int,
+                                              C.c_float, C.c_int]
+        L.ko_sgm.argtypes = [P(KoVolume), P(KoVolume), C.c_int, P(KoImage), C.c_int, C.c_int, C.c_float, C.c_float,
+                             C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ko_costvol_minimum.argtypes = [P(KoImage), C.c_int, P(KoVolume), C.c_int, C.c_uint]
+        L.ko_costvol_minimum_elem.argtypes = [P(KoImage), P(KoVolume)]
+        L.ko_costvol_minimum_subpix.argtypes = [P(KoImage), P(KoVolume), C.c_uint, C.c_float, P(KoImage)]
+        L.ko_dense_stereo_subpixel_refine.argtypes = [P(KoImage)] * 5
+        L.ko_left_right_check_f32.argtypes = [P(KoImage), P(KoImage), C.c_float, C.c_float]
+        L.ko_left_right_check_i8.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
+        L.ko_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ko_hamming.restype = C.c_uint
+        L.ko_pipeline_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_void_p, C.c_void_p]
+        L.ko_pipeline_u8.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def num_threads() -> int:
+    return int(lib().ko_num_threads())
+
+
+def _img(a: np.ndarray) -> KoImage:
+    """(H, W) or (H, W, words) C-contiguous-in-x array -> ko_image (row pitch from strides)."""
+    assert a.ndim in (2, 3)
+    if a.ndim == 3:
+        assert a.strides[2] == a.itemsize and a.strides[1] == a.itemsize * a.shape[2]
+    else:
+        assert a.strides[1] == a.itemsize
+    return KoImage(a.strides[0], a.ctypes.data, a.shape[1], a.shape[0])
+
+
+def _vol(a: np.ndarray) -> KoVolume:
+    assert a.ndim == 3 and a.strides[2] == a.itemsize
+    return KoVolume(a.strides[1], a.ctypes.data, a.shape[2], a.shape[1], a.strides[0], a.shape[0])
+
+
+def _img_type(a: np.ndarray) -> int:
+    if a.dtype == np.uint8:
+        return IMG_U8
+    if a.dtype == np.float32:
+        return IMG_F32
+    raise TypeError(a.dtype)
+
+
+def census(img: np.ndarray, window: int) -> np.ndarray:
+    h, w = img.shape
+    out = np.zeros((h, w, WORDS[window]), np.uint64)
+    lib().ko_census(C.byref(_img(out)), C.byref(_img(img)), window, _img_type(img))
+    return out
+
+
+def hamming(p: np.ndarray, q: np.ndarray, popc_mode: int = POPC32_COMPAT) -> int:
+    p = np.ascontiguousarray(p, np.uint64).ravel()
+    q = np.ascontiguousarray(q, np.uint64).ravel()
+    return int(lib().ko_hamming(p.ctypes.data, q.ctypes.data, p.size, popc_mode))
+
+
+def census_stereo(left: np.ndarray, right: np.ndarray, max_disp: int) -> np.ndarray:
+    h, w = left.shape[:2]
+    disp = np.zeros((h, w), np.int8)
+    lib().ko_census_stereo(C.byref(_img(disp)), C.byref(_img(left)), C.byref(_img(right)), max_disp)
+    return disp
+
+
+def census_stereo_volume(left: np.ndarray, right: np.ndarray, max_disp: int, sd: float, vol_dtype=np.float32,
+                         popc_mode: int = POPC32_COMPAT, depth: int | None = None,
+                         fill: float = 0.0) -> np.ndarray:
+    h, w, words = left.shape
+    vol = np.full((depth or max_disp, h, w), fill, np.dtype(vol_dtype))
+    lib().ko_census_stereo_volume(C.byref(_vol(vol)), C.byref(_img(left)), C.byref(_img(right)), words,
+                                  _VOL_TYPES[vol.dtype], max_disp, sd, popc_mode)
+    return vol
+
+
+def sgm(vol_c: np.ndarray, left: np.ndarray, max_disp: int, p1: float, p2: float, dohoriz=True, dovert=True,
+        doreverse=True, dodiag=False) -> np.ndarray:
+    vol_h = np.empty(vol_c.shape, np.float32)
+    lib().ko_sgm(C.byref(_vol(vol_h)), C.byref(_vol(vol_c)), _VOL_TYPES[vol_c.dtype], C.byref(_img(left)),
+                 _img_type(left), max_disp, p1, p2, int(dohoriz), int(dovert), int(doreverse), int(dodiag))
+    return vol_h
+
+
+def costvol_minimum(vol: np.ndarray, max_disp: int, disp_dtype=np.float32) -> np.ndarray:
+    d, h, w = vol.shape
+    disp = np.zeros((h, w), np.dtype(disp_dtype))
+    dt = DISP_I8 if disp.dtype == np.int8 else DISP_F32
+    lib().ko_costvol_minimum(C.byref(_img(disp)), dt, C.byref(_vol(vol)), _VOL_TYPES[vol.dtype], max_disp)
+    return disp
+
+
+def costvol_minimum_elem(vol: np.ndarray) -> np.ndarray:
+    d, h, w = vol.shape
+    disp = np.zeros((h, w), np.float32)
+    lib().ko_costvol_minimum_elem(C.byref(_img(disp)), C.byref(_vol(vol)))
+    return disp
+
+
+def costvol_minimum_subpix(vol: np.ndarray, max_disp: int, sd: float):
+    d, h, w = vol.shape
+    disp = np.zeros((h, w), np.float32)
+    mask = np.zeros((h, w), np.uint8)
+    lib().ko_costvol_minimum_subpix(C.byref(_img(disp)), C.byref(_vol(vol)), max_disp, sd, C.byref(_img(mask)))
+    return disp, mask
+
+
+def dense_stereo_subpixel_refine(disp: np.ndarray, left: np.ndarray, right: np.ndarray):
+    h, w = disp.shape
+    out = np.zeros((h, w), np.float32)
+    mask = np.zeros((h, w), np.uint8)
+    lib().ko_dense_stereo_subpixel_refine(C.byref(_img(out)), C.byref(_img(disp)), C.byref(_img(left)),
+                                          C.byref(_img(right)), C.byref(_img(mask)))
+    return out, mask
+
+
+def left_right_check_f32(disp_l: np.ndarray, disp_r: np.ndarray, sd: float = -1.0, max_diff: float = 0.5):
+    out = np.array(disp_l, np.float32, copy=True)
+    lib().ko_left_right_check_f32(C.byref(_img(out)), C.byref(_img(disp_r)), sd, max_diff)
+    return out
+
+
+def left_right_check_i8(disp_l: np.ndarray, disp_r: np.ndarray, sd: int = -1, max_diff: int = 0):
+    out = np.array(disp_l, np.int8, copy=True)
+    lib().ko_left_right_check_i8(C.byref(_img(out)), C.byref(_img(disp_r)), sd, max_diff)
+    return out
+
+
+def pipeline_u8(left: np.ndarray, right: np.ndarray, max_disp: int, window: int = WIN_9x7,
+                popc_mode: int = POPC32_COMPAT, p1: float = 0.01, p2: float = 0.02, dohoriz=True, dovert=True,
+                doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff: float = 1.0,
+                want_volume: bool = False):
+    """applications/stereo2/main.cpp:375-454 on a pair of (H, W) uint8 images."""
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    h, w = left.shape
+    disp = np.zeros((h, w), np.float32)
+    vol = np.zeros((max_disp, h, w), np.float32) if want_volume else None
+    rc = lib().ko_pipeline_u8(left.ctypes.data, right.ctypes.data, w, h, max_disp, window, popc_mode, p1, p2,
+                              int(dohoriz), int(dovert), int(doreverse), int(dodiag), int(subpix), int(lrcheck),
+                              lr_maxdiff, disp.ctypes.data, vol.ctypes.data if want_volume else None)
+    if rc != 0:
+        raise MemoryError("ko_pipeline_u8 failed")
+    return (disp, vol) if want_volume else disp

@@ -1,0 +1,517 @@
+/* TEST INFRASTRUCTURE ONLY -- see kangaroo_oracle.h.
+ *
+ * Scalar CPU restatement of the reference kernel bodies, one function per operator, OpenMP over
+ * rows / scanlines.  IEEE fp32 (build with -ffp-contract=off, no -ffast-math) in the reference's
+ * operation order.  The reference is compiled with -use_fast_math (CMakeLists.txt:141): its
+ * approximate divides differ from the IEEE ones here by <= 2 ulp, inside the
+ * 1e-5 / 0.01 px parity bars.  GPU float->unsigned conversions saturate (cvt.rzi); where the
+ * reference relies on that (Q7) it is emulated explicitly.
+ */
+#include "kangaroo_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int ko_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---- accessors: Image.h:247-257 (RowPtr/operator()), Volume.h:125-147 ---- */
+static inline char* img_at(const ko_image* im, size_t x, size_t y, size_t elem) {
+    return (char*)im->ptr + y * im->pitch + x * elem;
+}
+static inline char* vol_at(const ko_volume* v, size_t x, size_t y, size_t z, size_t elem) {
+    return (char*)v->ptr + z * v->img_pitch + y * v->pitch + x * elem;
+}
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* Image.h:297-303 GetWithClampedRange, as float for both input types (u8 -> float is exact and
+ * order preserving, so `q < p` is the same predicate). */
+static inline float px_clamped(const ko_image* im, int in_type, int x, int y) {
+    x = clampi(x, 0, (int)im->w - 1);
+    y = clampi(y, 0, (int)im->h - 1);
+    if (in_type == KO_IMG_U8) return (float)*(const uint8_t*)img_at(im, (size_t)x, (size_t)y, 1);
+    return *(const float*)img_at(im, (size_t)x, (size_t)y, 4);
+}
+
+/* ---------------------------------------------------------------- census ---- */
+
+/* cu_census.cu:18-46.  bit i = (r+3)*9 + (c+4), set iff img.clamped(x+c,y+r) < img(x,y). */
+static uint64_t census9x7(const ko_image* in, int t, int x, int y) {
+    const float p = px_clamped(in, t, x, y);
+    uint64_t out = 0, bit = 1;
+    for (int r = -3; r <= 3; ++r)
+        for (int c = -4; c <= 4; ++c) {
+            if (px_clamped(in, t, x + c, y + r) < p) out |= bit;
+            bit <<= 1;
+        }
+    return out;
+}
+
+/* cu_census.cu:52-110.  x: rows -5..-1 then row 0 c=-5..0 ; y: row 0 c=1..5 then rows 1..5. */
+static void census11x11(const ko_image* in, int t, int x, int y, uint64_t o[2]) {
+    const float p = px_clamped(in, t, x, y);
+    uint64_t bit = 1;
+    o[0] = o[1] = 0;
+    for (int r = -5; r < 0; ++r)
+        for (int c = -5; c <= 5; ++c) {
+            if (px_clamped(in, t, x + c, y + r) < p) o[0] |= bit;
+            bit <<= 1;
+        }
+    for (int c = -5; c <= 0; ++c) {
+        if (px_clamped(in, t, x + c, y) < p) o[0] |= bit;
+        bit <<= 1;
+    }
+    bit = 1;
+    for (int c = 1; c <= 5; ++c) {
+        if (px_clamped(in, t, x + c, y) < p) o[1] |= bit;
+        bit <<= 1;
+    }
+    for (int r = 1; r <= 5; ++r)
+        for (int c = -5; c <= 5; ++c) {
+            if (px_clamped(in, t, x + c, y + r) < p) o[1] |= bit;
+            bit <<= 1;
+        }
+}
+
+/* cu_census.cu:116-177.  "16x16" is c in [-4,3], r in [-8,7]; 4 rows x 8 cols per word. */
+static void census16x16(const ko_image* in, int t, int x, int y, uint64_t o[4]) {
+    const float p = px_clamped(in, t, x, y);
+    for (int k = 0; k < 4; ++k) {
+        uint64_t bit = 1, acc = 0;
+        for (int r = -8 + 4 * k; r < -4 + 4 * k; ++r)
+            for (int c = -4; c < 4; ++c) {
+                if (px_clamped(in, t, x + c, y + r) < p) acc |= bit;
+                bit <<= 1;
+            }
+        o[k] = acc;
+    }
+}
+
+void ko_census(const ko_image* out, const ko_image* in, int window, int in_type) {
+    const int w = (int)in->w, h = (int)in->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            if (window == KO_WIN_9x7) {
+                *(uint64_t*)img_at(out, (size_t)x, (size_t)y, 8) = census9x7(in, in_type, x, y);
+            } else if (window == KO_WIN_11x11) {
+                census11x11(in, in_type, x, y, (uint64_t*)img_at(out, (size_t)x, (size_t)y, 16));
+            } else {
+                census16x16(in, in_type, x, y, (uint64_t*)img_at(out, (size_t)x, (size_t)y, 32));
+            }
+        }
+}
+
+/* ---------------------------------------------------------------- hamming ---- */
+
+/* hamming_distance.h:40-62: __popc (32-bit) applied to a 64-bit XOR => low 32 bits only (Q1). */
+unsigned ko_hamming(const uint64_t* p, const uint64_t* q, int words, int popc_mode) {
+    unsigned s = 0;
+    for (int i = 0; i < words; ++i) {
+        const uint64_t v = p[i] ^ q[i];
+        if (popc_mode == KO_POPC32_COMPAT) s += (unsigned)__builtin_popcount((uint32_t)v);
+        else s += (unsigned)__builtin_popcountll(v);
+    }
+    return s;
+}
+
+/* cu_census.cu:226-259 */
+void ko_census_stereo(const ko_image* disp, const ko_image* left, const ko_image* right, int maxDispVal) {
+    const int w = (int)disp->w, h = (int)disp->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint64_t p = *(const uint64_t*)img_at(left, (size_t)x, (size_t)y, 8);
+            unsigned bestScore = 0xFFFFF;
+            int bestDisp = 0; /* InvalidValue<char>::Value(), InvalidValue.h:50-53 */
+            int minDisp = maxDispVal < 0 ? maxDispVal : 0;
+            int maxDisp = maxDispVal > 0 ? maxDispVal : 0;
+            if (minDisp < x - ((int)left->w - 1)) minDisp = x - ((int)left->w - 1);
+            if (maxDisp > x) maxDisp = x;
+            for (int d = minDisp; d < maxDisp; ++d) {
+                const uint64_t q = *(const uint64_t*)img_at(right, (size_t)(x - d), (size_t)y, 8);
+                const unsigned score = ko_hamming(&p, &q, 1, KO_POPC32_COMPAT);
+                if (score < bestScore) { bestScore = score; bestDisp = d; }
+            }
+            *(int8_t*)img_at(disp, (size_t)x, (size_t)y, 1) = (int8_t)bestDisp;
+        }
+}
+
+/* cu_census.cu:272-299.  xd = (int)(x + sd*d) (float, truncation toward zero, Q12);
+ * score = Hamming / (float)(8*sizeof(T)) else 0.5; Tvol=unsigned short truncates to 0 (Q2). */
+void ko_census_stereo_volume(const ko_volume* vol, const ko_image* left, const ko_image* right, int words,
+                             int vol_type, int maxDispVal, float sd, int popc_mode) {
+    const int w = (int)left->w, h = (int)left->h;
+    const size_t esz = (size_t)words * 8;
+    const float bits = (float)(esz * 8);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint64_t* p = (const uint64_t*)img_at(left, (size_t)x, (size_t)y, esz);
+            for (int d = 0; d < maxDispVal; ++d) {
+                const int xd = (int)((float)x + sd * (float)d);
+                float score;
+                if (0 <= xd && xd < (int)right->w) {
+                    const uint64_t* q = (const uint64_t*)img_at(right, (size_t)xd, (size_t)y, esz);
+                    score = (float)ko_hamming(p, q, words, popc_mode) / bits;
+                } else {
+                    score = 0.5f;
+                }
+                if (vol_type == KO_VOL_F32) *(float*)vol_at(vol, (size_t)x, (size_t)y, (size_t)d, 4) = score;
+                else *(uint16_t*)vol_at(vol, (size_t)x, (size_t)y, (size_t)d, 2) = (uint16_t)score;
+            }
+        }
+}
+
+/* ---------------------------------------------------------------- SGM ---- */
+
+/* CostVolElem.h:12-15 operator float() */
+static inline float volc_get(const ko_volume* v, int t, int x, int y, int d) {
+    if (t == KO_VOL_F32) return *(const float*)vol_at(v, (size_t)x, (size_t)y, (size_t)d, 4);
+    const ko_costvolelem* e = (const ko_costvolelem*)vol_at(v, (size_t)x, (size_t)y, (size_t)d, 8);
+    return e->n > 0 ? e->sum / (float)e->n : 1E30f;
+}
+/* `last_c - c` (cu_semi_global_matching.cu:41): int arithmetic for uchar, float for float; both are
+ * exactly representable as the float difference of the converted values. */
+static inline float img_get(const ko_image* im, int t, int x, int y) {
+    if (t == KO_IMG_U8) return (float)*(const uint8_t*)img_at(im, (size_t)x, (size_t)y, 1);
+    return *(const float*)img_at(im, (size_t)x, (size_t)y, 4);
+}
+static inline int mini(int a, int b) { return a < b ? a : b; }
+
+/* One thread of KernSemiGlobalMatching (cu_semi_global_matching.cu:21-63): one scanline. */
+static void sgm_scanline(const ko_volume* H, const ko_volume* C, int ct, const ko_image* left, int it,
+                         int maxDispVal, float P1, float P2, int x, int y, int dx, int dy, int pathlen) {
+    const float MAX_ERROR = 1E30f;
+    float lastBestCr = 0.0f;
+    float last_c = img_get(left, it, x, y);
+    const int maxDisp0 = mini(maxDispVal, x + 1);
+    int lastMaxDisp = maxDisp0;
+    for (int d = 0; d < maxDisp0; ++d)
+        *(float*)vol_at(H, (size_t)x, (size_t)y, (size_t)d, 4) += volc_get(C, ct, x, y, d);
+    x += dx;
+    y += dy;
+    for (int r = 1; r < pathlen; ++r) {
+        const float c = img_get(left, it, x, y);
+        const float diff = last_c - c;
+        const float _P2 = P2 / (1.0f + fabsf(diff));
+        float bestCr = MAX_ERROR;
+        const int maxDisp = mini(maxDispVal, x + 1);
+        const int px = x - dx, py = y - dy;
+        for (int d = 0; d < maxDisp; ++d) {
+            float CM = lastBestCr + _P2;
+            if (d < lastMaxDisp) CM = fminf(CM, *(const float*)vol_at(H, (size_t)px, (size_t)py, (size_t)d, 4));
+            if (d > 0) CM = fminf(CM, *(const float*)vol_at(H, (size_t)px, (size_t)py, (size_t)(d - 1), 4) + P1);
+            if (d + 1 < lastMaxDisp)
+                CM = fminf(CM, *(const float*)vol_at(H, (size_t)px, (size_t)py, (size_t)(d + 1), 4) + P1);
+            const float Cr = CM + volc_get(C, ct, x, y, d) - lastBestCr;
+            bestCr = fminf(bestCr, Cr);
+            *(float*)vol_at(H, (size_t)x, (size_t)y, (size_t)d, 4) += Cr;
+        }
+        x += dx;
+        y += dy;
+        lastBestCr = bestCr;
+        last_c = c;
+        lastMaxDisp = maxDisp;
+    }
+}
+
+/* All scanlines of one direction.  Axis-aligned: exactly the launch of cu_semi_global_matching.cu:72-84
+ * (one thread per column / row, fixed pathlen).  Diagonal (extension): a scanline starts at every pixel
+ * of the entry edges (first row in travel direction, plus the side column the path moves away from)
+ * and runs until it leaves the image. */
+static void sgm_direction(const ko_volume* H, const ko_volume* C, int ct, const ko_image* left, int it,
+                          int maxDisp, float P1, float P2, int dx, int dy) {
+    const int w = (int)C->w, h = (int)C->h;
+    if (dx == 0) {
+        const int y0 = dy > 0 ? 0 : h - 1;
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int x = 0; x < w; ++x) sgm_scanline(H, C, ct, left, it, maxDisp, P1, P2, x, y0, 0, dy, h);
+    } else if (dy == 0) {
+        const int x0 = dx > 0 ? 0 : w - 1;
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int y = 0; y < h; ++y) sgm_scanline(H, C, ct, left, it, maxDisp, P1, P2, x0, y, dx, 0, w);
+    } else {
+        const int y0 = dy > 0 ? 0 : h - 1;
+        const int xs = dx > 0 ? 0 : w - 1;
+        const int n = w + h - 1;
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int s = 0; s < n; ++s) {
+            int sx, sy;
+            if (s < w) { sx = s; sy = y0; }
+            else { sx = xs; sy = dy > 0 ? (s - w + 1) : (h - 1 - (s - w + 1)); }
+            const int lenx = dx > 0 ? (w - sx) : (sx + 1);
+            const int leny = dy > 0 ? (h - sy) : (sy + 1);
+            sgm_scanline(H, C, ct, left, it, maxDisp, P1, P2, sx, sy, dx, dy, mini(lenx, leny));
+        }
+    }
+}
+
+/* cu_semi_global_matching.cu:65-86 */
+void ko_sgm(const ko_volume* volH, const ko_volume* volC, int volc_type, const ko_image* left, int img_type,
+            int maxDisp, float P1, float P2, int dohoriz, int dovert, int doreverse, int dodiag) {
+    /* volH.Memset(0): Volume.h:78-81 clears pitch*h*d bytes */
+    memset(volH->ptr, 0, volH->pitch * volH->h * volH->d);
+    if (dovert) sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, 0, 1);
+    if (dodiag) {
+        sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, 1, 1);
+        sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, -1, 1);
+    }
+    if (dovert && doreverse) sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, 0, -1);
+    if (dodiag && doreverse) {
+        sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, -1, -1);
+        sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, 1, -1);
+    }
+    if (dohoriz) {
+        sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, 1, 0);
+        if (doreverse) sgm_direction(volH, volC, volc_type, left, img_type, maxDisp, P1, P2, -1, 0);
+    }
+}
+
+/* ---------------------------------------------------------------- WTA ---- */
+
+static inline double vol_get_num(const ko_volume* v, int t, int x, int y, int d) {
+    switch (t) {
+        case KO_VOL_F32: return *(const float*)vol_at(v, (size_t)x, (size_t)y, (size_t)d, 4);
+        case KO_VOL_I32: return *(const int32_t*)vol_at(v, (size_t)x, (size_t)y, (size_t)d, 4);
+        case KO_VOL_U32: return *(const uint32_t*)vol_at(v, (size_t)x, (size_t)y, (size_t)d, 4);
+        case KO_VOL_U16: return *(const uint16_t*)vol_at(v, (size_t)x, (size_t)y, (size_t)d, 2);
+        default: return *(const uint8_t*)vol_at(v, (size_t)x, (size_t)y, (size_t)d, 1);
+    }
+}
+
+/* cu_dense_stereo.cu:25-43.  Comparison happens in Tvol; double holds every Tvol value exactly and
+ * orders them identically.  bestd is a Tdisp: for char it wraps past 127 (Q: Tdisp=char overflows). */
+void ko_costvol_minimum(const ko_image* disp, int disp_type, const ko_volume* vol, int vol_type,
+                        unsigned maxDispVal) {
+    const int w = (int)disp->w, h = (int)disp->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int bestd = 0;
+            double bestc = vol_get_num(vol, vol_type, x, y, 0);
+            /* min(unsigned, int): x+1 converts to unsigned; values are small positives */
+            const int maxDisp = (int)((maxDispVal < (unsigned)(x + 1)) ? maxDispVal : (unsigned)(x + 1));
+            for (int d = 1; d < maxDisp; ++d) {
+                const double c = vol_get_num(vol, vol_type, x, y, d);
+                if (c < bestc) { bestc = c; bestd = d; }
+            }
+            if (disp_type == KO_DISP_I8) *(int8_t*)img_at(disp, (size_t)x, (size_t)y, 1) = (int8_t)bestd;
+            else *(float*)img_at(disp, (size_t)x, (size_t)y, 4) = (float)bestd;
+        }
+}
+
+/* cu_dense_stereo.cu:735-755: c = sum / n (no n>0 test here: n==0 gives inf/NaN, never < bestc) */
+void ko_costvol_minimum_elem(const ko_image* disp, const ko_volume* vol) {
+    const int w = (int)disp->w, h = (int)disp->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float bestd = 0.0f, bestc = 1E30f;
+            for (int d = 0; d < (int)vol->d; ++d) {
+                const ko_costvolelem* e = (const ko_costvolelem*)vol_at(vol, (size_t)x, (size_t)y, (size_t)d, 8);
+                const float c = e->sum / (float)e->n;
+                if (c < bestc) { bestc = c; bestd = (float)d; }
+            }
+            *(float*)img_at(disp, (size_t)x, (size_t)y, 4) = bestd;
+        }
+}
+
+/* cu_dense_stereo.cu:66-109 */
+void ko_costvol_minimum_subpix(const ko_image* disp, const ko_volume* vol, unsigned maxDispVal, float sd,
+                               const ko_image* mask) {
+    const int w = (int)disp->w, h = (int)disp->h;
+    const int have_mask = mask && mask->ptr;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float bestd = 0.0f, bestc = 1E10f;
+            for (int d = 0; d < (int)maxDispVal; ++d) {
+                const int xr = (int)((float)x + sd * (float)d);
+                if (0 <= xr && xr < (int)vol->w) {
+                    const float c = *(const float*)vol_at(vol, (size_t)x, (size_t)y, (size_t)d, 4);
+                    if (c < bestc) { bestc = c; bestd = (float)d; }
+                }
+            }
+            float out = bestd;
+            unsigned char m = 0;
+            const int bestxr = (int)((float)x + sd * bestd);
+            if (0 < bestxr && bestxr < (int)vol->w - 1) {
+                const float dl = bestd - 1.0f, dr = bestd + 1.0f;
+                /* vol(x,y,dl): float -> size_t; the GPU's cvt.rzi.u64.f32 saturates -1 to 0 (Q7) */
+                const size_t il = dl < 0.0f ? 0 : (size_t)dl;
+                const size_t ir = (size_t)dr;
+                if (ir >= vol->d) {
+                    m = 1; /* reference reads one slice past the volume: undefined, skip the parabola */
+                } else {
+                    const float sl = *(const float*)vol_at(vol, (size_t)x, (size_t)y, il, 4);
+                    const float sr = *(const float*)vol_at(vol, (size_t)x, (size_t)y, ir, 4);
+                    const float subpixdisp = bestd - (sr - sl) / (2.0f * (sr - 2.0f * bestc + sl));
+                    if (dl < subpixdisp && subpixdisp < dr) out = subpixdisp;
+                }
+            }
+            *(float*)img_at(disp, (size_t)x, (size_t)y, 4) = out;
+            if (have_mask) *(uint8_t*)img_at(mask, (size_t)x, (size_t)y, 1) = m;
+        }
+}
+
+/* ---------------------------------------------------------------- subpixel refine ---- */
+
+/* patch_score.h:257-298, SANDPatchScore<float,2,ImgAccessRaw> on unsigned char images */
+static float sand5x5(const ko_image* i1, int x1, int y1, const ko_image* i2, int x2, int y2) {
+    float sum1 = 0.0f, sum2 = 0.0f, sad = 0.0f;
+    for (int r = -2; r <= 2; ++r)
+        for (int c = -2; c <= 2; ++c) {
+            sum1 += (float)*(const uint8_t*)img_at(i1, (size_t)(x1 + c), (size_t)(y1 + r), 1);
+            sum2 += (float)*(const uint8_t*)img_at(i2, (size_t)(x2 + c), (size_t)(y2 + r), 1);
+        }
+    const float mean1 = sum1 / 25.0f, mean2 = sum2 / 25.0f;
+    for (int r = -2; r <= 2; ++r)
+        for (int c = -2; c <= 2; ++c) {
+            const float a = (float)*(const uint8_t*)img_at(i1, (size_t)(x1 + c), (size_t)(y1 + r), 1);
+            const float b = (float)*(const uint8_t*)img_at(i2, (size_t)(x2 + c), (size_t)(y2 + r), 1);
+            sad += fabsf((a - mean1) - (b - mean2));
+        }
+    return sad;
+}
+
+/* cu_dense_stereo.cu:580-619 */
+void ko_dense_stereo_subpixel_refine(const ko_image* out, const ko_image* disp, const ko_image* left,
+                                     const ko_image* right, const ko_image* mask) {
+    const int w = (int)disp->w, h = (int)disp->h;
+    const int have_mask = mask && mask->ptr;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const int bestDisp = *(const uint8_t*)img_at(disp, (size_t)x, (size_t)y, 1);
+            float res = NAN;
+            unsigned char m = 0;
+            /* windows: left cols x-2..x+2, right cols x-bestDisp-1-2 .. x-bestDisp+1+2, rows y-2..y+2 */
+            if (y < 2 || y + 2 >= h || x < 2 || x + 2 >= w || x - bestDisp - 3 < 0 || x - bestDisp + 3 >= w) {
+                m = 1; /* reference: unguarded reads (Q8) */
+            } else {
+                const float d1 = (float)(bestDisp + 1), d2 = (float)bestDisp, d3 = (float)(bestDisp - 1);
+                const float s1 = sand5x5(left, x, y, right, x - (bestDisp + 1), y);
+                const float s2 = sand5x5(left, x, y, right, x - bestDisp, y);
+                const float s3 = sand5x5(left, x, y, right, x - (bestDisp - 1), y);
+                const float denom = (d1 - d2) * (d1 - d3) * (d2 - d3);
+                const float A = (d3 * (s2 - s1) + d2 * (s1 - s3) + d1 * (s3 - s2)) / denom;
+                const float B = (d3 * d3 * (s1 - s2) + d2 * d2 * (s3 - s1) + d1 * d1 * (s2 - s3)) / denom;
+                const float newDisp = -B / (2.0f * A);
+                if (d3 < newDisp && newDisp < d1) res = newDisp;
+            }
+            *(float*)img_at(out, (size_t)x, (size_t)y, 4) = res;
+            if (have_mask) *(uint8_t*)img_at(mask, (size_t)x, (size_t)y, 1) = m;
+        }
+}
+
+/* ---------------------------------------------------------------- left-right check ---- */
+
+/* cu_dense_stereo.cu:512-532 with TD=float; InvalidValue<float>: NaN / isfinite (InvalidValue.h:18-47) */
+void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff) {
+    const int w = (int)dispL->w, h = (int)dispL->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float* pl = (float*)img_at(dispL, (size_t)x, (size_t)y, 4);
+            const float dl = *pl;
+            const float xr = (float)x + sd * dl;
+            if (0.0f <= xr && xr < (float)dispR->w) {
+                const float dr = *(const float*)img_at(dispR, (size_t)xr, (size_t)y, 4);
+                if (!isfinite(dr) || fabsf(dl - dr) > maxDiff) *pl = NAN;
+            } else {
+                *pl = NAN;
+            }
+        }
+}
+
+/* GPU float -> signed char conversion saturates (cvt.rzi.s8.f32) */
+static inline int8_t sat_i8(float v) {
+    if (!(v == v)) return 0;
+    if (v <= -128.0f) return -128;
+    if (v >= 127.0f) return 127;
+    return (int8_t)v;
+}
+
+/* cu_dense_stereo.cu:512-539 with TD=char: xr is computed in char; InvalidValue<char>::IsValid(v) = !v
+ * while Value() = 0 (InvalidValue.h:50-59, Q10). */
+void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sdi, int maxDiffi) {
+    const int w = (int)dispL->w, h = (int)dispL->h;
+    const float sd = (float)sdi, maxDiff = (float)maxDiffi;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int8_t* pl = (int8_t*)img_at(dispL, (size_t)x, (size_t)y, 1);
+            const int8_t dl = *pl;
+            const int8_t xr = sat_i8((float)x + sd * (float)dl);
+            if (0 <= xr && (size_t)xr < dispR->w) {
+                const int8_t dr = *(const int8_t*)img_at(dispR, (size_t)xr, (size_t)y, 1);
+                const int valid = !(uint8_t)dr;
+                if (!valid || (float)abs((int)dl - (int)dr) > maxDiff) *pl = 0;
+            } else {
+                *pl = 0;
+            }
+        }
+}
+
+/* ---------------------------------------------------------------- whole path ---- */
+
+/* applications/stereo2/main.cpp:375-454 with use_census, no cost-volume filters, no median:
+ *   img = u8/255 (ElementwiseScaleBias, :376) ; Census (:380) ; CensusStereoVolume sd=-1 (:384) and,
+ *   for the LR check, sd=+1 (:385) ; SemiGlobalMatching<float,float,float> on vol[0] only (:423-427) ;
+ *   CostVolMinimumSubpix / CostVolMinimum<float,float> on both (:430-436) ;
+ *   LeftRightCheck(disp[1],disp[0],+1) then LeftRightCheck(disp[0],disp[1],-1) (:451-454). */
+int ko_pipeline_u8(const uint8_t* left, const uint8_t* right, int w, int h, int maxDisp, int window,
+                   int popc_mode, float P1, float P2, int dohoriz, int dovert, int doreverse, int dodiag,
+                   int subpix, int lrcheck, float lr_maxdiff, float* disp_out, float* volH_out) {
+    const int words = window == KO_WIN_9x7 ? 1 : (window == KO_WIN_11x11 ? 2 : 4);
+    const size_t npx = (size_t)w * (size_t)h;
+    float* imgf[2] = {(float*)malloc(npx * 4), (float*)malloc(npx * 4)};
+    uint64_t* cen[2] = {(uint64_t*)malloc(npx * 8 * (size_t)words), (uint64_t*)malloc(npx * 8 * (size_t)words)};
+    float* volC = (float*)malloc(npx * (size_t)maxDisp * 4);
+    float* volH = volH_out ? volH_out : (float*)malloc(npx * (size_t)maxDisp * 4);
+    float* dispR = lrcheck ? (float*)malloc(npx * 4) : NULL;
+    if (!imgf[0] || !imgf[1] || !cen[0] || !cen[1] || !volC || !volH || (lrcheck && !dispR)) return -1;
+    const uint8_t* src[2] = {left, right};
+    ko_image fi[2], ci[2];
+    for (int i = 0; i < 2; ++i) {
+        for (size_t k = 0; k < npx; ++k) imgf[i][k] = (float)src[i][k] * (1.0f / 255.0f);
+        fi[i] = (ko_image){(size_t)w * 4, imgf[i], (size_t)w, (size_t)h};
+        ci[i] = (ko_image){(size_t)w * 8 * (size_t)words, cen[i], (size_t)w, (size_t)h};
+        ko_census(&ci[i], &fi[i], window, KO_IMG_F32);
+    }
+    ko_volume vC = {(size_t)w * 4, volC, (size_t)w, (size_t)h, npx * 4, (size_t)maxDisp};
+    ko_volume vH = {(size_t)w * 4, volH, (size_t)w, (size_t)h, npx * 4, (size_t)maxDisp};
+    ko_image dL = {(size_t)w * 4, disp_out, (size_t)w, (size_t)h};
+    ko_image dR = {(size_t)w * 4, dispR, (size_t)w, (size_t)h};
+    if (lrcheck) { /* right-reference volume is NOT aggregated (main.cpp:424 loops i<1) */
+        ko_census_stereo_volume(&vC, &ci[1], &ci[0], words, KO_VOL_F32, maxDisp, +1.0f, popc_mode);
+        if (subpix) ko_costvol_minimum_subpix(&dR, &vC, (unsigned)maxDisp, +1.0f, NULL);
+        else ko_costvol_minimum(&dR, KO_DISP_F32, &vC, KO_VOL_F32, (unsigned)maxDisp);
+    }
+    ko_census_stereo_volume(&vC, &ci[0], &ci[1], words, KO_VOL_F32, maxDisp, -1.0f, popc_mode);
+    const ko_volume* vfinal = &vC;
+    if (dohoriz || dovert || dodiag) {
+        ko_sgm(&vH, &vC, KO_VOL_F32, &fi[0], KO_IMG_F32, maxDisp, P1, P2, dohoriz, dovert, doreverse, dodiag);
+        vfinal = &vH; /* the app copies vol[2] back into vol[0] (:426) */
+    }
+    if (subpix) ko_costvol_minimum_subpix(&dL, vfinal, (unsigned)maxDisp, -1.0f, NULL);
+    else ko_costvol_minimum(&dL, KO_DISP_F32, vfinal, KO_VOL_F32, (unsigned)maxDisp);
+    if (lrcheck) {
+        ko_left_right_check_f32(&dR, &dL, +1.0f, lr_maxdiff);
+        ko_left_right_check_f32(&dL, &dR, -1.0f, lr_maxdiff);
+    }
+    free(imgf[0]); free(imgf[1]); free(cen[0]); free(cen[1]); free(volC);
+    if (!volH_out) free(volH);
+    if (dispR) free(dispR);
+    return 0;
+}

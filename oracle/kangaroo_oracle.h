@@ -1,0 +1,91 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the census / semi-global-matching
+ * path of arpg/Kangaroo.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product path (kangaroo_b200/, libroo_b200.so)
+ * never links, imports or calls it.
+ *
+ * Parity pinning: the reference ships no tests or golden vectors.  This
+ * restatement is pinned against outputs of the UNMODIFIED reference kernels (oracle/_ref, built by
+ * oracle/Makefile from /root/reference/src) run on a B200; those outputs are committed as
+ * tests/golden/ (.npz files) together with the generating script tests/golden/make_golden.py, and
+ * tests/test_oracle_golden.py checks every function below against them.
+ *
+ * Every function cites the reference file:line it follows (paths relative to /root/reference).
+ * Images / volumes use the reference's own pitched layout (include/kangaroo/Image.h:617-620,
+ * Volume.h:363-369): element (x,y,z) at (char*)ptr + z*img_pitch + y*pitch + x*sizeof(T).
+ */
+#ifndef KANGAROO_ORACLE_H
+#define KANGAROO_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { size_t pitch; void* ptr; size_t w; size_t h; } ko_image;
+typedef struct { size_t pitch; void* ptr; size_t w; size_t h; size_t img_pitch; size_t d; } ko_volume;
+
+/* include/kangaroo/CostVolElem.h:10-19 */
+typedef struct { int32_t n; float sum; } ko_costvolelem;
+
+enum { KO_WIN_9x7 = 0, KO_WIN_11x11 = 1, KO_WIN_16x16 = 2 };
+enum { KO_IMG_U8 = 0, KO_IMG_F32 = 1 };
+/* popcount mode: 0 = the reference's 32-bit __popc on 64-bit words (hamming_distance.h:40-62,
+ * low 32 bits of every word only), 1 = full 64-bit popcount (extension) */
+enum { KO_POPC32_COMPAT = 0, KO_POPC64 = 1 };
+enum { KO_VOL_U16 = 0, KO_VOL_F32 = 1, KO_VOL_I32 = 2, KO_VOL_U32 = 3, KO_VOL_U8 = 4, KO_VOL_ELEM = 5 };
+enum { KO_DISP_I8 = 0, KO_DISP_F32 = 1 };
+
+int ko_num_threads(void);
+
+/* src/cu_census.cu:18-46 (9x7), :52-110 (11x11), :116-177 (16x16); out holds 1/2/4 uint64 per px */
+void ko_census(const ko_image* out, const ko_image* in, int window, int in_type);
+
+/* include/kangaroo/hamming_distance.h:40-62 */
+unsigned ko_hamming(const uint64_t* p, const uint64_t* q, int words, int popc_mode);
+
+/* src/cu_census.cu:226-266 */
+void ko_census_stereo(const ko_image* disp_i8, const ko_image* left, const ko_image* right, int maxDisp);
+
+/* src/cu_census.cu:272-314 ; vol_type in {KO_VOL_U16, KO_VOL_F32} */
+void ko_census_stereo_volume(const ko_volume* vol, const ko_image* left, const ko_image* right, int words,
+                             int vol_type, int maxDisp, float sd, int popc_mode);
+
+/* src/cu_semi_global_matching.cu:21-89.  volc_type in {KO_VOL_F32, KO_VOL_ELEM}; img_type in
+ * {KO_IMG_U8, KO_IMG_F32}.  Path order: down, [down-right, down-left], up, [up-left, up-right],
+ * right, left; the bracketed diagonal sweeps (dodiag) are an extension with the same per-path
+ * kernel body -- with dodiag == 0 this is exactly the reference. */
+void ko_sgm(const ko_volume* volH, const ko_volume* volC, int volc_type, const ko_image* left, int img_type,
+            int maxDisp, float P1, float P2, int dohoriz, int dovert, int doreverse, int dodiag);
+
+/* src/cu_dense_stereo.cu:25-60 (guarded: the reference kernel has no bounds test) */
+void ko_costvol_minimum(const ko_image* disp, int disp_type, const ko_volume* vol, int vol_type, unsigned maxDisp);
+
+/* src/cu_dense_stereo.cu:735-763 */
+void ko_costvol_minimum_elem(const ko_image* disp_f32, const ko_volume* vol_elem);
+
+/* src/cu_dense_stereo.cu:66-116.  mask_u8 (optional, may be NULL / ptr==NULL) receives 1 where the
+ * reference reads out of bounds (bestd+1 == vol.d) and this restatement skipped the parabola. */
+void ko_costvol_minimum_subpix(const ko_image* disp_f32, const ko_volume* vol_f32, unsigned maxDisp, float sd,
+                               const ko_image* mask_u8);
+
+/* src/cu_dense_stereo.cu:580-627 + include/kangaroo/patch_score.h:257-298.  Pixels whose 5x5 windows
+ * leave the images (reference: unguarded reads) get NaN and mask 1. */
+void ko_dense_stereo_subpixel_refine(const ko_image* out_f32, const ko_image* disp_u8, const ko_image* left_u8,
+                                     const ko_image* right_u8, const ko_image* mask_u8);
+
+/* src/cu_dense_stereo.cu:512-546 */
+void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff);
+void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd, int maxDiff);
+
+/* Whole path as applications/stereo2/main.cpp:380-454 runs it (census -> volume(s) -> SGM -> WTA/subpix
+ * -> LR check), on tightly packed host arrays; used as the CPU baseline.  scratch volumes are
+ * allocated inside.  Returns 0 on success. */
+int ko_pipeline_u8(const uint8_t* left, const uint8_t* right, int w, int h, int maxDisp, int window,
+                   int popc_mode, float P1, float P2, int dohoriz, int dovert, int doreverse, int dodiag,
+                   int subpix, int lrcheck, float lr_maxdiff, float* disp_out, float* volH_out /* may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

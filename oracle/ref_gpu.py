@@ -1,0 +1,172 @@
+"""TEST INFRASTRUCTURE ONLY -- runs the UNMODIFIED reference kernels (oracle/_ref/libkangaroo_ref.so,
+built by oracle/Makefile from /root/reference/src) on the current CUDA device.
+
+numpy in, numpy out; device memory comes from torch.  Works only for w <= 1024 and h <= 1024
+(the reference launches one thread per row/column element in a single block).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libkangaroo_ref.so")
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(SO)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        L = C.CDLL(SO)
+        z, p, i, f, u = C.c_size_t, C.c_void_p, C.c_int, C.c_float, C.c_uint
+        L.kref_census.argtypes = [p, z, p, z, z, z, i, i]
+        L.kref_census_stereo.argtypes = [p, z, p, p, z, z, z, i]
+        L.kref_census_stereo_volume.argtypes = [p, z, z, z, p, p, z, z, z, i, i, i, f]
+        L.kref_sgm.argtypes = [p, p, z, z, z, z, p, z, z, z, z, i, i, f, f, i, i, i]
+        L.kref_costvol_minimum.argtypes = [p, z, p, z, z, z, z, z, i, i, u]
+        L.kref_costvol_minimum_elem.argtypes = [p, z, p, z, z, z, z, z]
+        L.kref_costvol_minimum_subpix.argtypes = [p, z, p, z, z, z, z, z, u, f]
+        L.kref_dense_stereo_subpixel_refine.argtypes = [p, z, p, p, p, z, z, z]
+        L.kref_left_right_check_f32.argtypes = [p, p, z, z, z, f, f]
+        L.kref_left_right_check_i8.argtypes = [p, p, z, z, z, i, i]
+        _lib = L
+    return _lib
+
+
+def _dev(a: np.ndarray):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+
+
+def _back(t, dtype, shape) -> np.ndarray:
+    return t.cpu().numpy().view(dtype).reshape(shape).copy()
+
+
+def _ck(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"reference {what} failed: code {rc}")
+
+
+def census(img: np.ndarray, window: int) -> np.ndarray:
+    import torch
+    h, w = img.shape
+    words = {0: 1, 1: 2, 2: 4}[window]
+    d_in = _dev(img)
+    d_out = torch.zeros(h * w * words * 8, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_census(d_out.data_ptr(), w * words * 8, d_in.data_ptr(), w * img.itemsize, w, h, window,
+                          0 if img.dtype == np.uint8 else 1), "Census")
+    return _back(d_out, np.uint64, (h, w, words))
+
+
+def census_stereo(left: np.ndarray, right: np.ndarray, max_disp: int) -> np.ndarray:
+    import torch
+    h, w = left.shape[:2]
+    dl, dr = _dev(left), _dev(right)
+    out = torch.zeros(h * w, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_census_stereo(out.data_ptr(), w, dl.data_ptr(), dr.data_ptr(), w * 8, w, h, max_disp),
+        "CensusStereo")
+    return _back(out, np.int8, (h, w))
+
+
+def census_stereo_volume(left, right, max_disp: int, sd: float, vol_dtype=np.float32, depth=None, fill=0.0):
+    import torch
+    h, w, words = left.shape
+    vol_dtype = np.dtype(vol_dtype)
+    depth = depth or max_disp
+    dl, dr = _dev(left), _dev(right)
+    vol = _dev(np.full((depth, h, w), fill, vol_dtype))
+    _ck(lib().kref_census_stereo_volume(vol.data_ptr(), w * vol_dtype.itemsize, w * h * vol_dtype.itemsize, depth,
+                                        dl.data_ptr(), dr.data_ptr(), w * words * 8, w, h, words,
+                                        1 if vol_dtype == np.float32 else 0, max_disp, sd), "CensusStereoVolume")
+    return _back(vol, vol_dtype, (depth, h, w))
+
+
+def sgm(vol_c: np.ndarray, left: np.ndarray, max_disp: int, p1: float, p2: float, dohoriz=True, dovert=True,
+        doreverse=True) -> np.ndarray:
+    import torch
+    d, h, w = vol_c.shape
+    elem = vol_c.dtype.itemsize == 8
+    dc, dleft = _dev(vol_c), _dev(left)
+    dh = torch.full((d * h * w * 4,), 0x7F, dtype=torch.uint8, device="cuda")  # garbage: SGM must memset
+    cs = vol_c.dtype.itemsize
+    _ck(lib().kref_sgm(dh.data_ptr(), dc.data_ptr(), w * 4, w * h * 4, w * cs, w * h * cs, dleft.data_ptr(),
+                       w * left.itemsize, w, h, d, 1 if elem else 0, max_disp, p1, p2, int(dohoriz), int(dovert),
+                       int(doreverse)), "SemiGlobalMatching")
+    return _back(dh, np.float32, (d, h, w))
+
+
+_VT = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.uint32): 2, np.dtype(np.uint16): 3,
+       np.dtype(np.uint8): 4}
+
+
+def costvol_minimum(vol: np.ndarray, max_disp: int, disp_dtype=np.float32) -> np.ndarray:
+    import torch
+    d, h, w = vol.shape
+    disp_dtype = np.dtype(disp_dtype)
+    dv = _dev(vol)
+    out = torch.zeros(h * w * disp_dtype.itemsize, dtype=torch.uint8, device="cuda")
+    vs = vol.dtype.itemsize
+    _ck(lib().kref_costvol_minimum(out.data_ptr(), w * disp_dtype.itemsize, dv.data_ptr(), w * vs, w * h * vs, w, h,
+                                   d, 0 if disp_dtype == np.int8 else 1, _VT[vol.dtype], max_disp), "CostVolMinimum")
+    return _back(out, disp_dtype, (h, w))
+
+
+def costvol_minimum_elem(vol: np.ndarray) -> np.ndarray:
+    import torch
+    d, h, w = vol.shape
+    dv = _dev(vol)
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_costvol_minimum_elem(out.data_ptr(), w * 4, dv.data_ptr(), w * 8, w * h * 8, w, h, d),
+        "CostVolMinimum(elem)")
+    return _back(out, np.float32, (h, w))
+
+
+def costvol_minimum_subpix(vol: np.ndarray, max_disp: int, sd: float) -> np.ndarray:
+    import torch
+    d, h, w = vol.shape
+    dv = _dev(vol)
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_costvol_minimum_subpix(out.data_ptr(), w * 4, dv.data_ptr(), w * 4, w * h * 4, w, h, d, max_disp,
+                                          sd), "CostVolMinimumSubpix")
+    return _back(out, np.float32, (h, w))
+
+
+def dense_stereo_subpixel_refine(disp: np.ndarray, left: np.ndarray, right: np.ndarray, pad: int = 8):
+    """The reference reads outside the images near the borders (Q8): the three inputs are embedded in
+    zero-padded parents so that those reads stay inside the allocation."""
+    import torch
+    h, w = disp.shape
+
+    def emb(a):
+        p = np.zeros((h + 2 * pad, w + 512), np.uint8)
+        p[pad:pad + h, 256:256 + w] = a
+        return p
+
+    pitch = w + 512
+    off = pad * pitch + 256
+    dd, dl, dr = _dev(emb(disp)), _dev(emb(left)), _dev(emb(right))
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_dense_stereo_subpixel_refine(out.data_ptr(), w * 4, dd.data_ptr() + off, dl.data_ptr() + off,
+                                                dr.data_ptr() + off, pitch, w, h), "DenseStereoSubpixelRefine")
+    return _back(out, np.float32, (h, w))
+
+
+def left_right_check_f32(disp_l, disp_r, sd=-1.0, max_diff=0.5) -> np.ndarray:
+    h, w = disp_l.shape
+    dl, dr = _dev(disp_l.astype(np.float32)), _dev(disp_r.astype(np.float32))
+    _ck(lib().kref_left_right_check_f32(dl.data_ptr(), dr.data_ptr(), w * 4, w, h, sd, max_diff), "LeftRightCheck")
+    return _back(dl, np.float32, (h, w))
+
+
+def left_right_check_i8(disp_l, disp_r, sd=-1, max_diff=0) -> np.ndarray:
+    h, w = disp_l.shape
+    dl, dr = _dev(disp_l.astype(np.int8)), _dev(disp_r.astype(np.int8))
+    _ck(lib().kref_left_right_check_i8(dl.data_ptr(), dr.data_ptr(), w, w, h, sd, max_diff), "LeftRightCheck<char>")
+    return _back(dl, np.int8, (h, w))

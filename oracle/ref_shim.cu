@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product path.
+//
+// Thin extern "C" shim over the UNMODIFIED reference operators so that tests and
+// the golden-vector generator can call them through ctypes.  This file contains no
+// reference code: it only includes the reference's public headers
+// (include/kangaroo/cu_census.h, cu_semi_global_matching.h, cu_dense_stereo.h) and
+// forwards plain pointers to the roo:: free functions.  It is compiled together
+// with /root/reference/src/{cu_census,cu_semi_global_matching,cu_dense_stereo}.cu
+// (from where they lie) into oracle/_ref/libkangaroo_ref.so by oracle/Makefile.
+//
+// The reference kernels launch one thread per pixel of a row/column in ONE block
+// (cu_census.cu:304-306, cu_semi_global_matching.cu:69-83), so every entry point
+// here refuses w > 1024 or h > 1024 instead of letting the launch fail silently.
+#include <cuda_runtime.h>
+#include <kangaroo/cu_census.h>
+#include <kangaroo/cu_semi_global_matching.h>
+#include <kangaroo/cu_dense_stereo.h>
+
+namespace {
+template <typename T>
+roo::Image<T> img(void* p, size_t pitch, size_t w, size_t h) {
+    return roo::Image<T>((T*)p, w, h, pitch);
+}
+template <typename T>
+roo::Volume<T> vol(void* p, size_t pitch, size_t img_pitch, size_t w, size_t h, size_t d) {
+    return roo::Volume<T>((T*)p, w, h, d, pitch, img_pitch);
+}
+int finish() {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return (int)e;
+}
+bool too_big(size_t w, size_t h) { return w > 1024 || h > 1024; }
+}  // namespace
+
+extern "C" {
+
+// window: 0 = 9x7 -> unsigned long, 1 = "11x11" -> ulong2, 2 = "16x16" -> ulong4
+// in_type: 0 = unsigned char, 1 = float
+int kref_census(void* out, size_t out_pitch, void* in, size_t in_pitch, size_t w, size_t h,
+                int window, int in_type) {
+    if (in_type == 0) {
+        roo::Image<unsigned char> i = img<unsigned char>(in, in_pitch, w, h);
+        if (window == 0) roo::Census(img<unsigned long>(out, out_pitch, w, h), i);
+        else if (window == 1) roo::Census(img<ulong2>(out, out_pitch, w, h), i);
+        else if (window == 2) roo::Census(img<ulong4>(out, out_pitch, w, h), i);
+        else return -1;
+    } else if (in_type == 1) {
+        roo::Image<float> i = img<float>(in, in_pitch, w, h);
+        if (window == 0) roo::Census(img<unsigned long>(out, out_pitch, w, h), i);
+        else if (window == 1) roo::Census(img<ulong2>(out, out_pitch, w, h), i);
+        else if (window == 2) roo::Census(img<ulong4>(out, out_pitch, w, h), i);
+        else return -1;
+    } else return -1;
+    return finish();
+}
+
+int kref_census_stereo(void* disp, size_t disp_pitch, void* l, void* r, size_t c_pitch,
+                       size_t w, size_t h, int maxDisp) {
+    if (too_big(w, h)) return -2;
+    roo::CensusStereo(img<char>(disp, disp_pitch, w, h), img<unsigned long>(l, c_pitch, w, h),
+                      img<unsigned long>(r, c_pitch, w, h), maxDisp);
+    return finish();
+}
+
+// words: 1/2/4 (unsigned long / ulong2 / ulong4); vol_type: 0 = unsigned short, 1 = float
+int kref_census_stereo_volume(void* v, size_t v_pitch, size_t v_img_pitch, size_t d, void* l, void* r,
+                              size_t c_pitch, size_t w, size_t h, int words, int vol_type,
+                              int maxDisp, float sd) {
+    if (too_big(w, h)) return -2;
+#define KREF_CSV(TV, TC)                                                                          \
+    roo::CensusStereoVolume<TV, TC>(vol<TV>(v, v_pitch, v_img_pitch, w, h, d),                    \
+                                    img<TC>(l, c_pitch, w, h), img<TC>(r, c_pitch, w, h), maxDisp, sd)
+    if (vol_type == 1) {
+        if (words == 1) KREF_CSV(float, unsigned long);
+        else if (words == 2) KREF_CSV(float, ulong2);
+        else if (words == 4) KREF_CSV(float, ulong4);
+        else return -1;
+    } else if (vol_type == 0) {
+        if (words == 1) KREF_CSV(unsigned short, unsigned long);
+        else if (words == 2) KREF_CSV(unsigned short, ulong2);
+        else if (words == 4) KREF_CSV(unsigned short, ulong4);
+        else return -1;
+    } else return -1;
+#undef KREF_CSV
+    return finish();
+}
+
+// volc_type: 0 = float (left image float), 1 = CostVolElem (left image unsigned char)
+int kref_sgm(void* vh, void* vc, size_t h_pitch, size_t h_img_pitch, size_t c_pitch, size_t c_img_pitch,
+             void* left, size_t left_pitch, size_t w, size_t h, size_t d, int volc_type, int maxDisp,
+             float P1, float P2, int dohoriz, int dovert, int doreverse) {
+    if (too_big(w, h)) return -2;
+    if (volc_type == 0)
+        roo::SemiGlobalMatching<float, float, float>(vol<float>(vh, h_pitch, h_img_pitch, w, h, d),
+                                                     vol<float>(vc, c_pitch, c_img_pitch, w, h, d),
+                                                     img<float>(left, left_pitch, w, h), maxDisp, P1, P2,
+                                                     dohoriz != 0, dovert != 0, doreverse != 0);
+    else if (volc_type == 1)
+        roo::SemiGlobalMatching<float, roo::CostVolElem, unsigned char>(
+            vol<float>(vh, h_pitch, h_img_pitch, w, h, d),
+            vol<roo::CostVolElem>(vc, c_pitch, c_img_pitch, w, h, d),
+            img<unsigned char>(left, left_pitch, w, h), maxDisp, P1, P2, dohoriz != 0, dovert != 0,
+            doreverse != 0);
+    else return -1;
+    return finish();
+}
+
+// disp_type: 0 = char, 1 = float; vol_type: 0 float, 1 int, 2 unsigned, 3 unsigned short, 4 unsigned char
+// NOTE the reference kernel is unguarded (cu_dense_stereo.cu:25-43): only call with w%32==0 && h%32==0.
+int kref_costvol_minimum(void* disp, size_t disp_pitch, void* v, size_t v_pitch, size_t v_img_pitch,
+                         size_t w, size_t h, size_t d, int disp_type, int vol_type, unsigned maxDisp) {
+    if ((w % 32) || (h % 32)) return -3;
+#define KREF_CVM(TD, TV)                                                                          \
+    roo::CostVolMinimum<TD, TV>(img<TD>(disp, disp_pitch, w, h), vol<TV>(v, v_pitch, v_img_pitch, w, h, d), maxDisp)
+    if (disp_type == 0) {
+        if (vol_type == 0) KREF_CVM(char, float);
+        else if (vol_type == 1) KREF_CVM(char, int);
+        else if (vol_type == 2) KREF_CVM(char, unsigned int);
+        else if (vol_type == 3) KREF_CVM(char, unsigned short);
+        else if (vol_type == 4) KREF_CVM(char, unsigned char);
+        else return -1;
+    } else if (disp_type == 1) {
+        if (vol_type == 0) KREF_CVM(float, float);
+        else if (vol_type == 3) KREF_CVM(float, unsigned short);
+        else return -1;
+    } else return -1;
+#undef KREF_CVM
+    return finish();
+}
+
+int kref_costvol_minimum_elem(void* disp, size_t disp_pitch, void* v, size_t v_pitch, size_t v_img_pitch,
+                              size_t w, size_t h, size_t d) {
+    if ((w % 32) || (h % 32)) return -3;
+    roo::CostVolMinimum(img<float>(disp, disp_pitch, w, h),
+                        vol<roo::CostVolElem>(v, v_pitch, v_img_pitch, w, h, d));
+    return finish();
+}
+
+int kref_costvol_minimum_subpix(void* disp, size_t disp_pitch, void* v, size_t v_pitch, size_t v_img_pitch,
+                                size_t w, size_t h, size_t d, unsigned maxDisp, float sd) {
+    roo::CostVolMinimumSubpix(img<float>(disp, disp_pitch, w, h),
+                              vol<float>(v, v_pitch, v_img_pitch, w, h, d), maxDisp, sd);
+    return finish();
+}
+
+int kref_dense_stereo_subpixel_refine(void* out, size_t out_pitch, void* disp, void* l, void* r,
+                                      size_t u8_pitch, size_t w, size_t h) {
+    roo::DenseStereoSubpixelRefine(img<float>(out, out_pitch, w, h), img<unsigned char>(disp, u8_pitch, w, h),
+                                   img<unsigned char>(l, u8_pitch, w, h), img<unsigned char>(r, u8_pitch, w, h));
+    return finish();
+}
+
+int kref_left_right_check_f32(void* dl, void* dr, size_t pitch, size_t w, size_t h, float sd, float maxDiff) {
+    roo::LeftRightCheck(img<float>(dl, pitch, w, h), img<float>(dr, pitch, w, h), sd, maxDiff);
+    return finish();
+}
+
+int kref_left_right_check_i8(void* dl, void* dr, size_t pitch, size_t w, size_t h, int sd, int maxDiff) {
+    roo::LeftRightCheck(img<char>(dl, pitch, w, h), img<char>(dr, pitch, w, h), sd, maxDiff);
+    return finish();
+}
+
+}  // extern "C"

@@ -434,15 +434,18 @@ void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float
         }
 }
 
-/* GPU float -> signed char conversion saturates (cvt.rzi.s8.f32) */
-static inline int8_t sat_i8(float v) {
-    if (!(v == v)) return 0;
-    if (v <= -128.0f) return -128;
-    if (v >= 127.0f) return 127;
-    return (int8_t)v;
+/* float -> char on the GPU: the sm_100a PTX of the reference is cvt.rzi.ftz.s32.f32 followed by
+ * cvt.s64.s8, i.e. truncate to int32 (saturating) and keep the low 8 bits sign-extended (wraps). */
+static inline int8_t wrap_i8(float v) {
+    int32_t i;
+    if (!(v == v)) i = 0;
+    else if (v <= -2147483648.0f) i = INT32_MIN;
+    else if (v >= 2147483648.0f) i = INT32_MAX;
+    else i = (int32_t)v;
+    return (int8_t)(uint8_t)((uint32_t)i & 0xFFu);
 }
 
-/* cu_dense_stereo.cu:512-539 with TD=char: xr is computed in char; InvalidValue<char>::IsValid(v) = !v
+/* cu_dense_stereo.cu:512-539 with TD=char: xr is computed in char (wraps for x > 127); InvalidValue<char>::IsValid(v) = !v
  * while Value() = 0 (InvalidValue.h:50-59, Q10). */
 void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sdi, int maxDiffi) {
     const int w = (int)dispL->w, h = (int)dispL->h;
@@ -452,7 +455,7 @@ void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd
         for (int x = 0; x < w; ++x) {
             int8_t* pl = (int8_t*)img_at(dispL, (size_t)x, (size_t)y, 1);
             const int8_t dl = *pl;
-            const int8_t xr = sat_i8((float)x + sd * (float)dl);
+            const int8_t xr = wrap_i8((float)x + sd * (float)dl);
             if (0 <= xr && (size_t)xr < dispR->w) {
                 const int8_t dr = *(const int8_t*)img_at(dispR, (size_t)xr, (size_t)y, 1);
                 const int valid = !(uint8_t)dr;

@@ -1,0 +1,268 @@
+"""Pins the CPU oracle (oracle/kangaroo_oracle.c) against outputs of the UNMODIFIED reference kernels
+(tests/golden/*.npz, produced on a B200 by tests/golden/make_golden.py) and against hand-authored
+known-answer vectors.  Runs without a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as ko
+
+from conftest import GOLDEN
+
+
+def relerr(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(a), 1e-30)
+
+
+# ---------------------------------------------------------------- golden: census
+
+@pytest.mark.parametrize("name", ["u8", "tie", "f32"])
+@pytest.mark.parametrize("win", [0, 1, 2])
+def test_census_matches_reference(golden, name, win):
+    g = golden("census")
+    out = ko.census(g["img_" + name], win)
+    assert np.array_equal(out, g[f"out_{name}_{win}"])
+
+
+def test_census_stereo_matches_reference(golden):
+    g = golden("census_stereo")
+    cl, cr = ko.census(g["left"], 0), ko.census(g["right"], 0)
+    for md in (16, -16, 5):
+        assert np.array_equal(ko.census_stereo(cl, cr, md), g[f"disp_{md}"]), md
+
+
+@pytest.mark.parametrize("win", [0, 1, 2])
+def test_census_stereo_volume_matches_reference(golden, win):
+    g = golden("census_stereo_volume")
+    cl, cr = ko.census(g["left"], win), ko.census(g["right"], win)
+    for sd in (-1, 1):
+        v = ko.census_stereo_volume(cl, cr, 16, float(sd), np.float32, depth=18, fill=7.0)
+        assert np.array_equal(v, g[f"f32_w{win}_sd{sd}"])  # bit-exact, untouched slices included
+    v = ko.census_stereo_volume(cl, cr, 16, -1.0, np.uint16, depth=16, fill=9)
+    assert np.array_equal(v, g[f"u16_w{win}"])
+    assert (v == 0).all()  # Q2: the unsigned short instantiation truncates every score to 0
+
+
+# ---------------------------------------------------------------- golden: SGM
+
+def test_sgm_matches_reference_all_flags(golden):
+    g = golden("sgm")
+    for hz in (0, 1):
+        for vt in (0, 1):
+            for rv in (0, 1):
+                H = ko.sgm(g["volc"], g["left_f32"], 12, 0.01, 0.02, hz, vt, rv)
+                ref = g[f"H_h{hz}v{vt}r{rv}"]
+                assert relerr(ref, H).max() <= 1e-5, (hz, vt, rv)
+                assert np.array_equal(ref == 0, H == 0)
+
+
+def test_sgm_matches_reference_variants(golden):
+    g = golden("sgm")
+    H = ko.sgm(g["volc"], g["left_f32"], 7, 0.05, 0.3)
+    assert relerr(g["H_md7"], H).max() <= 1e-5
+    assert (H[7:] == 0).all()
+    H = ko.sgm(g["volc_rand"], g["left_f32"], 12, 0.1, 0.4)
+    assert relerr(g["H_rand"], H).max() <= 1e-5
+    elem = np.zeros(g["volc_elem_n"].shape, ko.COSTVOLELEM)
+    elem["n"], elem["sum"] = g["volc_elem_n"], g["volc_elem_sum"]
+    H = ko.sgm(elem, g["left_u8"], 12, 1.0, 8.0)
+    assert relerr(g["H_elem"], H).max() <= 1e-5
+
+
+def test_sgm_zero_above_diagonal(golden):
+    g = golden("sgm")
+    H = ko.sgm(g["volc"], g["left_f32"], 12, 0.01, 0.02)
+    d, h, w = H.shape
+    dd, xx = np.arange(d)[:, None, None], np.arange(w)[None, None, :]
+    assert (H[np.broadcast_to(dd > xx, H.shape)] == 0).all()  # Q6
+
+
+# ---------------------------------------------------------------- golden: WTA
+
+def test_costvol_minimum_matches_reference(golden):
+    g = golden("costvol_minimum")
+    assert np.array_equal(ko.costvol_minimum(g["vol_f32"], 20, np.float32), g["disp_f32_f32"])
+    assert np.array_equal(ko.costvol_minimum(g["vol_f32"], 13, np.int8), g["disp_i8_f32"])
+    for nm in ("i32", "u32", "u16", "u8"):
+        assert np.array_equal(ko.costvol_minimum(g["vol_" + nm], 20, np.int8), g["disp_i8_" + nm]), nm
+    assert np.array_equal(ko.costvol_minimum(g["vol_u16"], 20, np.float32), g["disp_f32_u16"])
+    el = np.zeros(g["elem_n"].shape, ko.COSTVOLELEM)
+    el["n"], el["sum"] = g["elem_n"], g["elem_sum"]
+    assert np.array_equal(ko.costvol_minimum_elem(el), g["disp_elem"])
+
+
+def test_costvol_minimum_subpix_matches_reference(golden):
+    g = golden("costvol_minimum_subpix")
+    for key, sd, vol, md in (("disp_sd-1", -1.0, g["vol"], 16), ("disp_sd1", 1.0, g["vol"], 16),
+                             ("disp_sgm", -1.0, g["vol_sgm"], 12)):
+        d, m = ko.costvol_minimum_subpix(vol, md, sd)
+        assert (m == 0).all()  # depth = maxDisp + 1: no out-of-bounds tap
+        ref = g[key]
+        # div.approx in the reference vs IEEE here; the accept test can flip on rounding-level noise
+        assert (np.abs(ref - d) <= 1e-4).mean() >= 0.999, key
+
+
+def test_dense_stereo_subpixel_refine_matches_reference(golden):
+    g = golden("dense_stereo_subpixel_refine")
+    out, mask = ko.dense_stereo_subpixel_refine(g["disp"], g["left"], g["right"])
+    ref = g["out"]
+    inner = mask == 0
+    assert inner.mean() > 0.5
+    # the accept test `d-1 < new < d+1` can flip on a rounding-level difference: allow a handful
+    same_validity = np.isfinite(ref[inner]) == np.isfinite(out[inner])
+    assert same_validity.mean() >= 0.999
+    both = inner & np.isfinite(ref) & np.isfinite(out)
+    assert both.sum() > 100
+    assert np.abs(ref[both] - out[both]).max() <= 0.01
+
+
+def test_left_right_check_matches_reference(golden):
+    g = golden("left_right_check")
+    for key, sd, md in (("f32_sd-1_0.5", -1.0, 0.5), ("f32_sd1_4", 1.0, 4.0)):
+        out = ko.left_right_check_f32(g["dl"], g["dr"], sd, md)
+        assert np.array_equal(np.isnan(out), np.isnan(g[key])), key
+        ok = ~np.isnan(out)
+        assert np.array_equal(out[ok], g[key][ok]), key
+    for key, sd, md in (("i8_sd-1_0", -1, 0), ("i8_sd1_2", 1, 2)):
+        assert np.array_equal(ko.left_right_check_i8(g["dli"], g["dri"], sd, md), g[key]), key
+
+
+def test_pipeline_stages_match_reference(golden):
+    g = golden("pipeline")
+    L, R = g["left"], g["right"]
+    for win in (0, 2):
+        disp, H = ko.pipeline_u8(L, R, 32, window=win, subpix=True, lrcheck=True, lr_maxdiff=1.0, want_volume=True)
+        lf = L.astype(np.float32) * np.float32(1.0 / 255.0)
+        assert np.array_equal(ko.census(lf, win), g[f"w{win}_census0"])
+        assert relerr(g[f"w{win}_H"], H).max() <= 1e-5
+        ref = g[f"w{win}_disp0_lr"]
+        # bestd == maxDisp-1 reads slice maxDisp in the reference (zero slice in the golden run)
+        top = np.rint(g[f"w{win}_disp0"]) >= 31
+        agree = (np.isnan(ref) == np.isnan(disp)) | top
+        assert agree.mean() >= 0.999
+        both = np.isfinite(ref) & np.isfinite(disp) & ~top
+        assert (np.abs(ref - disp)[both] <= 0.01).mean() >= 0.999
+
+
+def test_oracle_pin_report_is_within_bars():
+    """The big-shape comparison (reference GPU kernels vs this oracle) recorded by make_golden.py."""
+    with open(os.path.join(GOLDEN, "ORACLE_PIN_REPORT.json")) as f:
+        rep = json.load(f)
+    assert len(rep["cases"]) == 4
+    for c in rep["cases"]:
+        for k, v in c.items():
+            if k.endswith("bitexact") or k == "sgm_zero_region_exact":
+                assert v is True, (c["w"], k)
+        assert c["wta_int_agree"] >= 0.999
+        assert c["subpix_max_abs"] <= 0.01
+        # reference = -use_fast_math (div.approx), oracle = IEEE; rounding noise accumulates along the
+        # paths (1e-5 at 1024x375x128, 4.9e-5 at 1024x1024x256)
+        assert c["sgm_max_rel"] <= 1e-4
+
+
+# ---------------------------------------------------------------- known-answer vectors (authored)
+
+def test_kat_constant_image():
+    img = np.full((20, 30), 7, np.uint8)
+    for win in (0, 1, 2):
+        c = ko.census(img, win)
+        assert (c == 0).all()
+        v = ko.census_stereo_volume(c, c, 8, -1.0)
+        d, xx = np.arange(8)[:, None, None], np.arange(30)[None, None, :]
+        assert np.array_equal(v, np.broadcast_to(np.where(d <= xx, 0.0, 0.5), v.shape).astype(np.float32))
+
+
+def test_kat_ramp_9x7():
+    ramp = np.tile(np.arange(30, dtype=np.uint8), (20, 1))
+    c = ko.census(ramp, 0)
+    exp = sum(1 << (r * 9 + cc) for r in range(7) for cc in range(4))
+    assert int(c[10, 10, 0]) == exp
+    assert int(c[10, 2, 0]) == exp  # clamp-to-edge repeats column 0, still < p
+    assert int(c[10, 0, 0]) == 0    # nothing is < the minimum
+
+
+def test_kat_single_bright_pixel_bit_order():
+    img = np.zeros((40, 40), np.uint8)
+    img[20, 20] = 200
+    # a neighbour at offset (c, r) from the bright pixel sees it at (-c, -r)
+    c9 = ko.census(255 - img, 0)  # invert: the single DARK pixel is the only one < neighbours
+    for (dx, dy) in ((1, 0), (-4, -3), (4, 3), (0, 2), (-1, -1)):
+        word = int(c9[20 + dy, 20 + dx, 0])
+        r, c = -dy, -dx
+        assert word == 1 << ((r + 3) * 9 + (c + 4)), (dx, dy)
+    c11 = ko.census(255 - img, 1)
+    assert int(c11[20, 20 + 5, 0]) == 1 << 55 and int(c11[20, 20 + 5, 1]) == 0      # r=0, c=-5 -> x bit 55
+    assert int(c11[20, 20, 0]) == 0 and int(c11[20, 20, 1]) == 0                    # centre: strict <
+    assert int(c11[20, 20 - 1, 1]) == 1 and int(c11[20, 20 - 1, 0]) == 0            # r=0, c=+1 -> y bit 0
+    assert int(c11[20 - 1, 20 + 5, 1]) == 1 << 5                                    # r=+1, c=-5 -> y bit 5
+    assert int(c11[20 + 5, 20 + 5, 0]) == 1                                         # r=-5, c=-5 -> x bit 0
+    c16 = ko.census(255 - img, 2)
+    assert [int(v) for v in c16[20 + 8, 20 + 4]] == [1, 0, 0, 0]                    # r=-8, c=-4 -> x bit 0
+    assert [int(v) for v in c16[20, 20 - 3]] == [0, 0, 1 << 7, 0]                   # r=0, c=+3 -> z bit 7
+    assert [int(v) for v in c16[20 - 7, 20 - 3]] == [0, 0, 0, 1 << 31]              # r=7, c=3 -> w bit 31
+    assert [int(v) for v in c16[20 + 1, 20 + 4]] == [0, 1 << 24, 0, 0]              # r=-1, c=-4 -> y bit 24
+    assert (c16[:, :, :] >> np.uint64(32) == 0).all()                               # only low halves used
+
+
+def test_kat_hamming_q1_witness():
+    p = np.array([0], np.uint64)
+    q = np.array([1 << 40], np.uint64)
+    assert ko.hamming(p, q, ko.POPC32_COMPAT) == 0
+    assert ko.hamming(p, q, ko.POPC64) == 1
+    assert ko.hamming(np.array([0xFFFFFFFF] * 4, np.uint64), np.zeros(4, np.uint64)) == 128
+
+
+def test_kat_sgm_one_row_hand_computed():
+    # 4x1x3 volume, P1=1, P2=4, constant image, horizontal forward path only
+    C = np.array([[[5, 1, 4, 2]], [[9, 3, 1, 6]], [[9, 9, 2, 1]]], np.float32)  # (d, y, x)
+    left = np.zeros((1, 4), np.float32)
+    H = ko.sgm(C, left, 3, 1.0, 4.0, dohoriz=True, dovert=False, doreverse=False)
+    # x=0: maxDisp=1, H(0,0)=5, lastBestCr=0 (not the row minimum!), lastMaxDisp=1
+    # x=1: maxDisp=2. d=0: CM=min(0+4, H(0,0)=5)=4 (d+1<1 false) -> Cr=4+1-0=5
+    #               d=1: CM=min(4, [d<1 false], H(0,0)+1=6)=4 -> Cr=4+3=7 ; best=5
+    # x=2: maxDisp=3, lastMaxDisp=2, lastBest=5. d=0: CM=min(9, 5, H(1,1)+1=8)=5 -> Cr=5+4-5=4
+    #               d=1: CM=min(9, 7, 5+1=6)=6 -> Cr=6+1-5=2 ; d=2: CM=min(9, 7+1)=8 -> Cr=8+2-5=5 ; best=2
+    # x=3: lastMaxDisp=3, lastBest=2. d=0: CM=min(6, 4, 2+1=3)=3 -> Cr=3+2-2=3
+    #               d=1: CM=min(6, 2, 4+1, 5+1)=2 -> Cr=2+6-2=6 ; d=2: CM=min(6, 5, 2+1)=3 -> Cr=3+1-2=2
+    exp = np.array([[[5, 5, 4, 3]], [[0, 7, 2, 6]], [[0, 0, 5, 2]]], np.float32)
+    assert np.array_equal(H, exp)
+
+
+def test_kat_parabola_and_q7():
+    vol = np.full((9, 1, 12), 10.0, np.float32)
+    vol[4, 0, 8], vol[5, 0, 8], vol[6, 0, 8] = 3.0, 1.0, 2.0
+    d, m = ko.costvol_minimum_subpix(vol, 8, -1.0)
+    assert abs(d[0, 8] - (5 - (2 - 3) / (2 * (2 - 2 + 3)))) < 1e-6  # 5.1667
+    # Q7: bestd = 0 reads slice 0 for the left tap (GPU float->unsigned saturation): -0.5 when sr > bestc
+    vol2 = np.full((9, 1, 12), 10.0, np.float32)
+    vol2[0, 0, 5], vol2[1, 0, 5] = 1.0, 2.0
+    d2, _ = ko.costvol_minimum_subpix(vol2, 8, -1.0)
+    assert d2[0, 5] == -0.5
+    # top edge: bestd + 1 == vol.d -> integer kept and flagged
+    vol3 = np.full((8, 1, 12), 10.0, np.float32)
+    vol3[7, 0, 9] = 1.0
+    d3, m3 = ko.costvol_minimum_subpix(vol3, 8, -1.0)
+    assert d3[0, 9] == 7.0 and m3[0, 9] == 1
+
+
+def test_kat_left_right_check():
+    dl = np.zeros((1, 16), np.float32)
+    dr = np.zeros((1, 16), np.float32)
+    dl[0, 10] = 3.0
+    dr[0, 7] = 3.4
+    assert ko.left_right_check_f32(dl, dr, -1.0, 0.5)[0, 10] == 3.0
+    dr[0, 7] = 3.6
+    assert np.isnan(ko.left_right_check_f32(dl, dr, -1.0, 0.5)[0, 10])
+    dl[0, 2] = 5.0  # x + sd*dl < 0 -> invalid
+    assert np.isnan(ko.left_right_check_f32(dl, dr, -1.0, 0.5)[0, 2])
+
+
+def test_diagonal_extension_reduces_to_reference_without_dodiag(golden):
+    g = golden("sgm")
+    a = ko.sgm(g["volc"], g["left_f32"], 12, 0.01, 0.02, dodiag=False)
+    b = ko.sgm(g["volc"], g["left_f32"], 12, 0.01, 0.02, dodiag=True)
+    assert relerr(g["H_h1v1r1"], a).max() <= 1e-5
+    assert not np.array_equal(a, b)
+    assert (b >= a - 1e-6).all()  # four more non-negative path costs

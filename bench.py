@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- census + SGM + WTA throughput on B200 (BASELINE.json metric: stereo pairs/s and
+SGM Mpix*disp/s, % of HBM roofline).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3                      # this repo's CUDA engine
+  python bench.py --impl reference --gpus 1 --steps 20 --warmup 3     # CPU arm: OpenMP port of the reference kernels
+
+A step = one pass of the whole hot path (census x2 -> Hamming cost -> 8 SGM sweeps -> WTA) over one
+batch of synthetic stereo pairs per GPU.  Default workload = BASELINE.json configs[1]: 1280x720, 128
+disparities, 8-path SGM + WTA.  One process per GPU; pairs are independent, so ranks share nothing on
+the data path (weak scaling, no collective) -- torch.distributed is used only for the timing barrier
+and the max-over-ranks reduction.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (w, h, D, paths, subpix, lrcheck, default pairs per step per GPU, synthetic config id)
+    "c1_640x480x64_4path": (640, 480, 64, 4, 0, 0, 16, 1),
+    "c2_1280x720x128_8path_wta": (1280, 720, 128, 8, 0, 0, 8, 2),
+    "c3_kitti_1242x375x128_4path": (1242, 375, 128, 4, 0, 0, 16, 3),
+    "c4_1920x1080x256_8path_subpix_lr": (1920, 1080, 256, 8, 1, 1, 2, 4),
+}
+DEFAULT_WORKLOAD = "c2_1280x720x128_8path_wta"
+P1, P2 = 0.01, 0.02  # applications/stereo2/main.cpp:246-247
+L2_BYTES = 126e6
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pairs(w, h, D, cfg, n):
+    from kangaroo_b200.synth import stereo_pair
+    ls, rs = [], []
+    for i in range(n):
+        L, R, _ = stereo_pair(w, h, D, config=cfg, index=i % 4)  # 4 distinct pairs, cycled (generation is CPU-bound)
+        ls.append(np.roll(L, i // 4, axis=0))
+        rs.append(np.roll(R, i // 4, axis=0))
+    return np.stack(ls), np.stack(rs)
+
+
+def cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, rows=None, reps=1):
+    """Times the OpenMP port of the reference kernels (oracle/) on `reps` pairs cropped to `rows` rows."""
+    import oracle as ko
+    from kangaroo_b200.synth import stereo_pair
+    L, R, _ = stereo_pair(w, h, D, config=cfg)
+    rows = rows or h
+    L, R = np.ascontiguousarray(L[:rows]), np.ascontiguousarray(R[:rows])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ko.pipeline_u8(L, R, D, dodiag=(paths == 8), subpix=bool(subpix), lrcheck=bool(lrcheck), p1=P1, p2=P2)
+    dt = (time.perf_counter() - t0) / reps
+    frac = rows / h
+    return frac / dt, dt, ko.num_threads(), rows
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference has no CPU implementation (its kernels are CUDA-only), so this arm is
+    the OpenMP scalar port of its kernel bodies (oracle/kangaroo_oracle.c) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, h, D, paths, subpix, lrcheck, _, cfg = WORKLOADS[wl]
+    # bounded sample: full pairs if the run is short, else a row crop so that K+W steps stay within minutes
+    total = args.steps + args.warmup
+    rows = h if total <= 8 else max(32, int(h * 8 / total))
+    for _ in range(args.warmup):
+        cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, rows)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, cores, rows = cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, rows)
+    dt = time.perf_counter() - t0
+    pairs = args.steps * rows / h
+    value = pairs / dt
+    sample = f"{rows} of {h} rows of one {w}x{h}x{D} pair per step ({paths}-path), {args.steps} steps"
+    out = {"impl": "reference", "metric": "stereo_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "mpix_disp_per_s": value * w * h * D / 1e6,
+           "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": "9x7",
+                      "note": "reference kernels are CUDA-only; CPU arm = OpenMP scalar port of the kernel bodies"},
+           "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="stereo pairs per step per GPU (0 = workload default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = args.workload
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kangaroo_b200 import capi, roo
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kangaroo_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w, h, D, paths, subpix, lrcheck, dbatch, cfg = WORKLOADS[wl]
+    B = args.batch or dbatch
+    K, W = args.steps, args.warmup
+    Lh, Rh = make_pairs(w, h, D, cfg + 10 * rank, B)
+    left = torch.from_numpy(Lh).cuda()
+    right = torch.from_numpy(Rh).cuda()
+    disp = torch.empty((B, h, w), dtype=torch.float32, device="cuda")
+    eng = roo.StereoEngine(w, h, D, window=roo.WIN_9x7, P1=P1, P2=P2, dohoriz=True, dovert=True, doreverse=True,
+                           dodiag=(paths == 8), subpix=bool(subpix), lrcheck=bool(lrcheck), max_batch=B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value) + live per-kernel timing for the roofline ----
+    for _ in range(W):
+        eng.run_device(left, right, disp)
+    barrier()
+    eng.set_profiling(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        eng.run_device(left, right, disp)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = capi.launch_count() - launches0
+    clk = clocks.stop()
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (H2D + compute + D2H every step) ----
+    e2e = None
+    if not args.no_e2e:
+        lp, rp = torch.from_numpy(Lh).pin_memory(), torch.from_numpy(Rh).pin_memory()
+        dp = torch.empty((B, h, w), dtype=torch.float32).pin_memory()
+        # the host arm pipelines upload / compute / download over groups of max_batch pairs: use smaller groups
+        g = max(1, B // 4)
+        eng_h = roo.StereoEngine(w, h, D, window=roo.WIN_9x7, P1=P1, P2=P2, dodiag=(paths == 8), subpix=bool(subpix),
+                                 lrcheck=bool(lrcheck), max_batch=g)
+        for _ in range(W):
+            eng_h.run_host(lp, rp, dp)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            eng_h.run_host(lp, rp, dp)  # synchronous: returns when the disparities are in host memory
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * K / float(tt.item()), "unit": "pairs/s", "h2d_bytes_per_step": int(2 * B * w * h),
+               "d2h_bytes_per_step": int(B * w * h * 4), "api": "roo_engine_run_host (pinned host buffers)",
+               "pairs_in_flight": g}
+        eng_h.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        S = paths
+        sweep_ms, sweep_n = prof["sweep"]
+        # algorithmic bytes: fp32 aggregate swept S times, first sweep write-only:
+        # 4 B * (2S - 1) per pixel*disparity over the S sweep launches of one batch
+        bytes_per_launch = 4.0 * (2 * S - 1) / S * w * h * D * B
+        achieved = bytes_per_launch / (sweep_ms / max(sweep_n, 1) * 1e-3) / 1e9 if sweep_n else None
+        step_kernel_ms = sum(v[0] for v in prof.values())
+        out = {
+            "metric": "stereo_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "mpix_disp_per_s": value * w * h * D / 1e6,
+            "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": "9x7",
+                       "popcount": "popc32-compat", "subpix": subpix, "lrcheck": lrcheck, "pairs_per_step_per_gpu": B,
+                       "sharding": f"pair-batch x{world}, no collective",
+                       "l2": f"per-step working set {B * w * h * D * 5 / 1e9:.2f} GB (fp32 aggregate + u8 cost) vs "
+                             f"{L2_BYTES / 1e6:.0f} MB L2: inputs larger than L2, no flush"},
+            "roofline": {"bound": "hbm", "kernel": "sgm_sweep_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "avg_launch_ms": sweep_ms / max(sweep_n, 1), "launches_timed": sweep_n,
+                         "share_of_step": sweep_ms / step_kernel_ms if step_kernel_ms else None},
+            "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            rows = min(h, 240)  # bounded sample: ~10-30 s of CPU work
+            v, dt, cores, rows = cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, rows)
+            out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                   "sample": f"{rows} of {h} rows of one {w}x{h}x{D} pair, {paths}-path, {dt:.1f} s"}
+        print(json.dumps(out), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,9 @@ const char* roo_b200_version(void);
 const char* roo_status_string(int status);
 /* Number of kernels this library has launched in this process (all threads), for bench.py. */
 unsigned long long roo_launch_count(void);
+/* 0 (default): divisions as the reference's -use_fast_math build (div.approx.ftz) -> results bit-identical to
+ * the reference kernels; 1: IEEE division -> bit-identical to the CPU oracle.  Process-wide. */
+void roo_set_ieee_division(int on);
 
 /* ---- granular operators: one per reference launcher -------------------------------------- */
 
@@ -116,6 +119,7 @@ typedef struct roo_pipeline_params_t {
     int lrcheck;          /* 1: right-reference WTA on the un-aggregated volume + both LeftRightChecks (main.cpp:385,432,451-454) */
     float lr_maxdiff;
     int max_batch;        /* stereo pairs in flight per call (scratch is sized for this many) */
+    int keep_volume;      /* 1: the last sweep also writes the aggregate so roo_engine_export_volume() works */
 } roo_pipeline_params_t;
 
 int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t* params);
@@ -134,6 +138,14 @@ int roo_engine_run_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t
 int roo_engine_export_volume(roo_engine_t* e, int slot, const roo_volume_t* volH, void* stream);
 /* Same for the census descriptors of the last run: side 0 = left, 1 = right. */
 int roo_engine_export_census(roo_engine_t* e, int slot, int side, const roo_image_t* census, void* stream);
+
+/* Per-kernel device timing for bench.py: with profiling on, the engine records a CUDA event after
+ * every launch on the launching stream; roo_engine_get_profile (call after synchronising) returns the
+ * accumulated milliseconds and launch counts per kernel kind since profiling was switched on. */
+enum roo_prof_kind { ROO_PROF_CENSUS = 0, ROO_PROF_COST = 1, ROO_PROF_SWEEP = 2, ROO_PROF_WTA = 3, ROO_PROF_LRCHECK = 4,
+                     ROO_PROF_KINDS = 5 };
+int roo_engine_set_profiling(roo_engine_t* e, int on);
+int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long long* launches_by_kind);
 
 #ifdef __cplusplus
 }

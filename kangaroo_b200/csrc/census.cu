@@ -1,0 +1,396 @@
+// Census transform and Hamming matching cost (granular operators on the reference's pitched
+// layouts + the engine's internal disparity-innermost byte cost volume).
+//
+// Replaces src/cu_census.cu of the reference: KernCensus9x7 (:18-46), KernCensus11x11 (:52-110),
+// KernCensus16x16 (:116-177), KernCensusStereo (:226-259), KernCensusStereoVolume (:272-299).
+// Nothing here is derived from those kernels' structure: the window is staged once per CTA in
+// shared memory (clamp-to-edge applied while staging), descriptors are built from registers and
+// stored with one 8/16/32-byte vector store per pixel, rows are processed by independent CTAs
+// (no w <= 1024 limit), and every launch takes an explicit stream and a batch dimension.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace roo_b200 {
+
+// ------------------------------------------------------------------------------------------------
+// Census
+// ------------------------------------------------------------------------------------------------
+template <int WIN> struct CensusGeom;
+template <> struct CensusGeom<ROO_WIN_9x7>   { static constexpr int CX0 = -4, CX1 = 4, RY0 = -3, RY1 = 3, WORDS = 1; };
+template <> struct CensusGeom<ROO_WIN_11x11> { static constexpr int CX0 = -5, CX1 = 5, RY0 = -5, RY1 = 5, WORDS = 2; };
+template <> struct CensusGeom<ROO_WIN_16x16> { static constexpr int CX0 = -4, CX1 = 3, RY0 = -8, RY1 = 7, WORDS = 4; };
+
+constexpr int CENSUS_TX = 32, CENSUS_TY = 8;
+
+template <typename Tin, int WIN>
+__global__ void __launch_bounds__(CENSUS_TX * CENSUS_TY)
+census_kernel(char* __restrict__ out, size_t out_pitch, size_t out_batch, const char* __restrict__ in, size_t in_pitch,
+              size_t in_batch, int w, int h) {
+    using G = CensusGeom<WIN>;
+    constexpr int SW = CENSUS_TX + G::CX1 - G::CX0;
+    constexpr int SH = CENSUS_TY + G::RY1 - G::RY0;
+    __shared__ Tin tile[SH][SW + 1];
+
+    in += (size_t)blockIdx.z * in_batch;
+    out += (size_t)blockIdx.z * out_batch;
+    const int x0 = blockIdx.x * CENSUS_TX, y0 = blockIdx.y * CENSUS_TY;
+    const int tid = threadIdx.y * CENSUS_TX + threadIdx.x;
+
+    // stage the window tile, clamp-to-edge (Image.h:297-303 GetWithClampedRange)
+    for (int i = tid; i < SH * SW; i += CENSUS_TX * CENSUS_TY) {
+        const int ty = i / SW, tx = i - ty * SW;
+        const int gx = clampi(x0 + tx + G::CX0, 0, w - 1);
+        const int gy = clampi(y0 + ty + G::RY0, 0, h - 1);
+        tile[ty][tx] = *reinterpret_cast<const Tin*>(in + (size_t)gy * in_pitch + (size_t)gx * sizeof(Tin));
+    }
+    __syncthreads();
+
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int cx = threadIdx.x - G::CX0, cy = threadIdx.y - G::RY0;  // centre inside the tile
+    const Tin p = tile[cy][cx];
+
+    if (WIN == ROO_WIN_9x7) {
+        // bit (r+3)*9 + (c+4)  (cu_census.cu:29-41)
+        unsigned long long o = 0;
+#pragma unroll
+        for (int r = -3; r <= 3; ++r)
+#pragma unroll
+            for (int c = -4; c <= 4; ++c)
+                o |= (unsigned long long)(tile[cy + r][cx + c] < p) << ((r + 3) * 9 + (c + 4));
+        *reinterpret_cast<unsigned long long*>(out + (size_t)y * out_pitch + (size_t)x * 8) = o;
+    } else if (WIN == ROO_WIN_11x11) {
+        // x: rows -5..-1 (bits 0..54) + row 0 c=-5..0 (55..60); y: row 0 c=1..5 (0..4) + rows 1..5 (5..59)
+        unsigned long long ox = 0, oy = 0;
+#pragma unroll
+        for (int r = -5; r < 0; ++r)
+#pragma unroll
+            for (int c = -5; c <= 5; ++c)
+                ox |= (unsigned long long)(tile[cy + r][cx + c] < p) << ((r + 5) * 11 + (c + 5));
+#pragma unroll
+        for (int c = -5; c <= 0; ++c) ox |= (unsigned long long)(tile[cy][cx + c] < p) << (55 + c + 5);
+#pragma unroll
+        for (int c = 1; c <= 5; ++c) oy |= (unsigned long long)(tile[cy][cx + c] < p) << (c - 1);
+#pragma unroll
+        for (int r = 1; r <= 5; ++r)
+#pragma unroll
+            for (int c = -5; c <= 5; ++c)
+                oy |= (unsigned long long)(tile[cy + r][cx + c] < p) << (5 + (r - 1) * 11 + (c + 5));
+        *reinterpret_cast<ulonglong2*>(out + (size_t)y * out_pitch + (size_t)x * 16) = make_ulonglong2(ox, oy);
+    } else {
+        // four words of 4 rows x 8 cols, low 32 bits each (cu_census.cu:126-174)
+        unsigned o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned acc = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = -4; c < 4; ++c)
+                    acc |= (unsigned)(tile[cy - 8 + 4 * k + r][cx + c] < p) << (r * 8 + (c + 4));
+            o[k] = acc;
+        }
+        struct { unsigned long long x, y, z, w; } v = {o[0], o[1], o[2], o[3]};
+        char* dst = out + (size_t)y * out_pitch + (size_t)x * 32;  // ulong4 is 16-byte aligned
+        reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(v.x, v.y);
+        reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(v.z, v.w);
+    }
+}
+
+template <typename Tin>
+static int census_dispatch(char* out, size_t out_pitch, size_t out_batch, const char* in, size_t in_pitch,
+                           size_t in_batch, int w, int h, int batch, int window, cudaStream_t st) {
+    dim3 block(CENSUS_TX, CENSUS_TY), grid(cdiv(w, CENSUS_TX), cdiv(h, CENSUS_TY), batch);
+    switch (window) {
+        case ROO_WIN_9x7:
+            census_kernel<Tin, ROO_WIN_9x7><<<grid, block, 0, st>>>(out, out_pitch, out_batch, in, in_pitch, in_batch, w, h);
+            break;
+        case ROO_WIN_11x11:
+            census_kernel<Tin, ROO_WIN_11x11><<<grid, block, 0, st>>>(out, out_pitch, out_batch, in, in_pitch, in_batch, w, h);
+            break;
+        case ROO_WIN_16x16:
+            census_kernel<Tin, ROO_WIN_16x16><<<grid, block, 0, st>>>(out, out_pitch, out_batch, in, in_pitch, in_batch, w, h);
+            break;
+        default: return ROO_ERR_INVALID_ARGUMENT;
+    }
+    count_launch();
+    return launch_status();
+}
+
+int launch_census(char* out, size_t out_pitch, size_t out_batch, const char* in, size_t in_pitch, size_t in_batch,
+                  int w, int h, int batch, int window, int in_type, cudaStream_t st) {
+    if (in_type == ROO_IMG_U8)
+        return census_dispatch<unsigned char>(out, out_pitch, out_batch, in, in_pitch, in_batch, w, h, batch, window, st);
+    if (in_type == ROO_IMG_F32)
+        return census_dispatch<float>(out, out_pitch, out_batch, in, in_pitch, in_batch, w, h, batch, window, st);
+    return ROO_ERR_INVALID_ARGUMENT;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CensusStereo: direct Hamming WTA on unsigned long descriptors (cu_census.cu:226-259)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+census_stereo_kernel(Img<signed char> disp, Img<unsigned long long> left, Img<unsigned long long> right, int maxDispVal) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= disp.w) return;
+    const unsigned long long p = left(x, y);
+    const unsigned long long* __restrict__ rrow = right.row(y);
+    unsigned bestScore = 0xFFFFF;
+    int bestDisp = 0;  // InvalidValue<char>::Value()
+    int minDisp = max(min(maxDispVal, 0), x - (left.w - 1));
+    int maxDisp = min(max(0, maxDispVal), x);
+    for (int d = minDisp; d < maxDisp; ++d) {
+        const unsigned score = hamming_word<false>(p, rrow[x - d]);
+        if (score < bestScore) { bestScore = score; bestDisp = d; }
+    }
+    disp(x, y) = (signed char)bestDisp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CensusStereoVolume into the reference's d-outermost volume (cu_census.cu:272-299)
+// One CTA per 128-pixel row segment; the right-image descriptors the segment can reach
+// (x + sd*d, d < maxDisp) are staged in shared memory once; each store instruction writes 32
+// consecutive x of one disparity slice (128 B for float).
+// ------------------------------------------------------------------------------------------------
+constexpr int CSV_TX = 128;
+
+template <int WORDS, typename Tvol, bool POPC64>
+__global__ void __launch_bounds__(CSV_TX)
+census_stereo_volume_kernel(Vol<Tvol> vol, const char* __restrict__ left, const char* __restrict__ right,
+                            size_t c_pitch, int rw, int maxDisp, int sdi) {
+    extern __shared__ unsigned long long cache_r[];  // [(CSV_TX + maxDisp - 1) * WORDS], word-major
+    const int x0 = blockIdx.x * CSV_TX, y = blockIdx.y;
+    const int x = x0 + threadIdx.x;
+    const int span = CSV_TX + maxDisp - 1;
+    // right-image x range touched by this segment: sd=-1: [x0-(maxDisp-1), x0+TX) ; sd=+1: [x0, x0+TX+maxDisp-1)
+    const int rx0 = sdi < 0 ? x0 - (maxDisp - 1) : x0;
+    const unsigned long long* rrow = reinterpret_cast<const unsigned long long*>(right + (size_t)y * c_pitch);
+    for (int i = threadIdx.x; i < span; i += CSV_TX) {
+        const int gx = rx0 + i;
+        const bool ok = gx >= 0 && gx < rw;
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k) cache_r[k * span + i] = ok ? rrow[(size_t)gx * WORDS + k] : 0ull;
+    }
+    __syncthreads();
+    if (x >= vol.w) return;
+    unsigned long long p[WORDS];
+    const unsigned long long* lrow = reinterpret_cast<const unsigned long long*>(left + (size_t)y * c_pitch);
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) p[k] = lrow[(size_t)x * WORDS + k];
+    const float inv_bits = 1.0f / (float)(WORDS * 64);  // power of two: exact, equals the reference's divide
+    for (int d = 0; d < maxDisp; ++d) {
+        const int xd = x + sdi * d;
+        float score = 0.5f;
+        if (xd >= 0 && xd < rw) {
+            const int i = xd - rx0;
+            unsigned hd = 0;
+#pragma unroll
+            for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], cache_r[k * span + i]);
+            score = (float)hd * inv_bits;
+        }
+        vol(x, y, d) = (Tvol)score;  // Tvol = unsigned short truncates to 0 (reference quirk Q2)
+    }
+}
+
+template <int WORDS, typename Tvol>
+static int csv_launch(const roo_volume_t* vol, const roo_image_t* l, const roo_image_t* r, int maxDisp, int sdi,
+                      int popc_mode, cudaStream_t st) {
+    dim3 grid(cdiv((int)l->w, CSV_TX), (unsigned)l->h), block(CSV_TX);
+    const size_t smem = (size_t)(CSV_TX + maxDisp - 1) * WORDS * 8;
+    if (smem > 200 * 1024) return ROO_ERR_UNSUPPORTED;
+    auto kern = popc_mode == ROO_POPC64 ? census_stereo_volume_kernel<WORDS, Tvol, true>
+                                        : census_stereo_volume_kernel<WORDS, Tvol, false>;
+    if (smem > 48 * 1024) ROO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, st>>>(Vol<Tvol>(*vol), (const char*)l->ptr, (const char*)r->ptr, l->pitch, (int)r->w,
+                                    maxDisp, sdi);
+    count_launch();
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine-internal raw Hamming cost: C8[pair][y][x][DP] bytes, disparity innermost, so that one warp
+// of an aggregation sweep reads its 32*DPL disparities of a pixel with one coalesced load.
+// Stores the raw count h; the sweeps multiply by 1/bits (exact).  d > x (no right pixel) stores
+// bits/2, the reference's 0.5.
+// ------------------------------------------------------------------------------------------------
+template <int WORDS, bool POPC64>
+__global__ void __launch_bounds__(256)
+cost_u8_kernel(unsigned char* __restrict__ c8, const unsigned long long* __restrict__ cl,
+               const unsigned long long* __restrict__ cr, int w, int h, int DP, int maxDisp) {
+    // thread -> 4 consecutive disparities of one pixel; consecutive threads -> consecutive d groups
+    const int groups = DP >> 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npx = (long long)w * h;
+    const long long pix = gid / groups;
+    if (pix >= npx) return;
+    const int g = (int)(gid - pix * groups);
+    const size_t boff = (size_t)blockIdx.y * (size_t)npx;
+    const int x = (int)(pix % w);
+    const unsigned long long* lp = cl + (boff + (size_t)pix) * WORDS;
+    unsigned long long p[WORDS];
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) p[k] = lp[k];
+    unsigned packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int d = g * 4 + j;
+        unsigned hd = WORDS * 32;  // 0.5 * bits
+        if (d < maxDisp && d <= x) {
+            const unsigned long long* rp = cr + (boff + (size_t)pix - d) * WORDS;
+            hd = 0;
+#pragma unroll
+            for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], rp[k]);
+        }
+        packed |= hd << (8 * j);
+    }
+    reinterpret_cast<unsigned*>(c8 + (boff + (size_t)pix) * DP)[g] = packed;
+}
+
+int launch_cost_u8(unsigned char* c8, const void* cl, const void* cr, int w, int h, int batch, int DP, int maxDisp,
+                   int words, int popc_mode, cudaStream_t st) {
+    const long long threads = (long long)w * h * (DP >> 2);
+    dim3 grid((unsigned)cdiv(threads, 256), batch), block(256);
+    const auto* l = (const unsigned long long*)cl;
+    const auto* r = (const unsigned long long*)cr;
+    const bool p64 = popc_mode == ROO_POPC64;
+#define ROO_COST(W)                                                                                  \
+    if (p64) cost_u8_kernel<W, true><<<grid, block, 0, st>>>(c8, l, r, w, h, DP, maxDisp);           \
+    else cost_u8_kernel<W, false><<<grid, block, 0, st>>>(c8, l, r, w, h, DP, maxDisp)
+    if (words == 1) { ROO_COST(1); }
+    else if (words == 2) { ROO_COST(2); }
+    else if (words == 4) { ROO_COST(4); }
+    else return ROO_ERR_INVALID_ARGUMENT;
+#undef ROO_COST
+    count_launch();
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine: disparity straight from the descriptors, i.e. CensusStereoVolume(vol, self, other, maxDisp, sd)
+// followed by CostVolMinimum<float,float> or CostVolMinimumSubpix(disp, vol, maxDisp, sd) without ever
+// materialising vol.  Used for the right-reference disparity of the LR check (sd = +1,
+// stereo2/main.cpp:385,432,435: vol[1] is never aggregated) and for the left one when no SGM path is
+// enabled (sd = -1).  The raw costs are h/bits with out-of-image taps = 0.5.
+// ------------------------------------------------------------------------------------------------
+template <int WORDS, bool POPC64, bool IEEE>
+__global__ void __launch_bounds__(128)
+census_wta_kernel(float* __restrict__ disp, const unsigned long long* __restrict__ cself,
+                  const unsigned long long* __restrict__ cother, int w, int h, int maxDisp, int subpix, int sdi) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t rowoff = ((size_t)blockIdx.z * h + y) * (size_t)w;
+    const unsigned long long* sp = cself + (rowoff + x) * WORDS;
+    const unsigned long long* orow = cother + rowoff * WORDS;
+    unsigned long long p[WORDS];
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) p[k] = sp[k];
+    const float inv_bits = 1.0f / (float)(WORDS * 64);
+    auto cost = [&](int d) -> float {
+        const int xd = x + sdi * d;
+        if (xd < 0 || xd >= w) return 0.5f;
+        unsigned hd = 0;
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], orow[(size_t)xd * WORDS + k]);
+        return (float)hd * inv_bits;
+    };
+    float out;
+    if (!subpix) {
+        // CostVolMinimum (cu_dense_stereo.cu:25-43): d < min(maxDisp, x+1), slices beyond x+sd*d range hold 0.5
+        int bestd = 0;
+        float bestc = cost(0);
+        const int md = min(maxDisp, x + 1);
+        for (int d = 1; d < md; ++d) {
+            const float c = cost(d);
+            if (c < bestc) { bestc = c; bestd = d; }
+        }
+        out = (float)bestd;
+    } else {
+        // CostVolMinimumSubpix (cu_dense_stereo.cu:66-109)
+        int bestd = 0;
+        float bestc = 1E10f;
+        for (int d = 0; d < maxDisp; ++d) {
+            const int xr = x + sdi * d;
+            if (0 <= xr && xr < w) {
+                const float c = cost(d);
+                if (c < bestc) { bestc = c; bestd = d; }
+            }
+        }
+        out = (float)bestd;
+        const int bestxr = x + sdi * bestd;
+        if (0 < bestxr && bestxr < w - 1 && bestd + 1 < maxDisp) {
+            const float sl = cost(max(bestd - 1, 0));  // GPU float->unsigned saturation of bestd-1 (Q7)
+            const float sr = cost(bestd + 1);
+            const float sub = parabola_vertex<IEEE>((float)bestd, bestc, sl, sr);
+            if ((float)(bestd - 1) < sub && sub < (float)(bestd + 1)) out = sub;
+        }
+    }
+    disp[rowoff + x] = out;
+}
+
+int launch_census_wta(float* disp, const void* cself, const void* cother, int w, int h, int batch, int maxDisp,
+                      int words, int popc_mode, int subpix, int sdi, cudaStream_t st) {
+    dim3 grid(cdiv(w, 128), h, batch), block(128);
+    const auto* a = (const unsigned long long*)cself;
+    const auto* b = (const unsigned long long*)cother;
+    const bool p64 = popc_mode == ROO_POPC64, ieee = g_ieee_div.load() != 0;
+#define ROO_RW(W, P, I) census_wta_kernel<W, P, I><<<grid, block, 0, st>>>(disp, a, b, w, h, maxDisp, subpix, sdi)
+#define ROO_RW2(W)                                                                 \
+    if (p64) { if (ieee) ROO_RW(W, true, true); else ROO_RW(W, true, false); }     \
+    else { if (ieee) ROO_RW(W, false, true); else ROO_RW(W, false, false); }
+    if (words == 1) { ROO_RW2(1) }
+    else if (words == 2) { ROO_RW2(2) }
+    else if (words == 4) { ROO_RW2(4) }
+    else return ROO_ERR_INVALID_ARGUMENT;
+#undef ROO_RW2
+#undef ROO_RW
+    count_launch();
+    return launch_status();
+}
+
+}  // namespace roo_b200
+
+using namespace roo_b200;
+
+extern "C" int roo_census(const roo_image_t* census, const roo_image_t* img, int window, int in_type, void* stream) {
+    if (window < 0 || window > 2 || (in_type != ROO_IMG_U8 && in_type != ROO_IMG_F32)) return ROO_ERR_INVALID_ARGUMENT;
+    const size_t words = window == ROO_WIN_9x7 ? 1 : (window == ROO_WIN_11x11 ? 2 : 4);
+    if (!valid_image(img, in_type == ROO_IMG_U8 ? 1 : 4) || !valid_image(census, words * 8)) return ROO_ERR_INVALID_ARGUMENT;
+    if (census->w != img->w || census->h != img->h) return ROO_ERR_INVALID_ARGUMENT;
+    return launch_census((char*)census->ptr, census->pitch, 0, (const char*)img->ptr, img->pitch, 0, (int)img->w,
+                         (int)img->h, 1, window, in_type, as_stream(stream));
+}
+
+extern "C" int roo_census_stereo(const roo_image_t* disp, const roo_image_t* left, const roo_image_t* right, int maxDisp,
+                                 void* stream) {
+    if (!valid_image(disp, 1) || !valid_image(left, 8) || !valid_image(right, 8)) return ROO_ERR_INVALID_ARGUMENT;
+    if (left->w != disp->w || left->h != disp->h || right->w != disp->w || right->h != disp->h)
+        return ROO_ERR_INVALID_ARGUMENT;
+    dim3 grid(cdiv((int)disp->w, 256), (unsigned)disp->h), block(256);
+    census_stereo_kernel<<<grid, block, 0, as_stream(stream)>>>(Img<signed char>(*disp), Img<unsigned long long>(*left),
+                                                                Img<unsigned long long>(*right), maxDisp);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int roo_census_stereo_volume(const roo_volume_t* vol, const roo_image_t* left, const roo_image_t* right,
+                                        int words, int vol_type, int maxDisp, float sd, int popc_mode, void* stream) {
+    if (words != 1 && words != 2 && words != 4) return ROO_ERR_INVALID_ARGUMENT;
+    if (vol_type != ROO_VOL_F32 && vol_type != ROO_VOL_U16) return ROO_ERR_INVALID_ARGUMENT;
+    if (sd != -1.0f && sd != 1.0f) return ROO_ERR_UNSUPPORTED;  // Q12: only integer unit steps are exact
+    if (!valid_volume(vol, vol_type == ROO_VOL_F32 ? 4 : 2) || !valid_image(left, (size_t)words * 8) ||
+        !valid_image(right, (size_t)words * 8))
+        return ROO_ERR_INVALID_ARGUMENT;
+    if (vol->w != left->w || vol->h != left->h || right->h != left->h || left->pitch != right->pitch)
+        return ROO_ERR_INVALID_ARGUMENT;
+    if (maxDisp <= 0) return ROO_OK;  // reference: empty loop
+    if ((size_t)maxDisp > vol->d) return ROO_ERR_INVALID_ARGUMENT;
+    const int sdi = sd < 0 ? -1 : 1;
+    cudaStream_t st = as_stream(stream);
+#define ROO_CSV(W)                                                                         \
+    return vol_type == ROO_VOL_F32 ? csv_launch<W, float>(vol, left, right, maxDisp, sdi, popc_mode, st) \
+                                   : csv_launch<W, unsigned short>(vol, left, right, maxDisp, sdi, popc_mode, st)
+    if (words == 1) { ROO_CSV(1); }
+    if (words == 2) { ROO_CSV(2); }
+    ROO_CSV(4);
+#undef ROO_CSV
+}

@@ -1,0 +1,285 @@
+// Fused per-frame engine: the whole path of applications/stereo2/main.cpp:375-454
+//   Census x2 -> [right-reference WTA on raw costs] -> Hamming cost -> SGM sweeps -> WTA/parabola
+//   (epilogue of the last sweep) -> LeftRightCheck x2
+// on engine-owned scratch in the internal disparity-innermost layout, for a batch of stereo pairs
+// per launch.  Host side is plain C++ behind the C ABI of include/roo_b200.h.
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace roo_b200 {
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_ieee_div{0};
+}  // namespace roo_b200
+
+using namespace roo_b200;
+
+struct roo_engine {
+    roo_pipeline_params_t p;
+    int device = 0;
+    int DP = 0, words = 0;
+    size_t npx = 0;
+    // scratch (device)
+    unsigned long long* cen[2] = {nullptr, nullptr};  // [batch][h][w][words]
+    unsigned char* c8 = nullptr;                      // [batch][h][w][DP]
+    float* H = nullptr;                               // [batch][h][w][DP]
+    float* dispR = nullptr;                           // [batch][h][w]
+    // staging for run_host (device) and its streams
+    unsigned char* in_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][side]
+    float* out_dev[2] = {nullptr, nullptr};
+    cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    size_t scratch_bytes = 0;
+    int last_batch = 0;
+    // optional per-kernel timing (roo_engine_set_profiling): one event after every launch
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_kinds;   // kind of the launch that ENDS at event i (-1 = group start marker)
+    size_t prof_used = 0;
+    double prof_ms[ROO_PROF_KINDS] = {0};
+    long long prof_n[ROO_PROF_KINDS] = {0};
+};
+
+static void prof_mark(roo_engine* e, int kind, cudaStream_t st) {
+    if (!e->profiling) return;
+    if (e->prof_used == e->prof_events.size()) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        e->prof_events.push_back(ev);
+        e->prof_kinds.push_back(kind);
+    }
+    e->prof_kinds[e->prof_used] = kind;
+    cudaEventRecord(e->prof_events[e->prof_used++], st);
+}
+
+static int engine_group(roo_engine* e, const unsigned char* left, const unsigned char* right, float* disp, int batch,
+                        cudaStream_t st) {
+    const roo_pipeline_params_t& p = e->p;
+    const int w = p.w, h = p.h;
+    const size_t npx = e->npx;
+    int rc;
+    prof_mark(e, -1, st);
+    for (int side = 0; side < 2; ++side) {
+        rc = launch_census((char*)e->cen[side], (size_t)w * e->words * 8, npx * e->words * 8,
+                           (const char*)(side == 0 ? left : right), (size_t)w, npx, w, h, batch, p.window, ROO_IMG_U8, st);
+        if (rc) return rc;
+        prof_mark(e, ROO_PROF_CENSUS, st);
+    }
+    if (p.lrcheck) {
+        rc = launch_census_wta(e->dispR, e->cen[1], e->cen[0], w, h, batch, p.max_disp, e->words, p.popc_mode, p.subpix, +1, st);
+        if (rc) return rc;
+        prof_mark(e, ROO_PROF_WTA, st);
+    }
+    int dxs[8], dys[8];
+    const int ndir = sgm_directions(p.dohoriz, p.dovert, p.doreverse, p.dodiag, dxs, dys);
+    if (ndir == 0) {
+        rc = launch_census_wta(disp, e->cen[0], e->cen[1], w, h, batch, p.max_disp, e->words, p.popc_mode, p.subpix, -1, st);
+        if (rc) return rc;
+        prof_mark(e, ROO_PROF_WTA, st);
+    } else {
+        rc = launch_cost_u8(e->c8, e->cen[0], e->cen[1], w, h, batch, e->DP, p.max_disp, e->words, p.popc_mode, st);
+        if (rc) return rc;
+        prof_mark(e, ROO_PROF_COST, st);
+        SweepArgs a{};
+        a.H = e->H; a.h_pair = npx * e->DP; a.C = e->c8; a.c_pair = npx * e->DP;
+        a.img = (const char*)left; a.img_pitch = (size_t)w; a.img_pair = npx; a.img_type = ROO_IMG_U8;
+        a.img_scale = p.img_scale; a.cost_scale = 1.0f / (float)(e->words * 64);
+        a.w = w; a.h = h; a.DP = e->DP; a.maxDisp = p.max_disp; a.batch = batch;
+        a.P1 = p.P1; a.P2 = p.P2; a.cost_kind = COST_U8; a.subpix = p.subpix; a.disp = disp; a.disp_pair = npx;
+        for (int i = 0; i < ndir; ++i) {
+            a.dx = dxs[i]; a.dy = dys[i]; a.first = i == 0;
+            a.epi = i + 1 < ndir ? EPI_NONE : (p.keep_volume ? EPI_WTA_WRITE : EPI_WTA_ONLY);
+            rc = launch_sweep(a, st);
+            if (rc) return rc;
+            prof_mark(e, ROO_PROF_SWEEP, st);
+        }
+    }
+    if (p.lrcheck) {
+        // LeftRightCheck(disp[1], disp[0], +1, maxdiff); LeftRightCheck(disp[0], disp[1], -1, maxdiff) (main.cpp:451-454)
+        rc = launch_lr_check_f32(e->dispR, (size_t)w * 4, disp, (size_t)w * 4, w, h, batch, npx * 4, npx * 4, +1.0f, p.lr_maxdiff, st);
+        if (rc) return rc;
+        prof_mark(e, ROO_PROF_LRCHECK, st);
+        rc = launch_lr_check_f32(disp, (size_t)w * 4, e->dispR, (size_t)w * 4, w, h, batch, npx * 4, npx * 4, -1.0f, p.lr_maxdiff, st);
+        if (rc) return rc;
+        prof_mark(e, ROO_PROF_LRCHECK, st);
+    }
+    e->last_batch = batch;
+    return ROO_OK;
+}
+
+static void engine_free(roo_engine* e) {
+    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
+        if (e->ev_in[b]) cudaEventDestroy(e->ev_in[b]);
+        if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
+        if (e->ev_out[b]) cudaEventDestroy(e->ev_out[b]);
+    }
+    for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+    if (e->s_compute) cudaStreamDestroy(e->s_compute);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
+}
+
+extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t* params) {
+    if (!out || !params) return ROO_ERR_INVALID_ARGUMENT;
+    const roo_pipeline_params_t& p = *params;
+    if (p.w <= 0 || p.h <= 0 || p.max_disp <= 0 || p.max_batch <= 0 || p.window < 0 || p.window > 2)
+        return ROO_ERR_INVALID_ARGUMENT;
+    if (p.max_disp > 256) return ROO_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ROO_ERR_NO_DEVICE;
+    roo_engine* e = new (std::nothrow) roo_engine();
+    if (!e) return ROO_ERR_OUT_OF_MEMORY;
+    e->p = p;
+    cudaGetDevice(&e->device);
+    e->DP = disp_padded(p.max_disp);
+    e->words = p.window == ROO_WIN_9x7 ? 1 : (p.window == ROO_WIN_11x11 ? 2 : 4);
+    e->npx = (size_t)p.w * p.h;
+    const size_t B = (size_t)p.max_batch, npx = e->npx;
+    auto alloc = [&](void** ptr, size_t bytes) -> bool {
+        if (cudaMalloc(ptr, bytes) != cudaSuccess) return false;
+        e->scratch_bytes += bytes;
+        return true;
+    };
+    int dxs[8], dys[8];
+    const int ndir = sgm_directions(p.dohoriz, p.dovert, p.doreverse, p.dodiag, dxs, dys);
+    bool ok = alloc((void**)&e->cen[0], B * npx * e->words * 8) && alloc((void**)&e->cen[1], B * npx * e->words * 8);
+    if (ok && ndir > 0) ok = alloc((void**)&e->c8, B * npx * e->DP) && alloc((void**)&e->H, B * npx * e->DP * 4);
+    if (ok && p.lrcheck) ok = alloc((void**)&e->dispR, B * npx * 4);
+    if (!ok) {
+        cudaGetLastError();
+        engine_free(e);
+        delete e;
+        return ROO_ERR_OUT_OF_MEMORY;
+    }
+    *out = e;
+    return ROO_OK;
+}
+
+extern "C" int roo_engine_destroy(roo_engine_t* e) {
+    if (!e) return ROO_ERR_INVALID_ARGUMENT;
+    cudaDeviceSynchronize();
+    engine_free(e);
+    delete e;
+    return ROO_OK;
+}
+
+extern "C" size_t roo_engine_scratch_bytes(const roo_engine_t* e) { return e ? e->scratch_bytes : 0; }
+
+extern "C" int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const uint8_t* right, float* disp, int n_pairs,
+                                     void* stream) {
+    if (!e || !left || !right || !disp || n_pairs < 0) return ROO_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+    for (int g = 0; g < n_pairs; g += e->p.max_batch) {
+        const int batch = n_pairs - g < e->p.max_batch ? n_pairs - g : e->p.max_batch;
+        const int rc = engine_group(e, left + (size_t)g * e->npx, right + (size_t)g * e->npx, disp + (size_t)g * e->npx, batch, st);
+        if (rc) return rc;
+    }
+    return ROO_OK;
+}
+
+// Host buffers: upload group g+1 and download group g-1 while group g computes (three streams, two
+// staging buffers).  Pinned host memory makes the copies truly asynchronous.
+extern "C" int roo_engine_run_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
+                                   int n_pairs) {
+    if (!e || !left_host || !right_host || !disp_host || n_pairs < 0) return ROO_ERR_INVALID_ARGUMENT;
+    const size_t npx = e->npx, B = (size_t)e->p.max_batch;
+    if (!e->s_compute) {
+        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][0], B * npx));
+            ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][1], B * npx));
+            ROO_CUDA_TRY(cudaMalloc((void**)&e->out_dev[b], B * npx * 4));
+            e->scratch_bytes += 2 * B * npx + B * npx * 4;
+            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[b], cudaEventDisableTiming));
+            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
+            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    int gi = 0;
+    for (int g = 0; g < n_pairs; g += (int)B, ++gi) {
+        const int b = gi & 1;
+        const size_t batch = (size_t)(n_pairs - g) < B ? (size_t)(n_pairs - g) : B;
+        if (gi >= 2) {
+            ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_done[b], 0));      // inputs of group gi-2 consumed
+            ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_compute, e->ev_out[b], 0));  // output of group gi-2 downloaded
+        }
+        ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][0], left_host + (size_t)g * npx, batch * npx, cudaMemcpyHostToDevice, e->s_in));
+        ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][1], right_host + (size_t)g * npx, batch * npx, cudaMemcpyHostToDevice, e->s_in));
+        ROO_CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
+        ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_compute, e->ev_in[b], 0));
+        const int rc = engine_group(e, e->in_dev[b][0], e->in_dev[b][1], e->out_dev[b], (int)batch, e->s_compute);
+        if (rc) return rc;
+        ROO_CUDA_TRY(cudaEventRecord(e->ev_done[b], e->s_compute));
+        ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_done[b], 0));
+        ROO_CUDA_TRY(cudaMemcpyAsync(disp_host + (size_t)g * npx, e->out_dev[b], batch * npx * 4, cudaMemcpyDeviceToHost, e->s_out));
+        ROO_CUDA_TRY(cudaEventRecord(e->ev_out[b], e->s_out));
+    }
+    ROO_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+    ROO_CUDA_TRY(cudaStreamSynchronize(e->s_compute));
+    return ROO_OK;
+}
+
+extern "C" int roo_engine_export_volume(roo_engine_t* e, int slot, const roo_volume_t* volH, void* stream) {
+    if (!e || !e->H || !e->p.keep_volume || slot < 0 || slot >= e->last_batch) return ROO_ERR_INVALID_ARGUMENT;
+    if (!valid_volume(volH, 4) || (int)volH->w != e->p.w || (int)volH->h != e->p.h || (int)volH->d < e->p.max_disp)
+        return ROO_ERR_INVALID_ARGUMENT;
+    return launch_internal_to_vol(volH, e->H + (size_t)slot * e->npx * e->DP, e->DP, e->p.max_disp, as_stream(stream));
+}
+
+extern "C" int roo_engine_export_census(roo_engine_t* e, int slot, int side, const roo_image_t* census, void* stream) {
+    if (!e || slot < 0 || slot >= e->last_batch || side < 0 || side > 1) return ROO_ERR_INVALID_ARGUMENT;
+    const size_t esz = (size_t)e->words * 8;
+    if (!valid_image(census, esz) || (int)census->w != e->p.w || (int)census->h != e->p.h) return ROO_ERR_INVALID_ARGUMENT;
+    ROO_CUDA_TRY(cudaMemcpy2DAsync(census->ptr, census->pitch, e->cen[side] + (size_t)slot * e->npx * e->words,
+                                   (size_t)e->p.w * esz, (size_t)e->p.w * esz, (size_t)e->p.h, cudaMemcpyDeviceToDevice,
+                                   as_stream(stream)));
+    return ROO_OK;
+}
+
+extern "C" int roo_engine_set_profiling(roo_engine_t* e, int on) {
+    if (!e) return ROO_ERR_INVALID_ARGUMENT;
+    e->profiling = on != 0;
+    e->prof_used = 0;
+    for (int k = 0; k < ROO_PROF_KINDS; ++k) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
+    return ROO_OK;
+}
+
+extern "C" int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long long* launches_by_kind) {
+    if (!e || !ms_by_kind || !launches_by_kind) return ROO_ERR_INVALID_ARGUMENT;
+    // fold the events recorded since the last call (the caller has synchronised the stream)
+    for (size_t i = 1; i < e->prof_used; ++i) {
+        const int kind = e->prof_kinds[i];
+        if (kind < 0) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, e->prof_events[i - 1], e->prof_events[i]) == cudaSuccess) {
+            e->prof_ms[kind] += ms;
+            e->prof_n[kind] += 1;
+        }
+    }
+    e->prof_used = 0;
+    for (int k = 0; k < ROO_PROF_KINDS; ++k) { ms_by_kind[k] = e->prof_ms[k]; launches_by_kind[k] = e->prof_n[k]; }
+    return ROO_OK;
+}
+
+extern "C" const char* roo_b200_version(void) { return "kangaroo_b200 0.1 (sm_100a)"; }
+
+extern "C" unsigned long long roo_launch_count(void) { return g_launches.load(); }
+
+extern "C" void roo_set_ieee_division(int on) { g_ieee_div.store(on ? 1 : 0); }
+
+extern "C" const char* roo_status_string(int status) {
+    switch (status) {
+        case ROO_OK: return "ok";
+        case ROO_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case ROO_ERR_UNSUPPORTED: return "unsupported configuration";
+        case ROO_ERR_OUT_OF_MEMORY: return "out of memory";
+        case ROO_ERR_NO_DEVICE: return "no CUDA device";
+        default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown";
+    }
+}

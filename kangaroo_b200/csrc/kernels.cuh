@@ -1,0 +1,52 @@
+// Internal launch API shared between the translation units of libroo_b200.
+#pragma once
+#include "common.cuh"
+
+namespace roo_b200 {
+
+// ---- census.cu ----
+int launch_census(char* out, size_t out_pitch, size_t out_batch, const char* in, size_t in_pitch, size_t in_batch,
+                  int w, int h, int batch, int window, int in_type, cudaStream_t st);
+int launch_cost_u8(unsigned char* c8, const void* cl, const void* cr, int w, int h, int batch, int DP, int maxDisp,
+                   int words, int popc_mode, cudaStream_t st);
+int launch_census_wta(float* disp, const void* cself, const void* cother, int w, int h, int batch, int maxDisp,
+                      int words, int popc_mode, int subpix, int sdi, cudaStream_t st);
+
+// ---- sgm.cu ----
+enum CostKind { COST_F32 = 0, COST_U8 = 1 };
+enum EpiKind { EPI_NONE = 0, EPI_WTA_WRITE = 1, EPI_WTA_ONLY = 2 };
+
+// One aggregation sweep (one path direction) over `batch` pairs on the internal layout
+// H[pair][y][x][DP] (fp32, disparity innermost, DP = 32 * ceil(maxDisp/32) rounded to 32/64/128/256).
+struct SweepArgs {
+    float* H;            // in/out aggregate
+    size_t h_pair;       // elements between pairs
+    const void* C;       // cost, same indexing as H: float or unsigned char
+    size_t c_pair;       // elements between pairs
+    const char* img;     // left image used for the adaptive P2 (u8 or f32, pitched)
+    size_t img_pitch, img_pair;  // bytes
+    int img_type;        // ROO_IMG_U8 / ROO_IMG_F32
+    float img_scale;     // intensity = u8 * img_scale (ignored for f32)
+    float cost_scale;    // U8 cost: cost = count * cost_scale
+    int w, h, DP, maxDisp, batch;
+    float P1, P2;
+    int dx, dy;
+    int first;           // 1: H holds nothing yet (treated as 0, not read)
+    int cost_kind;       // CostKind
+    int epi;             // EpiKind
+    int subpix;          // epilogue: 0 CostVolMinimum<float,float>, 1 CostVolMinimumSubpix(sd=-1)
+    float* disp;         // epilogue output [pair][y][x]
+    size_t disp_pair;    // elements
+};
+int launch_sweep(const SweepArgs& a, cudaStream_t st);
+inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : 256)); }
+
+// direction list in execution order (reference order down, up, right, left; diagonals are an extension)
+int launch_internal_to_vol(const roo_volume_t* dst, const float* src, int DP, int maxDisp, cudaStream_t st);
+int sgm_directions(int dohoriz, int dovert, int doreverse, int dodiag, int dxs[8], int dys[8]);
+
+// ---- wta.cu ----
+int launch_lr_check_f32(float* dispL, size_t pitchL, const float* dispR, size_t pitchR, int w, int h, int batch,
+                        size_t batchL, size_t batchR, float sd, float maxDiff, cudaStream_t st);
+
+}  // namespace roo_b200

@@ -1,0 +1,280 @@
+"""Python mirror of the reference's operator surface for the census / SGM path.
+
+Same names and argument meaning as namespace roo (include/kangaroo/cu_census.h:12-38,
+cu_semi_global_matching.h:10-12, cu_dense_stereo.h:13-47,81-85); every call goes through the C ABI
+(include/roo_b200.h) into the CUDA library.  torch is used only to own device memory and streams.
+Like the reference launchers the calls are asynchronous; unlike them a failure raises RooError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import (DISP_F32, DISP_I8, IMG_F32, IMG_U8, POPC32_COMPAT, POPC64, VOL_ELEM, VOL_F32, VOL_I32, VOL_U16,
+                   VOL_U32, VOL_U8, WIN_9x7, WIN_11x11, WIN_16x16, WORDS, check, lib)
+
+COSTVOLELEM = np.dtype([("n", np.int32), ("sum", np.float32)])  # CostVolElem.h:10-19
+ULONG = np.dtype(np.uint64)                                     # unsigned long
+ULONG2 = np.dtype((np.uint64, (2,)))                            # ulong2
+ULONG4 = np.dtype((np.uint64, (4,)))                            # ulong4
+
+_VOL_TYPES = {np.dtype(np.uint16): VOL_U16, np.dtype(np.float32): VOL_F32, np.dtype(np.int32): VOL_I32,
+              np.dtype(np.uint32): VOL_U32, np.dtype(np.uint8): VOL_U8, COSTVOLELEM: VOL_ELEM}
+
+
+def _stream(stream) -> int:
+    if stream is None:
+        return torch.cuda.current_stream().cuda_stream
+    return stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+
+
+def _align(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
+class Image:
+    """roo::Image<T, TargetDevice, Manage>: a pitched device image (Image.h:43-44, 77-83)."""
+
+    def __init__(self, w: int, h: int, dtype, pitch: int | None = None, device=None):
+        self.dtype = np.dtype(dtype)
+        self.w, self.h = int(w), int(h)
+        row = self.w * self.dtype.itemsize
+        self.pitch = int(pitch) if pitch is not None else _align(row, 512)  # cudaMallocPitch-like
+        assert self.pitch >= row
+        self.buf = torch.zeros(self.pitch * self.h, dtype=torch.uint8, device=device or "cuda")
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def c(self) -> capi.RooImage:
+        return capi.RooImage(self.pitch, self.ptr, self.w, self.h)
+
+    def sub_image(self, x: int, y: int, w: int, h: int) -> "Image":
+        """Image::SubImage (Image.h): a view that keeps the parent pitch."""
+        v = object.__new__(Image)
+        v.dtype, v.w, v.h, v.pitch = self.dtype, w, h, self.pitch
+        off = y * self.pitch + x * self.dtype.itemsize
+        v.buf = self.buf[off:]
+        return v
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray, pitch: int | None = None, device=None) -> "Image":
+        a = np.ascontiguousarray(a)
+        h, w = a.shape[:2]
+        dt = a.dtype if a.ndim == 2 else np.dtype((a.dtype, (a.shape[2],)))
+        im = cls(w, h, dt, pitch, device)
+        im.upload(a)
+        return im
+
+    def upload(self, a: np.ndarray) -> None:
+        row = self.w * self.dtype.itemsize
+        host = np.zeros((self.h, self.pitch), np.uint8)
+        host[:, :row] = np.ascontiguousarray(a).view(np.uint8).reshape(self.h, row)
+        self.buf[: self.pitch * self.h].copy_(torch.from_numpy(host.reshape(-1)))
+
+    def numpy(self) -> np.ndarray:
+        row = self.w * self.dtype.itemsize
+        host = self.buf[: self.pitch * (self.h - 1) + row].cpu().numpy()
+        full = np.zeros(self.pitch * self.h, np.uint8)
+        full[: host.size] = host
+        rows = np.ascontiguousarray(full.reshape(self.h, self.pitch)[:, :row])
+        base = self.dtype.base
+        out = rows.view(base)
+        if self.dtype.shape:
+            return out.reshape(self.h, self.w, *self.dtype.shape).copy()
+        return out.reshape(self.h, self.w).copy()
+
+
+class Volume:
+    """roo::Volume<T, TargetDevice, Manage> (Volume.h:21-60): d outermost, x fastest."""
+
+    def __init__(self, w: int, h: int, d: int, dtype, pitch: int | None = None, device=None):
+        self.dtype = np.dtype(dtype)
+        self.w, self.h, self.d = int(w), int(h), int(d)
+        row = self.w * self.dtype.itemsize
+        self.pitch = int(pitch) if pitch is not None else _align(row, 512)
+        self.img_pitch = self.pitch * self.h  # Memory.h:70-78
+        self.buf = torch.zeros(self.img_pitch * self.d, dtype=torch.uint8, device=device or "cuda")
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def c(self) -> capi.RooVolume:
+        return capi.RooVolume(self.pitch, self.ptr, self.w, self.h, self.img_pitch, self.d)
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray, pitch: int | None = None, device=None) -> "Volume":
+        d, h, w = a.shape
+        v = cls(w, h, d, a.dtype, pitch, device)
+        v.upload(a)
+        return v
+
+    def upload(self, a: np.ndarray) -> None:
+        row = self.w * self.dtype.itemsize
+        host = np.zeros((self.d * self.h, self.pitch), np.uint8)
+        host[:, :row] = np.ascontiguousarray(a).view(np.uint8).reshape(self.d * self.h, row)
+        self.buf.copy_(torch.from_numpy(host.reshape(-1)))
+
+    def fill_bytes(self, v: int) -> None:
+        self.buf.fill_(v)
+
+    def numpy(self) -> np.ndarray:
+        row = self.w * self.dtype.itemsize
+        rows = np.ascontiguousarray(self.buf.cpu().numpy().reshape(self.d * self.h, self.pitch)[:, :row])
+        return rows.view(self.dtype).reshape(self.d, self.h, self.w).copy()
+
+
+def _img_type(im: Image) -> int:
+    if im.dtype == np.uint8:
+        return IMG_U8
+    if im.dtype == np.float32:
+        return IMG_F32
+    raise TypeError(f"image type {im.dtype}")
+
+
+def _window_of(census: Image) -> int:
+    words = census.dtype.itemsize // 8
+    return {1: WIN_9x7, 2: WIN_11x11, 4: WIN_16x16}[words]
+
+
+# ---------------------------------------------------------------------------------------------------
+# operators (reference names)
+# ---------------------------------------------------------------------------------------------------
+
+def Census(census: Image, img: Image, stream=None) -> None:
+    """roo::Census (cu_census.h:13-23): the descriptor type of `census` picks the window."""
+    check(lib().roo_census(C.byref(census.c()), C.byref(img.c()), _window_of(census), _img_type(img), _stream(stream)),
+          "Census")
+
+
+def CensusStereo(disp: Image, left: Image, right: Image, maxDisp: int, stream=None) -> None:
+    check(lib().roo_census_stereo(C.byref(disp.c()), C.byref(left.c()), C.byref(right.c()), maxDisp, _stream(stream)),
+          "CensusStereo")
+
+
+def CensusStereoVolume(vol: Volume, left: Image, right: Image, maxDisp: int, sd: float, popc_mode: int = POPC32_COMPAT,
+                       stream=None) -> None:
+    check(lib().roo_census_stereo_volume(C.byref(vol.c()), C.byref(left.c()), C.byref(right.c()),
+                                         left.dtype.itemsize // 8, _VOL_TYPES[vol.dtype], maxDisp, sd, popc_mode,
+                                         _stream(stream)), "CensusStereoVolume")
+
+
+def SemiGlobalMatching(volH: Volume, volC: Volume, left: Image, maxDisp: int, P1: float, P2: float, dohoriz: bool,
+                       dovert: bool, doreverse: bool, dodiag: bool = False, stream=None) -> None:
+    check(lib().roo_sgm(C.byref(volH.c()), C.byref(volC.c()), _VOL_TYPES[volC.dtype], C.byref(left.c()),
+                        _img_type(left), maxDisp, P1, P2, int(dohoriz), int(dovert), int(doreverse), int(dodiag),
+                        _stream(stream)), "SemiGlobalMatching")
+
+
+def CostVolMinimum(disp: Image, vol: Volume, maxDisp: int | None = None, stream=None) -> None:
+    """roo::CostVolMinimum<Tdisp,Tvol>(disp, vol, maxDisp) and CostVolMinimum(Image<float>, Volume<CostVolElem>)."""
+    if vol.dtype == COSTVOLELEM:
+        check(lib().roo_costvol_minimum_elem(C.byref(disp.c()), C.byref(vol.c()), _stream(stream)), "CostVolMinimum")
+        return
+    dt = DISP_I8 if disp.dtype == np.int8 else DISP_F32
+    check(lib().roo_costvol_minimum(C.byref(disp.c()), dt, C.byref(vol.c()), _VOL_TYPES[vol.dtype], maxDisp,
+                                    _stream(stream)), "CostVolMinimum")
+
+
+def CostVolMinimumSubpix(disp: Image, vol: Volume, maxDisp: int, sd: float, stream=None) -> None:
+    check(lib().roo_costvol_minimum_subpix(C.byref(disp.c()), C.byref(vol.c()), maxDisp, sd, _stream(stream)),
+          "CostVolMinimumSubpix")
+
+
+def DenseStereoSubpixelRefine(dDispOut: Image, dDisp: Image, dCamLeft: Image, dCamRight: Image, stream=None) -> None:
+    check(lib().roo_dense_stereo_subpixel_refine(C.byref(dDispOut.c()), C.byref(dDisp.c()), C.byref(dCamLeft.c()),
+                                                 C.byref(dCamRight.c()), _stream(stream)), "DenseStereoSubpixelRefine")
+
+
+def LeftRightCheck(dispL: Image, dispR: Image, sd=-1, maxDiff=None, stream=None) -> None:
+    """roo::LeftRightCheck: char overload (sd=-1, maxDiff=0) or float overload (sd=-1, maxDiff=0.5)."""
+    if dispL.dtype == np.int8:
+        check(lib().roo_left_right_check_i8(C.byref(dispL.c()), C.byref(dispR.c()), int(sd),
+                                            0 if maxDiff is None else int(maxDiff), _stream(stream)), "LeftRightCheck")
+    else:
+        check(lib().roo_left_right_check_f32(C.byref(dispL.c()), C.byref(dispR.c()), float(sd),
+                                             0.5 if maxDiff is None else float(maxDiff), _stream(stream)),
+              "LeftRightCheck")
+
+
+def set_ieee_division(on: bool) -> None:
+    lib().roo_set_ieee_division(int(on))
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused engine
+# ---------------------------------------------------------------------------------------------------
+
+class StereoEngine:
+    """The whole per-frame path (stereo2/main.cpp:375-454) on engine-owned scratch, batched."""
+
+    def __init__(self, w: int, h: int, max_disp: int, window: int = WIN_9x7, popc_mode: int = POPC32_COMPAT,
+                 P1: float = 0.01, P2: float = 0.02, img_scale: float = 1.0 / 255.0, dohoriz=True, dovert=True,
+                 doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff: float = 1.0,
+                 max_batch: int = 1, keep_volume: bool = False):
+        self.params = capi.PipelineParams(w, h, max_disp, window, popc_mode, P1, P2, np.float32(img_scale),
+                                          int(dohoriz), int(dovert), int(doreverse), int(dodiag), int(subpix),
+                                          int(lrcheck), lr_maxdiff, max_batch, int(keep_volume))
+        self.w, self.h, self.max_disp = w, h, max_disp
+        self._h = C.c_void_p()
+        check(lib().roo_engine_create(C.byref(self._h), C.byref(self.params)), "roo_engine_create")
+
+    def close(self) -> None:
+        if self._h:
+            lib().roo_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def scratch_bytes(self) -> int:
+        return int(lib().roo_engine_scratch_bytes(self._h))
+
+    def run_device(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor | None = None, stream=None):
+        """left/right: (n, h, w) uint8 CUDA tensors (contiguous); returns (n, h, w) float32."""
+        assert left.is_cuda and left.dtype == torch.uint8 and left.is_contiguous() and right.is_contiguous()
+        n = left.shape[0]
+        if disp is None:
+            disp = torch.empty((n, self.h, self.w), dtype=torch.float32, device=left.device)
+        check(lib().roo_engine_run_device(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(), n,
+                                          _stream(stream)), "roo_engine_run_device")
+        return disp
+
+    def run_host(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+        """Host (ideally pinned) tensors in, host tensor out; H2D + compute + D2H, synchronous."""
+        assert not left.is_cuda and left.dtype == torch.uint8 and disp.dtype == torch.float32
+        check(lib().roo_engine_run_host(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(), left.shape[0]),
+              "roo_engine_run_host")
+        return disp
+
+    def set_profiling(self, on: bool) -> None:
+        check(lib().roo_engine_set_profiling(self._h, int(on)), "roo_engine_set_profiling")
+
+    def get_profile(self) -> dict:
+        """{kind: (total_ms, launches)} since profiling was switched on; synchronise the stream first."""
+        n = len(capi.PROF_KINDS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        check(lib().roo_engine_get_profile(self._h, ms, cnt), "roo_engine_get_profile")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(capi.PROF_KINDS)}
+
+    def export_volume(self, slot: int = 0, depth: int | None = None) -> Volume:
+        v = Volume(self.w, self.h, depth or self.max_disp, np.float32)
+        check(lib().roo_engine_export_volume(self._h, slot, C.byref(v.c()), _stream(None)), "roo_engine_export_volume")
+        return v
+
+    def export_census(self, slot: int, side: int) -> Image:
+        words = WORDS[self.params.window]
+        im = Image(self.w, self.h, np.dtype((np.uint64, (words,))) if words > 1 else ULONG)
+        check(lib().roo_engine_export_census(self._h, slot, side, C.byref(im.c()), _stream(None)),
+              "roo_engine_export_census")
+        return im

@@ -1,0 +1,52 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/roo_b200.h declares, and the POD mirrors are binary-compatible with roo::Image / roo::Volume.
+No compute call is made (there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+from kangaroo_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "roo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(roo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = capi.lib()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/roo_b200.h but not exported"
+    assert sorted(capi.SYMBOLS) == names  # the ctypes table covers the header exactly
+
+
+def test_pod_layout_matches_reference_structs():
+    # roo::Image {size_t pitch; T* ptr; size_t w; size_t h;} = 32 B, roo::Volume adds img_pitch, d = 48 B
+    assert C.sizeof(capi.RooImage) == 32 and C.sizeof(capi.RooVolume) == 48
+    assert [f[0] for f in capi.RooImage._fields_] == ["pitch", "ptr", "w", "h"]
+    assert [f[0] for f in capi.RooVolume._fields_] == ["pitch", "ptr", "w", "h", "img_pitch", "d"]
+    assert capi.RooVolume.img_pitch.offset == 32 and capi.RooVolume.d.offset == 40
+
+
+def test_status_strings_and_version_need_no_gpu():
+    assert capi.status_string(0) == "ok"
+    assert "invalid" in capi.status_string(-1)
+    assert b"sm_100a" in capi.lib().roo_b200_version()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under kangaroo_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("kangaroo_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"\bimport oracle\b|from oracle\b|kangaroo_oracle|libkangaroo_ref|oracle/", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,384 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, the committed golden vectors of
+the reference, and -- where oracle/_ref is present -- the reference kernels themselves.
+
+Bars (BASELINE.json north_star): census descriptors and integer matching costs bit-exact; aggregated
+costs within 1e-5 relative (bit-exact against the oracle under IEEE division, bit-exact against the
+reference kernels under the default div.approx mode); integer WTA identical on >= 99.9 % of pixels;
+subpixel disparity within 0.01 px.
+"""
+import numpy as np
+import pytest
+
+import oracle as ko
+from kangaroo_b200.synth import stereo_pair
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from kangaroo_b200 import roo  # noqa: E402
+from oracle import ref_gpu  # noqa: E402
+
+HAVE_REF = ref_gpu.available()
+
+
+def relerr(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(a), 1e-30)
+
+
+@pytest.fixture(autouse=True)
+def _default_fp_mode():
+    roo.set_ieee_division(False)
+    yield
+    roo.set_ieee_division(False)
+
+
+def census_dtype(win):
+    return np.dtype((np.uint64, (roo.WORDS[win],)))
+
+
+def gpu_census(img, win, pitch=None):
+    h, w = img.shape
+    out = roo.Image(w, h, census_dtype(win))
+    roo.Census(out, roo.Image.from_numpy(img, pitch=pitch))
+    return out.numpy()
+
+
+# ------------------------------------------------------------------------------------------ census
+
+@pytest.mark.parametrize("win", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(40, 48), (37, 101), (5, 3), (1, 1), (9, 260)])
+def test_census_bitexact_vs_oracle(win, shape):
+    rng = np.random.default_rng(win * 100 + shape[0])
+    for img in (rng.integers(0, 256, shape, dtype=np.uint8), rng.integers(0, 3, shape, dtype=np.uint8),
+                rng.random(shape, dtype=np.float32)):
+        assert np.array_equal(gpu_census(img, win), ko.census(img, win))
+
+
+@pytest.mark.parametrize("win", [0, 1, 2])
+def test_census_matches_reference_golden(golden, win):
+    g = golden("census")
+    for nm in ("u8", "tie", "f32"):
+        assert np.array_equal(gpu_census(g["img_" + nm], win), g[f"out_{nm}_{win}"])
+
+
+def test_census_honours_pitch_and_subimage():
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (50, 70), dtype=np.uint8)
+    parent = roo.Image.from_numpy(img, pitch=131)  # odd pitch
+    out = roo.Image(70, 50, census_dtype(0), pitch=70 * 8 + 24)
+    roo.Census(out, parent)
+    assert np.array_equal(out.numpy(), ko.census(img, 0))
+    # SubImage view: clamp-to-edge applies to the VIEW's borders, as in the reference
+    sub = parent.sub_image(10, 7, 40, 30)
+    outs = roo.Image(40, 30, census_dtype(1))
+    roo.Census(outs, sub)
+    assert np.array_equal(outs.numpy(), ko.census(np.ascontiguousarray(img[7:37, 10:50]), 1))
+
+
+def test_census_large_kat_constant_and_ramp():
+    img = np.full((720, 1280), 9, np.uint8)
+    assert (gpu_census(img, 0) == 0).all()
+    ramp = np.tile((np.arange(1280) % 251).astype(np.uint8), (64, 1))
+    assert np.array_equal(gpu_census(ramp, 2), ko.census(ramp, 2))
+
+
+# ------------------------------------------------------------------------------------------ matching cost
+
+def test_census_stereo_vs_oracle_and_golden(golden):
+    g = golden("census_stereo")
+    cl, cr = ko.census(g["left"], 0), ko.census(g["right"], 0)
+    for md in (16, -16, 5, 0, 300):
+        disp = roo.Image(64, 24, np.int8)
+        roo.CensusStereo(disp, roo.Image.from_numpy(cl), roo.Image.from_numpy(cr), md)
+        assert np.array_equal(disp.numpy(), ko.census_stereo(cl, cr, md)), md
+        if f"disp_{md}" in g.files:
+            assert np.array_equal(disp.numpy(), g[f"disp_{md}"]), md
+
+
+@pytest.mark.parametrize("win", [0, 1, 2])
+@pytest.mark.parametrize("popc", [ko.POPC32_COMPAT, ko.POPC64])
+def test_census_stereo_volume_bitexact(golden, win, popc):
+    g = golden("census_stereo_volume")
+    cl, cr = ko.census(g["left"], win), ko.census(g["right"], win)
+    L, R = roo.Image.from_numpy(cl), roo.Image.from_numpy(cr)
+    for sd in (-1.0, 1.0):
+        vol = roo.Volume.from_numpy(np.full((18, 24, 64), 7.0, np.float32))
+        roo.CensusStereoVolume(vol, L, R, 16, sd, popc_mode=popc)
+        got = vol.numpy()
+        assert np.array_equal(got, ko.census_stereo_volume(cl, cr, 16, sd, np.float32, popc, depth=18, fill=7.0))
+        if popc == ko.POPC32_COMPAT:
+            assert np.array_equal(got, g[f"f32_w{win}_sd{int(sd)}"])
+    v16 = roo.Volume.from_numpy(np.full((16, 24, 64), 9, np.uint16))
+    roo.CensusStereoVolume(v16, L, R, 16, -1.0, popc_mode=popc)
+    assert (v16.numpy() == 0).all()  # Q2
+
+
+def test_census_stereo_volume_wide_and_maxdisp_gt_width():
+    L, R, _ = stereo_pair(1300, 6, 128, config=7)  # wider than the reference's 1024 limit
+    cl, cr = ko.census(L, 0), ko.census(R, 0)
+    vol = roo.Volume(1300, 6, 128, np.float32)
+    roo.CensusStereoVolume(vol, roo.Image.from_numpy(cl), roo.Image.from_numpy(cr), 128, -1.0)
+    assert np.array_equal(vol.numpy(), ko.census_stereo_volume(cl, cr, 128, -1.0))
+    Ls, Rs, _ = stereo_pair(20, 4, 8, config=8)
+    cl, cr = ko.census(Ls, 2), ko.census(Rs, 2)
+    vol = roo.Volume(20, 4, 40, np.float32)
+    roo.CensusStereoVolume(vol, roo.Image.from_numpy(cl), roo.Image.from_numpy(cr), 40, 1.0)
+    assert np.array_equal(vol.numpy(), ko.census_stereo_volume(cl, cr, 40, 1.0))
+    with pytest.raises(roo.capi.RooError):
+        roo.CensusStereoVolume(vol, roo.Image.from_numpy(cl), roo.Image.from_numpy(cr), 40, 0.5)  # Q12
+
+
+# ------------------------------------------------------------------------------------------ SGM
+
+def gpu_sgm(volc, left, md, p1, p2, hz=True, vt=True, rv=True, dg=False, depth=None):
+    d, h, w = volc.shape
+    vh = roo.Volume(w, h, depth or d, np.float32)
+    vh.fill_bytes(0x7F)  # garbage: SemiGlobalMatching must clear it (volH.Memset(0))
+    roo.SemiGlobalMatching(vh, roo.Volume.from_numpy(volc), roo.Image.from_numpy(left), md, p1, p2, hz, vt, rv, dg)
+    return vh.numpy()
+
+
+def test_sgm_golden_all_flag_combinations_bitexact_vs_reference(golden):
+    """Default fp mode computes P2/(1+|dI|) with div.approx like the reference build: the aggregate is
+    bit-identical to what the reference kernels produced on a B200."""
+    g = golden("sgm")
+    for hz in (0, 1):
+        for vt in (0, 1):
+            for rv in (0, 1):
+                H = gpu_sgm(g["volc"], g["left_f32"], 12, 0.01, 0.02, hz, vt, rv)
+                assert np.array_equal(H, g[f"H_h{hz}v{vt}r{rv}"]), (hz, vt, rv)
+    assert np.array_equal(gpu_sgm(g["volc"], g["left_f32"], 7, 0.05, 0.3), g["H_md7"])
+    assert np.array_equal(gpu_sgm(g["volc_rand"], g["left_f32"], 12, 0.1, 0.4), g["H_rand"])
+    elem = np.zeros(g["volc_elem_n"].shape, ko.COSTVOLELEM)
+    elem["n"], elem["sum"] = g["volc_elem_n"], g["volc_elem_sum"]
+    H = gpu_sgm(elem, g["left_u8"], 12, 1.0, 8.0)
+    assert relerr(g["H_elem"], H).max() <= 1e-6  # sum/n is a second approximate divide: allow 1 ulp
+
+
+@pytest.mark.parametrize("dodiag", [False, True])
+@pytest.mark.parametrize("shape", [(40, 24, 12), (70, 33, 40), (130, 20, 64), (300, 9, 200), (16, 16, 100)])
+def test_sgm_ieee_mode_bitexact_vs_oracle(shape, dodiag):
+    w, h, D = shape
+    L, R, _ = stereo_pair(w, h, D, config=11)
+    cl, cr = ko.census(L, 0), ko.census(R, 0)
+    volc = ko.census_stereo_volume(cl, cr, D, -1.0)
+    lf = L.astype(np.float32) * np.float32(1 / 255)
+    roo.set_ieee_division(True)
+    for flags in ((1, 1, 1), (1, 0, 1), (0, 1, 0)):
+        H = gpu_sgm(volc, lf, D, 0.01, 0.02, *flags, dodiag)
+        O = ko.sgm(volc, lf, D, 0.01, 0.02, *flags, dodiag)
+        assert np.array_equal(H, O), (shape, flags)
+    roo.set_ieee_division(False)
+    H = gpu_sgm(volc, lf, D, 0.01, 0.02, 1, 1, 1, dodiag)
+    O = ko.sgm(volc, lf, D, 0.01, 0.02, 1, 1, 1, dodiag)
+    assert relerr(O, H).max() <= 1e-5
+
+
+def test_sgm_u8_image_and_depth_larger_than_maxdisp():
+    L, R, _ = stereo_pair(64, 24, 16, config=12)
+    volc = ko.census_stereo_volume(ko.census(L, 2), ko.census(R, 2), 16, -1.0, depth=20, fill=3.0)
+    roo.set_ieee_division(True)
+    H = gpu_sgm(volc, L, 16, 2.0, 30.0)
+    O = ko.sgm(volc, L, 16, 2.0, 30.0)
+    assert np.array_equal(H, O)
+    assert (H[16:] == 0).all()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg", [(640, 480, 64, 1), (1024, 375, 128, 3)])
+def test_sgm_bitexact_vs_live_reference_kernels(cfg):
+    w, h, D, c = cfg
+    L, R, _ = stereo_pair(w, h, D, config=c)
+    lf = L.astype(np.float32) * np.float32(1 / 255)
+    cl, cr = ref_gpu.census(L, 0), ref_gpu.census(R, 0)
+    assert np.array_equal(gpu_census(L, 0), cl)
+    volc = ref_gpu.census_stereo_volume(cl, cr, D, -1.0)
+    vol = roo.Volume(w, h, D, np.float32)
+    roo.CensusStereoVolume(vol, roo.Image.from_numpy(cl), roo.Image.from_numpy(cr), D, -1.0)
+    assert np.array_equal(vol.numpy(), volc)
+    ref_h = ref_gpu.sgm(volc, lf, D, 0.01, 0.02, 1, 1, 1)
+    H = gpu_sgm(volc, lf, D, 0.01, 0.02)
+    assert np.array_equal(H, ref_h)
+
+
+# ------------------------------------------------------------------------------------------ WTA & co
+
+def test_costvol_minimum_all_instantiations(golden):
+    g = golden("costvol_minimum")
+
+    def run(vol, md, dt):
+        d, h, w = vol.shape
+        disp = roo.Image(w, h, dt)
+        roo.CostVolMinimum(disp, roo.Volume.from_numpy(vol), md)
+        return disp.numpy()
+
+    assert np.array_equal(run(g["vol_f32"], 20, np.float32), g["disp_f32_f32"])
+    assert np.array_equal(run(g["vol_f32"], 13, np.int8), g["disp_i8_f32"])
+    for nm in ("i32", "u32", "u16", "u8"):
+        assert np.array_equal(run(g["vol_" + nm], 20, np.int8), g["disp_i8_" + nm]), nm
+    assert np.array_equal(run(g["vol_u16"], 20, np.float32), g["disp_f32_u16"])
+    el = np.zeros(g["elem_n"].shape, ko.COSTVOLELEM)
+    el["n"], el["sum"] = g["elem_n"], g["elem_sum"]
+    disp = roo.Image(64, 32, np.float32)
+    roo.CostVolMinimum(disp, roo.Volume.from_numpy(el))
+    assert np.array_equal(disp.numpy(), g["disp_elem"])
+    # unguarded in the reference (Q5): here any shape works
+    rng = np.random.default_rng(3)
+    v = rng.random((9, 13, 45), dtype=np.float32)
+    assert np.array_equal(run(v, 9, np.float32), ko.costvol_minimum(v, 9, np.float32))
+
+
+def test_costvol_minimum_subpix(golden):
+    g = golden("costvol_minimum_subpix")
+    for key, sd, vol, md in (("disp_sd-1", -1.0, g["vol"], 16), ("disp_sd1", 1.0, g["vol"], 16),
+                             ("disp_sgm", -1.0, g["vol_sgm"], 12)):
+        d, h, w = vol.shape
+        disp = roo.Image(w, h, np.float32)
+        roo.CostVolMinimumSubpix(disp, roo.Volume.from_numpy(vol), md, sd)
+        assert np.array_equal(disp.numpy(), g[key]), key  # same div.approx as the reference: bit-exact
+        roo.set_ieee_division(True)
+        roo.CostVolMinimumSubpix(disp, roo.Volume.from_numpy(vol), md, sd)
+        assert np.array_equal(disp.numpy(), ko.costvol_minimum_subpix(vol, md, sd)[0]), key
+        roo.set_ieee_division(False)
+    # top edge: bestd + 1 == vol.d keeps the integer disparity
+    vol3 = np.full((8, 1, 12), 10.0, np.float32)
+    vol3[7, 0, 9] = 1.0
+    disp = roo.Image(12, 1, np.float32)
+    roo.CostVolMinimumSubpix(disp, roo.Volume.from_numpy(vol3), 8, -1.0)
+    assert disp.numpy()[0, 9] == 7.0
+
+
+def test_dense_stereo_subpixel_refine(golden):
+    g = golden("dense_stereo_subpixel_refine")
+    h, w = g["disp"].shape
+    out = roo.Image(w, h, np.float32)
+    roo.DenseStereoSubpixelRefine(out, roo.Image.from_numpy(g["disp"]), roo.Image.from_numpy(g["left"]),
+                                  roo.Image.from_numpy(g["right"]))
+    got = out.numpy()
+    oref, mask = ko.dense_stereo_subpixel_refine(g["disp"], g["left"], g["right"])
+    assert np.isnan(got[mask == 1]).all()  # guarded where the reference reads out of bounds
+    inner = mask == 0
+    for ref in (g["out"], oref):
+        assert (np.isfinite(ref[inner]) == np.isfinite(got[inner])).mean() >= 0.999
+        both = inner & np.isfinite(ref) & np.isfinite(got)
+        assert np.abs(ref[both] - got[both]).max() <= 0.01
+
+
+def test_left_right_check(golden):
+    g = golden("left_right_check")
+    for key, sd, md in (("f32_sd-1_0.5", -1.0, 0.5), ("f32_sd1_4", 1.0, 4.0)):
+        dl = roo.Image.from_numpy(g["dl"])
+        roo.LeftRightCheck(dl, roo.Image.from_numpy(g["dr"]), sd, md)
+        out = dl.numpy()
+        assert np.array_equal(np.isnan(out), np.isnan(g[key])), key
+        assert np.array_equal(out[~np.isnan(out)], g[key][~np.isnan(out)]), key
+    for key, sd, md in (("i8_sd-1_0", -1, 0), ("i8_sd1_2", 1, 2)):
+        dl = roo.Image.from_numpy(g["dli"])
+        roo.LeftRightCheck(dl, roo.Image.from_numpy(g["dri"]), sd, md)
+        assert np.array_equal(dl.numpy(), g[key]), key
+
+
+# ------------------------------------------------------------------------------------------ fused engine
+
+def run_engine(L, R, D, batch=1, **kw):
+    h, w = L.shape
+    eng = roo.StereoEngine(w, h, D, max_batch=batch, keep_volume=True, **kw)
+    l = torch.from_numpy(np.stack([L] * batch)).cuda()
+    r = torch.from_numpy(np.stack([R] * batch)).cuda()
+    disp = eng.run_device(l, r).cpu().numpy()
+    vol = eng.export_volume(0).numpy() if (kw.get("dohoriz", True) or kw.get("dovert", True)) else None
+    cen = eng.export_census(0, 0).numpy().reshape(h, w, -1)
+    eng.close()
+    return disp, vol, cen
+
+
+def test_engine_matches_reference_golden_pipeline(golden):
+    g = golden("pipeline")
+    L, R = g["left"], g["right"]
+    for win in (0, 2):
+        disp, H, cen = run_engine(L, R, 32, window=win, subpix=True, lrcheck=True, lr_maxdiff=1.0)
+        assert np.array_equal(cen, g[f"w{win}_census0"])
+        assert np.array_equal(H, g[f"w{win}_H"])  # bit-identical to the reference kernels' aggregate
+        ref = g[f"w{win}_disp0_lr"]
+        top = np.rint(g[f"w{win}_disp0"]) >= 31  # the reference read one slice past maxDisp there (Q7)
+        assert ((np.isnan(ref) == np.isnan(disp[0])) | top).mean() >= 0.999
+        both = np.isfinite(ref) & np.isfinite(disp[0]) & ~top
+        assert (np.abs(ref - disp[0])[both] <= 0.01).mean() >= 0.999
+
+
+@pytest.mark.parametrize("win", [0, 1, 2])
+@pytest.mark.parametrize("opts", [dict(), dict(dodiag=True), dict(subpix=True, lrcheck=True),
+                                  dict(dohoriz=False, dovert=False, subpix=True, lrcheck=True),
+                                  dict(popc_mode=ko.POPC64, dodiag=True, subpix=True)])
+def test_engine_ieee_bitexact_vs_oracle(win, opts):
+    L, R, _ = stereo_pair(150, 41, 48, config=21)
+    roo.set_ieee_division(True)
+    disp, H, cen = run_engine(L, R, 48, batch=3, window=win, **opts)
+    od, oH = ko.pipeline_u8(L, R, 48, window=win, want_volume=True, **opts)
+    assert np.array_equal(cen, ko.census(L, win))
+    if H is not None:
+        assert np.array_equal(H, oH)
+    for b in range(3):  # every batch slot computes the same thing
+        assert np.array_equal(np.isnan(disp[b]), np.isnan(od))
+        ok = ~np.isnan(od)
+        assert np.array_equal(disp[b][ok], od[ok])
+
+
+def test_engine_c1_full_size_vs_oracle():
+    """BASELINE config 1: 640x480, 64 disparities, 4 paths -- the reference's own CPU-runnable case."""
+    L, R, gt = stereo_pair(640, 480, 64, config=1)
+    disp, H, cen = run_engine(L, R, 64)
+    od, oH = ko.pipeline_u8(L, R, 64, want_volume=True)
+    assert np.array_equal(cen, ko.census(L, 0))
+    assert relerr(oH, H).max() <= 1e-5
+    dd, xx = np.arange(64)[:, None, None], np.arange(640)[None, None, :]
+    assert (H[np.broadcast_to(dd > xx, H.shape)] == 0).all()
+    assert (disp[0] == od).mean() >= 0.999
+    valid = np.arange(640)[None, :] >= gt
+    assert (np.abs(disp[0] - gt)[valid] <= 1).mean() > 0.8  # and it is a sensible disparity map
+
+
+def test_engine_c2_full_size_properties_and_oracle():
+    """BASELINE config 2: 1280x720, 128 disparities, 8 paths + WTA (beyond the reference's 1024 limit)."""
+    L, R, gt = stereo_pair(1280, 720, 128, config=2)
+    roo.set_ieee_division(True)
+    disp, H, cen = run_engine(L, R, 128, dodiag=True)
+    od, oH = ko.pipeline_u8(L, R, 128, dodiag=True, want_volume=True)
+    assert np.array_equal(H, oH)
+    assert np.array_equal(disp[0], od)
+    # size-independent properties: idempotence, batch invariance, flipping rows flips the result of a
+    # horizontal-only aggregation
+    d2, _, _ = run_engine(L, R, 128, batch=2, dodiag=True)
+    assert np.array_equal(d2[0], disp[0]) and np.array_equal(d2[1], disp[0])
+    # (64-bit popcount: the compat mode only compares the upper half of the window, Q1, which is not flip-invariant)
+    dh, _, _ = run_engine(L, R, 128, dovert=False, popc_mode=ko.POPC64)
+    dhf, _, _ = run_engine(L[::-1].copy(), R[::-1].copy(), 128, dovert=False, popc_mode=ko.POPC64)
+    assert np.array_equal(dhf[0][::-1], dh[0])
+
+
+def test_engine_run_host_equals_run_device():
+    L, R, _ = stereo_pair(320, 200, 64, config=31)
+    n = 5
+    eng = roo.StereoEngine(320, 200, 64, max_batch=2, subpix=True, lrcheck=True)
+    lh = torch.from_numpy(np.stack([np.roll(L, i, 0) for i in range(n)])).pin_memory()
+    rh = torch.from_numpy(np.stack([np.roll(R, i, 0) for i in range(n)])).pin_memory()
+    out = torch.empty((n, 200, 320), dtype=torch.float32).pin_memory()
+    eng.run_host(lh, rh, out)
+    dev = eng.run_device(lh.cuda(), rh.cuda()).cpu()
+    torch.cuda.synchronize()
+    a, b = out.numpy(), dev.numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    eng.close()
+
+
+def test_invalid_arguments_are_reported_not_ignored():
+    img = roo.Image(16, 16, np.uint8)
+    cen = roo.Image(8, 16, census_dtype(0))
+    with pytest.raises(roo.capi.RooError):
+        roo.Census(cen, img)  # size mismatch
+    with pytest.raises(roo.capi.RooError):
+        roo.StereoEngine(64, 64, 300)  # > 256 disparities

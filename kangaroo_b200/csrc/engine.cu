@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sgm_step.cuh"
 
 namespace roo_b200 {
 std::atomic<unsigned long long> g_launches{0};
@@ -26,6 +27,7 @@ struct roo_engine {
     unsigned char* c8 = nullptr;                      // [batch][h][w][DP]
     float* H = nullptr;                               // [batch][h][w][DP]
     float* dispR = nullptr;                           // [batch][h][w]
+    float* imgf = nullptr;                            // [batch][h][w] adaptive-P2 intensity (u8 * img_scale)
     // staging for run_host (device) and its streams
     unsigned char* in_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][side]
     float* out_dev[2] = {nullptr, nullptr};
@@ -81,11 +83,12 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
     } else {
         rc = launch_cost_u8(e->c8, e->cen[0], e->cen[1], w, h, batch, e->DP, p.max_disp, e->words, p.popc_mode, st);
         if (rc) return rc;
+        rc = launch_image_to_f32(e->imgf, left, (size_t)w, npx, ROO_IMG_U8, w, h, batch, p.img_scale, st);
+        if (rc) return rc;
         prof_mark(e, ROO_PROF_COST, st);
         SweepArgs a{};
         a.H = e->H; a.h_pair = npx * e->DP; a.C = e->c8; a.c_pair = npx * e->DP;
-        a.img = (const char*)left; a.img_pitch = (size_t)w; a.img_pair = npx; a.img_type = ROO_IMG_U8;
-        a.img_scale = p.img_scale; a.cost_scale = 1.0f / (float)(e->words * 64);
+        a.img = e->imgf; a.img_pair = npx; a.cost_scale = 1.0f / (float)(e->words * 64);
         a.w = w; a.h = h; a.DP = e->DP; a.maxDisp = p.max_disp; a.batch = batch;
         a.P1 = p.P1; a.P2 = p.P2; a.cost_kind = COST_U8; a.subpix = p.subpix; a.disp = disp; a.disp_pair = npx;
         for (int i = 0; i < ndir; ++i) {
@@ -110,7 +113,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
 }
 
 static void engine_free(roo_engine* e) {
-    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR);
+    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->imgf);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
         if (e->ev_in[b]) cudaEventDestroy(e->ev_in[b]);
@@ -147,7 +150,9 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     int dxs[8], dys[8];
     const int ndir = sgm_directions(p.dohoriz, p.dovert, p.doreverse, p.dodiag, dxs, dys);
     bool ok = alloc((void**)&e->cen[0], B * npx * e->words * 8) && alloc((void**)&e->cen[1], B * npx * e->words * 8);
-    if (ok && ndir > 0) ok = alloc((void**)&e->c8, B * npx * e->DP) && alloc((void**)&e->H, B * npx * e->DP * 4);
+    if (ok && ndir > 0)
+        ok = alloc((void**)&e->c8, B * npx * e->DP) && alloc((void**)&e->H, B * npx * e->DP * 4) &&
+             alloc((void**)&e->imgf, B * npx * 4);
     if (ok && p.lrcheck) ok = alloc((void**)&e->dispR, B * npx * 4);
     if (!ok) {
         cudaGetLastError();

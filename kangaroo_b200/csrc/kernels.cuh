@@ -13,7 +13,6 @@ int launch_census_wta(float* disp, const void* cself, const void* cother, int w,
                       int words, int popc_mode, int subpix, int sdi, cudaStream_t st);
 
 // ---- sgm.cu ----
-enum CostKind { COST_F32 = 0, COST_U8 = 1 };
 enum EpiKind { EPI_NONE = 0, EPI_WTA_WRITE = 1, EPI_WTA_ONLY = 2 };
 
 // One aggregation sweep (one path direction) over `batch` pairs on the internal layout
@@ -23,22 +22,22 @@ struct SweepArgs {
     size_t h_pair;       // elements between pairs
     const void* C;       // cost, same indexing as H: float or unsigned char
     size_t c_pair;       // elements between pairs
-    const char* img;     // left image used for the adaptive P2 (u8 or f32, pitched)
-    size_t img_pitch, img_pair;  // bytes
-    int img_type;        // ROO_IMG_U8 / ROO_IMG_F32
-    float img_scale;     // intensity = u8 * img_scale (ignored for f32)
+    const float* img;    // adaptive-P2 intensity image, tightly packed fp32 [pair][y][x] (launch_image_to_f32)
+    size_t img_pair;     // elements between pairs
     float cost_scale;    // U8 cost: cost = count * cost_scale
     int w, h, DP, maxDisp, batch;
     float P1, P2;
     int dx, dy;
     int first;           // 1: H holds nothing yet (treated as 0, not read)
-    int cost_kind;       // CostKind
+    int cost_kind;       // CostKind (sgm_step.cuh): 0 fp32, 1 u8 Hamming counts
     int epi;             // EpiKind
     int subpix;          // epilogue: 0 CostVolMinimum<float,float>, 1 CostVolMinimumSubpix(sd=-1)
     float* disp;         // epilogue output [pair][y][x]
     size_t disp_pair;    // elements
 };
 int launch_sweep(const SweepArgs& a, cudaStream_t st);
+int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pair, int img_type, int w, int h,
+                        int batch, float scale, cudaStream_t st);
 inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : 256)); }
 
 // direction list in execution order (reference order down, up, right, left; diagonals are an extension)

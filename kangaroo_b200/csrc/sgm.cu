@@ -21,67 +21,14 @@
 // divide and add, bit-identical to the CPU oracle.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sgm_step.cuh"
+
+#include <type_traits>
 
 namespace roo_b200 {
 
 constexpr int SWEEP_WARPS = 4;   // warps (= scanlines) per CTA
 constexpr int SWEEP_PF = 4;      // prefetch distance in path steps
-constexpr float SGM_MAX_ERROR = 1E30f;
-
-template <int N> struct VecF;
-template <> struct VecF<1> { using T = float; };
-template <> struct VecF<2> { using T = float2; };
-template <> struct VecF<4> { using T = float4; };
-
-template <int DPL>
-__device__ __forceinline__ void load_f(float (&v)[DPL], const float* p) {
-    if constexpr (DPL == 8) {
-        const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else if constexpr (DPL == 4) {
-        const float4 a = *reinterpret_cast<const float4*>(p);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    } else if constexpr (DPL == 2) {
-        const float2 a = *reinterpret_cast<const float2*>(p);
-        v[0] = a.x; v[1] = a.y;
-    } else {
-        v[0] = *p;
-    }
-}
-template <int DPL>
-__device__ __forceinline__ void store_f(float* p, const float (&v)[DPL]) {
-    if constexpr (DPL == 8) {
-        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
-    } else if constexpr (DPL == 4) {
-        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if constexpr (DPL == 2) {
-        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
-    } else {
-        *p = v[0];
-    }
-}
-
-// raw cost of one step as loaded (converted to float at use)
-template <int DPL, int COST> struct RawCost;
-template <int DPL> struct RawCost<DPL, COST_F32> {
-    float v[DPL];
-    __device__ __forceinline__ void load(const void* base, size_t idx) { load_f<DPL>(v, (const float*)base + idx); }
-    __device__ __forceinline__ float get(int j, float) const { return v[j]; }
-};
-template <int DPL> struct RawCost<DPL, COST_U8> {
-    unsigned w[(DPL + 3) / 4];
-    __device__ __forceinline__ void load(const void* base, size_t idx) {
-        const unsigned char* p = (const unsigned char*)base + idx;
-        if constexpr (DPL == 8) { const uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
-        else if constexpr (DPL == 4) w[0] = *reinterpret_cast<const unsigned*>(p);
-        else if constexpr (DPL == 2) w[0] = *reinterpret_cast<const unsigned short*>(p);
-        else w[0] = *p;
-    }
-    __device__ __forceinline__ float get(int j, float scale) const {
-        return (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * scale;  // count * 1/bits: exact
-    }
-};
 
 template <int DPL, int COST>
 struct Stage {
@@ -107,148 +54,141 @@ __device__ __forceinline__ Scanline scanline_of(int s, int w, int h, int dx, int
     return sl;
 }
 
-template <int DPL, int COST, int EPI>
+template <int DPL, int COST, int EPI, bool FIRST, bool IEEE>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
-sgm_sweep_kernel(const SweepArgs a, const int n_scan, const int ieee) {
+sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * SWEEP_WARPS + (threadIdx.x >> 5);
     if (s >= n_scan) return;
     const int pair = blockIdx.y;
-    const Scanline sl = scanline_of(s, a.w, a.h, a.dx, a.dy);
-
-    float* __restrict__ H = a.H + (size_t)pair * a.h_pair;
-    const void* Cbase = COST == COST_F32 ? (const void*)((const float*)a.C + (size_t)pair * a.c_pair)
-                                         : (const void*)((const unsigned char*)a.C + (size_t)pair * a.c_pair);
-    const char* __restrict__ img = a.img + (size_t)pair * a.img_pair;
-    const bool first = a.first != 0;
+    const int w = a.w, dx = a.dx, M = a.maxDisp, subpix = a.subpix;
+    const float P1 = a.P1, P2 = a.P2, cscale = a.cost_scale;
+    const Scanline sl = scanline_of(s, w, a.h, dx, a.dy);
+    const int len = sl.len;
     const int d0 = lane * DPL;
-    const int DP = a.DP;
+    constexpr int DP = 32 * DPL;
+    constexpr int CE = RawCost<DPL, COST>::ELEM;
+    constexpr int PF = SWEEP_PF;
 
-    auto elem_index = [&](int r) -> size_t {
-        const int x = sl.x0 + r * a.dx, y = sl.y0 + r * a.dy;
-        return ((size_t)y * a.w + x) * DP + d0;
+    // element (x0,y0,d0) and the per-step strides; every access below is pointer + running offset
+    const size_t e0 = ((size_t)sl.y0 * w + sl.x0) * DP + d0;
+    const ptrdiff_t pstep = (ptrdiff_t)a.dy * w + dx;      // pixels per path step
+    const ptrdiff_t estep = pstep * DP;                    // elements per path step
+    float* hst = a.H + (size_t)pair * a.h_pair + e0;                                  // store cursor
+    const float* hld = hst;                                                           // load cursor (runs PF ahead)
+    const char* cld = (const char*)a.C + ((size_t)pair * a.c_pair + e0) * CE;
+    const float* ild = a.img + (size_t)pair * a.img_pair + (size_t)sl.y0 * w + sl.x0;
+    float* dst = (EPI != EPI_NONE) ? a.disp + (size_t)pair * a.disp_pair + (size_t)sl.y0 * w + sl.x0 : nullptr;
+
+    Stage<DPL, COST> ring[PF];
+    auto load_stage = [&](Stage<DPL, COST>& st) {
+        if (!FIRST) load_f<DPL>(st.hin, hld);
+        st.c.load(cld);
+        st.pix = *ild;
+        hld += estep; cld += estep * CE; ild += pstep;
     };
-    auto load_stage = [&](Stage<DPL, COST>& st, int r) {
-        const int x = sl.x0 + r * a.dx, y = sl.y0 + r * a.dy;
-        const size_t idx = ((size_t)y * a.w + x) * DP + d0;
-        if (!first) load_f<DPL>(st.hin, H + idx);
-        st.c.load(Cbase, idx);
-        const char* prow = img + (size_t)y * a.img_pitch;
-        st.pix = a.img_type == ROO_IMG_U8 ? (float)((const unsigned char*)prow)[x] * a.img_scale
-                                          : ((const float*)prow)[x];
-    };
+#pragma unroll
+    for (int k = 0; k < PF; ++k)
+        if (k < len) load_stage(ring[k]);
 
-    Stage<DPL, COST> ring[SWEEP_PF];
+    float hp[DPL];
 #pragma unroll
-    for (int k = 0; k < SWEEP_PF; ++k)
-        if (k < sl.len) load_stage(ring[k], k);
+    for (int j = 0; j < DPL; ++j) hp[j] = ROO_INF;   // path start: no previous pixel
+    float lastBest = 0.0f, last_c = 0.0f;
+    int x = sl.x0;
+    int r = 0;  // steps done
 
-    float hp[DPL];          // previous pixel's H row, +inf where d >= its disparity range
-    float lastBest = 0.0f;  // reference: lastBestCr starts at 0, NOT at the first pixel's minimum
-    float last_c = 0.0f;
-    const float INF = __int_as_float(0x7f800000);
-
-    for (int r0 = 0; r0 < sl.len; r0 += SWEEP_PF) {
-#pragma unroll
-        for (int k = 0; k < SWEEP_PF; ++k) {
-            const int r = r0 + k;
-            if (r >= sl.len) break;
-            Stage<DPL, COST> cur = ring[k];
-            if (r + SWEEP_PF < sl.len) load_stage(ring[k], r + SWEEP_PF);
-
-            const int x = sl.x0 + r * a.dx, y = sl.y0 + r * a.dy;
-            const int maxDisp = min(a.maxDisp, x + 1);
-            float hnew[DPL];
-            float best = SGM_MAX_ERROR;
-            if (r == 0) {
-                // start pixel: volH += volC (cu_semi_global_matching.cu:31-35)
-#pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    const float hin = first ? 0.0f : cur.hin[j];
-                    const bool in = d0 + j < maxDisp;
-                    hnew[j] = in ? hin + cur.c.get(j, a.cost_scale) : hin;
-                    hp[j] = in ? hnew[j] : INF;
-                }
-            } else {
-                const float diff = last_c - cur.pix;
-                const float denom = 1.0f + fabsf(diff);
-                float up = __shfl_up_sync(0xffffffffu, hp[DPL - 1], 1);
-                float dn = __shfl_down_sync(0xffffffffu, hp[0], 1);
-                if (lane == 0) up = INF;    // d-1 < 0
-                if (lane == 31) dn = INF;   // d+1 beyond the padded range
-                const float base = ieee ? sgm_p2_base<true>(lastBest, a.P2, denom) : sgm_p2_base<false>(lastBest, a.P2, denom);
-#pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    const float hm = j > 0 ? hp[j - 1] : up;
-                    const float hq = j < DPL - 1 ? hp[j + 1] : dn;
-                    float CM = fminf(base, hp[j]);
-                    CM = fminf(CM, hm + a.P1);
-                    CM = fminf(CM, hq + a.P1);
-                    const float Cr = (CM + cur.c.get(j, a.cost_scale)) - lastBest;
-                    const float hin = first ? 0.0f : cur.hin[j];
-                    const bool in = d0 + j < maxDisp;
-                    if (in) best = fminf(best, Cr);
-                    hnew[j] = in ? hin + Cr : hin;
-                }
-#pragma unroll
-                for (int j = 0; j < DPL; ++j) hp[j] = (d0 + j < maxDisp) ? hnew[j] : INF;
-                lastBest = warp_min_f32(best);
-            }
-            last_c = cur.pix;
-
-            const size_t idx = ((size_t)y * a.w + x) * DP + d0;
-            if (EPI != EPI_WTA_ONLY) store_f<DPL>(H + idx, hnew);
-
-            if (EPI != EPI_NONE) {
-                // winner-takes-all over d < min(maxDisp, x+1): first (lowest-d) minimum
-                float lc = INF;
-                int ld = 0;
-#pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    const float v = hp[j];  // == hnew in range, +inf outside
-                    if (v < lc) { lc = v; ld = d0 + j; }
-                }
-                const float m = warp_min_f32(lc);
-                const unsigned ball = __ballot_sync(0xffffffffu, lc == m);
-                const int win = __ffs(ball) - 1;
-                int bestd = __shfl_sync(0xffffffffu, ld, win);
-                float bestc = m;
-                float out;
-                if (!a.subpix) {
-                    out = (float)bestd;  // CostVolMinimum<float,float> (cu_dense_stereo.cu:25-43)
-                } else {
-                    // CostVolMinimumSubpix, sd = -1 (cu_dense_stereo.cu:66-109): bestc starts at 1e10
-                    if (!(bestc < 1E10f)) { bestc = 1E10f; bestd = 0; }
-                    out = (float)bestd;
-                    const int bestxr = x - bestd;
-                    if (0 < bestxr && bestxr < a.w - 1 && bestd + 1 < a.maxDisp) {
-                        const int dl = max(bestd - 1, 0);  // float->unsigned saturation in the reference (Q7)
-                        const int dr = bestd + 1;
-                        float slc = 0.0f, src = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < DPL; ++j) {
-                            if (d0 + j == dl) slc = hnew[j];
-                            if (d0 + j == dr) src = hnew[j];
-                        }
-                        const float sl_ = __shfl_sync(0xffffffffu, slc, dl / DPL);
-                        const float sr_ = __shfl_sync(0xffffffffu, src, dr / DPL);
-                        const float sub = ieee ? parabola_vertex<true>((float)bestd, bestc, sl_, sr_)
-                                               : parabola_vertex<false>((float)bestd, bestc, sl_, sr_);
-                        if ((float)(bestd - 1) < sub && sub < (float)(bestd + 1)) out = sub;
-                    }
-                }
-                if (lane == 0) a.disp[(size_t)pair * a.disp_pair + (size_t)y * a.w + x] = out;
-            }
+    // one path step on ring slot `slot`; refills the slot with the stage PF steps ahead
+    auto step = [&](auto masked_tag, Stage<DPL, COST>& st, float p2) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        const float denom = 1.0f + fabsf(last_c - st.pix);
+        float hnew[DPL], best;
+        const int lim = MASKED ? min(M, x + 1) - d0 : 0;
+        sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, st.c, cscale, st.hin, lim, lane, hnew, hp, best);
+        lastBest = best;
+        last_c = st.pix;
+        if (EPI != EPI_WTA_ONLY) store_f<DPL>(hst, hnew);
+        hst += estep;
+        if (EPI != EPI_NONE) {
+            const float out = wta_epilogue<DPL, IEEE>(hp, lane, x, w, M, subpix);
+            if (lane == 0) *dst = out;
+            dst += pstep;
         }
+        x += dx;
+        ++r;
+        if (r + PF - 1 < len) load_stage(st);
+    };
+    // n steps starting at ring slot 0 (n is a multiple of PF except for the last phase of the scanline)
+    auto phase = [&](auto masked_tag, int n) {
+        int i = 0;
+        for (; i + PF <= n; i += PF) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) step(masked_tag, ring[k], P2);
+        }
+#pragma unroll
+        for (int k = 0; k < PF - 1; ++k)
+            if (i + k < n) step(masked_tag, ring[k], P2);
+    };
+
+    // Lanes are all in range once x + 1 >= DP (possible only when maxDisp fills the padded range): those steps
+    // run the unmasked body.  x is monotonic along a scanline, so a scanline is at most one masked and one
+    // unmasked phase; phase lengths are rounded to multiples of PF (towards the masked side, which is always valid).
+    int nA, nB;       // steps in the first / second phase, AFTER the start pixel
+    bool a_masked;    // first phase masked?
+    {
+        const int rest = len - 1;
+        const int x1 = sl.x0 + dx;                       // x of step 1
+        const int xf = (M == DP) ? DP - 1 : 0x3fffffff;  // unmasked iff x >= xf
+        if (dx > 0) {
+            a_masked = true;
+            const int need = max(0, xf - x1);            // masked steps required
+            nA = min(rest, (need + PF - 1) / PF * PF);
+        } else if (dx == 0) {
+            a_masked = x1 < xf;
+            nA = rest;
+        } else {
+            a_masked = false;
+            const int ok = max(0, x1 - xf + 1);          // unmasked steps available
+            nA = min(rest, ok / PF * PF);
+        }
+        nB = rest - nA;
     }
+
+    // start pixel: `volH += volC`, lastBestCr = 0 (cu_semi_global_matching.cu:31-35) == a step with P2 = 0
+    step(std::true_type{}, ring[0], 0.0f);
+    lastBest = 0.0f;
+    // rotate so that the next step is ring slot 0 again
+    {
+        const Stage<DPL, COST> t = ring[0];
+#pragma unroll
+        for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
+        ring[PF - 1] = t;
+    }
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+        const int n = ph == 0 ? nA : nB;
+        const bool masked = ph == 0 ? a_masked : !a_masked;
+        if (n <= 0) continue;
+        if (masked) phase(std::true_type{}, n);
+        else phase(std::false_type{}, n);
+        // a phase that is followed by another one is a multiple of PF: the ring is back at slot 0
+    }
+}
+
+template <int DPL, int COST, int EPI>
+static void sweep_launch3(const SweepArgs& a, int n_scan, dim3 grid, cudaStream_t st) {
+    const bool ieee = g_ieee_div.load() != 0;
+#define ROO_SWEEP(F, I) sgm_sweep_kernel<DPL, COST, EPI, F, I><<<grid, SWEEP_WARPS * 32, 0, st>>>(a, n_scan)
+    if (a.first) { if (ieee) ROO_SWEEP(true, true); else ROO_SWEEP(true, false); }
+    else { if (ieee) ROO_SWEEP(false, true); else ROO_SWEEP(false, false); }
+#undef ROO_SWEEP
 }
 
 template <int DPL, int COST>
 static void sweep_launch_epi(const SweepArgs& a, int n_scan, dim3 grid, cudaStream_t st) {
-    const int ieee = g_ieee_div.load();
-    if (a.epi == EPI_NONE) sgm_sweep_kernel<DPL, COST, EPI_NONE><<<grid, SWEEP_WARPS * 32, 0, st>>>(a, n_scan, ieee);
-    else if (a.epi == EPI_WTA_WRITE) sgm_sweep_kernel<DPL, COST, EPI_WTA_WRITE><<<grid, SWEEP_WARPS * 32, 0, st>>>(a, n_scan, ieee);
-    else sgm_sweep_kernel<DPL, COST, EPI_WTA_ONLY><<<grid, SWEEP_WARPS * 32, 0, st>>>(a, n_scan, ieee);
+    if (a.epi == EPI_NONE) sweep_launch3<DPL, COST, EPI_NONE>(a, n_scan, grid, st);
+    else if (a.epi == EPI_WTA_WRITE) sweep_launch3<DPL, COST, EPI_WTA_WRITE>(a, n_scan, grid, st);
+    else sweep_launch3<DPL, COST, EPI_WTA_ONLY>(a, n_scan, grid, st);
 }
 
 template <int DPL>
@@ -267,6 +207,29 @@ int launch_sweep(const SweepArgs& a, cudaStream_t st) {
         case 256: sweep_launch_cost<8>(a, n_scan, grid, st); break;
         default: return ROO_ERR_UNSUPPORTED;
     }
+    count_launch();
+    return launch_status();
+}
+
+// Adaptive-P2 intensity image as tightly packed fp32 [pair][y][x]: u8 * scale (stereo2/main.cpp:376 uses
+// 1/255; scale 1 reproduces the uchar instantiation's integer difference exactly) or a pitched fp32 copy.
+template <typename Tin>
+__global__ void __launch_bounds__(256)
+image_to_f32_kernel(float* __restrict__ dst, const char* __restrict__ src, size_t pitch, size_t src_pair, int w, int h,
+                    float scale) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const Tin v = reinterpret_cast<const Tin*>(src + (size_t)blockIdx.z * src_pair + (size_t)y * pitch)[x];
+    dst[((size_t)blockIdx.z * h + y) * w + x] = sizeof(Tin) == 1 ? (float)v * scale : (float)v;
+}
+
+int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pair, int img_type, int w, int h,
+                        int batch, float scale, cudaStream_t st) {
+    dim3 grid(cdiv(w, 256), h, batch);
+    if (img_type == ROO_IMG_U8)
+        image_to_f32_kernel<unsigned char><<<grid, 256, 0, st>>>(dst, (const char*)src, pitch, src_pair, w, h, scale);
+    else
+        image_to_f32_kernel<float><<<grid, 256, 0, st>>>(dst, (const char*)src, pitch, src_pair, w, h, scale);
     count_launch();
     return launch_status();
 }
@@ -373,10 +336,11 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
 
     const int w = (int)volC->w, h = (int)volC->h, DP = disp_padded(maxDisp);
     const size_t n = (size_t)w * h * DP;
-    float* scratch = nullptr;  // [Ci | Hi], stream-ordered pool memory
-    ROO_CUDA_TRY(cudaMallocAsync((void**)&scratch, 2 * n * sizeof(float), st));
+    float* scratch = nullptr;  // [Ci | Hi | fp32 image], stream-ordered pool memory
+    ROO_CUDA_TRY(cudaMallocAsync((void**)&scratch, (2 * n + (size_t)w * h) * sizeof(float), st));
     float* Ci = scratch;
     float* Hi = scratch + n;
+    float* imgf = scratch + 2 * n;
     const int ieee = g_ieee_div.load();
     dim3 tgrid(cdiv(w, 32), DP / 32, h);
     if (volc_type == ROO_VOL_F32)
@@ -385,11 +349,11 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
         vol_to_internal_kernel<roo_costvolelem_t><<<tgrid, 256, 0, st>>>(Ci, Vol<roo_costvolelem_t>(*volC), DP, maxDisp, ieee);
     count_launch();
     int rc = launch_status();
+    if (rc == 0) rc = launch_image_to_f32(imgf, left->ptr, left->pitch, 0, img_type, w, h, 1, 1.0f, st);
 
     SweepArgs a{};
     a.H = Hi; a.h_pair = n; a.C = Ci; a.c_pair = n;
-    a.img = (const char*)left->ptr; a.img_pitch = left->pitch; a.img_pair = 0; a.img_type = img_type;
-    a.img_scale = 1.0f; a.cost_scale = 1.0f;
+    a.img = imgf; a.img_pair = 0; a.cost_scale = 1.0f;
     a.w = w; a.h = h; a.DP = DP; a.maxDisp = maxDisp; a.batch = 1;
     a.P1 = P1; a.P2 = P2; a.cost_kind = COST_F32; a.epi = EPI_NONE; a.subpix = 0; a.disp = nullptr; a.disp_pair = 0;
     for (int i = 0; i < ndir && rc == 0; ++i) {

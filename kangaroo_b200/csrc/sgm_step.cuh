@@ -1,0 +1,143 @@
+// One step of the reference's path recurrence (src/cu_semi_global_matching.cu:39-56), written for a
+// warp that holds the 32*DPL disparities of one pixel in registers (lane l owns [l*DPL, (l+1)*DPL)).
+// Shared by the single-path sweep kernel (sgm.cu) and the fused vertical-group kernel (sgm_fused.cu).
+#pragma once
+#include "common.cuh"
+
+namespace roo_b200 {
+
+constexpr float SGM_MAX_ERROR = 1E30f;  // cu_semi_global_matching.cu:24
+#define ROO_INF __int_as_float(0x7f800000)
+
+template <int DPL>
+__device__ __forceinline__ void load_f(float (&v)[DPL], const float* p) {
+    if constexpr (DPL == 8) {
+        const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if constexpr (DPL == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else if constexpr (DPL == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(p);
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        v[0] = *p;
+    }
+}
+template <int DPL>
+__device__ __forceinline__ void store_f(float* p, const float (&v)[DPL]) {
+    if constexpr (DPL == 8) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else if constexpr (DPL == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (DPL == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+        *p = v[0];
+    }
+}
+
+// raw matching cost of one pixel as loaded; converted to float at use
+enum CostKind { COST_F32 = 0, COST_U8 = 1 };
+template <int DPL, int COST> struct RawCost;
+template <int DPL> struct RawCost<DPL, COST_F32> {
+    float v[DPL];
+    __device__ __forceinline__ void load(const void* p) { load_f<DPL>(v, (const float*)p); }
+    __device__ __forceinline__ float get(int j, float) const { return v[j]; }
+    static constexpr int ELEM = 4;
+};
+template <int DPL> struct RawCost<DPL, COST_U8> {
+    unsigned w[(DPL + 3) / 4];
+    __device__ __forceinline__ void load(const void* p) {
+        if constexpr (DPL == 8) { const uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
+        else if constexpr (DPL == 4) w[0] = *reinterpret_cast<const unsigned*>(p);
+        else if constexpr (DPL == 2) w[0] = *reinterpret_cast<const unsigned short*>(p);
+        else w[0] = *reinterpret_cast<const unsigned char*>(p);
+    }
+    // Hamming count * (1/bits): exact (power-of-two scale), equals the reference's count / bits
+    __device__ __forceinline__ float get(int j, float scale) const {
+        return (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * scale;
+    }
+    static constexpr int ELEM = 1;
+};
+
+// The recurrence for one pixel of one path.
+//   hp[]      previous pixel's aggregate row on this path, +inf where d >= that pixel's disparity range
+//   lastBest  min_d Cr of the previous pixel (0 at a path start)
+//   denom     1 + |I(prev) - I(cur)|
+//   P2        0 at a path start: together with hp = +inf and lastBest = 0 this makes Cr == cost, i.e. the
+//             start pixel's `volH += volC` (cu_semi_global_matching.cu:31-35) is the same code path
+//   lim       (MASKED only) number of in-range disparities of this lane: min(maxDisp, x+1) - lane*DPL
+// Outputs hnew = hin + Cr (hin where out of range), hp_out = hnew masked with +inf, best = min_d Cr.
+template <int DPL, bool MASKED, bool FIRST, bool IEEE, typename CostT>
+__device__ __forceinline__ void sgm_step(const float (&hp)[DPL], float lastBest, float denom, float P1, float P2,
+                                         const CostT& cost, float cost_scale, const float (&hin)[DPL], int lim,
+                                         int lane, float (&hnew)[DPL], float (&hp_out)[DPL], float& best_out) {
+    float hpP[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) hpP[j] = hp[j] + P1;
+    float up = __shfl_up_sync(0xffffffffu, hpP[DPL - 1], 1);   // H(prev, d-1) + P1 for j == 0
+    float dn = __shfl_down_sync(0xffffffffu, hpP[0], 1);       // H(prev, d+1) + P1 for j == DPL-1
+    if (lane == 0) up = ROO_INF;
+    if (lane == 31) dn = ROO_INF;
+    const float base = sgm_p2_base<IEEE>(lastBest, P2, denom);
+    float best = SGM_MAX_ERROR;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+        const float hm = j > 0 ? hpP[j - 1] : up;
+        const float hq = j < DPL - 1 ? hpP[j + 1] : dn;
+        const float CM = fminf(fminf(base, hp[j]), fminf(hm, hq));
+        const float Cr = (CM + cost.get(j, cost_scale)) - lastBest;
+        const float h = FIRST ? Cr : hin[j] + Cr;
+        if (MASKED) {
+            const bool in = j < lim;
+            best = in ? fminf(best, Cr) : best;
+            hnew[j] = in ? h : (FIRST ? 0.0f : hin[j]);
+            hp_out[j] = in ? h : ROO_INF;
+        } else {
+            best = fminf(best, Cr);
+            hnew[j] = h;
+            hp_out[j] = h;
+        }
+    }
+    best_out = warp_min_f32(best);
+}
+
+// Winner-takes-all (+ optional parabola) over the masked row hp[] of pixel x -- CostVolMinimum<float,float>
+// (cu_dense_stereo.cu:25-43) or CostVolMinimumSubpix with sd = -1 (cu_dense_stereo.cu:66-109).
+template <int DPL, bool IEEE>
+__device__ __forceinline__ float wta_epilogue(const float (&hp)[DPL], int lane, int x, int w, int maxDispVal, int subpix) {
+    const int d0 = lane * DPL;
+    float lc = ROO_INF;
+    int ld = 0;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j)
+        if (hp[j] < lc) { lc = hp[j]; ld = d0 + j; }
+    const float m = warp_min_f32(lc);
+    const unsigned ball = __ballot_sync(0xffffffffu, lc == m);
+    const int win = __ffs(ball) - 1;           // lowest lane = lowest disparity among equal minima
+    int bestd = __shfl_sync(0xffffffffu, ld, win);
+    if (!subpix) return (float)bestd;
+    float bestc = m;
+    if (!(bestc < 1E10f)) { bestc = 1E10f; bestd = 0; }  // the reference starts from bestc = 1e10
+    float out = (float)bestd;
+    const int bestxr = x - bestd;
+    if (0 < bestxr && bestxr < w - 1 && bestd + 1 < maxDispVal) {  // bestd+1 == vol.d: out of bounds in the reference
+        const int dl = max(bestd - 1, 0);      // float -> unsigned saturation in the reference (Q7)
+        const int dr = bestd + 1;
+        float slc = 0.0f, src = 0.0f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            if (d0 + j == dl) slc = hp[j];
+            if (d0 + j == dr) src = hp[j];
+        }
+        const float sl = __shfl_sync(0xffffffffu, slc, dl / DPL);
+        const float sr = __shfl_sync(0xffffffffu, src, dr / DPL);
+        const float sub = parabola_vertex<IEEE>((float)bestd, bestc, sl, sr);
+        if ((float)(bestd - 1) < sub && sub < (float)(bestd + 1)) out = sub;
+    }
+    return out;
+}
+
+}  // namespace roo_b200

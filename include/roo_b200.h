@@ -120,6 +120,7 @@ typedef struct roo_pipeline_params_t {
     float lr_maxdiff;
     int max_batch;        /* stereo pairs in flight per call (scratch is sized for this many) */
     int keep_volume;      /* 1: the last sweep also writes the aggregate so roo_engine_export_volume() works */
+    int fuse_vertical;    /* >= 0 (default 0): aggregate a vertical path and its two diagonals in one pass; -1: one pass per path */
 } roo_pipeline_params_t;
 
 int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t* params);

@@ -28,6 +28,9 @@ struct roo_engine {
     float* H = nullptr;                               // [batch][h][w][DP]
     float* dispR = nullptr;                           // [batch][h][w]
     float* imgf = nullptr;                            // [batch][h][w] adaptive-P2 intensity (u8 * img_scale)
+    float* edge = nullptr;                            // fused vertical groups: band-to-band state rows
+    int* flags = nullptr;                             //                        and their progress flags
+    SgmPlan plan{};
     // staging for run_host (device) and its streams
     unsigned char* in_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][side]
     float* out_dev[2] = {nullptr, nullptr};
@@ -74,8 +77,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         if (rc) return rc;
         prof_mark(e, ROO_PROF_WTA, st);
     }
-    int dxs[8], dys[8];
-    const int ndir = sgm_directions(p.dohoriz, p.dovert, p.doreverse, p.dodiag, dxs, dys);
+    const int ndir = e->plan.n;
     if (ndir == 0) {
         rc = launch_census_wta(disp, e->cen[0], e->cen[1], w, h, batch, p.max_disp, e->words, p.popc_mode, p.subpix, -1, st);
         if (rc) return rc;
@@ -92,9 +94,9 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         a.w = w; a.h = h; a.DP = e->DP; a.maxDisp = p.max_disp; a.batch = batch;
         a.P1 = p.P1; a.P2 = p.P2; a.cost_kind = COST_U8; a.subpix = p.subpix; a.disp = disp; a.disp_pair = npx;
         for (int i = 0; i < ndir; ++i) {
-            a.dx = dxs[i]; a.dy = dys[i]; a.first = i == 0;
+            a.first = i == 0;
             a.epi = i + 1 < ndir ? EPI_NONE : (p.keep_volume ? EPI_WTA_WRITE : EPI_WTA_ONLY);
-            rc = launch_sweep(a, st);
+            rc = launch_pass(a, e->plan.pass[i], e->edge, e->flags, st);
             if (rc) return rc;
             prof_mark(e, ROO_PROF_SWEEP, st);
         }
@@ -113,7 +115,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
 }
 
 static void engine_free(roo_engine* e) {
-    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->imgf);
+    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->imgf); cudaFree(e->edge); cudaFree(e->flags);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
         if (e->ev_in[b]) cudaEventDestroy(e->ev_in[b]);
@@ -147,13 +149,18 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
         e->scratch_bytes += bytes;
         return true;
     };
-    int dxs[8], dys[8];
-    const int ndir = sgm_directions(p.dohoriz, p.dovert, p.doreverse, p.dodiag, dxs, dys);
+    e->plan = sgm_plan(p.dohoriz, p.dovert, p.doreverse, p.dodiag, p.fuse_vertical >= 0 ? 1 : 0);
+    const int ndir = e->plan.n;
+    bool fused = false;
+    for (int i = 0; i < ndir; ++i) fused |= e->plan.pass[i].fused != 0;
     bool ok = alloc((void**)&e->cen[0], B * npx * e->words * 8) && alloc((void**)&e->cen[1], B * npx * e->words * 8);
     if (ok && ndir > 0)
         ok = alloc((void**)&e->c8, B * npx * e->DP) && alloc((void**)&e->H, B * npx * e->DP * 4) &&
              alloc((void**)&e->imgf, B * npx * 4);
     if (ok && p.lrcheck) ok = alloc((void**)&e->dispR, B * npx * 4);
+    if (ok && fused)
+        ok = alloc((void**)&e->edge, B * vgroup_edge_floats(p.w, p.h, e->DP) * 4) &&
+             alloc((void**)&e->flags, B * (size_t)vgroup_bands(p.w, p.h, e->DP) * 4);
     if (!ok) {
         cudaGetLastError();
         engine_free(e);

@@ -40,6 +40,33 @@ int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pa
                         int batch, float scale, cudaStream_t st);
 inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : 256)); }
 
+// ---- sgm_fused.cu: the three paths sharing a y travel direction in one pass ----
+struct VGroupArgs {
+    float* H; size_t h_pair;
+    const void* C; size_t c_pair;
+    const float* img; size_t img_pair;
+    float cost_scale;
+    int w, h, maxDisp, batch;
+    float P1, P2;
+    int fwd;            // 1: (0,+1),(+1,+1),(-1,+1) ; 0: (0,-1),(-1,-1),(+1,-1)
+    float* edge_hp;     // [pair][band][h][3][DP]  states handed from band b to band b+1
+    float* edge_sc;     // [pair][band][h][8]
+    int* progress;      // [pair][band] rows published
+    int n_bands;
+};
+size_t vgroup_edge_floats(int w, int h, int DP);   // per pair
+int vgroup_bands(int w, int h, int DP);
+int launch_vgroup(const SweepArgs& s, int fwd, float* edge, int* progress, cudaStream_t st);
+
+// Execution plan of one SemiGlobalMatching call: passes in the reference's order (down, up, right, left;
+// cu_semi_global_matching.cu:71-85), the diagonal extension inserted after the vertical path of the same
+// travel direction.  A vertical path and its two diagonals become ONE fused pass when `fuse` is set.
+struct SgmPass { int fused; int dx, dy; };   // fused: dy = travel direction, dx unused
+struct SgmPlan { int n; SgmPass pass[8]; };
+SgmPlan sgm_plan(int dohoriz, int dovert, int doreverse, int dodiag, int fuse);
+// runs pass i of the plan; a.first / a.epi are set by the caller
+int launch_pass(SweepArgs a, const SgmPass& pass, float* edge, int* progress, cudaStream_t st);
+
 // direction list in execution order (reference order down, up, right, left; diagonals are an extension)
 int launch_internal_to_vol(const roo_volume_t* dst, const float* src, int DP, int maxDisp, cudaStream_t st);
 int sgm_directions(int dohoriz, int dovert, int doreverse, int dodiag, int dxs[8], int dys[8]);

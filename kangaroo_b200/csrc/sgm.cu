@@ -248,6 +248,37 @@ int sgm_directions(int dohoriz, int dovert, int doreverse, int dodiag, int dxs[8
     return n;
 }
 
+SgmPlan sgm_plan(int dohoriz, int dovert, int doreverse, int dodiag, int fuse) {
+    SgmPlan pl{};
+    auto add = [&](int fused, int dx, int dy) { pl.pass[pl.n++] = SgmPass{fused, dx, dy}; };
+    // a fused group needs the vertical path of that travel direction, and must not be the last pass
+    // (the winner-takes-all epilogue rides on a single-path sweep)
+    const bool f = fuse && dodiag && dovert && dohoriz;
+    if (f) add(1, 0, 1);
+    else {
+        if (dovert) add(0, 0, 1);                                // cu_semi_global_matching.cu:72
+        if (dodiag) { add(0, 1, 1); add(0, -1, 1); }
+    }
+    if (doreverse) {
+        if (f) add(1, 0, -1);
+        else {
+            if (dovert) add(0, 0, -1);                           // :74
+            if (dodiag) { add(0, -1, -1); add(0, 1, -1); }
+        }
+    }
+    if (dohoriz) {
+        add(0, 1, 0);                                            // :81
+        if (doreverse) add(0, -1, 0);                            // :83
+    }
+    return pl;
+}
+
+int launch_pass(SweepArgs a, const SgmPass& pass, float* edge, int* progress, cudaStream_t st) {
+    if (pass.fused) return launch_vgroup(a, pass.dy > 0 ? 1 : 0, edge, progress, st);
+    a.dx = pass.dx; a.dy = pass.dy;
+    return launch_sweep(a, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Layout adapters for the granular roo_sgm(): roo::Volume (d outermost, x fastest) <-> internal
 // (d innermost).  32(x) x 32(d) tiles through shared memory; both sides coalesced.
@@ -330,17 +361,22 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
     } else {
         ROO_CUDA_TRY(cudaMemset2DAsync(volH->ptr, volH->img_pitch, 0, volH->pitch * volH->h, volH->d, st));
     }
-    int dxs[8], dys[8];
-    const int ndir = sgm_directions(dohoriz, dovert, doreverse, dodiag, dxs, dys);
-    if (ndir == 0 || maxDisp <= 0) return ROO_OK;
+    const SgmPlan plan = sgm_plan(dohoriz, dovert, doreverse, dodiag, 1);
+    if (plan.n == 0 || maxDisp <= 0) return ROO_OK;
 
     const int w = (int)volC->w, h = (int)volC->h, DP = disp_padded(maxDisp);
     const size_t n = (size_t)w * h * DP;
-    float* scratch = nullptr;  // [Ci | Hi | fp32 image], stream-ordered pool memory
-    ROO_CUDA_TRY(cudaMallocAsync((void**)&scratch, (2 * n + (size_t)w * h) * sizeof(float), st));
+    bool fused = false;
+    for (int i = 0; i < plan.n; ++i) fused |= plan.pass[i].fused != 0;
+    const size_t edge_n = fused ? vgroup_edge_floats(w, h, DP) : 0;
+    const size_t flag_n = fused ? (size_t)vgroup_bands(w, h, DP) : 0;
+    float* scratch = nullptr;  // [Ci | Hi | fp32 image | edge rows | flags], stream-ordered pool memory
+    ROO_CUDA_TRY(cudaMallocAsync((void**)&scratch, (2 * n + (size_t)w * h + edge_n + flag_n) * sizeof(float), st));
     float* Ci = scratch;
     float* Hi = scratch + n;
     float* imgf = scratch + 2 * n;
+    float* edge = imgf + (size_t)w * h;
+    int* flags = reinterpret_cast<int*>(edge + edge_n);
     const int ieee = g_ieee_div.load();
     dim3 tgrid(cdiv(w, 32), DP / 32, h);
     if (volc_type == ROO_VOL_F32)
@@ -356,9 +392,9 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
     a.img = imgf; a.img_pair = 0; a.cost_scale = 1.0f;
     a.w = w; a.h = h; a.DP = DP; a.maxDisp = maxDisp; a.batch = 1;
     a.P1 = P1; a.P2 = P2; a.cost_kind = COST_F32; a.epi = EPI_NONE; a.subpix = 0; a.disp = nullptr; a.disp_pair = 0;
-    for (int i = 0; i < ndir && rc == 0; ++i) {
-        a.dx = dxs[i]; a.dy = dys[i]; a.first = i == 0;
-        rc = launch_sweep(a, st);
+    for (int i = 0; i < plan.n && rc == 0; ++i) {
+        a.first = i == 0;
+        rc = launch_pass(a, plan.pass[i], edge, flags, st);
     }
     if (rc == 0) rc = launch_internal_to_vol(volH, Hi, DP, maxDisp, st);
     cudaError_t fe = cudaFreeAsync(scratch, st);

@@ -216,10 +216,11 @@ class StereoEngine:
     def __init__(self, w: int, h: int, max_disp: int, window: int = WIN_9x7, popc_mode: int = POPC32_COMPAT,
                  P1: float = 0.01, P2: float = 0.02, img_scale: float = 1.0 / 255.0, dohoriz=True, dovert=True,
                  doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff: float = 1.0,
-                 max_batch: int = 1, keep_volume: bool = False):
+                 max_batch: int = 1, keep_volume: bool = False, fuse_vertical: bool = True):
         self.params = capi.PipelineParams(w, h, max_disp, window, popc_mode, P1, P2, np.float32(img_scale),
                                           int(dohoriz), int(dovert), int(doreverse), int(dodiag), int(subpix),
-                                          int(lrcheck), lr_maxdiff, max_batch, int(keep_volume))
+                                          int(lrcheck), lr_maxdiff, max_batch, int(keep_volume),
+                                          0 if fuse_vertical else -1)
         self.w, self.h, self.max_disp = w, h, max_disp
         self._h = C.c_void_p()
         check(lib().roo_engine_create(C.byref(self._h), C.byref(self.params)), "roo_engine_create")

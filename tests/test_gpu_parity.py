@@ -359,6 +359,26 @@ def test_engine_c2_full_size_properties_and_oracle():
     assert np.array_equal(dhf[0][::-1], dh[0])
 
 
+@pytest.mark.parametrize("shape", [(20, 90, 32), (257, 130, 64), (33, 17, 40), (500, 64, 128), (96, 40, 256)])
+def test_fused_vertical_group_equals_separate_sweeps_and_oracle(shape):
+    """The fused pass (vertical path + its two diagonals, sgm_fused.cu) must be bit-identical to three
+    single-path sweeps, for tall, wide, tiny and 256-disparity shapes, in every batch slot."""
+    w, h, D = shape
+    L, R, _ = stereo_pair(w, h, D, config=41)
+    roo.set_ieee_division(True)
+    df, Hf, _ = run_engine(L, R, D, batch=3, dodiag=True, subpix=True, fuse_vertical=True)
+    ds, Hs, _ = run_engine(L, R, D, batch=3, dodiag=True, subpix=True, fuse_vertical=False)
+    od, oH = ko.pipeline_u8(L, R, D, dodiag=True, subpix=True, want_volume=True)
+    assert np.array_equal(Hf, Hs)
+    assert np.array_equal(Hf, oH)
+    for b in range(3):
+        assert np.array_equal(df[b], ds[b]) and np.array_equal(df[b], od)
+    roo.set_ieee_division(False)
+    df2, Hf2, _ = run_engine(L, R, D, dodiag=True, doreverse=False, fuse_vertical=True)
+    ds2, Hs2, _ = run_engine(L, R, D, dodiag=True, doreverse=False, fuse_vertical=False)
+    assert np.array_equal(Hf2, Hs2) and np.array_equal(df2, ds2)
+
+
 def test_engine_run_host_equals_run_device():
     L, R, _ = stereo_pair(320, 200, 64, config=31)
     n = 5

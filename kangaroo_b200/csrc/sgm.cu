@@ -80,16 +80,19 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
     const float* ild = a.img + (size_t)pair * a.img_pair + (size_t)sl.y0 * w + sl.x0;
     float* dst = (EPI != EPI_NONE) ? a.disp + (size_t)pair * a.disp_pair + (size_t)sl.y0 * w + sl.x0 : nullptr;
 
+    // Prefetch ring.  Loads are UNCONDITIONAL (past the end of the scanline the cursor stops advancing and re-reads
+    // the last pixel): a predicated load has to preserve its destination when off, and the register move ptxas
+    // inserts for that waits on the load, exposing the DRAM latency once per ring revolution.
     Stage<DPL, COST> ring[PF];
-    auto load_stage = [&](Stage<DPL, COST>& st) {
+    auto load_stage = [&](Stage<DPL, COST>& st, bool advance) {
+        const ptrdiff_t es = advance ? estep : 0, ps = advance ? pstep : 0;
+        hld += es; cld += es * CE; ild += ps;
         if (!FIRST) load_f<DPL>(st.hin, hld);
         st.c.load(cld);
         st.pix = *ild;
-        hld += estep; cld += estep * CE; ild += pstep;
     };
 #pragma unroll
-    for (int k = 0; k < PF; ++k)
-        if (k < len) load_stage(ring[k]);
+    for (int k = 0; k < PF; ++k) load_stage(ring[k], k > 0 && k < len);
 
     float hp[DPL];
 #pragma unroll
@@ -116,7 +119,7 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
         }
         x += dx;
         ++r;
-        if (r + PF - 1 < len) load_stage(st);
+        load_stage(st, r + PF - 1 < len);
     };
     // n steps starting at ring slot 0 (n is a multiple of PF except for the last phase of the scanline)
     auto phase = [&](auto masked_tag, int n) {
@@ -370,13 +373,16 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
     for (int i = 0; i < plan.n; ++i) fused |= plan.pass[i].fused != 0;
     const size_t edge_n = fused ? vgroup_edge_floats(w, h, DP) : 0;
     const size_t flag_n = fused ? (size_t)vgroup_bands(w, h, DP) : 0;
-    float* scratch = nullptr;  // [Ci | Hi | fp32 image | edge rows | flags], stream-ordered pool memory
-    ROO_CUDA_TRY(cudaMallocAsync((void**)&scratch, (2 * n + (size_t)w * h + edge_n + flag_n) * sizeof(float), st));
+    // [Ci | Hi | fp32 image | edge rows | flags], stream-ordered pool memory; every segment 256-byte aligned
+    auto al = [](size_t nfloats) { return (nfloats + 63) / 64 * 64; };
+    const size_t img_n = al((size_t)w * h);
+    float* scratch = nullptr;
+    ROO_CUDA_TRY(cudaMallocAsync((void**)&scratch, (2 * al(n) + img_n + al(edge_n) + al(flag_n)) * sizeof(float), st));
     float* Ci = scratch;
-    float* Hi = scratch + n;
-    float* imgf = scratch + 2 * n;
-    float* edge = imgf + (size_t)w * h;
-    int* flags = reinterpret_cast<int*>(edge + edge_n);
+    float* Hi = Ci + al(n);
+    float* imgf = Hi + al(n);
+    float* edge = imgf + img_n;
+    int* flags = reinterpret_cast<int*>(edge + al(edge_n));
     const int ieee = g_ieee_div.load();
     dim3 tgrid(cdiv(w, 32), DP / 32, h);
     if (volc_type == ROO_VOL_F32)

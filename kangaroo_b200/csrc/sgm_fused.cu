@@ -77,6 +77,52 @@ __device__ __forceinline__ void stcg_row(float* p, const float (&v)[DPL]) {
     }
 }
 
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+template <int DPL>
+__device__ __forceinline__ void cp_async_row(float* smem_dst, const float* gsrc) {
+    static_assert(DPL >= 4, "cp.async.cg moves 16 bytes");
+#pragma unroll
+    for (int q = 0; q < DPL / 4; ++q) cp_async_16(smem_dst + 4 * q, gsrc + 4 * q);
+}
+
+// shared-memory vector access by 32-bit shared-window address
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(unsigned addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <int DPL>
+__device__ __forceinline__ void lds_vec(float (&v)[DPL], unsigned addr) {
+    if constexpr (DPL >= 4) {
+#pragma unroll
+        for (int q = 0; q < DPL / 4; ++q) {
+            const float4 t = lds_f4(addr + 16 * q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else if constexpr (DPL == 2) {
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+    } else {
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
+    }
+}
+template <int DPL>
+__device__ __forceinline__ void sts_vec(unsigned addr, const float (&v)[DPL]) {
+    if constexpr (DPL >= 4) {
+#pragma unroll
+        for (int q = 0; q < DPL / 4; ++q) sts_f4(addr + 16 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    } else if constexpr (DPL == 2) {
+        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v[0]) : "memory");
+    }
+}
+
 template <int DPL, int COST>
 struct VStage {
     float hin[DPL];
@@ -84,14 +130,17 @@ struct VStage {
     float pix;
 };
 
+// Ordering of shared-memory accesses between warps of one CTA.  Data and flag both live in shared memory
+// and every access is issued through the same in-order LSU pipeline of the SM, so program order (enforced
+// for the compiler by the volatile flag accesses and this barrier) is enough; a MEMBAR here would also wait
+// for the warp's outstanding GLOBAL prefetch loads and serialise every row on DRAM latency.
+__device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
+
 // smem control words
-struct VCtl { volatile int halo_ready; volatile int rows_done; volatile int copied; int pad; };
+struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 
 constexpr int VG_R = 8;   // rows per hand-off chunk between bands (flag / fence cost is paid once per chunk)
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
+constexpr int VG_S = 4;   // depth (rows) of the in-band state ring in shared memory
 
 template <int DPL, int COST, bool FIRST, bool IEEE, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
@@ -99,17 +148,20 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int DP = 32 * DPL;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
     constexpr int PF = VG_PF;
-    constexpr int R = VG_R, RING = 2 * VG_R;
+    constexpr int R = VG_R, RING = 2 * VG_R, S = VG_S;
     extern __shared__ __align__(16) float smem[];
-    float* s_hp = smem;                                // [2 parity][NW][2 paths][DP]  in-band states of the previous row
-    float* s_sc = s_hp + 2 * NW * 2 * DP;              // [2 parity][NW][4]: lastBest(vertical), lastBest(anti-diag), pix, -
-    float* s_halo = s_sc + 2 * NW * 4;                 // [RING rows][3][DP]  upstream band's columns 0,1 (row ring)
+    float* s_hp = smem;                                // [S rows][NW][2 paths][DP]  in-band states (row ring)
+    float* s_sc = s_hp + S * NW * 2 * DP;              // [S rows][NW][4]: lastBest(vertical), lastBest(anti-diag), pix, -
+    float* s_halo = s_sc + S * NW * 4;                 // [RING rows][3][DP]  upstream band's columns 0,1 (row ring)
     float* s_hsc = s_halo + RING * 3 * DP;             // [RING][8]
     float* s_edge = s_hsc + RING * 8;                  // [RING rows][3][DP]  this band's columns 0,1 for downstream
     float* s_esc = s_edge + RING * 3 * DP;             // [RING][8]
     VCtl* ctl = reinterpret_cast<VCtl*>(s_esc + RING * 8);
+    volatile int* prog = reinterpret_cast<volatile int*>(ctl + 1);   // [NW] rows < prog[j] of column j are done
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: ptxas then knows it is warp-uniform, and every branch on it (roles, masks,
+    // path starts) is a uniform branch without divergence bookkeeping around the shuffles / redux below
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // pair fastest: the resident window of CTAs then holds the same few bands of EVERY pair, so the
     // band-to-band pipeline of each pair has only a short ramp
     const int pair = blockIdx.x % a.batch, band = blockIdx.x / a.batch;
@@ -131,7 +183,12 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     float* e_sc = a.edge_sc + ((size_t)pair * a.n_bands + band) * (size_t)h * 8;
     int* my_flag = a.progress + (size_t)pair * a.n_bands + band;
 
-    if (threadIdx.x == 0) { ctl->halo_ready = hbeg; ctl->rows_done = ymin; ctl->copied = ymin; }
+    // active rows of skewed column u: x' = u + y' in [0, w)
+    const int u = ulo + warp;
+    const int y_in = max(0, -u), y_out = min(h - 1, w - 1 - u);
+    const bool any = warp < NW && y_in <= y_out;
+    if (threadIdx.x == 0) { ctl->halo_ready = hbeg; ctl->copied = ymin; }
+    if (warp < NW && lane == 0) prog[warp] = any ? y_in : 0x7fffffff;   // rows before y_in never happen
     __syncthreads();
 
     if (warp == NW) {
@@ -143,69 +200,75 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         const int cp_end = downstream ? ymax + 1 : ymin;  // nothing to publish for the last band
         while (hr < hend || cp < cp_end) {
             bool progress = false;
-            const int rd = ctl->rows_done;
-            // ---- stage a chunk of upstream rows into the halo ring
+            // ---- stage a chunk of upstream rows into the halo ring (readers: the last two columns)
             if (hr < hend) {
                 const int n = min(R, hend - hr);
-                // ring slot of row y was last used by row y-RING, consumed while computing row y-RING+1
-                if (rd >= hr + n - RING + 1) {
+                const int rdh = min(prog[NW - 1], prog[NW - 2]);
+                // ring slot of row y was last used by row y-RING, read while computing row y-RING+1
+                if (rdh >= hr + n - RING + 1) {
                     if (seen < hr + n) {
                         if (lane == 0) seen = ld_acquire_gpu(p_flag);
                         seen = __shfl_sync(0xffffffffu, seen, 0);
                     }
                     if (seen >= hr + n) {
+                        // asynchronous global->shared copies (LDGSTS): all rows of the chunk are in flight at
+                        // once and no registers are staged; one wait for the whole chunk
                         for (int y = hr; y < hr + n; ++y) {
                             const float* src = p_hp + (size_t)y * 3 * DP + lane * DPL;
                             float* dst = s_halo + (size_t)(y % RING) * 3 * DP + lane * DPL;
-                            float r0[DPL], r1[DPL], r2[DPL];
-                            ldcg_row<DPL>(r0, src);
-                            ldcg_row<DPL>(r1, src + DP);
-                            ldcg_row<DPL>(r2, src + 2 * DP);
-                            sts_row<DPL>(dst, r0);
-                            sts_row<DPL>(dst + DP, r1);
-                            sts_row<DPL>(dst + 2 * DP, r2);
-                            if (lane < 8) s_hsc[(y % RING) * 8 + lane] = __ldcg(p_sc + (size_t)y * 8 + lane);
+                            if constexpr (DPL >= 4) {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) cp_async_row<DPL>(dst + q * DP, src + q * DP);
+                            } else {   // < 16 B per lane: cp.async would need .ca, and L1 must not cache rows still being written
+                                float r0[DPL], r1[DPL], r2[DPL];
+                                ldcg_row<DPL>(r0, src); ldcg_row<DPL>(r1, src + DP); ldcg_row<DPL>(r2, src + 2 * DP);
+                                sts_row<DPL>(dst, r0); sts_row<DPL>(dst + DP, r1); sts_row<DPL>(dst + 2 * DP, r2);
+                            }
+                            if (lane < 2) cp_async_16(s_hsc + (y % RING) * 8 + lane * 4, p_sc + (size_t)y * 8 + lane * 4);
                         }
-                        __threadfence_block();
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
                         __syncwarp();
                         hr += n;
-                        if (lane == 0) ctl->halo_ready = hr;
+                        if (lane == 0) { __threadfence_block(); ctl->halo_ready = hr; }
                         progress = true;
                     }
                 }
             }
-            // ---- publish finished rows of this band's columns 0,1
-            if (cp < cp_end && rd > cp && (rd - cp >= R || rd == ymax + 1)) {
-                __threadfence_block();
-                for (int y = cp; y < rd; ++y) {
-                    const float* src = s_edge + (size_t)(y % RING) * 3 * DP + lane * DPL;
-                    float* dst = e_hp + (size_t)y * 3 * DP + lane * DPL;
-                    float r0[DPL], r1[DPL], r2[DPL];
-                    lds_row<DPL>(r0, src);
-                    lds_row<DPL>(r1, src + DP);
-                    lds_row<DPL>(r2, src + 2 * DP);
-                    stcg_row<DPL>(dst, r0);
-                    stcg_row<DPL>(dst + DP, r1);
-                    stcg_row<DPL>(dst + 2 * DP, r2);
-                    if (lane < 8) __stcg(e_sc + (size_t)y * 8 + lane, s_esc[(y % RING) * 8 + lane]);
+            // ---- publish finished rows of this band's columns 0,1 (writers: the first two columns)
+            if (cp < cp_end) {
+                const int rd = min(min(prog[0], prog[1]), ymax + 1);
+                if (rd > cp && (rd - cp >= R || rd == ymax + 1)) {
+                    __threadfence_block();
+                    for (int y = cp; y < rd; ++y) {
+                        const float* src = s_edge + (size_t)(y % RING) * 3 * DP + lane * DPL;
+                        float* dst = e_hp + (size_t)y * 3 * DP + lane * DPL;
+                        float r0[DPL], r1[DPL], r2[DPL];
+                        lds_row<DPL>(r0, src);
+                        lds_row<DPL>(r1, src + DP);
+                        lds_row<DPL>(r2, src + 2 * DP);
+                        stcg_row<DPL>(dst, r0);
+                        stcg_row<DPL>(dst + DP, r1);
+                        stcg_row<DPL>(dst + 2 * DP, r2);
+                        if (lane < 8) __stcg(e_sc + (size_t)y * 8 + lane, s_esc[(y % RING) * 8 + lane]);
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    cp = rd;
+                    if (lane == 0) {
+                        st_release_gpu(my_flag, rd == ymax + 1 ? 0x7fffffff : rd);
+                        ctl->copied = rd;
+                    }
+                    progress = true;
                 }
-                __threadfence();
-                __syncwarp();
-                cp = rd;
-                if (lane == 0) {
-                    st_release_gpu(my_flag, rd == ymax + 1 ? 0x7fffffff : rd);
-                    ctl->copied = rd;
-                }
-                progress = true;
             }
-            if (!progress) __nanosleep(40);
+            if (!progress) __nanosleep(200);
         }
         return;
     }
+    if (!any) return;
 
     // -------------------------------------------------------------------- compute warps
-    const int u = ulo + warp;
-    const int y_in = max(0, -u), y_out = min(h - 1, w - 1 - u);   // active rows of this skewed column
     const int d0 = lane * DPL;
     const int xf = (M == DP) ? DP - 1 : 0x3fffffff;               // all lanes in range iff true x >= xf
 
@@ -214,25 +277,55 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     const int x0 = fwd ? xp0 : w - 1 - xp0, y0 = fwd ? y_in : h - 1 - y_in;
     const ptrdiff_t pstep = fwd ? (ptrdiff_t)(w + 1) : -(ptrdiff_t)(w + 1);
     const ptrdiff_t estep = pstep * DP;
-    const bool any = y_in <= y_out;
-    const size_t e0 = any ? ((size_t)y0 * w + x0) * DP + d0 : 0;
+    const size_t e0 = ((size_t)y0 * w + x0) * DP + d0;
     float* hst = a.H + (size_t)pair * a.h_pair + e0;
     const float* hld = hst;
     const char* cld = (const char*)a.C + ((size_t)pair * a.c_pair + e0) * CE;
-    const float* ild = a.img + (size_t)pair * a.img_pair + (any ? (size_t)y0 * w + x0 : 0);
+    const float* ild = a.img + (size_t)pair * a.img_pair + (size_t)y0 * w + x0;
 
+    // Prefetch ring.  Loads are UNCONDITIONAL (past the end of the column the cursor simply stops advancing and
+    // re-reads the last pixel): a predicated load must keep the old register value when off, which makes ptxas
+    // insert a register move that waits for the load.
     VStage<DPL, COST> ring[PF];
-    auto load_stage = [&](VStage<DPL, COST>& st) {
+    auto load_stage = [&](VStage<DPL, COST>& st, bool advance) {
+        const ptrdiff_t es = advance ? estep : 0, ps = advance ? pstep : 0;
+        hld += es; cld += es * CE; ild += ps;
         if (!FIRST) load_f<DPL>(st.hin, hld);
         st.c.load(cld);
         st.pix = *ild;
-        hld += estep; cld += estep * CE; ild += pstep;
     };
 #pragma unroll
-    for (int k = 0; k < PF; ++k) {
-        const int yl = ymin + k;
-        if (yl >= y_in && yl <= y_out) load_stage(ring[k]);
-    }
+    for (int k = 0; k < PF; ++k) load_stage(ring[k], k > 0 && y_in + k <= y_out);
+
+    // ---- shared-memory addressing, resolved once per warp (32-bit shared-window addresses) ----
+    // State rows of the previous image row come either from the in-band ring (slot (y-1) & (S-1), stride one
+    // slot) or, for the two highest columns, from the upstream halo ring (slot (y-1) & (RING-1), stride one
+    // halo row): the same  base + ((y-1) & mask) * stride  serves both, so the row loop has no role branches.
+    const unsigned sh_hp = (unsigned)__cvta_generic_to_shared(s_hp), sh_sc = (unsigned)__cvta_generic_to_shared(s_sc);
+    const unsigned sh_halo = (unsigned)__cvta_generic_to_shared(s_halo), sh_hsc = (unsigned)__cvta_generic_to_shared(s_hsc);
+    const unsigned sh_edge = (unsigned)__cvta_generic_to_shared(s_edge), sh_esc = (unsigned)__cvta_generic_to_shared(s_esc);
+    constexpr unsigned SLOT_B = NW * 2 * DP * 4, SLOTSC_B = NW * 16, HROW_B = 3 * DP * 4, HSC_B = 32;
+    const bool vIn = warp + 1 < NW, aIn = warp + 2 < NW;
+    const unsigned vBase = vIn ? sh_hp + (warp + 1) * 2 * DP * 4 + lane * DPL * 4 : sh_halo + lane * DPL * 4;
+    const unsigned vStride = vIn ? SLOT_B : HROW_B, vMask = vIn ? S - 1 : RING - 1;
+    const unsigned vScBase = vIn ? sh_sc + (warp + 1) * 16 : sh_hsc, vScStride = vIn ? SLOTSC_B : HSC_B;
+    const unsigned aBase = aIn ? sh_hp + ((warp + 2) * 2 + 1) * DP * 4 + lane * DPL * 4
+                               : sh_halo + (warp + 2 == NW ? 1 : 2) * DP * 4 + lane * DPL * 4;
+    const unsigned aStride = aIn ? SLOT_B : HROW_B, aMask = aIn ? S - 1 : RING - 1;
+    const unsigned aScBase = aIn ? sh_sc + (warp + 2) * 16 : sh_hsc + (warp + 2 == NW ? 0 : 16);
+    const unsigned aScStride = aIn ? SLOTSC_B : HSC_B;
+    const unsigned myBase = sh_hp + warp * 2 * DP * 4 + lane * DPL * 4, myScBase = sh_sc + warp * 16;
+    const bool edge_out = warp < 2 && downstream;
+    const unsigned eBase = sh_edge + (warp == 0 ? 0 : 2) * DP * 4 + lane * DPL * 4, eScBase = sh_esc + warp * 16;
+    // hand-off flags: rows < *flag of the producer are done.  Absent producers / consumers read a constant.
+    volatile int* const fV = vIn ? prog + warp + 1 : &ctl->halo_ready;
+    volatile int* const fA = aIn ? prog + warp + 2 : &ctl->halo_ready;
+    volatile int* const fW1 = warp >= 1 ? prog + warp - 1 : fV;   // no consumer: alias a flag that is already waited on
+    volatile int* const fW2 = warp >= 2 ? prog + warp - 2 : fV;
+    volatile int* const fC = edge_out ? &ctl->copied : fV;
+    const int vCap = vIn ? 0x7fffffff : hend, aCap = aIn ? 0x7fffffff : hend;
+    const int wOff = S - 2;            // consumers must have finished row y-S+1  <=>  prog >= y-S+2
+    const int cOff = RING - 1;         // downstream ring slot free once rows < y-RING+1 were copied out
 
     // diagonal path state (registers)
     float hpd[DPL];
@@ -240,119 +333,86 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     for (int j = 0; j < DPL; ++j) hpd[j] = ROO_INF;
     float lbd = 0.0f, pixd = 0.0f;
 
-    auto row_body = [&](auto masked_tag, VStage<DPL, COST>& st, int y, int xp, int x) {
+    // EDGE rows contain a path start (y == 0, x' == 0 or x' == w-1); all other rows take the lean body.
+    auto row_body = [&](auto masked_tag, auto edge_tag, VStage<DPL, COST>& st, int y, int xp, int x) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        const int p = y & 1;
+        constexpr bool EDGE = decltype(edge_tag)::value;
         const int lim = MASKED ? min(M, x + 1) - d0 : 0;
-        const float* nb_hp = s_hp + (size_t)((p ^ 1) * NW) * 2 * DP + lane * DPL;   // previous row's in-band states
-        const float* nb_sc = s_sc + (size_t)((p ^ 1) * NW) * 4;
-        const float* ha_hp = s_halo + (size_t)((y - 1 + RING) % RING) * 3 * DP + lane * DPL;   // upstream row y-1
-        const float* ha_sc = s_hsc + ((y - 1 + RING) % RING) * 8;
-        float H1[DPL], H2[DPL], H3[DPL], hp[DPL], hp1[DPL], hp3[DPL], b1, b2, b3;
-
-        // ---- vertical path: previous pixel (x', y'-1) lives in column u+1
-        float lb = 0.0f, pp = st.pix, p2 = 0.0f;
-        if (y > 0) {
-            if (warp + 1 < NW) {
-                lds_row<DPL>(hp, nb_hp + (size_t)(warp + 1) * 2 * DP);
-                lb = nb_sc[(warp + 1) * 4 + 0];
-                pp = nb_sc[(warp + 1) * 4 + 2];
-            } else {                       // upstream column 0: {rec0; sc0 = lastBest(vertical), sc2 = pix}
-                lds_row<DPL>(hp, ha_hp);
-                lb = ha_sc[0];
-                pp = ha_sc[2];
+        const float pix = st.pix;
+        float hpV[DPL], hpA[DPL], H3[DPL], cost[DPL];
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) cost[j] = st.c.get(j, cscale);
+        const unsigned ym1 = (unsigned)(y - 1);
+        lds_vec<DPL>(hpV, vBase + (ym1 & vMask) * vStride);
+        lds_vec<DPL>(hpA, aBase + (ym1 & aMask) * aStride);
+        const float4 scV = lds_f4(vScBase + (ym1 & vMask) * vScStride);   // {lastBest(vertical), lastBest(anti), pix, -}
+        const float4 scA = lds_f4(aScBase + (ym1 & aMask) * aScStride);
+        float lbV = scV.x, ppV = scV.z, p2V = P2, lbA = scA.y, ppA = scA.z, p2A = P2, p2D = P2;
+        bool sV = false, sD = false, sA = false;
+        if (EDGE) {
+            sV = y == 0; sD = y == 0 || xp == 0; sA = y == 0 || xp == w - 1;
+            if (sV) { lbV = 0.0f; ppV = pix; p2V = 0.0f; }
+            if (sD) { lbd = 0.0f; p2D = 0.0f; }
+            if (sA) { lbA = 0.0f; ppA = pix; p2A = 0.0f; }
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                hpV[j] = sV ? ROO_INF : hpV[j];
+                hpd[j] = sD ? ROO_INF : hpd[j];
+                hpA[j] = sA ? ROO_INF : hpA[j];
             }
-            p2 = P2;
-        } else {
-#pragma unroll
-            for (int j = 0; j < DPL; ++j) hp[j] = ROO_INF;
         }
-        sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lb, 1.0f + fabsf(pp - st.pix), P1, p2, st.c, cscale, st.hin, lim, lane, H1, hp1, b1);
-        if (y == 0) b1 = 0.0f;
-
-        // ---- diagonal path: previous pixel (x'-1, y'-1) is this column's previous row
-        const bool s1 = y == 0 || xp == 0;
-        if (s1) {
-#pragma unroll
-            for (int j = 0; j < DPL; ++j) hpd[j] = ROO_INF;
-            lbd = 0.0f;
-        }
-        sgm_step<DPL, MASKED, false, IEEE>(hpd, lbd, 1.0f + fabsf(pixd - st.pix), P1, s1 ? 0.0f : P2, st.c, cscale, H1, lim, lane, H2, hpd, b2);
-        lbd = s1 ? 0.0f : b2;
-        pixd = st.pix;
-
-        // ---- anti-diagonal path: previous pixel (x'+1, y'-1) lives in column u+2
-        const bool s2 = y == 0 || xp == w - 1;
-        lb = 0.0f; pp = st.pix; p2 = 0.0f;
-        if (!s2) {
-            if (warp + 2 < NW) {
-                lds_row<DPL>(hp, nb_hp + ((size_t)(warp + 2) * 2 + 1) * DP);
-                lb = nb_sc[(warp + 2) * 4 + 1];
-                pp = nb_sc[(warp + 2) * 4 + 2];
-            } else if (warp + 2 == NW) {   // upstream column 0: {rec1; sc1 = lastBest(anti), sc2 = pix}
-                lds_row<DPL>(hp, ha_hp + DP);
-                lb = ha_sc[1];
-                pp = ha_sc[2];
-            } else {                       // upstream column 1: {rec2; sc3 = lastBest(anti), sc4 = pix}
-                lds_row<DPL>(hp, ha_hp + 2 * DP);
-                lb = ha_sc[3];
-                pp = ha_sc[4];
-            }
-            p2 = P2;
-        } else {
-#pragma unroll
-            for (int j = 0; j < DPL; ++j) hp[j] = ROO_INF;
-        }
-        sgm_step<DPL, MASKED, false, IEEE>(hp, lb, 1.0f + fabsf(pp - st.pix), P1, p2, st.c, cscale, H2, lim, lane, H3, hp3, b3);
-        if (s2) b3 = 0.0f;
+        float bV, bD, bA;
+        sgm_step3<DPL, MASKED, FIRST, IEEE>(hpV, lbV, 1.0f + fabsf(ppV - pix), p2V,
+                                            hpd, lbd, 1.0f + fabsf(pixd - pix), p2D,
+                                            hpA, lbA, 1.0f + fabsf(ppA - pix), p2A,
+                                            cost, st.hin, P1, lim, lane, H3, bV, bD, bA);
+        if (EDGE) { if (sV) bV = 0.0f; if (sD) bD = 0.0f; if (sA) bA = 0.0f; }
+        lbd = bD;
+        pixd = pix;
 
         // ---- publish this pixel's states for the next row, store the aggregate
-        float* my_hp = s_hp + (size_t)((p * NW + warp) * 2) * DP + lane * DPL;
-        sts_row<DPL>(my_hp, hp1);
-        sts_row<DPL>(my_hp + DP, hp3);
-        if (lane == 0) {
-            float* my_sc = s_sc + (size_t)(p * NW + warp) * 4;
-            my_sc[0] = b1; my_sc[1] = b3; my_sc[2] = st.pix;
-        }
-        if (warp < 2 && downstream) {
-            float* dst = s_edge + (size_t)(y % RING) * 3 * DP + lane * DPL;
-            float* dsc = s_esc + (y % RING) * 8;
-            if (warp == 0) {
-                sts_row<DPL>(dst, hp1);
-                sts_row<DPL>(dst + DP, hp3);
-                if (lane == 0) { dsc[0] = b1; dsc[1] = b3; dsc[2] = st.pix; }
-            } else {
-                sts_row<DPL>(dst + 2 * DP, hp3);
-                if (lane == 0) { dsc[3] = b3; dsc[4] = st.pix; }
-            }
+        const unsigned slot = (unsigned)y & (S - 1);
+        sts_vec<DPL>(myBase + slot * SLOT_B, hpV);
+        sts_vec<DPL>(myBase + slot * SLOT_B + DP * 4, hpA);
+        if (lane == 0) sts_f4(myScBase + slot * SLOTSC_B, make_float4(bV, bA, pix, 0.0f));
+        if (edge_out) {
+            const unsigned er = (unsigned)y & (RING - 1);
+            if (warp == 0) sts_vec<DPL>(eBase + er * HROW_B, hpV);
+            sts_vec<DPL>(eBase + er * HROW_B + (warp == 0 ? DP * 4 : 0), hpA);
+            if (lane == 0) sts_f4(eScBase + er * HSC_B, make_float4(bV, bA, pix, 0.0f));
         }
         store_f<DPL>(hst, H3);
         hst += estep;
     };
 
-    for (int yb = ymin; yb <= ymax; yb += PF) {
+    // No CTA-wide barrier: the columns of a band form a dataflow pipeline through shared memory.  Column j
+    // may start row y once columns j+1, j+2 have finished row y-1 (read-after-write) and columns j-1, j-2 have
+    // finished row y-S+1 (so the ring slot of row y-S is free: write-after-read).
+    for (int yb = y_in; yb <= y_out; yb += PF) {
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
             const int y = yb + k;
-            if (y > ymax) break;
-            if (y >= y_in && y <= y_out) {
-                // the last two columns read the upstream band's row y-1; the first two feed the downstream ring
-                if (warp >= NW - 2 && y - 1 >= hbeg && y - 1 < hend) {
-                    while (ctl->halo_ready < y) __nanosleep(20);
-                    __threadfence_block();
-                }
-                if (warp < 2 && downstream) {
-                    while (ctl->copied < y - RING + 1) __nanosleep(20);
-                }
-                const int xp = u + y;
-                const int x = fwd ? xp : w - 1 - xp;
-                if (x >= xf) row_body(std::false_type{}, ring[k], y, xp, x);
-                else row_body(std::true_type{}, ring[k], y, xp, x);
+            if (y > y_out) break;
+            const int xp = u + y;
+            // all hand-offs of this row in one polling loop (the flags are read back to back)
+            // (an upstream band only publishes rows < hend: rows beyond that need no upstream state)
+            while (*fV < min(y, vCap) || *fA < min(y, aCap) || min(*fW1, *fW2) < y - wOff || (edge_out && *fC < y - cOff)) {}
+            smem_order();
+
+            const int x = fwd ? xp : w - 1 - xp;
+            const bool edge = y == 0 || xp == 0 || xp == w - 1;
+            if (edge) {
+                if (x >= xf) row_body(std::false_type{}, std::true_type{}, ring[k], y, xp, x);
+                else row_body(std::true_type{}, std::true_type{}, ring[k], y, xp, x);
+            } else {
+                if (x >= xf) row_body(std::false_type{}, std::false_type{}, ring[k], y, xp, x);
+                else row_body(std::true_type{}, std::false_type{}, ring[k], y, xp, x);
             }
-            const int yl = y + PF;
-            if (yl >= y_in && yl <= y_out) load_stage(ring[k]);
-            named_bar_sync(1, NW * 32);                  // compute warps only: row y's states are in shared memory
-            if (warp == 0 && lane == 0) { __threadfence_block(); ctl->rows_done = y + 1; }
+
+            load_stage(ring[k], y + PF <= y_out);
+            __syncwarp();
+            smem_order();
+            if (lane == 0) prog[warp] = (y == y_out) ? 0x7fffffff : y + 1;
         }
     }
 }
@@ -364,7 +424,8 @@ template <int DPL, int COST>
 static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     constexpr int DP = 32 * DPL;
     constexpr int VG_NW = vg_nw(DPL);
-    const size_t smem = (size_t)(2 * VG_NW * 2 * DP + 2 * VG_NW * 4 + 2 * (2 * VG_R * (3 * DP + 8))) * sizeof(float) + sizeof(VCtl);
+    const size_t smem = (size_t)(VG_S * VG_NW * 2 * DP + VG_S * VG_NW * 4 + 2 * (2 * VG_R * (3 * DP + 8))) * sizeof(float) +
+                        sizeof(VCtl) + VG_NW * sizeof(int);
     dim3 grid(a.n_bands * a.batch), block((VG_NW + 1) * 32);
     const bool ieee = g_ieee_div.load() != 0;
 #define ROO_VG(F, I)                                                                                          \

@@ -104,6 +104,61 @@ __device__ __forceinline__ void sgm_step(const float (&hp)[DPL], float lastBest,
     best_out = warp_min_f32(best);
 }
 
+// Three path steps of one pixel at once -- the vertical, diagonal and anti-diagonal path of a fused
+// vertical group (sgm_fused.cu), applied in that order to the same aggregate: H1 = hin + CrV, H2 = H1 + CrD,
+// H3 = H2 + CrA.  Numerically identical to three sgm_step() calls; written as ONE straight-line block so
+// that the three recurrences -- which only meet in the final additions -- are scheduled interleaved and a
+// pixel costs one chain latency (shuffle -> min -> redux) instead of three.  The matching cost is decoded
+// once.  hpX are in/out: previous pixel's row on entry, this pixel's masked row on exit.
+template <int DPL, bool MASKED, bool FIRST, bool IEEE>
+__device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float denV, float p2V,
+                                          float (&hpD)[DPL], float lbD, float denD, float p2D,
+                                          float (&hpA)[DPL], float lbA, float denA, float p2A,
+                                          const float (&cost)[DPL], const float (&hin)[DPL], float P1, int lim,
+                                          int lane, float (&H3)[DPL], float& bV, float& bD, float& bA) {
+    float pV[DPL], pD[DPL], pA[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) { pV[j] = hpV[j] + P1; pD[j] = hpD[j] + P1; pA[j] = hpA[j] + P1; }
+    float upV = __shfl_up_sync(0xffffffffu, pV[DPL - 1], 1), dnV = __shfl_down_sync(0xffffffffu, pV[0], 1);
+    float upD = __shfl_up_sync(0xffffffffu, pD[DPL - 1], 1), dnD = __shfl_down_sync(0xffffffffu, pD[0], 1);
+    float upA = __shfl_up_sync(0xffffffffu, pA[DPL - 1], 1), dnA = __shfl_down_sync(0xffffffffu, pA[0], 1);
+    if (lane == 0) { upV = ROO_INF; upD = ROO_INF; upA = ROO_INF; }
+    if (lane == 31) { dnV = ROO_INF; dnD = ROO_INF; dnA = ROO_INF; }
+    const float baseV = sgm_p2_base<IEEE>(lbV, p2V, denV);
+    const float baseD = sgm_p2_base<IEEE>(lbD, p2D, denD);
+    const float baseA = sgm_p2_base<IEEE>(lbA, p2A, denA);
+    float mV = SGM_MAX_ERROR, mD = SGM_MAX_ERROR, mA = SGM_MAX_ERROR;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+        const float cmV = fminf(fminf(baseV, hpV[j]), fminf(j > 0 ? pV[j - 1] : upV, j < DPL - 1 ? pV[j + 1] : dnV));
+        const float cmD = fminf(fminf(baseD, hpD[j]), fminf(j > 0 ? pD[j - 1] : upD, j < DPL - 1 ? pD[j + 1] : dnD));
+        const float cmA = fminf(fminf(baseA, hpA[j]), fminf(j > 0 ? pA[j - 1] : upA, j < DPL - 1 ? pA[j + 1] : dnA));
+        const float crV = (cmV + cost[j]) - lbV;
+        const float crD = (cmD + cost[j]) - lbD;
+        const float crA = (cmA + cost[j]) - lbA;
+        const float h1 = FIRST ? crV : hin[j] + crV;
+        const float h2 = h1 + crD;
+        const float h3 = h2 + crA;
+        if (MASKED) {
+            const bool in = j < lim;
+            mV = in ? fminf(mV, crV) : mV;
+            mD = in ? fminf(mD, crD) : mD;
+            mA = in ? fminf(mA, crA) : mA;
+            hpV[j] = in ? h1 : ROO_INF;
+            hpD[j] = in ? h2 : ROO_INF;
+            hpA[j] = in ? h3 : ROO_INF;
+            H3[j] = in ? h3 : (FIRST ? 0.0f : hin[j]);
+        } else {
+            mV = fminf(mV, crV); mD = fminf(mD, crD); mA = fminf(mA, crA);
+            hpV[j] = h1; hpD[j] = h2; hpA[j] = h3;
+            H3[j] = h3;
+        }
+    }
+    bV = warp_min_f32(mV);
+    bD = warp_min_f32(mD);
+    bA = warp_min_f32(mA);
+}
+
 // Winner-takes-all (+ optional parabola) over the masked row hp[] of pixel x -- CostVolMinimum<float,float>
 // (cu_dense_stereo.cu:25-43) or CostVolMinimumSubpix with sd = -1 (cu_dense_stereo.cu:66-109).
 template <int DPL, bool IEEE>

@@ -140,6 +140,9 @@ __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
 struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 
 constexpr int VG_R = 8;   // rows per hand-off chunk between bands (flag / fence cost is paid once per chunk)
+#ifndef VG_SPIN_NS
+#define VG_SPIN_NS 30
+#endif
 constexpr int VG_S = 4;   // depth (rows) of the in-band state ring in shared memory
 
 template <int DPL, int COST, bool FIRST, bool IEEE, int NW>
@@ -202,17 +205,19 @@ sgm_vgroup_kernel(const VGroupArgs a) {
             bool progress = false;
             // ---- stage a chunk of upstream rows into the halo ring (readers: the last two columns)
             if (hr < hend) {
-                const int n = min(R, hend - hr);
+                // adaptive batch: whatever the upstream band has published and the ring can take (1..R rows) --
+                // the hand-off latency is one turn of this loop, not the time to fill a fixed chunk.  The paths
+                // that run across the bands (anti-diagonal: a new band every NW/2 rows) are a serial chain of such
+                // hand-offs, so this latency, not the copy bandwidth, bounds a single pair's pass.
                 const int rdh = min(prog[NW - 1], prog[NW - 2]);
+                if (seen <= hr) {
+                    if (lane == 0) seen = ld_acquire_gpu(p_flag);
+                    seen = __shfl_sync(0xffffffffu, seen, 0);
+                }
                 // ring slot of row y was last used by row y-RING, read while computing row y-RING+1
-                if (rdh >= hr + n - RING + 1) {
-                    if (seen < hr + n) {
-                        if (lane == 0) seen = ld_acquire_gpu(p_flag);
-                        seen = __shfl_sync(0xffffffffu, seen, 0);
-                    }
-                    if (seen >= hr + n) {
-                        // asynchronous global->shared copies (LDGSTS): all rows of the chunk are in flight at
-                        // once and no registers are staged; one wait for the whole chunk
+                const int n = min(min(R, hend - hr), min(seen - hr, rdh + RING - 1 - hr));
+                if (n > 0) {
+                    {
                         for (int y = hr; y < hr + n; ++y) {
                             const float* src = p_hp + (size_t)y * 3 * DP + lane * DPL;
                             float* dst = s_halo + (size_t)(y % RING) * 3 * DP + lane * DPL;
@@ -238,9 +243,10 @@ sgm_vgroup_kernel(const VGroupArgs a) {
             // ---- publish finished rows of this band's columns 0,1 (writers: the first two columns)
             if (cp < cp_end) {
                 const int rd = min(min(prog[0], prog[1]), ymax + 1);
-                if (rd > cp && (rd - cp >= R || rd == ymax + 1)) {
+                if (rd > cp) {   // publish every finished row at once (see the latency note above)
                     __threadfence_block();
-                    for (int y = cp; y < rd; ++y) {
+                    const int rd_lim = min(rd, cp + RING);
+                    for (int y = cp; y < rd_lim; ++y) {
                         const float* src = s_edge + (size_t)(y % RING) * 3 * DP + lane * DPL;
                         float* dst = e_hp + (size_t)y * 3 * DP + lane * DPL;
                         float r0[DPL], r1[DPL], r2[DPL];
@@ -396,7 +402,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
             const int xp = u + y;
             // all hand-offs of this row in one polling loop (the flags are read back to back)
             // (an upstream band only publishes rows < hend: rows beyond that need no upstream state)
-            while (*fV < min(y, vCap) || *fA < min(y, aCap) || min(*fW1, *fW2) < y - wOff || (edge_out && *fC < y - cOff)) {}
+            while (*fV < min(y, vCap) || *fA < min(y, aCap) || min(*fW1, *fW2) < y - wOff || (edge_out && *fC < y - cOff)) { __nanosleep(VG_SPIN_NS); }
             smem_order();
 
             const int x = fwd ? xp : w - 1 - xp;

@@ -30,7 +30,10 @@
 
 namespace roo_b200 {
 
-constexpr int VG_PF = 3;     // rows of prefetch
+// rows of prefetch, staged in shared memory by cp.async (LDGSTS): under load a DRAM access takes ~3000 SM
+// cycles on B200, so a band needs ~60-80 KB in flight per SM to stream at HBM speed -- far more than a
+// register ring can hold, and without unrolling the row loop
+__host__ __device__ constexpr int vg_pfs(int DPL, int CE) { return DPL >= 8 ? (CE == 4 ? 2 : 4) : (DPL == 4 && CE == 4 ? 4 : 8); }   // (227 KB of shared memory per CTA)
 // skewed columns (compute warps) per band: 16 (+1 communication warp) leaves 120 registers per thread, enough
 // for DPL <= 4; the 256-disparity variant keeps twice the state per lane and runs 12 + 1 warps
 constexpr int vg_nw(int DPL) { return DPL >= 8 ? 12 : 16; }
@@ -81,6 +84,26 @@ __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) 
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// BYTES per lane from global to a 32-bit shared address; 16-byte pieces bypass L1 (.cg), smaller ones use .ca
+// (only used for data that is read-only during the pass)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_bytes(unsigned sdst, const void* gsrc) {
+    if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+        for (int q = 0; q < BYTES / 16; ++q)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16 * q), "l"((const char*)gsrc + 16 * q) : "memory");
+    } else if constexpr (BYTES == 8) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst), "l"(gsrc) : "memory");
+    } else if constexpr (BYTES == 4) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
+    } else {
+        static_assert(BYTES == 2 || BYTES == 1, "unsupported cp.async size");
+        // 1- and 2-byte cost rows (DPL 1/2 with u8 costs): plain load + shared store
+        if constexpr (BYTES == 2) { const unsigned short v = *(const unsigned short*)gsrc; asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst), "h"(v) : "memory"); }
+        else { const unsigned v = *(const unsigned char*)gsrc; asm volatile("st.shared.u8 [%0], %1;" ::"r"(sdst), "r"(v) : "memory"); }
+    }
+}
+
 template <int DPL>
 __device__ __forceinline__ void cp_async_row(float* smem_dst, const float* gsrc) {
     static_assert(DPL >= 4, "cp.async.cg moves 16 bytes");
@@ -139,7 +162,7 @@ __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
 // smem control words
 struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 
-constexpr int VG_R = 8;   // rows per hand-off chunk between bands (flag / fence cost is paid once per chunk)
+__host__ __device__ constexpr int vg_r(int DPL) { return DPL >= 8 ? 4 : 8; }   // max rows per hand-off batch between bands (ring = 2x)
 #ifndef VG_SPIN_NS
 #define VG_SPIN_NS 30
 #endif
@@ -150,8 +173,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int DP = 32 * DPL;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    constexpr int PF = VG_PF;
-    constexpr int R = VG_R, RING = 2 * VG_R, S = VG_S;
+    constexpr int PFS = vg_pfs(DPL, CE);
+    constexpr int R = vg_r(DPL), RING = 2 * R, S = VG_S;
+    constexpr int STAGE_B = DP * 4 + DP * CE + 16;   // one prefetched pixel: aggregate row, cost row, intensity
     extern __shared__ __align__(16) float smem[];
     float* s_hp = smem;                                // [S rows][NW][2 paths][DP]  in-band states (row ring)
     float* s_sc = s_hp + S * NW * 2 * DP;              // [S rows][NW][4]: lastBest(vertical), lastBest(anti-diag), pix, -
@@ -161,6 +185,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     float* s_esc = s_edge + RING * 3 * DP;             // [RING][8]
     VCtl* ctl = reinterpret_cast<VCtl*>(s_esc + RING * 8);
     volatile int* prog = reinterpret_cast<volatile int*>(ctl + 1);   // [NW] rows < prog[j] of column j are done
+    char* s_pf = reinterpret_cast<char*>(ctl + 1) + ((NW * 4 + 15) / 16) * 16;   // [NW][PFS][STAGE_B] prefetch stages
 
     // warp index through a shuffle: ptxas then knows it is warp-uniform, and every branch on it (roles, masks,
     // path starts) is a uniform branch without divergence bookkeeping around the shuffles / redux below
@@ -289,19 +314,20 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     const char* cld = (const char*)a.C + ((size_t)pair * a.c_pair + e0) * CE;
     const float* ild = a.img + (size_t)pair * a.img_pair + (size_t)y0 * w + x0;
 
-    // Prefetch ring.  Loads are UNCONDITIONAL (past the end of the column the cursor simply stops advancing and
-    // re-reads the last pixel): a predicated load must keep the old register value when off, which makes ptxas
-    // insert a register move that waits for the load.
-    VStage<DPL, COST> ring[PF];
-    auto load_stage = [&](VStage<DPL, COST>& st, bool advance) {
-        const ptrdiff_t es = advance ? estep : 0, ps = advance ? pstep : 0;
-        hld += es; cld += es * CE; ild += ps;
-        if (!FIRST) load_f<DPL>(st.hin, hld);
-        st.c.load(cld);
-        st.pix = *ild;
+    // Prefetch: row y+PFS-1 is copied global -> shared (asynchronously, no registers) while row y is computed.
+    // Every lane copies and later reads its own bytes; only the intensity (lane 0) needs a __syncwarp.
+    const unsigned pfBase = (unsigned)__cvta_generic_to_shared(s_pf) + warp * PFS * STAGE_B;
+    auto issue_row = [&](int yl) {
+        if (yl <= y_out) {
+            const unsigned dst = pfBase + ((unsigned)yl & (PFS - 1)) * STAGE_B;
+            if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hld);
+            cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cld);
+            if (lane == 0) cp_async_bytes<4>(dst + DP * 4 + DP * CE, ild);
+            hld += estep; cld += estep * CE; ild += pstep;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-#pragma unroll
-    for (int k = 0; k < PF; ++k) load_stage(ring[k], k > 0 && y_in + k <= y_out);
+    for (int k = 0; k < PFS - 1; ++k) issue_row(y_in + k);
 
     // ---- shared-memory addressing, resolved once per warp (32-bit shared-window addresses) ----
     // State rows of the previous image row come either from the in-band ring (slot (y-1) & (S-1), stride one
@@ -340,14 +366,19 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     float lbd = 0.0f, pixd = 0.0f;
 
     // EDGE rows contain a path start (y == 0, x' == 0 or x' == w-1); all other rows take the lean body.
-    auto row_body = [&](auto masked_tag, auto edge_tag, VStage<DPL, COST>& st, int y, int xp, int x) {
+    auto row_body = [&](auto masked_tag, auto edge_tag, int y, int xp, int x) {
         constexpr bool MASKED = decltype(masked_tag)::value;
         constexpr bool EDGE = decltype(edge_tag)::value;
         const int lim = MASKED ? min(M, x + 1) - d0 : 0;
-        const float pix = st.pix;
-        float hpV[DPL], hpA[DPL], H3[DPL], cost[DPL];
+        const unsigned stg = pfBase + ((unsigned)y & (PFS - 1)) * STAGE_B;
+        float hin[DPL], hpV[DPL], hpA[DPL], H3[DPL], cost[DPL];
+        if (!FIRST) lds_vec<DPL>(hin, stg + lane * DPL * 4);
+        RawCost<DPL, COST> rc;
+        rc.lds(stg + DP * 4 + lane * DPL * CE);
+        float pix;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + DP * CE));
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) cost[j] = st.c.get(j, cscale);
+        for (int j = 0; j < DPL; ++j) cost[j] = rc.get(j, cscale);
         const unsigned ym1 = (unsigned)(y - 1);
         lds_vec<DPL>(hpV, vBase + (ym1 & vMask) * vStride);
         lds_vec<DPL>(hpA, aBase + (ym1 & aMask) * aStride);
@@ -371,7 +402,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         sgm_step3<DPL, MASKED, FIRST, IEEE>(hpV, lbV, 1.0f + fabsf(ppV - pix), p2V,
                                             hpd, lbd, 1.0f + fabsf(pixd - pix), p2D,
                                             hpA, lbA, 1.0f + fabsf(ppA - pix), p2A,
-                                            cost, st.hin, P1, lim, lane, H3, bV, bD, bA);
+                                            cost, hin, P1, lim, lane, H3, bV, bD, bA);
         if (EDGE) { if (sV) bV = 0.0f; if (sD) bD = 0.0f; if (sA) bA = 0.0f; }
         lbd = bD;
         pixd = pix;
@@ -394,32 +425,29 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     // No CTA-wide barrier: the columns of a band form a dataflow pipeline through shared memory.  Column j
     // may start row y once columns j+1, j+2 have finished row y-1 (read-after-write) and columns j-1, j-2 have
     // finished row y-S+1 (so the ring slot of row y-S is free: write-after-read).
-    for (int yb = y_in; yb <= y_out; yb += PF) {
-#pragma unroll
-        for (int k = 0; k < PF; ++k) {
-            const int y = yb + k;
-            if (y > y_out) break;
-            const int xp = u + y;
-            // all hand-offs of this row in one polling loop (the flags are read back to back)
-            // (an upstream band only publishes rows < hend: rows beyond that need no upstream state)
-            while (*fV < min(y, vCap) || *fA < min(y, aCap) || min(*fW1, *fW2) < y - wOff || (edge_out && *fC < y - cOff)) { __nanosleep(VG_SPIN_NS); }
-            smem_order();
+#pragma unroll 1
+    for (int y = y_in; y <= y_out; ++y) {
+        issue_row(y + PFS - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(PFS - 1) : "memory");   // row y's stage has landed
+        __syncwarp();
+        const int xp = u + y;
+        // all hand-offs of this row in one polling loop (the flags are read back to back)
+        // (an upstream band only publishes rows < hend: rows beyond that need no upstream state)
+        while (*fV < min(y, vCap) || *fA < min(y, aCap) || min(*fW1, *fW2) < y - wOff || (edge_out && *fC < y - cOff)) { __nanosleep(VG_SPIN_NS); }
+        smem_order();
 
-            const int x = fwd ? xp : w - 1 - xp;
-            const bool edge = y == 0 || xp == 0 || xp == w - 1;
-            if (edge) {
-                if (x >= xf) row_body(std::false_type{}, std::true_type{}, ring[k], y, xp, x);
-                else row_body(std::true_type{}, std::true_type{}, ring[k], y, xp, x);
-            } else {
-                if (x >= xf) row_body(std::false_type{}, std::false_type{}, ring[k], y, xp, x);
-                else row_body(std::true_type{}, std::false_type{}, ring[k], y, xp, x);
-            }
-
-            load_stage(ring[k], y + PF <= y_out);
-            __syncwarp();
-            smem_order();
-            if (lane == 0) prog[warp] = (y == y_out) ? 0x7fffffff : y + 1;
+        const int x = fwd ? xp : w - 1 - xp;
+        const bool edge = y == 0 || xp == 0 || xp == w - 1;
+        if (edge) {
+            if (x >= xf) row_body(std::false_type{}, std::true_type{}, y, xp, x);
+            else row_body(std::true_type{}, std::true_type{}, y, xp, x);
+        } else {
+            if (x >= xf) row_body(std::false_type{}, std::false_type{}, y, xp, x);
+            else row_body(std::true_type{}, std::false_type{}, y, xp, x);
         }
+        __syncwarp();
+        smem_order();
+        if (lane == 0) prog[warp] = (y == y_out) ? 0x7fffffff : y + 1;
     }
 }
 
@@ -430,8 +458,9 @@ template <int DPL, int COST>
 static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     constexpr int DP = 32 * DPL;
     constexpr int VG_NW = vg_nw(DPL);
-    const size_t smem = (size_t)(VG_S * VG_NW * 2 * DP + VG_S * VG_NW * 4 + 2 * (2 * VG_R * (3 * DP + 8))) * sizeof(float) +
-                        sizeof(VCtl) + VG_NW * sizeof(int);
+    constexpr int CE = RawCost<DPL, COST>::ELEM;
+    const size_t smem = (size_t)(VG_S * VG_NW * 2 * DP + VG_S * VG_NW * 4 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
+                        sizeof(VCtl) + ((VG_NW * 4 + 15) / 16) * 16 + (size_t)VG_NW * vg_pfs(DPL, CE) * (DP * 4 + DP * CE + 16);
     dim3 grid(a.n_bands * a.batch), block((VG_NW + 1) * 32);
     const bool ieee = g_ieee_div.load() != 0;
 #define ROO_VG(F, I)                                                                                          \

@@ -44,6 +44,14 @@ template <int DPL, int COST> struct RawCost;
 template <int DPL> struct RawCost<DPL, COST_F32> {
     float v[DPL];
     __device__ __forceinline__ void load(const void* p) { load_f<DPL>(v, (const float*)p); }
+    __device__ __forceinline__ void lds(unsigned saddr) {   // from a 32-bit shared-window address
+        if constexpr (DPL >= 4) {
+#pragma unroll
+            for (int q = 0; q < DPL / 4; ++q)
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3]) : "r"(saddr + 16 * q));
+        } else if constexpr (DPL == 2) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(saddr));
+        else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(saddr));
+    }
     __device__ __forceinline__ float get(int j, float) const { return v[j]; }
     static constexpr int ELEM = 4;
 };
@@ -54,6 +62,12 @@ template <int DPL> struct RawCost<DPL, COST_U8> {
         else if constexpr (DPL == 4) w[0] = *reinterpret_cast<const unsigned*>(p);
         else if constexpr (DPL == 2) w[0] = *reinterpret_cast<const unsigned short*>(p);
         else w[0] = *reinterpret_cast<const unsigned char*>(p);
+    }
+    __device__ __forceinline__ void lds(unsigned saddr) {
+        if constexpr (DPL == 8) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
+        else if constexpr (DPL == 4) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(saddr));
+        else if constexpr (DPL == 2) { unsigned short t; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(saddr)); w[0] = t; }
+        else asm volatile("ld.shared.u8 %0, [%1];" : "=r"(w[0]) : "r"(saddr));
     }
     // Hamming count * (1/bits): exact (power-of-two scale), equals the reference's count / bits
     __device__ __forceinline__ float get(int j, float scale) const {

@@ -1,0 +1,203 @@
+// roo.hpp -- header-only C++ shim that re-creates the reference's operator surface for the census /
+// semi-global-matching path on top of the C ABI in roo_b200.h.
+//
+// A translation unit of an application written against Kangaroo
+//   #include <kangaroo/cu_census.h> / cu_semi_global_matching.h / cu_dense_stereo.h
+// can include this header instead and link libroo_b200.so: the free functions below have the reference's
+// names, argument order and meaning, and the same explicit instantiation set
+// (cu_census.cu:309-314, cu_semi_global_matching.cu:88-89, cu_dense_stereo.cu:54-60).
+//
+// roo::Image / roo::Volume here are minimal non-owning views with the reference's member layout
+// (Image.h:617-620, Volume.h:363-369) -- when this header is used NEXT to the real kangaroo headers, define
+// ROO_B200_USE_KANGAROO_TYPES before including it and the real roo::Image / roo::Volume are used instead
+// (they are layout-compatible with roo_image_t / roo_volume_t).
+//
+// Like the reference launchers the operators return void, are asynchronous and report nothing
+// (cu_census.cu:180-220 never check the launch); define ROO_B200_THROW to turn a non-zero status into a
+// std::runtime_error.  Every call goes to the stream set with roo::SetStream() (default: the legacy default
+// stream, which is what the reference uses).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+
+#include <vector_types.h>   // ulong2, ulong4 (CUDA toolkit)
+
+#include "../roo_b200.h"
+
+namespace roo {
+
+#ifndef ROO_B200_USE_KANGAROO_TYPES
+struct TargetDevice {};
+struct DontManage {};
+// include/kangaroo/CostVolElem.h:10-19
+struct alignas(8) CostVolElem { int n; float sum; };
+
+template <typename T, typename Target = TargetDevice, typename Management = DontManage>
+struct Image {
+    Image() : pitch(0), ptr(nullptr), w(0), h(0) {}
+    Image(T* p, size_t w_, size_t h_) : pitch(sizeof(T) * w_), ptr(p), w(w_), h(h_) {}
+    Image(T* p, size_t w_, size_t h_, size_t pitch_) : pitch(pitch_), ptr(p), w(w_), h(h_) {}
+    Image SubImage(size_t x, size_t y, size_t width, size_t height) const {
+        return Image((T*)((unsigned char*)ptr + y * pitch) + x, width, height, pitch);
+    }
+    size_t pitch;
+    T* ptr;
+    size_t w;
+    size_t h;
+};
+
+template <typename T, typename Target = TargetDevice, typename Management = DontManage>
+struct Volume {
+    Volume() : pitch(0), ptr(nullptr), w(0), h(0), img_pitch(0), d(0) {}
+    // (the reference's 4-argument constructor leaves d unset, Volume.h:55-59; this one sets it)
+    Volume(T* p, size_t w_, size_t h_, size_t d_) : pitch(sizeof(T) * w_), ptr(p), w(w_), h(h_), img_pitch(sizeof(T) * w_ * h_), d(d_) {}
+    Volume(T* p, size_t w_, size_t h_, size_t d_, size_t pitch_) : pitch(pitch_), ptr(p), w(w_), h(h_), img_pitch(pitch_ * h_), d(d_) {}
+    Volume(T* p, size_t w_, size_t h_, size_t d_, size_t pitch_, size_t img_pitch_) : pitch(pitch_), ptr(p), w(w_), h(h_), img_pitch(img_pitch_), d(d_) {}
+    Image<T, Target, DontManage> ImageXY(size_t z) const {
+        return Image<T, Target, DontManage>((T*)((unsigned char*)ptr + z * img_pitch), w, h, pitch);
+    }
+    size_t pitch;
+    T* ptr;
+    size_t w;
+    size_t h;
+    size_t img_pitch;
+    size_t d;
+};
+#endif  // ROO_B200_USE_KANGAROO_TYPES
+
+static_assert(sizeof(Image<float>) == sizeof(roo_image_t), "roo::Image must be layout-compatible with roo_image_t");
+static_assert(sizeof(Volume<float>) == sizeof(roo_volume_t), "roo::Volume must be layout-compatible with roo_volume_t");
+
+namespace b200 {
+inline void*& stream_slot() { static thread_local void* s = nullptr; return s; }
+inline void done(int status, const char* what) {
+#ifdef ROO_B200_THROW
+    if (status != ROO_OK) throw std::runtime_error(std::string(what) + ": " + roo_status_string(status));
+#else
+    (void)status; (void)what;
+#endif
+}
+template <typename T> roo_image_t c(const Image<T>& i) { return roo_image_t{i.pitch, (void*)i.ptr, i.w, i.h}; }
+template <typename T> roo_volume_t c(const Volume<T>& v) { return roo_volume_t{v.pitch, (void*)v.ptr, v.w, v.h, v.img_pitch, v.d}; }
+template <typename T> struct words;
+template <> struct words<unsigned long> { static constexpr int n = 1, win = ROO_WIN_9x7; };
+template <> struct words<ulong2> { static constexpr int n = 2, win = ROO_WIN_11x11; };
+template <> struct words<ulong4> { static constexpr int n = 4, win = ROO_WIN_16x16; };
+template <typename T> struct voltype;
+template <> struct voltype<float> { static constexpr int v = ROO_VOL_F32; };
+template <> struct voltype<int> { static constexpr int v = ROO_VOL_I32; };
+template <> struct voltype<unsigned int> { static constexpr int v = ROO_VOL_U32; };
+template <> struct voltype<unsigned short> { static constexpr int v = ROO_VOL_U16; };
+template <> struct voltype<unsigned char> { static constexpr int v = ROO_VOL_U8; };
+template <> struct voltype<CostVolElem> { static constexpr int v = ROO_VOL_ELEM; };
+template <typename T> struct imgtype;
+template <> struct imgtype<unsigned char> { static constexpr int v = ROO_IMG_U8; };
+template <> struct imgtype<float> { static constexpr int v = ROO_IMG_F32; };
+}  // namespace b200
+
+// extension: the stream every operator below launches on (thread-local; default 0 = legacy default stream)
+inline void SetStream(void* cuda_stream) { b200::stream_slot() = cuda_stream; }
+
+// ---- cu_census.h:12-23 -----------------------------------------------------------------------------
+inline void Census(Image<unsigned long> census, Image<unsigned char> img) { auto a = b200::c(census), b = b200::c(img); b200::done(roo_census(&a, &b, ROO_WIN_9x7, ROO_IMG_U8, b200::stream_slot()), "Census"); }
+inline void Census(Image<ulong2> census, Image<unsigned char> img) { auto a = b200::c(census), b = b200::c(img); b200::done(roo_census(&a, &b, ROO_WIN_11x11, ROO_IMG_U8, b200::stream_slot()), "Census"); }
+inline void Census(Image<ulong4> census, Image<unsigned char> img) { auto a = b200::c(census), b = b200::c(img); b200::done(roo_census(&a, &b, ROO_WIN_16x16, ROO_IMG_U8, b200::stream_slot()), "Census"); }
+inline void Census(Image<unsigned long> census, Image<float> img) { auto a = b200::c(census), b = b200::c(img); b200::done(roo_census(&a, &b, ROO_WIN_9x7, ROO_IMG_F32, b200::stream_slot()), "Census"); }
+inline void Census(Image<ulong2> census, Image<float> img) { auto a = b200::c(census), b = b200::c(img); b200::done(roo_census(&a, &b, ROO_WIN_11x11, ROO_IMG_F32, b200::stream_slot()), "Census"); }
+inline void Census(Image<ulong4> census, Image<float> img) { auto a = b200::c(census), b = b200::c(img); b200::done(roo_census(&a, &b, ROO_WIN_16x16, ROO_IMG_F32, b200::stream_slot()), "Census"); }
+
+// ---- cu_census.h:33 ----------------------------------------------------------------------------------
+inline void CensusStereo(Image<char> disp, Image<unsigned long> left, Image<unsigned long> right, int maxDisp) {
+    auto d = b200::c(disp), l = b200::c(left), r = b200::c(right);
+    b200::done(roo_census_stereo(&d, &l, &r, maxDisp, b200::stream_slot()), "CensusStereo");
+}
+
+// ---- cu_census.h:36-38; instantiated for Tvol in {unsigned short, float} x T in {unsigned long, ulong2, ulong4}
+template <typename Tvol, typename T>
+inline void CensusStereoVolume(Volume<Tvol> vol, Image<T> left, Image<T> right, int maxDisp, float sd) {
+    static_assert(std::is_same<Tvol, float>::value || std::is_same<Tvol, unsigned short>::value, "Tvol");
+    auto v = b200::c(vol); auto l = b200::c(left), r = b200::c(right);
+    b200::done(roo_census_stereo_volume(&v, &l, &r, b200::words<T>::n, b200::voltype<Tvol>::v, maxDisp, sd,
+                                        ROO_POPC32_COMPAT, b200::stream_slot()), "CensusStereoVolume");
+}
+
+// ---- cu_semi_global_matching.h:10-12; instantiated <float,CostVolElem,unsigned char> and <float,float,float>
+template <typename TH, typename TC, typename Timg>
+inline void SemiGlobalMatching(Volume<TH> volH, Volume<TC> volC, Image<Timg> left, int maxDisp, float P1, float P2,
+                               bool dohoriz, bool dovert, bool doreverse) {
+    static_assert(std::is_same<TH, float>::value, "TH must be float");
+    auto h = b200::c(volH); auto cvol = b200::c(volC); auto l = b200::c(left);
+    b200::done(roo_sgm(&h, &cvol, b200::voltype<TC>::v, &l, b200::imgtype<Timg>::v, maxDisp, P1, P2, dohoriz, dovert,
+                       doreverse, /*dodiag=*/0, b200::stream_slot()), "SemiGlobalMatching");
+}
+// extension: the same call with the four diagonal paths
+template <typename TH, typename TC, typename Timg>
+inline void SemiGlobalMatching8(Volume<TH> volH, Volume<TC> volC, Image<Timg> left, int maxDisp, float P1, float P2,
+                                bool dohoriz, bool dovert, bool doreverse) {
+    auto h = b200::c(volH); auto cvol = b200::c(volC); auto l = b200::c(left);
+    b200::done(roo_sgm(&h, &cvol, b200::voltype<TC>::v, &l, b200::imgtype<Timg>::v, maxDisp, P1, P2, dohoriz, dovert,
+                       doreverse, /*dodiag=*/1, b200::stream_slot()), "SemiGlobalMatching8");
+}
+
+// ---- cu_dense_stereo.h:13-15; instantiated (char,{float,int,uint,ushort,uchar}) and (float,{float,ushort})
+template <typename Tdisp, typename Tvol>
+inline void CostVolMinimum(Image<Tdisp> disp, Volume<Tvol> vol, unsigned maxDisp) {
+    static_assert(std::is_same<Tdisp, char>::value || std::is_same<Tdisp, float>::value, "Tdisp");
+    auto d = b200::c(disp); auto v = b200::c(vol);
+    b200::done(roo_costvol_minimum(&d, std::is_same<Tdisp, char>::value ? ROO_DISP_I8 : ROO_DISP_F32, &v,
+                                   b200::voltype<Tvol>::v, maxDisp, b200::stream_slot()), "CostVolMinimum");
+}
+// ---- cu_dense_stereo.h:81-82
+inline void CostVolMinimum(Image<float> disp, Volume<CostVolElem> vol) {
+    auto d = b200::c(disp); auto v = b200::c(vol);
+    b200::done(roo_costvol_minimum_elem(&d, &v, b200::stream_slot()), "CostVolMinimum");
+}
+// ---- cu_dense_stereo.h:84-85
+inline void CostVolMinimumSubpix(Image<float> disp, Volume<float> vol, unsigned maxDisp, float sd) {
+    auto d = b200::c(disp); auto v = b200::c(vol);
+    b200::done(roo_costvol_minimum_subpix(&d, &v, maxDisp, sd, b200::stream_slot()), "CostVolMinimumSubpix");
+}
+// ---- cu_dense_stereo.h:45-47
+inline void DenseStereoSubpixelRefine(Image<float> dDispOut, const Image<unsigned char> dDisp,
+                                      const Image<unsigned char> dCamLeft, const Image<unsigned char> dCamRight) {
+    auto o = b200::c(dDispOut), d = b200::c(dDisp), l = b200::c(dCamLeft), r = b200::c(dCamRight);
+    b200::done(roo_dense_stereo_subpixel_refine(&o, &d, &l, &r, b200::stream_slot()), "DenseStereoSubpixelRefine");
+}
+// ---- cu_dense_stereo.h:37-41
+inline void LeftRightCheck(Image<char> dispL, Image<char> dispR, int sd = -1, int maxDiff = 0) {
+    auto l = b200::c(dispL), r = b200::c(dispR);
+    b200::done(roo_left_right_check_i8(&l, &r, sd, maxDiff, b200::stream_slot()), "LeftRightCheck");
+}
+inline void LeftRightCheck(Image<float> dispL, Image<float> dispR, float sd = -1, float maxDiff = 0.5) {
+    auto l = b200::c(dispL), r = b200::c(dispR);
+    b200::done(roo_left_right_check_f32(&l, &r, sd, maxDiff, b200::stream_slot()), "LeftRightCheck");
+}
+
+// ---- extension: the fused per-frame engine (census -> cost -> SGM -> WTA/subpixel -> LR check) --------
+class StereoEngine {
+public:
+    explicit StereoEngine(const roo_pipeline_params_t& p) : e_(nullptr) {
+        const int rc = roo_engine_create(&e_, &p);
+        if (rc != ROO_OK) throw std::runtime_error(std::string("roo_engine_create: ") + roo_status_string(rc));
+    }
+    ~StereoEngine() { if (e_) roo_engine_destroy(e_); }
+    StereoEngine(const StereoEngine&) = delete;
+    StereoEngine& operator=(const StereoEngine&) = delete;
+    // n tightly packed (h x w) uint8 pairs in device memory -> n (h x w) float disparity images
+    void RunDevice(const uint8_t* left, const uint8_t* right, float* disp, int n, void* stream = nullptr) {
+        b200::done(roo_engine_run_device(e_, left, right, disp, n, stream), "roo_engine_run_device");
+    }
+    // the same with host buffers (pinned recommended): upload, compute and download are pipelined
+    void RunHost(const uint8_t* left, const uint8_t* right, float* disp, int n) {
+        b200::done(roo_engine_run_host(e_, left, right, disp, n), "roo_engine_run_host");
+    }
+    roo_engine_t* handle() { return e_; }
+private:
+    roo_engine_t* e_;
+};
+
+}  // namespace roo

@@ -144,7 +144,7 @@ int roo_engine_export_census(roo_engine_t* e, int slot, int side, const roo_imag
  * every launch on the launching stream; roo_engine_get_profile (call after synchronising) returns the
  * accumulated milliseconds and launch counts per kernel kind since profiling was switched on. */
 enum roo_prof_kind { ROO_PROF_CENSUS = 0, ROO_PROF_COST = 1, ROO_PROF_SWEEP = 2, ROO_PROF_WTA = 3, ROO_PROF_LRCHECK = 4,
-                     ROO_PROF_KINDS = 5 };
+                     ROO_PROF_VGROUP = 5, ROO_PROF_KINDS = 6 };
 int roo_engine_set_profiling(roo_engine_t* e, int on);
 int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long long* launches_by_kind);
 

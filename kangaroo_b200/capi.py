@@ -17,7 +17,7 @@ IMG_U8, IMG_F32 = 0, 1
 POPC32_COMPAT, POPC64 = 0, 1
 VOL_U16, VOL_F32, VOL_I32, VOL_U32, VOL_U8, VOL_ELEM = 0, 1, 2, 3, 4, 5
 DISP_I8, DISP_F32 = 0, 1
-PROF_KINDS = ("census", "cost", "sweep", "wta", "lrcheck")
+PROF_KINDS = ("census", "cost", "sweep", "wta", "lrcheck", "vgroup")
 
 
 class RooImage(C.Structure):

@@ -98,7 +98,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
             a.epi = i + 1 < ndir ? EPI_NONE : (p.keep_volume ? EPI_WTA_WRITE : EPI_WTA_ONLY);
             rc = launch_pass(a, e->plan.pass[i], e->edge, e->flags, st);
             if (rc) return rc;
-            prof_mark(e, ROO_PROF_SWEEP, st);
+            prof_mark(e, e->plan.pass[i].fused ? ROO_PROF_VGROUP : ROO_PROF_SWEEP, st);
         }
     }
     if (p.lrcheck) {

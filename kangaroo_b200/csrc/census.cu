@@ -212,53 +212,82 @@ static int csv_launch(const roo_volume_t* vol, const roo_image_t* l, const roo_i
 // of an aggregation sweep reads its 32*DPL disparities of a pixel with one coalesced load.
 // Stores the raw count h; the sweeps multiply by 1/bits (exact).  d > x (no right pixel) stores
 // bits/2, the reference's 0.5.
+// One CTA per (row, 128-pixel segment): the descriptors the segment touches are staged in shared memory
+// once (coalesced); a thread owns 4 consecutive disparities of one pixel (one 32-bit store) and consecutive
+// threads write consecutive words, so the 128*DP-byte output of the CTA is one contiguous coalesced stream.
 // ------------------------------------------------------------------------------------------------
+constexpr int COST_TX = 128;   // pixels per CTA
 template <int WORDS, bool POPC64>
 __global__ void __launch_bounds__(256)
 cost_u8_kernel(unsigned char* __restrict__ c8, const unsigned long long* __restrict__ cl,
                const unsigned long long* __restrict__ cr, int w, int h, int DP, int maxDisp) {
-    // thread -> 4 consecutive disparities of one pixel; consecutive threads -> consecutive d groups
-    const int groups = DP >> 2;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long npx = (long long)w * h;
-    const long long pix = gid / groups;
-    if (pix >= npx) return;
-    const int g = (int)(gid - pix * groups);
-    const size_t boff = (size_t)blockIdx.y * (size_t)npx;
-    const int x = (int)(pix % w);
-    const unsigned long long* lp = cl + (boff + (size_t)pix) * WORDS;
-    unsigned long long p[WORDS];
-#pragma unroll
-    for (int k = 0; k < WORDS; ++k) p[k] = lp[k];
-    unsigned packed = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int d = g * 4 + j;
-        unsigned hd = WORDS * 32;  // 0.5 * bits
-        if (d < maxDisp && d <= x) {
-            const unsigned long long* rp = cr + (boff + (size_t)pix - d) * WORDS;
-            hd = 0;
-#pragma unroll
-            for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], rp[k]);
-        }
-        packed |= hd << (8 * j);
+    extern __shared__ unsigned long long s_r[];          // [WORDS][COST_TX + DP - 1] right descriptors x0-(DP-1) .. x0+TX-1
+    unsigned long long* s_l = s_r + WORDS * (COST_TX + DP - 1);   // [WORDS][COST_TX] left descriptors
+    const int x0 = blockIdx.x * COST_TX, y = blockIdx.y;
+    const size_t rowoff = ((size_t)blockIdx.z * h + y) * (size_t)w;
+    const int span = COST_TX + DP - 1;
+    const int rx0 = x0 - (DP - 1);
+    for (int i = threadIdx.x; i < span * WORDS; i += 256) {
+        const int px = i / WORDS, k = i - px * WORDS;
+        const int gx = rx0 + px;
+        s_r[k * span + px] = (gx >= 0 && gx < w) ? cr[(rowoff + gx) * WORDS + k] : 0ull;
     }
-    reinterpret_cast<unsigned*>(c8 + (boff + (size_t)pix) * DP)[g] = packed;
+    for (int i = threadIdx.x; i < COST_TX * WORDS; i += 256) {
+        const int px = i / WORDS, k = i - px * WORDS;
+        s_l[k * COST_TX + px] = (x0 + px < w) ? cl[(rowoff + x0 + px) * WORDS + k] : 0ull;
+    }
+    __syncthreads();
+    // lanes run over pixels (consecutive descriptors in shared memory: conflict-free), each thread packs 4
+    // consecutive disparities into one word of a padded output tile; the tile then leaves coalesced
+    const int groups = DP >> 2;                           // 32-bit words per pixel
+    const int gpad = groups + 1;
+    unsigned* s_out = reinterpret_cast<unsigned*>(s_l + WORDS * COST_TX);   // [COST_TX][groups + 1]
+    for (int i = threadIdx.x; i < COST_TX * groups; i += 256) {
+        const int px = i % COST_TX, g = i / COST_TX;
+        const int x = x0 + px;
+        unsigned long long p[WORDS];
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k) p[k] = s_l[k * COST_TX + px];
+        unsigned packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = g * 4 + j;
+            unsigned hd = WORDS * 32;                     // 0.5 * bits: no right pixel (the reference's 0.5)
+            if (d < maxDisp && d <= x) {
+                const int ri = px + (DP - 1) - d;         // index of x-d in s_r
+                hd = 0;
+#pragma unroll
+                for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], s_r[k * span + ri]);
+            }
+            packed |= hd << (8 * j);
+        }
+        s_out[px * gpad + g] = packed;
+    }
+    __syncthreads();
+    unsigned* out = reinterpret_cast<unsigned*>(c8 + (rowoff + x0) * DP);
+    const int npx = min(COST_TX, w - x0);
+    for (int i = threadIdx.x; i < npx * groups; i += 256) {   // consecutive threads -> consecutive 4-byte words
+        const int px = i / groups, g = i - px * groups;
+        out[i] = s_out[px * gpad + g];
+    }
 }
 
 int launch_cost_u8(unsigned char* c8, const void* cl, const void* cr, int w, int h, int batch, int DP, int maxDisp,
                    int words, int popc_mode, cudaStream_t st) {
-    const long long threads = (long long)w * h * (DP >> 2);
-    dim3 grid((unsigned)cdiv(threads, 256), batch), block(256);
+    dim3 grid(cdiv(w, COST_TX), h, batch), block(256);
     const auto* l = (const unsigned long long*)cl;
     const auto* r = (const unsigned long long*)cr;
     const bool p64 = popc_mode == ROO_POPC64;
-#define ROO_COST(W)                                                                                  \
-    if (p64) cost_u8_kernel<W, true><<<grid, block, 0, st>>>(c8, l, r, w, h, DP, maxDisp);           \
-    else cost_u8_kernel<W, false><<<grid, block, 0, st>>>(c8, l, r, w, h, DP, maxDisp)
-    if (words == 1) { ROO_COST(1); }
-    else if (words == 2) { ROO_COST(2); }
-    else if (words == 4) { ROO_COST(4); }
+    const size_t smem = (size_t)words * (COST_TX + DP - 1 + COST_TX) * 8 + (size_t)COST_TX * (DP / 4 + 1) * 4;
+#define ROO_COST(W)                                                                                        \
+    do {                                                                                                   \
+        auto kern = p64 ? cost_u8_kernel<W, true> : cost_u8_kernel<W, false>;                              \
+        if (smem > 48 * 1024) ROO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, block, smem, st>>>(c8, l, r, w, h, DP, maxDisp);                                      \
+    } while (0)
+    if (words == 1) ROO_COST(1);
+    else if (words == 2) ROO_COST(2);
+    else if (words == 4) ROO_COST(4);
     else return ROO_ERR_INVALID_ARGUMENT;
 #undef ROO_COST
     count_launch();

@@ -28,14 +28,6 @@
 namespace roo_b200 {
 
 constexpr int SWEEP_WARPS = 4;   // warps (= scanlines) per CTA
-constexpr int SWEEP_PF = 4;      // prefetch distance in path steps
-
-template <int DPL, int COST>
-struct Stage {
-    float hin[DPL];
-    RawCost<DPL, COST> c;
-    float pix;
-};
 
 struct Scanline { int x0, y0, len; };
 
@@ -54,11 +46,24 @@ __device__ __forceinline__ Scanline scanline_of(int s, int w, int h, int dx, int
     return sl;
 }
 
+// prefetch depth in path steps (stages of one pixel each, staged global -> shared by cp.async): under load a
+// DRAM access takes ~3000 SM cycles on B200, so each SM needs 60-80 KB in flight to stream at HBM speed
+__host__ __device__ constexpr int sweep_pfs(int DPL, int CE) { return DPL >= 8 ? 4 : (DPL == 4 && CE == 4 ? 4 : 8); }
+template <int DPL, int COST> __host__ __device__ constexpr int sweep_stage_bytes() { return 32 * DPL * 4 + 32 * DPL * RawCost<DPL, COST>::ELEM + 16; }
+
 template <int DPL, int COST, int EPI, bool FIRST, bool IEEE>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
+    constexpr int DP = 32 * DPL;
+    constexpr int CE = RawCost<DPL, COST>::ELEM;
+    constexpr int PFS = sweep_pfs(DPL, CE);
+    constexpr int STAGE_B = sweep_stage_bytes<DPL, COST>();
+    extern __shared__ __align__(16) unsigned char sweep_smem[];   // [SWEEP_WARPS][PFS][STAGE_B]
+
     const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * SWEEP_WARPS + (threadIdx.x >> 5);
+    // warp index through a shuffle: provably warp-uniform, so the branches below are uniform branches
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int s = blockIdx.x * SWEEP_WARPS + warp;
     if (s >= n_scan) return;
     const int pair = blockIdx.y;
     const int w = a.w, dx = a.dx, M = a.maxDisp, subpix = a.subpix;
@@ -66,50 +71,55 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
     const Scanline sl = scanline_of(s, w, a.h, dx, a.dy);
     const int len = sl.len;
     const int d0 = lane * DPL;
-    constexpr int DP = 32 * DPL;
-    constexpr int CE = RawCost<DPL, COST>::ELEM;
-    constexpr int PF = SWEEP_PF;
 
     // element (x0,y0,d0) and the per-step strides; every access below is pointer + running offset
     const size_t e0 = ((size_t)sl.y0 * w + sl.x0) * DP + d0;
     const ptrdiff_t pstep = (ptrdiff_t)a.dy * w + dx;      // pixels per path step
     const ptrdiff_t estep = pstep * DP;                    // elements per path step
     float* hst = a.H + (size_t)pair * a.h_pair + e0;                                  // store cursor
-    const float* hld = hst;                                                           // load cursor (runs PF ahead)
+    const float* hld = hst;                                                           // prefetch cursors
     const char* cld = (const char*)a.C + ((size_t)pair * a.c_pair + e0) * CE;
     const float* ild = a.img + (size_t)pair * a.img_pair + (size_t)sl.y0 * w + sl.x0;
     float* dst = (EPI != EPI_NONE) ? a.disp + (size_t)pair * a.disp_pair + (size_t)sl.y0 * w + sl.x0 : nullptr;
 
-    // Prefetch ring.  Loads are UNCONDITIONAL (past the end of the scanline the cursor stops advancing and re-reads
-    // the last pixel): a predicated load has to preserve its destination when off, and the register move ptxas
-    // inserts for that waits on the load, exposing the DRAM latency once per ring revolution.
-    Stage<DPL, COST> ring[PF];
-    auto load_stage = [&](Stage<DPL, COST>& st, bool advance) {
-        const ptrdiff_t es = advance ? estep : 0, ps = advance ? pstep : 0;
-        hld += es; cld += es * CE; ild += ps;
-        if (!FIRST) load_f<DPL>(st.hin, hld);
-        st.c.load(cld);
-        st.pix = *ild;
+    // Prefetch: step r+PFS-1 is copied global -> shared (asynchronously, no registers) while step r is computed.
+    // Every lane copies and later reads its own bytes; only the intensity (lane 0) needs the __syncwarp.
+    const unsigned pfBase = (unsigned)__cvta_generic_to_shared(sweep_smem) + warp * PFS * STAGE_B;
+    auto issue_step = [&](int rl) {
+        if (rl < len) {
+            const unsigned sd = pfBase + ((unsigned)rl & (PFS - 1)) * STAGE_B;
+            if (!FIRST) cp_async_bytes<DPL * 4>(sd + lane * DPL * 4, hld);
+            cp_async_bytes<DPL * CE>(sd + DP * 4 + lane * DPL * CE, cld);
+            if (lane == 0) cp_async_bytes<4>(sd + DP * 4 + DP * CE, ild);
+            hld += estep; cld += estep * CE; ild += pstep;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-#pragma unroll
-    for (int k = 0; k < PF; ++k) load_stage(ring[k], k > 0 && k < len);
+    for (int k = 0; k < PFS - 1; ++k) issue_step(k);
 
     float hp[DPL];
 #pragma unroll
     for (int j = 0; j < DPL; ++j) hp[j] = ROO_INF;   // path start: no previous pixel
     float lastBest = 0.0f, last_c = 0.0f;
     int x = sl.x0;
-    int r = 0;  // steps done
+    // all lanes in range iff x >= xf (possible only when maxDisp fills the padded range)
+    const int xf = (M == DP) ? DP - 1 : 0x3fffffff;
 
-    // one path step on ring slot `slot`; refills the slot with the stage PF steps ahead
-    auto step = [&](auto masked_tag, Stage<DPL, COST>& st, float p2) {
+    auto step = [&](auto masked_tag, int r) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        const float denom = 1.0f + fabsf(last_c - st.pix);
-        float hnew[DPL], best;
+        const unsigned stg = pfBase + ((unsigned)r & (PFS - 1)) * STAGE_B;
+        float hin[DPL], hnew[DPL], best, pix;
+        if (!FIRST) lds_vec<DPL>(hin, stg + lane * DPL * 4);
+        RawCost<DPL, COST> rc;
+        rc.lds(stg + DP * 4 + lane * DPL * CE);
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + DP * CE));
+        // start pixel: `volH += volC`, lastBestCr = 0 (cu_semi_global_matching.cu:31-35) == a step with P2 = 0
+        const float p2 = r == 0 ? 0.0f : P2;
+        const float denom = 1.0f + fabsf(last_c - pix);
         const int lim = MASKED ? min(M, x + 1) - d0 : 0;
-        sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, st.c, cscale, st.hin, lim, lane, hnew, hp, best);
-        lastBest = best;
-        last_c = st.pix;
+        sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, rc, cscale, hin, lim, lane, hnew, hp, best);
+        lastBest = r == 0 ? 0.0f : best;
+        last_c = pix;
         if (EPI != EPI_WTA_ONLY) store_f<DPL>(hst, hnew);
         hst += estep;
         if (EPI != EPI_NONE) {
@@ -118,70 +128,29 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
             dst += pstep;
         }
         x += dx;
-        ++r;
-        load_stage(st, r + PF - 1 < len);
-    };
-    // n steps starting at ring slot 0 (n is a multiple of PF except for the last phase of the scanline)
-    auto phase = [&](auto masked_tag, int n) {
-        int i = 0;
-        for (; i + PF <= n; i += PF) {
-#pragma unroll
-            for (int k = 0; k < PF; ++k) step(masked_tag, ring[k], P2);
-        }
-#pragma unroll
-        for (int k = 0; k < PF - 1; ++k)
-            if (i + k < n) step(masked_tag, ring[k], P2);
     };
 
-    // Lanes are all in range once x + 1 >= DP (possible only when maxDisp fills the padded range): those steps
-    // run the unmasked body.  x is monotonic along a scanline, so a scanline is at most one masked and one
-    // unmasked phase; phase lengths are rounded to multiples of PF (towards the masked side, which is always valid).
-    int nA, nB;       // steps in the first / second phase, AFTER the start pixel
-    bool a_masked;    // first phase masked?
-    {
-        const int rest = len - 1;
-        const int x1 = sl.x0 + dx;                       // x of step 1
-        const int xf = (M == DP) ? DP - 1 : 0x3fffffff;  // unmasked iff x >= xf
-        if (dx > 0) {
-            a_masked = true;
-            const int need = max(0, xf - x1);            // masked steps required
-            nA = min(rest, (need + PF - 1) / PF * PF);
-        } else if (dx == 0) {
-            a_masked = x1 < xf;
-            nA = rest;
-        } else {
-            a_masked = false;
-            const int ok = max(0, x1 - xf + 1);          // unmasked steps available
-            nA = min(rest, ok / PF * PF);
-        }
-        nB = rest - nA;
-    }
-
-    // start pixel: `volH += volC`, lastBestCr = 0 (cu_semi_global_matching.cu:31-35) == a step with P2 = 0
-    step(std::true_type{}, ring[0], 0.0f);
-    lastBest = 0.0f;
-    // rotate so that the next step is ring slot 0 again
-    {
-        const Stage<DPL, COST> t = ring[0];
-#pragma unroll
-        for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
-        ring[PF - 1] = t;
-    }
 #pragma unroll 1
-    for (int ph = 0; ph < 2; ++ph) {
-        const int n = ph == 0 ? nA : nB;
-        const bool masked = ph == 0 ? a_masked : !a_masked;
-        if (n <= 0) continue;
-        if (masked) phase(std::true_type{}, n);
-        else phase(std::false_type{}, n);
-        // a phase that is followed by another one is a multiple of PF: the ring is back at slot 0
+    for (int r = 0; r < len; ++r) {
+        issue_step(r + PFS - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(PFS - 1) : "memory");   // step r's stage has landed
+        __syncwarp();
+        if (x >= xf) step(std::false_type{}, r);
+        else step(std::true_type{}, r);
     }
 }
 
 template <int DPL, int COST, int EPI>
 static void sweep_launch3(const SweepArgs& a, int n_scan, dim3 grid, cudaStream_t st) {
     const bool ieee = g_ieee_div.load() != 0;
-#define ROO_SWEEP(F, I) sgm_sweep_kernel<DPL, COST, EPI, F, I><<<grid, SWEEP_WARPS * 32, 0, st>>>(a, n_scan)
+    constexpr int CE = RawCost<DPL, COST>::ELEM;
+    const size_t smem = (size_t)SWEEP_WARPS * sweep_pfs(DPL, CE) * sweep_stage_bytes<DPL, COST>();
+#define ROO_SWEEP(F, I)                                                                                  \
+    do {                                                                                                 \
+        auto kern = sgm_sweep_kernel<DPL, COST, EPI, F, I>;                                              \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<grid, SWEEP_WARPS * 32, smem, st>>>(a, n_scan);                                           \
+    } while (0)
     if (a.first) { if (ieee) ROO_SWEEP(true, true); else ROO_SWEEP(true, false); }
     else { if (ieee) ROO_SWEEP(false, true); else ROO_SWEEP(false, false); }
 #undef ROO_SWEEP

@@ -84,66 +84,11 @@ __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) 
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-// BYTES per lane from global to a 32-bit shared address; 16-byte pieces bypass L1 (.cg), smaller ones use .ca
-// (only used for data that is read-only during the pass)
-template <int BYTES>
-__device__ __forceinline__ void cp_async_bytes(unsigned sdst, const void* gsrc) {
-    if constexpr (BYTES % 16 == 0) {
-#pragma unroll
-        for (int q = 0; q < BYTES / 16; ++q)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16 * q), "l"((const char*)gsrc + 16 * q) : "memory");
-    } else if constexpr (BYTES == 8) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst), "l"(gsrc) : "memory");
-    } else if constexpr (BYTES == 4) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
-    } else {
-        static_assert(BYTES == 2 || BYTES == 1, "unsupported cp.async size");
-        // 1- and 2-byte cost rows (DPL 1/2 with u8 costs): plain load + shared store
-        if constexpr (BYTES == 2) { const unsigned short v = *(const unsigned short*)gsrc; asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst), "h"(v) : "memory"); }
-        else { const unsigned v = *(const unsigned char*)gsrc; asm volatile("st.shared.u8 [%0], %1;" ::"r"(sdst), "r"(v) : "memory"); }
-    }
-}
-
 template <int DPL>
 __device__ __forceinline__ void cp_async_row(float* smem_dst, const float* gsrc) {
     static_assert(DPL >= 4, "cp.async.cg moves 16 bytes");
 #pragma unroll
     for (int q = 0; q < DPL / 4; ++q) cp_async_16(smem_dst + 4 * q, gsrc + 4 * q);
-}
-
-// shared-memory vector access by 32-bit shared-window address
-__device__ __forceinline__ float4 lds_f4(unsigned addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_f4(unsigned addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-template <int DPL>
-__device__ __forceinline__ void lds_vec(float (&v)[DPL], unsigned addr) {
-    if constexpr (DPL >= 4) {
-#pragma unroll
-        for (int q = 0; q < DPL / 4; ++q) {
-            const float4 t = lds_f4(addr + 16 * q);
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-    } else if constexpr (DPL == 2) {
-        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
-    } else {
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
-    }
-}
-template <int DPL>
-__device__ __forceinline__ void sts_vec(unsigned addr, const float (&v)[DPL]) {
-    if constexpr (DPL >= 4) {
-#pragma unroll
-        for (int q = 0; q < DPL / 4; ++q) sts_f4(addr + 16 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-    } else if constexpr (DPL == 2) {
-        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v[0]), "f"(v[1]) : "memory");
-    } else {
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v[0]) : "memory");
-    }
 }
 
 template <int DPL, int COST>

@@ -20,7 +20,11 @@
 //     ping-pong: a band never waits for a band that waits for it, and lower block indices (scheduled
 //     first) never wait for higher ones.
 //   * a dedicated communication warp per CTA polls the upstream flag, stages the upstream edge rows into
-//     shared memory and publishes this band's flag, so the NW compute warps never touch the flags.
+//     shared memory and publishes this band's flag, so the compute warps never touch the global flags.
+//   * every compute warp owns TWO adjacent skewed columns (B = u, A = u+1) and advances both by one row per
+//     tick: the vertical path of B continues from A's state of the previous tick (registers), so only three
+//     state rows per tick go through shared memory, and the per-tick bookkeeping (hand-off flags, prefetch
+//     issue, addressing) is paid once for two pixels.
 // HBM traffic of the pass: read H (unless first) + read cost + write H -- the same as ONE single-path sweep.
 #include <type_traits>
 
@@ -30,14 +34,13 @@
 
 namespace roo_b200 {
 
-// rows of prefetch, staged in shared memory by cp.async (LDGSTS): under load a DRAM access takes ~3000 SM
-// cycles on B200, so a band needs ~60-80 KB in flight per SM to stream at HBM speed -- far more than a
-// register ring can hold, and without unrolling the row loop
-__host__ __device__ constexpr int vg_pfs(int DPL, int CE) { return DPL >= 8 ? (CE == 4 ? 2 : 4) : (DPL == 4 && CE == 4 ? 4 : 8); }   // (227 KB of shared memory per CTA)
-// skewed columns (compute warps) per band: 16 (+1 communication warp) leaves 120 registers per thread, enough
-// for DPL <= 4; the 256-disparity variant keeps twice the state per lane and runs 12 + 1 warps
-constexpr int vg_nw(int DPL) { return DPL >= 8 ? 12 : 16; }
-inline int vg_nw_of_dp(int DP) { return vg_nw(DP / 32); }
+// rows of prefetch per column, staged in shared memory by cp.async (LDGSTS): under load a DRAM access takes
+// ~3000 SM cycles on B200, so a band needs ~60-80 KB in flight per SM to stream at HBM speed -- far more
+// than a register ring can hold, and without unrolling the row loop.  (227 KB of shared memory per CTA.)
+__host__ __device__ constexpr int vg_pfs(int DPL, int CE) { return DPL >= 8 ? 2 : (DPL == 4 && CE == 4 ? 2 : 4); }
+// compute warps per band (each owns two skewed columns) + 1 communication warp
+__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : 12; }
+inline int vg_cols_of_dp(int DP) { return 2 * vg_nww(DP / 32); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -91,13 +94,6 @@ __device__ __forceinline__ void cp_async_row(float* smem_dst, const float* gsrc)
     for (int q = 0; q < DPL / 4; ++q) cp_async_16(smem_dst + 4 * q, gsrc + 4 * q);
 }
 
-template <int DPL, int COST>
-struct VStage {
-    float hin[DPL];
-    RawCost<DPL, COST> c;
-    float pix;
-};
-
 // Ordering of shared-memory accesses between warps of one CTA.  Data and flag both live in shared memory
 // and every access is issued through the same in-order LSU pipeline of the SM, so program order (enforced
 // for the compiler by the volatile flag accesses and this barrier) is enough; a MEMBAR here would also wait
@@ -107,33 +103,81 @@ __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
 // smem control words
 struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 
+
 __host__ __device__ constexpr int vg_r(int DPL) { return DPL >= 8 ? 4 : 8; }   // max rows per hand-off batch between bands (ring = 2x)
 #ifndef VG_SPIN_NS
 #define VG_SPIN_NS 30
 #endif
 constexpr int VG_S = 4;   // depth (rows) of the in-band state ring in shared memory
 
-template <int DPL, int COST, bool FIRST, bool IEEE, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
+// One pixel of the three paths.  V/D/A = vertical / diagonal / anti-diagonal.  hpV, hpD, hpA: previous pixel's
+// state rows on entry, this pixel's on exit.  Handles path starts when EDGE.
+template <int DPL, int COST, bool MASKED, bool EDGE, bool FIRST, bool IEEE>
+__device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, int x, int w, int M, float P1, float P2,
+                                         float cscale, float (&hpV)[DPL], float& lbV, float ppV,
+                                         float (&hpD)[DPL], float& lbD, float& pixD,
+                                         float (&hpA)[DPL], float& lbA, float ppA, float& pix_out, float* hst) {
+    constexpr int DP = 32 * DPL;
+    constexpr int CE = RawCost<DPL, COST>::ELEM;
+    const int lim = MASKED ? min(M, x + 1) - lane * DPL : 0;
+    float hin[DPL], H3[DPL], cost[DPL];
+    if (!FIRST) lds_vec<DPL>(hin, stg + lane * DPL * 4);
+    RawCost<DPL, COST> rc;
+    rc.lds(stg + DP * 4 + lane * DPL * CE);
+    float pix;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + DP * CE));
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) cost[j] = rc.get(j, cscale);
+    float p2V = P2, p2D = P2, p2A = P2;
+    bool sV = false, sD = false, sA = false;
+    if (EDGE) {
+        sV = y == 0; sD = y == 0 || xp == 0; sA = y == 0 || xp == w - 1;
+        if (sV) { lbV = 0.0f; ppV = pix; p2V = 0.0f; }
+        if (sD) { lbD = 0.0f; p2D = 0.0f; }
+        if (sA) { lbA = 0.0f; ppA = pix; p2A = 0.0f; }
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            hpV[j] = sV ? ROO_INF : hpV[j];
+            hpD[j] = sD ? ROO_INF : hpD[j];
+            hpA[j] = sA ? ROO_INF : hpA[j];
+        }
+    }
+    float bV, bD, bA;
+    sgm_step3<DPL, MASKED, FIRST, IEEE>(hpV, lbV, 1.0f + fabsf(ppV - pix), p2V,
+                                        hpD, lbD, 1.0f + fabsf(pixD - pix), p2D,
+                                        hpA, lbA, 1.0f + fabsf(ppA - pix), p2A,
+                                        cost, hin, P1, lim, lane, H3, bV, bD, bA);
+    if (EDGE) { if (sV) bV = 0.0f; if (sD) bD = 0.0f; if (sA) bA = 0.0f; }
+    lbV = bV; lbD = bD; lbA = bA;
+    pixD = pix;
+    pix_out = pix;
+    store_f<DPL>(hst, H3);
+}
+
+template <int DPL, int COST, bool FIRST, bool IEEE, int NWW>
+__global__ void __launch_bounds__((NWW + 1) * 32, 1)
 sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int DP = 32 * DPL;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
+    constexpr int NC = 2 * NWW;                       // skewed columns per band
     constexpr int PFS = vg_pfs(DPL, CE);
     constexpr int R = vg_r(DPL), RING = 2 * R, S = VG_S;
     constexpr int STAGE_B = DP * 4 + DP * CE + 16;   // one prefetched pixel: aggregate row, cost row, intensity
     extern __shared__ __align__(16) float smem[];
-    float* s_hp = smem;                                // [S rows][NW][2 paths][DP]  in-band states (row ring)
-    float* s_sc = s_hp + S * NW * 2 * DP;              // [S rows][NW][4]: lastBest(vertical), lastBest(anti-diag), pix, -
-    float* s_halo = s_sc + S * NW * 4;                 // [RING rows][3][DP]  upstream band's columns 0,1 (row ring)
+    // state rows of one warp and one image row: rec0 = B.vertical, rec1 = B.anti-diagonal, rec2 = A.anti-diagonal;
+    // scalars {B.lastBest(V), B.lastBest(A), B.pix, -, -, A.lastBest(A), A.pix, -}: the same record layout is
+    // used by the band-to-band edge rows, so a warp reads "the three rows of whoever is above me" with one formula
+    float* s_hp = smem;                                // [S rows][NWW][3][DP]
+    float* s_sc = s_hp + S * NWW * 3 * DP;             // [S rows][NWW][8]
+    float* s_halo = s_sc + S * NWW * 8;                // [RING rows][3][DP]  upstream band's lowest warp (row ring)
     float* s_hsc = s_halo + RING * 3 * DP;             // [RING][8]
-    float* s_edge = s_hsc + RING * 8;                  // [RING rows][3][DP]  this band's columns 0,1 for downstream
+    float* s_edge = s_hsc + RING * 8;                  // [RING rows][3][DP]  this band's lowest warp, for downstream
     float* s_esc = s_edge + RING * 3 * DP;             // [RING][8]
     VCtl* ctl = reinterpret_cast<VCtl*>(s_esc + RING * 8);
-    volatile int* prog = reinterpret_cast<volatile int*>(ctl + 1);   // [NW] rows < prog[j] of column j are done
-    char* s_pf = reinterpret_cast<char*>(ctl + 1) + ((NW * 4 + 15) / 16) * 16;   // [NW][PFS][STAGE_B] prefetch stages
+    volatile int* prog = reinterpret_cast<volatile int*>(ctl + 1);   // [NWW] rows < prog[v] of warp v are done
+    char* s_pf = reinterpret_cast<char*>(ctl + 1) + ((NWW * 4 + 15) / 16) * 16;   // [NWW][2 cols][PFS][STAGE_B]
 
-    // warp index through a shuffle: ptxas then knows it is warp-uniform, and every branch on it (roles, masks,
-    // path starts) is a uniform branch without divergence bookkeeping around the shuffles / redux below
+    // warp index through a shuffle: ptxas then knows it is warp-uniform, and every branch on it is a uniform branch
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // pair fastest: the resident window of CTAs then holds the same few bands of EVERY pair, so the
     // band-to-band pipeline of each pair has only a short ramp
@@ -142,12 +186,12 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     const bool fwd = a.fwd != 0;
     const float P1 = a.P1, P2 = a.P2, cscale = a.cost_scale;
 
-    const int ulo = w - (band + 1) * NW;                 // lowest skewed column of this band
-    const int ymin = max(0, -(ulo + NW - 1));
+    const int ulo = w - (band + 1) * NC;                 // lowest skewed column of this band
+    const int ymin = max(0, -(ulo + NC - 1));
     const int ymax = min(h - 1, w - 1 - ulo);
     // upstream band (higher u) and the rows of it this band consumes: row y-1 for every own row y >= 1
-    const int pulo = ulo + NW;
-    const int pymin = max(0, -(pulo + NW - 1));
+    const int pulo = ulo + NC;
+    const int pymin = max(0, -(pulo + NC - 1));
     const int pymax = band > 0 ? min(h - 1, w - 1 - pulo) : -1;
     const int hbeg = max(pymin, ymin - 1), hend = min(pymax, ymax - 1) + 1;   // [hbeg, hend) upstream rows to stage
     const bool downstream = band + 1 < a.n_bands;
@@ -156,15 +200,17 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     float* e_sc = a.edge_sc + ((size_t)pair * a.n_bands + band) * (size_t)h * 8;
     int* my_flag = a.progress + (size_t)pair * a.n_bands + band;
 
-    // active rows of skewed column u: x' = u + y' in [0, w)
-    const int u = ulo + warp;
-    const int y_in = max(0, -u), y_out = min(h - 1, w - 1 - u);
-    const bool any = warp < NW && y_in <= y_out;
+    // this warp's two skewed columns and their active rows (x' = u + y' in [0, w))
+    const int uB = ulo + 2 * warp, uA = uB + 1;
+    const int yinA = max(0, -uA), youtA = min(h - 1, w - 1 - uA);
+    const int yinB = max(0, -uB), youtB = min(h - 1, w - 1 - uB);
+    const int y_in = min(yinA, yinB), y_out = max(youtA, youtB);   // A enters first, B leaves last
+    const bool any = warp < NWW && y_in <= y_out;
     if (threadIdx.x == 0) { ctl->halo_ready = hbeg; ctl->copied = ymin; }
-    if (warp < NW && lane == 0) prog[warp] = any ? y_in : 0x7fffffff;   // rows before y_in never happen
+    if (warp < NWW && lane == 0) prog[warp] = any ? y_in : 0x7fffffff;   // rows before y_in never happen
     __syncthreads();
 
-    if (warp == NW) {
+    if (warp == NWW) {
         // ---------------------------------------------------------------- communication warp
         const float* p_hp = e_hp - (size_t)h * 3 * DP;   // upstream band's rows
         const float* p_sc = e_sc - (size_t)h * 8;
@@ -173,13 +219,13 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         const int cp_end = downstream ? ymax + 1 : ymin;  // nothing to publish for the last band
         while (hr < hend || cp < cp_end) {
             bool progress = false;
-            // ---- stage a chunk of upstream rows into the halo ring (readers: the last two columns)
+            // ---- stage upstream rows into the halo ring (reader: the highest warp)
             if (hr < hend) {
                 // adaptive batch: whatever the upstream band has published and the ring can take (1..R rows) --
                 // the hand-off latency is one turn of this loop, not the time to fill a fixed chunk.  The paths
-                // that run across the bands (anti-diagonal: a new band every NW/2 rows) are a serial chain of such
+                // that run across the bands (anti-diagonal: a new band every NC/2 rows) are a serial chain of such
                 // hand-offs, so this latency, not the copy bandwidth, bounds a single pair's pass.
-                const int rdh = min(prog[NW - 1], prog[NW - 2]);
+                const int rdh = prog[NWW - 1];
                 if (seen <= hr) {
                     if (lane == 0) seen = ld_acquire_gpu(p_flag);
                     seen = __shfl_sync(0xffffffffu, seen, 0);
@@ -187,36 +233,33 @@ sgm_vgroup_kernel(const VGroupArgs a) {
                 // ring slot of row y was last used by row y-RING, read while computing row y-RING+1
                 const int n = min(min(R, hend - hr), min(seen - hr, rdh + RING - 1 - hr));
                 if (n > 0) {
-                    {
-                        for (int y = hr; y < hr + n; ++y) {
-                            const float* src = p_hp + (size_t)y * 3 * DP + lane * DPL;
-                            float* dst = s_halo + (size_t)(y % RING) * 3 * DP + lane * DPL;
-                            if constexpr (DPL >= 4) {
+                    for (int y = hr; y < hr + n; ++y) {
+                        const float* src = p_hp + (size_t)y * 3 * DP + lane * DPL;
+                        float* dst = s_halo + (size_t)(y % RING) * 3 * DP + lane * DPL;
+                        if constexpr (DPL >= 4) {
 #pragma unroll
-                                for (int q = 0; q < 3; ++q) cp_async_row<DPL>(dst + q * DP, src + q * DP);
-                            } else {   // < 16 B per lane: cp.async would need .ca, and L1 must not cache rows still being written
-                                float r0[DPL], r1[DPL], r2[DPL];
-                                ldcg_row<DPL>(r0, src); ldcg_row<DPL>(r1, src + DP); ldcg_row<DPL>(r2, src + 2 * DP);
-                                sts_row<DPL>(dst, r0); sts_row<DPL>(dst + DP, r1); sts_row<DPL>(dst + 2 * DP, r2);
-                            }
-                            if (lane < 2) cp_async_16(s_hsc + (y % RING) * 8 + lane * 4, p_sc + (size_t)y * 8 + lane * 4);
+                            for (int q = 0; q < 3; ++q) cp_async_row<DPL>(dst + q * DP, src + q * DP);
+                        } else {   // < 16 B per lane: cp.async would need .ca, and L1 must not cache rows still being written
+                            float r0[DPL], r1[DPL], r2[DPL];
+                            ldcg_row<DPL>(r0, src); ldcg_row<DPL>(r1, src + DP); ldcg_row<DPL>(r2, src + 2 * DP);
+                            sts_row<DPL>(dst, r0); sts_row<DPL>(dst + DP, r1); sts_row<DPL>(dst + 2 * DP, r2);
                         }
-                        asm volatile("cp.async.commit_group;" ::: "memory");
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        __syncwarp();
-                        hr += n;
-                        if (lane == 0) { __threadfence_block(); ctl->halo_ready = hr; }
-                        progress = true;
+                        if (lane < 2) cp_async_16(s_hsc + (y % RING) * 8 + lane * 4, p_sc + (size_t)y * 8 + lane * 4);
                     }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    hr += n;
+                    if (lane == 0) { __threadfence_block(); ctl->halo_ready = hr; }
+                    progress = true;
                 }
             }
-            // ---- publish finished rows of this band's columns 0,1 (writers: the first two columns)
+            // ---- publish finished rows of this band's lowest warp
             if (cp < cp_end) {
-                const int rd = min(min(prog[0], prog[1]), ymax + 1);
+                const int rd = min((int)prog[0], ymax + 1);
                 if (rd > cp) {   // publish every finished row at once (see the latency note above)
                     __threadfence_block();
-                    const int rd_lim = min(rd, cp + RING);
-                    for (int y = cp; y < rd_lim; ++y) {
+                    for (int y = cp; y < rd; ++y) {
                         const float* src = s_edge + (size_t)(y % RING) * 3 * DP + lane * DPL;
                         float* dst = e_hp + (size_t)y * 3 * DP + lane * DPL;
                         float r0[DPL], r1[DPL], r2[DPL];
@@ -245,150 +288,152 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     if (!any) return;
 
     // -------------------------------------------------------------------- compute warps
-    const int d0 = lane * DPL;
     const int xf = (M == DP) ? DP - 1 : 0x3fffffff;               // all lanes in range iff true x >= xf
-
-    // cursors at the first active pixel; one row down the travel direction = +-(w+1) pixels
-    const int xp0 = u + y_in;
-    const int x0 = fwd ? xp0 : w - 1 - xp0, y0 = fwd ? y_in : h - 1 - y_in;
-    const ptrdiff_t pstep = fwd ? (ptrdiff_t)(w + 1) : -(ptrdiff_t)(w + 1);
+    const int d0 = lane * DPL;
+    const ptrdiff_t pstep = fwd ? (ptrdiff_t)(w + 1) : -(ptrdiff_t)(w + 1);   // one row down the travel direction
     const ptrdiff_t estep = pstep * DP;
-    const size_t e0 = ((size_t)y0 * w + x0) * DP + d0;
-    float* hst = a.H + (size_t)pair * a.h_pair + e0;
-    const float* hld = hst;
-    const char* cld = (const char*)a.C + ((size_t)pair * a.c_pair + e0) * CE;
-    const float* ild = a.img + (size_t)pair * a.img_pair + (size_t)y0 * w + x0;
 
-    // Prefetch: row y+PFS-1 is copied global -> shared (asynchronously, no registers) while row y is computed.
-    // Every lane copies and later reads its own bytes; only the intensity (lane 0) needs a __syncwarp.
-    const unsigned pfBase = (unsigned)__cvta_generic_to_shared(s_pf) + warp * PFS * STAGE_B;
+    // per-column cursors at the column's first active pixel
+    auto first_px = [&](int u, int yin, size_t& e0, size_t& p0) {
+        const int xp0 = u + yin;
+        const int x0 = fwd ? xp0 : w - 1 - xp0, y0 = fwd ? yin : h - 1 - yin;
+        p0 = (size_t)y0 * w + x0;
+        e0 = p0 * DP + d0;
+    };
+    size_t e0A = 0, p0A = 0, e0B = 0, p0B = 0;
+    if (yinA <= youtA) first_px(uA, yinA, e0A, p0A);
+    if (yinB <= youtB) first_px(uB, yinB, e0B, p0B);
+    float* const Hp = a.H + (size_t)pair * a.h_pair;
+    const char* const Cp = (const char*)a.C + (size_t)pair * a.c_pair * CE;
+    const float* const Ip = a.img + (size_t)pair * a.img_pair;
+    float* hstA = Hp + e0A; const float* hldA = hstA; const char* cldA = Cp + e0A * CE; const float* ildA = Ip + p0A;
+    float* hstB = Hp + e0B; const float* hldB = hstB; const char* cldB = Cp + e0B * CE; const float* ildB = Ip + p0B;
+
+    // Prefetch: row y+PFS-1 of both columns is copied global -> shared (asynchronously, no registers) while row y
+    // is computed.  Every lane copies and later reads its own bytes; only the intensity (lane 0) needs a __syncwarp.
+    const unsigned pfA = (unsigned)__cvta_generic_to_shared(s_pf) + (warp * 2) * PFS * STAGE_B;
+    const unsigned pfB = pfA + PFS * STAGE_B;
+    auto issue_px = [&](unsigned base, int yl, const float*& hld, const char*& cld, const float*& ild) {
+        const unsigned dst = base + ((unsigned)yl & (PFS - 1)) * STAGE_B;
+        if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hld);
+        cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cld);
+        if (lane == 0) cp_async_bytes<4>(dst + DP * 4 + DP * CE, ild);
+        hld += estep; cld += estep * CE; ild += pstep;
+    };
     auto issue_row = [&](int yl) {
-        if (yl <= y_out) {
-            const unsigned dst = pfBase + ((unsigned)yl & (PFS - 1)) * STAGE_B;
-            if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hld);
-            cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cld);
-            if (lane == 0) cp_async_bytes<4>(dst + DP * 4 + DP * CE, ild);
-            hld += estep; cld += estep * CE; ild += pstep;
-        }
+        if (yl >= yinA && yl <= youtA) issue_px(pfA, yl, hldA, cldA, ildA);
+        if (yl >= yinB && yl <= youtB) issue_px(pfB, yl, hldB, cldB, ildB);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     for (int k = 0; k < PFS - 1; ++k) issue_row(y_in + k);
 
     // ---- shared-memory addressing, resolved once per warp (32-bit shared-window addresses) ----
-    // State rows of the previous image row come either from the in-band ring (slot (y-1) & (S-1), stride one
-    // slot) or, for the two highest columns, from the upstream halo ring (slot (y-1) & (RING-1), stride one
-    // halo row): the same  base + ((y-1) & mask) * stride  serves both, so the row loop has no role branches.
+    // The three state rows of "the warp above" for image row y-1 come either from the in-band ring (slot
+    // (y-1) & (S-1)) or, for the highest warp, from the upstream halo ring (slot (y-1) & (RING-1)):
+    // base + ((y-1) & mask) * stride serves both, so the row loop has no role branches.
     const unsigned sh_hp = (unsigned)__cvta_generic_to_shared(s_hp), sh_sc = (unsigned)__cvta_generic_to_shared(s_sc);
     const unsigned sh_halo = (unsigned)__cvta_generic_to_shared(s_halo), sh_hsc = (unsigned)__cvta_generic_to_shared(s_hsc);
     const unsigned sh_edge = (unsigned)__cvta_generic_to_shared(s_edge), sh_esc = (unsigned)__cvta_generic_to_shared(s_esc);
-    constexpr unsigned SLOT_B = NW * 2 * DP * 4, SLOTSC_B = NW * 16, HROW_B = 3 * DP * 4, HSC_B = 32;
-    const bool vIn = warp + 1 < NW, aIn = warp + 2 < NW;
-    const unsigned vBase = vIn ? sh_hp + (warp + 1) * 2 * DP * 4 + lane * DPL * 4 : sh_halo + lane * DPL * 4;
-    const unsigned vStride = vIn ? SLOT_B : HROW_B, vMask = vIn ? S - 1 : RING - 1;
-    const unsigned vScBase = vIn ? sh_sc + (warp + 1) * 16 : sh_hsc, vScStride = vIn ? SLOTSC_B : HSC_B;
-    const unsigned aBase = aIn ? sh_hp + ((warp + 2) * 2 + 1) * DP * 4 + lane * DPL * 4
-                               : sh_halo + (warp + 2 == NW ? 1 : 2) * DP * 4 + lane * DPL * 4;
-    const unsigned aStride = aIn ? SLOT_B : HROW_B, aMask = aIn ? S - 1 : RING - 1;
-    const unsigned aScBase = aIn ? sh_sc + (warp + 2) * 16 : sh_hsc + (warp + 2 == NW ? 0 : 16);
-    const unsigned aScStride = aIn ? SLOTSC_B : HSC_B;
-    const unsigned myBase = sh_hp + warp * 2 * DP * 4 + lane * DPL * 4, myScBase = sh_sc + warp * 16;
-    const bool edge_out = warp < 2 && downstream;
-    const unsigned eBase = sh_edge + (warp == 0 ? 0 : 2) * DP * 4 + lane * DPL * 4, eScBase = sh_esc + warp * 16;
-    // hand-off flags: rows < *flag of the producer are done.  Absent producers / consumers read a constant.
-    volatile int* const fV = vIn ? prog + warp + 1 : &ctl->halo_ready;
-    volatile int* const fA = aIn ? prog + warp + 2 : &ctl->halo_ready;
-    volatile int* const fW1 = warp >= 1 ? prog + warp - 1 : fV;   // no consumer: alias a flag that is already waited on
-    volatile int* const fW2 = warp >= 2 ? prog + warp - 2 : fV;
-    volatile int* const fC = edge_out ? &ctl->copied : fV;
-    const int vCap = vIn ? 0x7fffffff : hend, aCap = aIn ? 0x7fffffff : hend;
-    const int wOff = S - 2;            // consumers must have finished row y-S+1  <=>  prog >= y-S+2
+    constexpr unsigned REC_B = DP * 4, SLOT_B = NWW * 3 * REC_B, SLOTSC_B = NWW * 32, HROW_B = 3 * REC_B, HSC_B = 32;
+    const bool upIn = warp + 1 < NWW;
+    const unsigned upBase = (upIn ? sh_hp + (warp + 1) * 3 * REC_B : sh_halo) + lane * DPL * 4;
+    const unsigned upStride = upIn ? SLOT_B : HROW_B, upMask = upIn ? S - 1 : RING - 1;
+    const unsigned upScBase = upIn ? sh_sc + (warp + 1) * 32 : sh_hsc, upScStride = upIn ? SLOTSC_B : HSC_B;
+    const unsigned myBase = sh_hp + warp * 3 * REC_B + lane * DPL * 4, myScBase = sh_sc + warp * 32;
+    const bool edge_out = warp == 0 && downstream;
+    const unsigned eBase = sh_edge + lane * DPL * 4;
+    // hand-off flags: rows < *flag of the producer are done
+    volatile int* const fUp = upIn ? prog + warp + 1 : &ctl->halo_ready;
+    volatile int* const fDn = warp >= 1 ? prog + warp - 1 : fUp;   // no consumer: alias a flag that is already waited on
+    const int upCap = upIn ? 0x7fffffff : hend;   // an upstream band only publishes rows < hend
+    const int wOff = S - 2;            // the consumer must have finished row y-S+1  <=>  prog >= y-S+2
     const int cOff = RING - 1;         // downstream ring slot free once rows < y-RING+1 were copied out
 
-    // diagonal path state (registers)
-    float hpd[DPL];
+    // register state: diagonal path of both columns; A's vertical state of the previous row (input of B's vertical path)
+    float dA[DPL], dB[DPL], vA[DPL];
 #pragma unroll
-    for (int j = 0; j < DPL; ++j) hpd[j] = ROO_INF;
-    float lbd = 0.0f, pixd = 0.0f;
+    for (int j = 0; j < DPL; ++j) { dA[j] = ROO_INF; dB[j] = ROO_INF; vA[j] = ROO_INF; }
+    float lbDA = 0.0f, pixDA = 0.0f, lbDB = 0.0f, pixDB = 0.0f, lbVA = 0.0f, pixA = 0.0f;
 
-    // EDGE rows contain a path start (y == 0, x' == 0 or x' == w-1); all other rows take the lean body.
-    auto row_body = [&](auto masked_tag, auto edge_tag, int y, int xp, int x) {
+    auto tick = [&](auto masked_tag, auto edge_tag, int y) {
         constexpr bool MASKED = decltype(masked_tag)::value;
         constexpr bool EDGE = decltype(edge_tag)::value;
-        const int lim = MASKED ? min(M, x + 1) - d0 : 0;
-        const unsigned stg = pfBase + ((unsigned)y & (PFS - 1)) * STAGE_B;
-        float hin[DPL], hpV[DPL], hpA[DPL], H3[DPL], cost[DPL];
-        if (!FIRST) lds_vec<DPL>(hin, stg + lane * DPL * 4);
-        RawCost<DPL, COST> rc;
-        rc.lds(stg + DP * 4 + lane * DPL * CE);
-        float pix;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + DP * CE));
-#pragma unroll
-        for (int j = 0; j < DPL; ++j) cost[j] = rc.get(j, cscale);
         const unsigned ym1 = (unsigned)(y - 1);
-        lds_vec<DPL>(hpV, vBase + (ym1 & vMask) * vStride);
-        lds_vec<DPL>(hpA, aBase + (ym1 & aMask) * aStride);
-        const float4 scV = lds_f4(vScBase + (ym1 & vMask) * vScStride);   // {lastBest(vertical), lastBest(anti), pix, -}
-        const float4 scA = lds_f4(aScBase + (ym1 & aMask) * aScStride);
-        float lbV = scV.x, ppV = scV.z, p2V = P2, lbA = scA.y, ppA = scA.z, p2A = P2, p2D = P2;
-        bool sV = false, sD = false, sA = false;
-        if (EDGE) {
-            sV = y == 0; sD = y == 0 || xp == 0; sA = y == 0 || xp == w - 1;
-            if (sV) { lbV = 0.0f; ppV = pix; p2V = 0.0f; }
-            if (sD) { lbd = 0.0f; p2D = 0.0f; }
-            if (sA) { lbA = 0.0f; ppA = pix; p2A = 0.0f; }
+        const unsigned up = upBase + (ym1 & upMask) * upStride;
+        const unsigned upsc = upScBase + (ym1 & upMask) * upScStride;
+        const unsigned slot = (unsigned)y & (S - 1);
+        const unsigned mine = myBase + slot * SLOT_B;
+        const bool actA = !EDGE || (y >= yinA && y <= youtA);
+        const bool actB = !EDGE || (y >= yinB && y <= youtB);
+        const float4 scUpB = lds_f4(upsc);        // upper warp's B: {lastBest(V), lastBest(A), pix, -}
+        const float4 scUpA = lds_f4(upsc + 16);   // upper warp's A: {-, lastBest(A), pix, -}
+        float bBV = 0.0f, bBA = 0.0f, pixB = 0.0f, bAA = 0.0f;
+        // ---- column B (lower): vertical continues from A's previous row (registers), anti-diagonal from upper B
+        if (actB) {
+            const int xp = uB + y, x = fwd ? xp : w - 1 - xp;
+            float hv[DPL], ha[DPL];
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                hpV[j] = sV ? ROO_INF : hpV[j];
-                hpd[j] = sD ? ROO_INF : hpd[j];
-                hpA[j] = sA ? ROO_INF : hpA[j];
+            for (int j = 0; j < DPL; ++j) hv[j] = vA[j];
+            lds_vec<DPL>(ha, up + REC_B);
+            float lbV = lbVA, lbA = scUpB.y;
+            vg_pixel<DPL, COST, MASKED, EDGE, FIRST, IEEE>(pfB + ((unsigned)y & (PFS - 1)) * STAGE_B, lane, y, xp, x, w, M, P1, P2,
+                                                           cscale, hv, lbV, pixA, dB, lbDB, pixDB, ha, lbA, scUpB.z, pixB, hstB);
+            hstB += estep;
+            sts_vec<DPL>(mine, hv);
+            sts_vec<DPL>(mine + REC_B, ha);
+            if (edge_out) {
+                const unsigned er = eBase + ((unsigned)y & (RING - 1)) * HROW_B;
+                sts_vec<DPL>(er, hv);
+                sts_vec<DPL>(er + REC_B, ha);
+            }
+            bBV = lbV; bBA = lbA;
+        }
+        // ---- column A (upper): vertical from upper B, anti-diagonal from upper A; its vertical state stays in registers
+        if (actA) {
+            const int xp = uA + y, x = fwd ? xp : w - 1 - xp;
+            float ha[DPL];
+            lds_vec<DPL>(vA, up);
+            lds_vec<DPL>(ha, up + 2 * REC_B);
+            lbVA = scUpB.x;
+            float lbA = scUpA.y;
+            vg_pixel<DPL, COST, MASKED, EDGE, FIRST, IEEE>(pfA + ((unsigned)y & (PFS - 1)) * STAGE_B, lane, y, xp, x, w, M, P1, P2,
+                                                           cscale, vA, lbVA, scUpB.z, dA, lbDA, pixDA, ha, lbA, scUpA.z, pixA, hstA);
+            hstA += estep;
+            sts_vec<DPL>(mine + 2 * REC_B, ha);
+            if (edge_out) sts_vec<DPL>(eBase + ((unsigned)y & (RING - 1)) * HROW_B + 2 * REC_B, ha);
+            bAA = lbA;
+        }
+        if (lane == 0) {
+            sts_f4(myScBase + slot * SLOTSC_B, make_float4(bBV, bBA, pixB, 0.0f));
+            sts_f4(myScBase + slot * SLOTSC_B + 16, make_float4(0.0f, bAA, pixA, 0.0f));
+            if (edge_out) {
+                const unsigned esc = sh_esc + ((unsigned)y & (RING - 1)) * HSC_B;
+                sts_f4(esc, make_float4(bBV, bBA, pixB, 0.0f));
+                sts_f4(esc + 16, make_float4(0.0f, bAA, pixA, 0.0f));
             }
         }
-        float bV, bD, bA;
-        sgm_step3<DPL, MASKED, FIRST, IEEE>(hpV, lbV, 1.0f + fabsf(ppV - pix), p2V,
-                                            hpd, lbd, 1.0f + fabsf(pixd - pix), p2D,
-                                            hpA, lbA, 1.0f + fabsf(ppA - pix), p2A,
-                                            cost, hin, P1, lim, lane, H3, bV, bD, bA);
-        if (EDGE) { if (sV) bV = 0.0f; if (sD) bD = 0.0f; if (sA) bA = 0.0f; }
-        lbd = bD;
-        pixd = pix;
-
-        // ---- publish this pixel's states for the next row, store the aggregate
-        const unsigned slot = (unsigned)y & (S - 1);
-        sts_vec<DPL>(myBase + slot * SLOT_B, hpV);
-        sts_vec<DPL>(myBase + slot * SLOT_B + DP * 4, hpA);
-        if (lane == 0) sts_f4(myScBase + slot * SLOTSC_B, make_float4(bV, bA, pix, 0.0f));
-        if (edge_out) {
-            const unsigned er = (unsigned)y & (RING - 1);
-            if (warp == 0) sts_vec<DPL>(eBase + er * HROW_B, hpV);
-            sts_vec<DPL>(eBase + er * HROW_B + (warp == 0 ? DP * 4 : 0), hpA);
-            if (lane == 0) sts_f4(eScBase + er * HSC_B, make_float4(bV, bA, pix, 0.0f));
-        }
-        store_f<DPL>(hst, H3);
-        hst += estep;
     };
 
-    // No CTA-wide barrier: the columns of a band form a dataflow pipeline through shared memory.  Column j
-    // may start row y once columns j+1, j+2 have finished row y-1 (read-after-write) and columns j-1, j-2 have
-    // finished row y-S+1 (so the ring slot of row y-S is free: write-after-read).
+    // No CTA-wide barrier: the warps of a band form a dataflow pipeline through shared memory.  Warp v may start
+    // row y once warp v+1 has finished row y-1 (read-after-write) and warp v-1 has finished row y-S+1 (so the
+    // ring slot of row y-S is free: write-after-read).
 #pragma unroll 1
     for (int y = y_in; y <= y_out; ++y) {
         issue_row(y + PFS - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(PFS - 1) : "memory");   // row y's stage has landed
+        asm volatile("cp.async.wait_group %0;" ::"n"(PFS - 1) : "memory");   // row y's stages have landed
         __syncwarp();
-        const int xp = u + y;
-        // all hand-offs of this row in one polling loop (the flags are read back to back)
-        // (an upstream band only publishes rows < hend: rows beyond that need no upstream state)
-        while (*fV < min(y, vCap) || *fA < min(y, aCap) || min(*fW1, *fW2) < y - wOff || (edge_out && *fC < y - cOff)) { __nanosleep(VG_SPIN_NS); }
+        while (*fUp < min(y, upCap) || *fDn < y - wOff || (edge_out && ctl->copied < y - cOff)) { __nanosleep(VG_SPIN_NS); }
         smem_order();
 
-        const int x = fwd ? xp : w - 1 - xp;
-        const bool edge = y == 0 || xp == 0 || xp == w - 1;
+        const int xpB = uB + y;                    // B is the leftmost of the two: x'_A = x'_B + 1
+        const int xlo = fwd ? xpB : w - 2 - xpB;   // smaller true x of the two pixels
+        const bool edge = y == 0 || xpB <= 0 || xpB + 1 >= w - 1 || y < max(yinA, yinB) || y > min(youtA, youtB);
         if (edge) {
-            if (x >= xf) row_body(std::false_type{}, std::true_type{}, y, xp, x);
-            else row_body(std::true_type{}, std::true_type{}, y, xp, x);
+            if (xlo >= xf) tick(std::false_type{}, std::true_type{}, y);
+            else tick(std::true_type{}, std::true_type{}, y);
         } else {
-            if (x >= xf) row_body(std::false_type{}, std::false_type{}, y, xp, x);
-            else row_body(std::true_type{}, std::false_type{}, y, xp, x);
+            if (xlo >= xf) tick(std::false_type{}, std::false_type{}, y);
+            else tick(std::true_type{}, std::false_type{}, y);
         }
         __syncwarp();
         smem_order();
@@ -396,21 +441,21 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     }
 }
 
-int vgroup_bands(int w, int h, int DP) { return cdiv(w + h - 1, vg_nw_of_dp(DP)); }
+int vgroup_bands(int w, int h, int DP) { return cdiv(w + h - 1, vg_cols_of_dp(DP)); }
 size_t vgroup_edge_floats(int w, int h, int DP) { return (size_t)vgroup_bands(w, h, DP) * h * (3 * (size_t)DP + 8); }
 
 template <int DPL, int COST>
 static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     constexpr int DP = 32 * DPL;
-    constexpr int VG_NW = vg_nw(DPL);
+    constexpr int NWW = vg_nww(DPL);
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    const size_t smem = (size_t)(VG_S * VG_NW * 2 * DP + VG_S * VG_NW * 4 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
-                        sizeof(VCtl) + ((VG_NW * 4 + 15) / 16) * 16 + (size_t)VG_NW * vg_pfs(DPL, CE) * (DP * 4 + DP * CE + 16);
-    dim3 grid(a.n_bands * a.batch), block((VG_NW + 1) * 32);
+    const size_t smem = (size_t)(VG_S * NWW * 3 * DP + VG_S * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
+                        sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * 2 * vg_pfs(DPL, CE) * (DP * 4 + DP * CE + 16);
+    dim3 grid(a.n_bands * a.batch), block((NWW + 1) * 32);
     const bool ieee = g_ieee_div.load() != 0;
 #define ROO_VG(F, I)                                                                                          \
     do {                                                                                                      \
-        auto kern = sgm_vgroup_kernel<DPL, COST, F, I, VG_NW>;                                                \
+        auto kern = sgm_vgroup_kernel<DPL, COST, F, I, NWW>;                                                  \
         if (smem > 48 * 1024) {                                                                               \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                              \

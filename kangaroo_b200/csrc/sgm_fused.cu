@@ -37,9 +37,9 @@ namespace roo_b200 {
 // rows of prefetch per column, staged in shared memory by cp.async (LDGSTS): under load a DRAM access takes
 // ~3000 SM cycles on B200, so a band needs ~60-80 KB in flight per SM to stream at HBM speed -- far more
 // than a register ring can hold, and without unrolling the row loop.  (227 KB of shared memory per CTA.)
-__host__ __device__ constexpr int vg_pfs(int DPL, int CE) { return DPL >= 8 ? 2 : (DPL == 4 && CE == 4 ? 2 : 4); }
+__host__ __device__ constexpr int vg_pfs(int DPL, int CE) { return DPL >= 8 ? 2 : (DPL == 4 ? (CE == 4 ? 2 : 4) : 8); }
 // compute warps per band (each owns two skewed columns) + 1 communication warp
-__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : 12; }
+__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : 16; }
 inline int vg_cols_of_dp(int DP) { return 2 * vg_nww(DP / 32); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -104,7 +104,7 @@ __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
 struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 
 
-__host__ __device__ constexpr int vg_r(int DPL) { return DPL >= 8 ? 4 : 8; }   // max rows per hand-off batch between bands (ring = 2x)
+__host__ __device__ constexpr int vg_r(int DPL) { return 4; }   // max rows per hand-off batch between bands (ring = 2x)
 #ifndef VG_SPIN_NS
 #define VG_SPIN_NS 30
 #endif

@@ -109,6 +109,7 @@ def cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, rows=None, reps=1)
     """Times the OpenMP port of the reference kernels (oracle/) on `reps` pairs cropped to `rows` rows."""
     import oracle as ko
     from kangaroo_b200.synth import stereo_pair
+    ko.use_all_cores()
     L, R, _ = stereo_pair(w, h, D, config=cfg)
     rows = rows or h
     L, R = np.ascontiguousarray(L[:rows]), np.ascontiguousarray(R[:rows])

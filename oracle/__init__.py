@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
         L = C.CDLL(_SO)
         P = C.POINTER
         L.ko_num_threads.restype = C.c_int
+        L.ko_set_num_threads.argtypes = [C.c_int]
         L.ko_census.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
         L.ko_census_stereo.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_int]
         L.ko_census_stereo_volume.argtypes = [P(KoVolume), P(KoImage), P(KoImage), C.c_int, C.c_int, C.c_int,
@@ -83,6 +84,20 @@ def lib() -> C.CDLL:
 
 def num_threads() -> int:
     return int(lib().ko_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().ko_set_num_threads(int(n))
+
+
+def use_all_cores() -> int:
+    """All host cores this process may run on (torchrun sets OMP_NUM_THREADS=1 for multi-rank launches)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    set_num_threads(n)
+    return num_threads()
 
 
 def _img(a: np.ndarray) -> KoImage:

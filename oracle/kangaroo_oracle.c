@@ -24,6 +24,14 @@ int ko_num_threads(void) {
 #endif
 }
 
+void ko_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---- accessors: Image.h:247-257 (RowPtr/operator()), Volume.h:125-147 ---- */
 static inline char* img_at(const ko_image* im, size_t x, size_t y, size_t elem) {
     return (char*)im->ptr + y * im->pitch + x * elem;

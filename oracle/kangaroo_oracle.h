@@ -37,6 +37,8 @@ enum { KO_VOL_U16 = 0, KO_VOL_F32 = 1, KO_VOL_I32 = 2, KO_VOL_U32 = 3, KO_VOL_U8
 enum { KO_DISP_I8 = 0, KO_DISP_F32 = 1 };
 
 int ko_num_threads(void);
+/* torchrun exports OMP_NUM_THREADS=1 for multi-rank launches: the CPU arm sets the thread count explicitly */
+void ko_set_num_threads(int n);
 
 /* src/cu_census.cu:18-46 (9x7), :52-110 (11x11), :116-177 (16x16); out holds 1/2/4 uint64 per px */
 void ko_census(const ko_image* out, const ko_image* in, int window, int in_type);

@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: (w, h, D, paths, subpix, lrcheck, default pairs per step per GPU, synthetic config id)
     "c1_640x480x64_4path": (640, 480, 64, 4, 0, 0, 16, 1),
-    "c2_1280x720x128_8path_wta": (1280, 720, 128, 8, 0, 0, 8, 2),
+    "c2_1280x720x128_8path_wta": (1280, 720, 128, 8, 0, 0, 16, 2),
     "c3_kitti_1242x375x128_4path": (1242, 375, 128, 4, 0, 0, 16, 3),
     "c4_1920x1080x256_8path_subpix_lr": (1920, 1080, 256, 8, 1, 1, 2, 4),
 }
@@ -155,7 +155,7 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
@@ -265,6 +265,15 @@ def main():
             kname, k_ms, k_n = "sgm_sweep_kernel", sw_ms, sw_n
             bytes_per_launch = 4.0 * (2 * S - 1) / max(S, 1) * unit
         achieved = bytes_per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+        # measured DRAM traffic per launch of that kernel from the committed ncu capture (scaled to this batch)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            inst = tr["kernels"].get(kname, [])
+            if inst and wl == DEFAULT_WORKLOAD:
+                traffic = sum(i["dram_bytes"] for i in inst) / len(inst) * B / tr["pairs_per_launch"]
+        except Exception:
+            traffic = None
         agg_bytes = 4.0 * (2 * S - 1) * unit
         agg_ms = (vg_ms + sw_ms) / K
         out = {
@@ -278,7 +287,7 @@ def main():
                        "l2": f"per-step working set {B * w * h * D * 5 / 1e9:.2f} GB (fp32 aggregate + u8 cost) vs "
                              f"{L2_BYTES / 1e6:.0f} MB L2: inputs larger than L2, no flush"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": k_ms / max(k_n, 1), "launches_timed": k_n,

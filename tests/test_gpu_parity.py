@@ -379,6 +379,39 @@ def test_fused_vertical_group_equals_separate_sweeps_and_oracle(shape):
     assert np.array_equal(Hf2, Hs2) and np.array_equal(df2, ds2)
 
 
+def test_engine_batch_slots_are_independent_and_groups_wrap():
+    """Different stereo pairs in every batch slot, more pairs than max_batch (several groups per call)."""
+    w, h, D = 161, 57, 64
+    pairs = [stereo_pair(w, h, D, config=51, index=i) for i in range(7)]
+    L = np.stack([p[0] for p in pairs])
+    R = np.stack([p[1] for p in pairs])
+    roo.set_ieee_division(True)
+    eng = roo.StereoEngine(w, h, D, dodiag=True, subpix=True, lrcheck=True, max_batch=3)
+    disp = eng.run_device(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy()
+    eng.close()
+    for i in range(7):
+        od = ko.pipeline_u8(L[i], R[i], D, dodiag=True, subpix=True, lrcheck=True)
+        assert np.array_equal(np.isnan(disp[i]), np.isnan(od)), i
+        assert np.array_equal(disp[i][~np.isnan(od)], od[~np.isnan(od)]), i
+
+
+@pytest.mark.parametrize("shape", [(5, 3, 4), (1, 1, 1), (40, 1, 16), (1, 40, 16), (33, 70, 32), (64, 64, 1), (31, 9, 200)])
+@pytest.mark.parametrize("dodiag", [False, True])
+def test_engine_degenerate_shapes(shape, dodiag):
+    """Images smaller than the census window / the disparity range / one band of the fused pass."""
+    w, h, D = shape
+    rng = np.random.default_rng(w * 1000 + h)
+    L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    roo.set_ieee_division(True)
+    for win in (0, 2):
+        disp, H, cen = run_engine(L, R, D, batch=2, window=win, dodiag=dodiag, subpix=True)
+        od, oH = ko.pipeline_u8(L, R, D, window=win, dodiag=dodiag, subpix=True, want_volume=True)
+        assert np.array_equal(cen, ko.census(L, win))
+        assert np.array_equal(H, oH)
+        assert np.array_equal(disp[0], od) and np.array_equal(disp[1], od)
+
+
 def test_engine_run_host_equals_run_device():
     L, R, _ = stereo_pair(320, 200, 64, config=31)
     n = 5

@@ -147,6 +147,8 @@ enum roo_prof_kind { ROO_PROF_CENSUS = 0, ROO_PROF_COST = 1, ROO_PROF_SWEEP = 2,
                      ROO_PROF_VGROUP = 5, ROO_PROF_KINDS = 6 };
 int roo_engine_set_profiling(roo_engine_t* e, int on);
 int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long long* launches_by_kind);
+/* development aid: in-kernel cycle counters of a -DVG_TIMING build (zeros in a normal build) */
+int roo_engine_debug_counters(roo_engine_t* e, unsigned long long* out, int n, int reset);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,7 @@ SYMBOLS = {
     "roo_engine_export_census": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _IMG, _S]),
     "roo_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "roo_engine_get_profile": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_longlong)]),
+    "roo_engine_debug_counters": (C.c_int, [C.c_void_p, _P(C.c_ulonglong), C.c_int, C.c_int]),
 }
 
 

@@ -160,7 +160,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     if (ok && p.lrcheck) ok = alloc((void**)&e->dispR, B * npx * 4);
     if (ok && fused)
         ok = alloc((void**)&e->edge, B * vgroup_edge_floats(p.w, p.h, e->DP) * 4) &&
-             alloc((void**)&e->flags, B * (size_t)vgroup_bands(p.w, p.h, e->DP) * 4);
+             alloc((void**)&e->flags, B * (size_t)vgroup_bands(p.w, p.h, e->DP) * 4 + 256);   // + debug counters (VG_TIMING builds)
     if (!ok) {
         cudaGetLastError();
         engine_free(e);
@@ -276,6 +276,15 @@ extern "C" int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long 
     }
     e->prof_used = 0;
     for (int k = 0; k < ROO_PROF_KINDS; ++k) { ms_by_kind[k] = e->prof_ms[k]; launches_by_kind[k] = e->prof_n[k]; }
+    return ROO_OK;
+}
+
+// Development aid: cycle counters written by a -DVG_TIMING build of sgm_fused.cu (zeros otherwise).
+extern "C" int roo_engine_debug_counters(roo_engine_t* e, unsigned long long* out, int n, int reset) {
+    if (!e || !e->flags || !out || n <= 0 || n > 32) return ROO_ERR_INVALID_ARGUMENT;
+    char* base = reinterpret_cast<char*>(e->flags) + (size_t)e->p.max_batch * vgroup_bands(e->p.w, e->p.h, e->DP) * 4;
+    ROO_CUDA_TRY(cudaMemcpy(out, base, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (reset) ROO_CUDA_TRY(cudaMemset(base, 0, 256));
     return ROO_OK;
 }
 

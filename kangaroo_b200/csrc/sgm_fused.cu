@@ -417,12 +417,26 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     // No CTA-wide barrier: the warps of a band form a dataflow pipeline through shared memory.  Warp v may start
     // row y once warp v+1 has finished row y-1 (read-after-write) and warp v-1 has finished row y-S+1 (so the
     // ring slot of row y-S is free: write-after-read).
+#ifdef VG_TIMING
+    long long tcp = 0, tup = 0, tdn = 0, tbody = 0;
+#endif
 #pragma unroll 1
     for (int y = y_in; y <= y_out; ++y) {
+#ifdef VG_TIMING
+        long long t0 = clock64();
+#endif
         issue_row(y + PFS - 1);
         asm volatile("cp.async.wait_group %0;" ::"n"(PFS - 1) : "memory");   // row y's stages have landed
         __syncwarp();
+#ifdef VG_TIMING
+        long long t1 = clock64(); tcp += t1 - t0;
+        while (*fUp < min(y, upCap)) { __nanosleep(VG_SPIN_NS); }
+        long long t2 = clock64(); tup += t2 - t1;
+        while (*fDn < y - wOff || (edge_out && ctl->copied < y - cOff)) { __nanosleep(VG_SPIN_NS); }
+        long long t3 = clock64(); tdn += t3 - t2;
+#else
         while (*fUp < min(y, upCap) || *fDn < y - wOff || (edge_out && ctl->copied < y - cOff)) { __nanosleep(VG_SPIN_NS); }
+#endif
         smem_order();
 
         const int xpB = uB + y;                    // B is the leftmost of the two: x'_A = x'_B + 1
@@ -438,7 +452,21 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         __syncwarp();
         smem_order();
         if (lane == 0) prog[warp] = (y == y_out) ? 0x7fffffff : y + 1;
+#ifdef VG_TIMING
+        tbody += clock64() - t3;
+#endif
     }
+#ifdef VG_TIMING
+    if (lane == 0) {
+        unsigned long long* dbg = reinterpret_cast<unsigned long long*>(a.progress + (size_t)a.n_bands * a.batch);
+        const int role = warp == NWW - 1 ? 2 : (warp == 0 ? 0 : 1);   // lowest / interior / highest warp
+        atomicAdd(dbg + role * 5 + 0, (unsigned long long)tcp);
+        atomicAdd(dbg + role * 5 + 1, (unsigned long long)tup);
+        atomicAdd(dbg + role * 5 + 2, (unsigned long long)tdn);
+        atomicAdd(dbg + role * 5 + 3, (unsigned long long)tbody);
+        atomicAdd(dbg + role * 5 + 4, (unsigned long long)(y_out - y_in + 1));
+    }
+#endif
 }
 
 int vgroup_bands(int w, int h, int DP) { return cdiv(w + h - 1, vg_cols_of_dp(DP)); }

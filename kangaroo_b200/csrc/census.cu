@@ -7,6 +7,8 @@
 // shared memory (clamp-to-edge applied while staging), descriptors are built from registers and
 // stored with one 8/16/32-byte vector store per pixel, rows are processed by independent CTAs
 // (no w <= 1024 limit), and every launch takes an explicit stream and a batch dimension.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -217,49 +219,67 @@ static int csv_launch(const roo_volume_t* vol, const roo_image_t* l, const roo_i
 // threads write consecutive words, so the 128*DP-byte output of the CTA is one contiguous coalesced stream.
 // ------------------------------------------------------------------------------------------------
 constexpr int COST_TX = 128;   // pixels per CTA
+
+// WT = the part of a descriptor word the popcount looks at: the reference's 32-bit __popc on 64-bit words
+// (hamming_distance.h:40-62) only ever sees the low half, so the compat mode stages 32-bit words.
 template <int WORDS, bool POPC64>
 __global__ void __launch_bounds__(256)
 cost_u8_kernel(unsigned char* __restrict__ c8, const unsigned long long* __restrict__ cl,
                const unsigned long long* __restrict__ cr, int w, int h, int DP, int maxDisp) {
-    extern __shared__ unsigned long long s_r[];          // [WORDS][COST_TX + DP - 1] right descriptors x0-(DP-1) .. x0+TX-1
-    unsigned long long* s_l = s_r + WORDS * (COST_TX + DP - 1);   // [WORDS][COST_TX] left descriptors
+    using WT = typename std::conditional<POPC64, unsigned long long, unsigned>::type;
+    extern __shared__ __align__(16) unsigned char cost_smem[];
+    const int span = COST_TX + DP - 1;
+    WT* s_r = reinterpret_cast<WT*>(cost_smem);                 // [WORDS][span] right descriptors x0-(DP-1) .. x0+TX-1
+    WT* s_l = s_r + WORDS * span;                               // [WORDS][COST_TX] left descriptors
+    unsigned* s_out = reinterpret_cast<unsigned*>(cost_smem + (size_t)WORDS * (span + COST_TX) * 8);   // [COST_TX][groups+1]
     const int x0 = blockIdx.x * COST_TX, y = blockIdx.y;
     const size_t rowoff = ((size_t)blockIdx.z * h + y) * (size_t)w;
-    const int span = COST_TX + DP - 1;
     const int rx0 = x0 - (DP - 1);
     for (int i = threadIdx.x; i < span * WORDS; i += 256) {
         const int px = i / WORDS, k = i - px * WORDS;
         const int gx = rx0 + px;
-        s_r[k * span + px] = (gx >= 0 && gx < w) ? cr[(rowoff + gx) * WORDS + k] : 0ull;
+        s_r[k * span + px] = (gx >= 0 && gx < w) ? (WT)cr[(rowoff + gx) * WORDS + k] : (WT)0;
     }
     for (int i = threadIdx.x; i < COST_TX * WORDS; i += 256) {
         const int px = i / WORDS, k = i - px * WORDS;
-        s_l[k * COST_TX + px] = (x0 + px < w) ? cl[(rowoff + x0 + px) * WORDS + k] : 0ull;
+        s_l[k * COST_TX + px] = (x0 + px < w) ? (WT)cl[(rowoff + x0 + px) * WORDS + k] : (WT)0;
     }
     __syncthreads();
     // lanes run over pixels (consecutive descriptors in shared memory: conflict-free), each thread packs 4
     // consecutive disparities into one word of a padded output tile; the tile then leaves coalesced
     const int groups = DP >> 2;                           // 32-bit words per pixel
     const int gpad = groups + 1;
-    unsigned* s_out = reinterpret_cast<unsigned*>(s_l + WORDS * COST_TX);   // [COST_TX][groups + 1]
+    auto popc = [](WT v) -> unsigned { return POPC64 ? (unsigned)__popcll((unsigned long long)v) : (unsigned)__popc((unsigned)v); };
+    // every pixel of the segment sees its whole disparity range: no per-disparity tests
+    const bool full = x0 >= DP - 1 && maxDisp == DP;
     for (int i = threadIdx.x; i < COST_TX * groups; i += 256) {
         const int px = i % COST_TX, g = i / COST_TX;
-        const int x = x0 + px;
-        unsigned long long p[WORDS];
+        WT p[WORDS];
 #pragma unroll
         for (int k = 0; k < WORDS; ++k) p[k] = s_l[k * COST_TX + px];
+        const int r0 = px + (DP - 1) - g * 4;             // index of x-d in s_r for d = 4g
         unsigned packed = 0;
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int d = g * 4 + j;
-            unsigned hd = WORDS * 32;                     // 0.5 * bits: no right pixel (the reference's 0.5)
-            if (d < maxDisp && d <= x) {
-                const int ri = px + (DP - 1) - d;         // index of x-d in s_r
-                hd = 0;
+            for (int j = 0; j < 4; ++j) {
+                unsigned hd = 0;
 #pragma unroll
-                for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], s_r[k * span + ri]);
+                for (int k = 0; k < WORDS; ++k) hd += popc(p[k] ^ s_r[k * span + r0 - j]);
+                packed |= hd << (8 * j);
             }
-            packed |= hd << (8 * j);
+        } else {
+            const int x = x0 + px;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = g * 4 + j;
+                unsigned hd = WORDS * 32;                 // 0.5 * bits: no right pixel (the reference's 0.5)
+                if (d < maxDisp && d <= x) {
+                    hd = 0;
+#pragma unroll
+                    for (int k = 0; k < WORDS; ++k) hd += popc(p[k] ^ s_r[k * span + r0 - j]);
+                }
+                packed |= hd << (8 * j);
+            }
         }
         s_out[px * gpad + g] = packed;
     }

@@ -412,6 +412,36 @@ def test_engine_degenerate_shapes(shape, dodiag):
         assert np.array_equal(disp[0], od) and np.array_equal(disp[1], od)
 
 
+def test_engine_kitti_shape_4path_bitexact_vs_oracle():
+    """BASELINE config 3 shape (1242x375, 128 disparities): wider than the reference's 1024 limit, 4 reference paths."""
+    L, R, gt = stereo_pair(1242, 375, 128, config=3)
+    roo.set_ieee_division(True)
+    disp, H, cen = run_engine(L, R, 128, batch=2, subpix=True, lrcheck=True, lr_maxdiff=1.0)
+    od, oH = ko.pipeline_u8(L, R, 128, subpix=True, lrcheck=True, lr_maxdiff=1.0, want_volume=True)
+    assert np.array_equal(H, oH)
+    for b in range(2):
+        assert np.array_equal(np.isnan(disp[b]), np.isnan(od))
+        assert np.array_equal(disp[b][~np.isnan(od)], od[~np.isnan(od)])
+
+
+def test_engine_256_disparities_8path_subpix_lr_vs_oracle():
+    """BASELINE config 4 feature set (256 disparities, 8 paths, subpixel, LR check) at a quarter of its pixels."""
+    L, R, gt = stereo_pair(960, 540, 256, config=4)
+    roo.set_ieee_division(True)
+    disp, H, cen = run_engine(L, R, 256, dodiag=True, subpix=True, lrcheck=True, lr_maxdiff=1.0)
+    od, oH = ko.pipeline_u8(L, R, 256, dodiag=True, subpix=True, lrcheck=True, lr_maxdiff=1.0, want_volume=True)
+    assert np.array_equal(H, oH)
+    assert np.array_equal(np.isnan(disp[0]), np.isnan(od))
+    assert np.array_equal(disp[0][~np.isnan(od)], od[~np.isnan(od)])
+    # default (reference-identical) division mode stays within the parity bars of the oracle
+    roo.set_ieee_division(False)
+    disp2, H2, _ = run_engine(L, R, 256, dodiag=True, subpix=True, lrcheck=True, lr_maxdiff=1.0)
+    assert relerr(oH, H2).max() <= 1e-4
+    both = np.isfinite(od) & np.isfinite(disp2[0])
+    assert (np.isnan(od) == np.isnan(disp2[0])).mean() >= 0.999
+    assert (np.abs(od - disp2[0])[both] <= 0.01).mean() >= 0.999
+
+
 def test_engine_run_host_equals_run_device():
     L, R, _ = stereo_pair(320, 200, 64, config=31)
     n = 5

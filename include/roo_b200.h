@@ -140,6 +140,15 @@ int roo_engine_export_volume(roo_engine_t* e, int slot, const roo_volume_t* volH
 /* Same for the census descriptors of the last run: side 0 = left, 1 = right. */
 int roo_engine_export_census(roo_engine_t* e, int slot, int side, const roo_image_t* census, void* stream);
 
+/* ---- multi-GPU: the batch is sharded across the GPUs of the box by pair index (one engine + one host thread per
+ * device, no collective: pairs are independent).  devices == NULL / n_devices <= 0: all visible devices. */
+typedef struct roo_multi_engine roo_multi_engine_t;
+int roo_multi_engine_create(roo_multi_engine_t** out, const roo_pipeline_params_t* params, const int* devices, int n_devices);
+int roo_multi_engine_destroy(roo_multi_engine_t* m);
+int roo_multi_engine_device_count(const roo_multi_engine_t* m);
+int roo_multi_engine_run_host(roo_multi_engine_t* m, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
+                              int n_pairs);
+
 /* Per-kernel device timing for bench.py: with profiling on, the engine records a CUDA event after
  * every launch on the launching stream; roo_engine_get_profile (call after synchronising) returns the
  * accumulated milliseconds and launch counts per kernel kind since profiling was switched on. */

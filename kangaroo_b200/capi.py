@@ -65,6 +65,10 @@ SYMBOLS = {
     "roo_engine_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "roo_engine_export_volume": (C.c_int, [C.c_void_p, C.c_int, _VOL, _S]),
     "roo_engine_export_census": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _IMG, _S]),
+    "roo_multi_engine_create": (C.c_int, [_P(C.c_void_p), _P(PipelineParams), _P(C.c_int), C.c_int]),
+    "roo_multi_engine_destroy": (C.c_int, [C.c_void_p]),
+    "roo_multi_engine_device_count": (C.c_int, [C.c_void_p]),
+    "roo_multi_engine_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "roo_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "roo_engine_get_profile": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_longlong)]),
     "roo_engine_debug_counters": (C.c_int, [C.c_void_p, _P(C.c_ulonglong), C.c_int, C.c_int]),

@@ -4,6 +4,7 @@
 // on engine-owned scratch in the internal disparity-innermost layout, for a batch of stereo pairs
 // per launch.  Host side is plain C++ behind the C ABI of include/roo_b200.h.
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -276,6 +277,90 @@ extern "C" int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long 
     }
     e->prof_used = 0;
     for (int k = 0; k < ROO_PROF_KINDS; ++k) { ms_by_kind[k] = e->prof_ms[k]; launches_by_kind[k] = e->prof_n[k]; }
+    return ROO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: stereo pairs are independent, so a batch is sharded across the GPUs of the box by pair index --
+// one engine, one host thread and one set of streams per device, no collective, nothing exchanged
+// (SURVEY.md 8e).  Host buffers in, host buffers out.
+// ------------------------------------------------------------------------------------------------
+struct roo_multi_engine {
+    std::vector<int> devices;
+    std::vector<roo_engine*> engines;
+    size_t npx = 0;
+};
+
+extern "C" int roo_multi_engine_create(roo_multi_engine_t** out, const roo_pipeline_params_t* params, const int* devices,
+                                       int n_devices) {
+    if (!out || !params) return ROO_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ROO_ERR_NO_DEVICE;
+    if (n_devices <= 0) n_devices = ndev;          // all visible devices
+    if (n_devices > ndev && !devices) return ROO_ERR_INVALID_ARGUMENT;
+    roo_multi_engine* m = new (std::nothrow) roo_multi_engine();
+    if (!m) return ROO_ERR_OUT_OF_MEMORY;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = ROO_OK;
+    for (int i = 0; i < n_devices && rc == ROO_OK; ++i) {
+        const int dev = devices ? devices[i] : i;
+        if (dev < 0 || dev >= ndev) { rc = ROO_ERR_INVALID_ARGUMENT; break; }
+        if (cudaSetDevice(dev) != cudaSuccess) { rc = ROO_ERR_NO_DEVICE; break; }
+        roo_engine* e = nullptr;
+        rc = roo_engine_create(&e, params);
+        if (rc == ROO_OK) { m->devices.push_back(dev); m->engines.push_back(e); }
+    }
+    cudaSetDevice(prev);
+    if (rc != ROO_OK) {
+        for (size_t i = 0; i < m->engines.size(); ++i) { cudaSetDevice(m->devices[i]); roo_engine_destroy(m->engines[i]); }
+        cudaSetDevice(prev);
+        delete m;
+        return rc;
+    }
+    m->npx = (size_t)params->w * params->h;
+    *out = m;
+    return ROO_OK;
+}
+
+extern "C" int roo_multi_engine_destroy(roo_multi_engine_t* m) {
+    if (!m) return ROO_ERR_INVALID_ARGUMENT;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (size_t i = 0; i < m->engines.size(); ++i) { cudaSetDevice(m->devices[i]); roo_engine_destroy(m->engines[i]); }
+    cudaSetDevice(prev);
+    delete m;
+    return ROO_OK;
+}
+
+extern "C" int roo_multi_engine_device_count(const roo_multi_engine_t* m) { return m ? (int)m->engines.size() : 0; }
+
+// contiguous block of pairs for device i of n (blocks differ by at most one pair)
+static void shard_of(int n_pairs, int n, int i, int* begin, int* count) {
+    const int base = n_pairs / n, rem = n_pairs % n;
+    *begin = i * base + (i < rem ? i : rem);
+    *count = base + (i < rem ? 1 : 0);
+}
+
+extern "C" int roo_multi_engine_run_host(roo_multi_engine_t* m, const uint8_t* left_host, const uint8_t* right_host,
+                                         float* disp_host, int n_pairs) {
+    if (!m || !left_host || !right_host || !disp_host || n_pairs < 0) return ROO_ERR_INVALID_ARGUMENT;
+    const int n = (int)m->engines.size();
+    std::vector<int> status(n, ROO_OK);
+    std::vector<std::thread> workers;
+    for (int i = 0; i < n; ++i) {
+        workers.emplace_back([&, i]() {
+            int begin = 0, count = 0;
+            shard_of(n_pairs, n, i, &begin, &count);
+            if (count == 0) return;
+            if (cudaSetDevice(m->devices[i]) != cudaSuccess) { status[i] = ROO_ERR_NO_DEVICE; return; }
+            const size_t off = (size_t)begin * m->npx;
+            status[i] = roo_engine_run_host(m->engines[i], left_host + off, right_host + off, disp_host + off, count);
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int i = 0; i < n; ++i)
+        if (status[i] != ROO_OK) return status[i];
     return ROO_OK;
 }
 

@@ -279,3 +279,50 @@ class StereoEngine:
         check(lib().roo_engine_export_census(self._h, slot, side, C.byref(im.c()), _stream(None)),
               "roo_engine_export_census")
         return im
+
+
+class MultiGpuStereoEngine:
+    """The batch sharded across the GPUs of the box by pair index: one engine + one host thread per device
+    inside the C++ library, no collective (roo_multi_engine_*).  Host tensors in, host tensor out."""
+
+    def __init__(self, w: int, h: int, max_disp: int, devices=None, **kw):
+        proto = StereoEngine.__new__(StereoEngine)
+        defaults = dict(window=WIN_9x7, popc_mode=POPC32_COMPAT, P1=0.01, P2=0.02, img_scale=1.0 / 255.0, dohoriz=True,
+                        dovert=True, doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff=1.0,
+                        max_batch=1, keep_volume=False, fuse_vertical=True)
+        defaults.update(kw)
+        d = defaults
+        self.params = capi.PipelineParams(w, h, max_disp, d["window"], d["popc_mode"], d["P1"], d["P2"],
+                                          np.float32(d["img_scale"]), int(d["dohoriz"]), int(d["dovert"]),
+                                          int(d["doreverse"]), int(d["dodiag"]), int(d["subpix"]), int(d["lrcheck"]),
+                                          d["lr_maxdiff"], d["max_batch"], int(d["keep_volume"]),
+                                          0 if d["fuse_vertical"] else -1)
+        del proto
+        self.w, self.h = w, h
+        self._h = C.c_void_p()
+        if devices is None:
+            arr, n = None, 0
+        else:
+            arr, n = (C.c_int * len(devices))(*devices), len(devices)
+        check(lib().roo_multi_engine_create(C.byref(self._h), C.byref(self.params), arr, n), "roo_multi_engine_create")
+
+    @property
+    def device_count(self) -> int:
+        return int(lib().roo_multi_engine_device_count(self._h))
+
+    def run_host(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+        assert not left.is_cuda and left.dtype == torch.uint8 and disp.dtype == torch.float32
+        check(lib().roo_multi_engine_run_host(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(),
+                                              left.shape[0]), "roo_multi_engine_run_host")
+        return disp
+
+    def close(self) -> None:
+        if self._h:
+            lib().roo_multi_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

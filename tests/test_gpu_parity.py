@@ -458,6 +458,29 @@ def test_engine_run_host_equals_run_device():
     eng.close()
 
 
+def test_multi_gpu_engine_shards_pairs_across_all_devices():
+    """In-library sharding (one engine + host thread per device, no collective): identical disparities whatever
+    the device count -- runs on however many GPUs are visible (1 on the default test box)."""
+    w, h, D, n = 200, 80, 64, 5
+    pairs = [stereo_pair(w, h, D, config=61, index=i) for i in range(n)]
+    L = torch.from_numpy(np.stack([p[0] for p in pairs])).pin_memory()
+    R = torch.from_numpy(np.stack([p[1] for p in pairs])).pin_memory()
+    out = torch.empty((n, h, w), dtype=torch.float32).pin_memory()
+    roo.set_ieee_division(True)
+    m = roo.MultiGpuStereoEngine(w, h, D, dodiag=True, subpix=True, max_batch=2)
+    assert m.device_count == torch.cuda.device_count()
+    m.run_host(L, R, out)
+    m.close()
+    for i in range(n):
+        od = ko.pipeline_u8(pairs[i][0], pairs[i][1], D, dodiag=True, subpix=True)
+        assert np.array_equal(out[i].numpy(), od), i
+    m1 = roo.MultiGpuStereoEngine(w, h, D, devices=[0], dodiag=True, subpix=True, max_batch=2)
+    out1 = torch.empty_like(out)
+    m1.run_host(L, R, out1)
+    m1.close()
+    assert torch.equal(out, out1)
+
+
 def test_invalid_arguments_are_reported_not_ignored():
     img = roo.Image(16, 16, np.uint8)
     cen = roo.Image(8, 16, census_dtype(0))

@@ -100,14 +100,24 @@ __device__ __forceinline__ void cp_async_row(float* smem_dst, const float* gsrc)
 // for the warp's outstanding GLOBAL prefetch loads and serialise every row on DRAM latency.
 __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
 
+#ifndef VG_SPIN_NS
+#define VG_SPIN_NS 30
+#endif
+// poll a monotonically growing shared-memory flag until it reaches `need`
+__device__ __forceinline__ void spin_until(unsigned flag_addr, int need) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(flag_addr) : "memory");
+    while (v < need) {
+        __nanosleep(VG_SPIN_NS);
+        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(flag_addr) : "memory");
+    }
+}
+
 // smem control words
 struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 
 
 __host__ __device__ constexpr int vg_r(int DPL) { return 4; }   // max rows per hand-off batch between bands (ring = 2x)
-#ifndef VG_SPIN_NS
-#define VG_SPIN_NS 30
-#endif
 constexpr int VG_S = 4;   // depth (rows) of the in-band state ring in shared memory
 
 // One pixel of the three paths.  V/D/A = vertical / diagonal / anti-diagonal.  hpV, hpD, hpA: previous pixel's
@@ -343,8 +353,12 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     const bool edge_out = warp == 0 && downstream;
     const unsigned eBase = sh_edge + lane * DPL * 4;
     // hand-off flags: rows < *flag of the producer are done
-    volatile int* const fUp = upIn ? prog + warp + 1 : &ctl->halo_ready;
-    volatile int* const fDn = warp >= 1 ? prog + warp - 1 : fUp;   // no consumer: alias a flag that is already waited on
+    // (32-bit shared-window addresses: the polling loops below are then LDS / ISETP / BRA / NANOSLEEP only)
+    const unsigned fUp = (unsigned)__cvta_generic_to_shared(upIn ? (const void*)(const_cast<int*>(prog) + warp + 1)
+                                                                 : (const void*)const_cast<int*>(&ctl->halo_ready));
+    const unsigned fDn = warp >= 1 ? (unsigned)__cvta_generic_to_shared(const_cast<int*>(prog) + warp - 1)
+                                   : fUp;   // no consumer: alias a flag that is already waited on
+    const unsigned fCp = (unsigned)__cvta_generic_to_shared(const_cast<int*>(&ctl->copied));
     const int upCap = upIn ? 0x7fffffff : hend;   // an upstream band only publishes rows < hend
     const int wOff = S - 2;            // the consumer must have finished row y-S+1  <=>  prog >= y-S+2
     const int cOff = RING - 1;         // downstream ring slot free once rows < y-RING+1 were copied out
@@ -414,6 +428,13 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         }
     };
 
+    // Row classes, resolved once per warp.  With x'_B = uB + y (B is the leftmost of the two columns, x'_A = x'_B + 1):
+    //   interior rows [eLo, eHi]: y >= 1, x'_B >= 1, x'_A <= w-2 and both columns active -- no path starts or ends;
+    //   unmasked rows [mLo, mHi]: the smaller true x of the two pixels (x'_B forward, w-2-x'_B backward) is >= xf.
+    int eLo = max(max(1, 1 - uB), max(yinA, yinB)), eHi = min(w - 3 - uB, min(youtA, youtB));
+    int mLo = fwd ? xf - uB : -0x3fffffff, mHi = fwd ? 0x3fffffff : (xf > w ? -0x3fffffff : w - 2 - uB - xf);
+    asm volatile("" : "+r"(eLo), "+r"(eHi), "+r"(mLo), "+r"(mHi));   // keep them in registers: no per-row rematerialisation
+
     // No CTA-wide barrier: the warps of a band form a dataflow pipeline through shared memory.  Warp v may start
     // row y once warp v+1 has finished row y-1 (read-after-write) and warp v-1 has finished row y-S+1 (so the
     // ring slot of row y-S is free: write-after-read).
@@ -430,23 +451,26 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         __syncwarp();
 #ifdef VG_TIMING
         long long t1 = clock64(); tcp += t1 - t0;
-        while (*fUp < min(y, upCap)) { __nanosleep(VG_SPIN_NS); }
+        spin_until(fUp, min(y, upCap));
         long long t2 = clock64(); tup += t2 - t1;
-        while (*fDn < y - wOff || (edge_out && ctl->copied < y - cOff)) { __nanosleep(VG_SPIN_NS); }
+        spin_until(fDn, y - wOff);
+        if (edge_out) spin_until(fCp, y - cOff);
         long long t3 = clock64(); tdn += t3 - t2;
 #else
-        while (*fUp < min(y, upCap) || *fDn < y - wOff || (edge_out && ctl->copied < y - cOff)) { __nanosleep(VG_SPIN_NS); }
+        // the flags only grow, so waiting for them one after the other is the same as waiting for all of them
+        spin_until(fUp, min(y, upCap));
+        spin_until(fDn, y - wOff);
+        if (edge_out) spin_until(fCp, y - cOff);
 #endif
         smem_order();
 
-        const int xpB = uB + y;                    // B is the leftmost of the two: x'_A = x'_B + 1
-        const int xlo = fwd ? xpB : w - 2 - xpB;   // smaller true x of the two pixels
-        const bool edge = y == 0 || xpB <= 0 || xpB + 1 >= w - 1 || y < max(yinA, yinB) || y > min(youtA, youtB);
+        const bool edge = y < eLo || y > eHi;
+        const bool unmasked = y >= mLo && y <= mHi;
         if (edge) {
-            if (xlo >= xf) tick(std::false_type{}, std::true_type{}, y);
+            if (unmasked) tick(std::false_type{}, std::true_type{}, y);
             else tick(std::true_type{}, std::true_type{}, y);
         } else {
-            if (xlo >= xf) tick(std::false_type{}, std::false_type{}, y);
+            if (unmasked) tick(std::false_type{}, std::false_type{}, y);
             else tick(std::true_type{}, std::false_type{}, y);
         }
         __syncwarp();

@@ -38,9 +38,13 @@ namespace roo_b200 {
 // ~3000 SM cycles on B200, so a band needs ~60-80 KB in flight per SM to stream at HBM speed -- far more
 // than a register ring can hold, and without unrolling the row loop.  (227 KB of shared memory per CTA.)
 __host__ __device__ constexpr int vg_pfs(int DPL, int CE) { return DPL >= 8 ? 2 : (DPL == 4 ? (CE == 4 ? 2 : 4) : 8); }
-// compute warps per band (each owns two skewed columns) + 1 communication warp
-__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : 16; }
-inline int vg_cols_of_dp(int DP) { return 2 * vg_nww(DP / 32); }
+// skewed columns per compute warp, and compute warps per band (+ 1 communication warp)
+#ifndef VG_NCW
+#define VG_NCW 4
+#endif
+__host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? 2 : VG_NCW; }
+__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : 32 / vg_ncw(DPL); }
+inline int vg_cols_of_dp(int DP) { return vg_ncw(DP / 32) * vg_nww(DP / 32); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -124,9 +128,9 @@ constexpr int VG_S = 4;   // depth (rows) of the in-band state ring in shared me
 // state rows on entry, this pixel's on exit.  Handles path starts when EDGE.
 template <int DPL, int COST, bool MASKED, bool EDGE, bool FIRST, bool IEEE>
 __device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, int x, int w, int M, float P1, float P2,
-                                         float cscale, float (&hpV)[DPL], float& lbV, float ppV,
+                                         float cscale, float pix, float (&hpV)[DPL], float& lbV, float ppV,
                                          float (&hpD)[DPL], float& lbD, float& pixD,
-                                         float (&hpA)[DPL], float& lbA, float ppA, float& pix_out, float* hst) {
+                                         float (&hpA)[DPL], float& lbA, float ppA, float* hst) {
     constexpr int DP = 32 * DPL;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
     const int lim = MASKED ? min(M, x + 1) - lane * DPL : 0;
@@ -134,8 +138,6 @@ __device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, 
     if (!FIRST) lds_vec<DPL>(hin, stg + lane * DPL * 4);
     RawCost<DPL, COST> rc;
     rc.lds(stg + DP * 4 + lane * DPL * CE);
-    float pix;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + DP * CE));
 #pragma unroll
     for (int j = 0; j < DPL; ++j) cost[j] = rc.get(j, cscale);
     float p2V = P2, p2D = P2, p2A = P2;
@@ -160,22 +162,22 @@ __device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, 
     if (EDGE) { if (sV) bV = 0.0f; if (sD) bD = 0.0f; if (sA) bA = 0.0f; }
     lbV = bV; lbD = bD; lbA = bA;
     pixD = pix;
-    pix_out = pix;
     store_f<DPL>(hst, H3);
 }
 
-template <int DPL, int COST, bool FIRST, bool IEEE, int NWW>
+template <int DPL, int COST, bool FIRST, bool IEEE, int NWW, int NCW>
 __global__ void __launch_bounds__((NWW + 1) * 32, 1)
 sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int DP = 32 * DPL;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    constexpr int NC = 2 * NWW;                       // skewed columns per band
+    constexpr int NC = NCW * NWW;                     // skewed columns per band
     constexpr int PFS = vg_pfs(DPL, CE);
     constexpr int R = vg_r(DPL), RING = 2 * R, S = VG_S;
-    constexpr int STAGE_B = DP * 4 + DP * CE + 16;   // one prefetched pixel: aggregate row, cost row, intensity
+    constexpr int STAGE_B = DP * 4 + DP * CE;        // one prefetched pixel: aggregate row, cost row
     extern __shared__ __align__(16) float smem[];
-    // state rows of one warp and one image row: rec0 = B.vertical, rec1 = B.anti-diagonal, rec2 = A.anti-diagonal;
-    // scalars {B.lastBest(V), B.lastBest(A), B.pix, -, -, A.lastBest(A), A.pix, -}: the same record layout is
+    // state rows of one warp and one image row, for its two lowest columns c0 and c1 (all that the warp below
+    // needs): rec0 = c0.vertical, rec1 = c0.anti-diagonal, rec2 = c1.anti-diagonal;
+    // scalars {c0.lastBest(V), c0.lastBest(A), c0.pix, -, -, c1.lastBest(A), c1.pix, -}: the same record layout is
     // used by the band-to-band edge rows, so a warp reads "the three rows of whoever is above me" with one formula
     float* s_hp = smem;                                // [S rows][NWW][3][DP]
     float* s_sc = s_hp + S * NWW * 3 * DP;             // [S rows][NWW][8]
@@ -185,7 +187,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     float* s_esc = s_edge + RING * 3 * DP;             // [RING][8]
     VCtl* ctl = reinterpret_cast<VCtl*>(s_esc + RING * 8);
     volatile int* prog = reinterpret_cast<volatile int*>(ctl + 1);   // [NWW] rows < prog[v] of warp v are done
-    char* s_pf = reinterpret_cast<char*>(ctl + 1) + ((NWW * 4 + 15) / 16) * 16;   // [NWW][2 cols][PFS][STAGE_B]
+    char* s_pf = reinterpret_cast<char*>(ctl + 1) + ((NWW * 4 + 15) / 16) * 16;   // [NWW][NCW cols][PFS][STAGE_B]
 
     // warp index through a shuffle: ptxas then knows it is warp-uniform, and every branch on it is a uniform branch
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -210,11 +212,12 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     float* e_sc = a.edge_sc + ((size_t)pair * a.n_bands + band) * (size_t)h * 8;
     int* my_flag = a.progress + (size_t)pair * a.n_bands + band;
 
-    // this warp's two skewed columns and their active rows (x' = u + y' in [0, w))
-    const int uB = ulo + 2 * warp, uA = uB + 1;
-    const int yinA = max(0, -uA), youtA = min(h - 1, w - 1 - uA);
-    const int yinB = max(0, -uB), youtB = min(h - 1, w - 1 - uB);
-    const int y_in = min(yinA, yinB), y_out = max(youtA, youtB);   // A enters first, B leaves last
+    // this warp's skewed columns u0 .. u0+NCW-1 (c0 = lowest u) and their active rows (x' = u + y' in [0, w))
+    const int u0 = ulo + NCW * warp;
+    int yin[NCW], yout[NCW];
+#pragma unroll
+    for (int c = 0; c < NCW; ++c) { yin[c] = max(0, -(u0 + c)); yout[c] = min(h - 1, w - 1 - (u0 + c)); }
+    const int y_in = yin[NCW - 1], y_out = yout[0];   // the highest column enters first, the lowest leaves last
     const bool any = warp < NWW && y_in <= y_out;
     if (threadIdx.x == 0) { ctl->halo_ready = hbeg; ctl->copied = ymin; }
     if (warp < NWW && lane == 0) prog[warp] = any ? y_in : 0x7fffffff;   // rows before y_in never happen
@@ -304,38 +307,60 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     const ptrdiff_t estep = pstep * DP;
 
     // per-column cursors at the column's first active pixel
-    auto first_px = [&](int u, int yin, size_t& e0, size_t& p0) {
-        const int xp0 = u + yin;
-        const int x0 = fwd ? xp0 : w - 1 - xp0, y0 = fwd ? yin : h - 1 - yin;
-        p0 = (size_t)y0 * w + x0;
-        e0 = p0 * DP + d0;
-    };
-    size_t e0A = 0, p0A = 0, e0B = 0, p0B = 0;
-    if (yinA <= youtA) first_px(uA, yinA, e0A, p0A);
-    if (yinB <= youtB) first_px(uB, yinB, e0B, p0B);
     float* const Hp = a.H + (size_t)pair * a.h_pair;
     const char* const Cp = (const char*)a.C + (size_t)pair * a.c_pair * CE;
     const float* const Ip = a.img + (size_t)pair * a.img_pair;
-    float* hstA = Hp + e0A; const float* hldA = hstA; const char* cldA = Cp + e0A * CE; const float* ildA = Ip + p0A;
-    float* hstB = Hp + e0B; const float* hldB = hstB; const char* cldB = Cp + e0B * CE; const float* ildB = Ip + p0B;
+    float* hst[NCW]; const float* hld[NCW]; const char* cld[NCW];
+#pragma unroll
+    for (int c = 0; c < NCW; ++c) {
+        size_t e0 = 0;
+        if (yin[c] <= yout[c]) {
+            const int xp0 = u0 + c + yin[c];
+            const int x0 = fwd ? xp0 : w - 1 - xp0, y0 = fwd ? yin[c] : h - 1 - yin[c];
+            e0 = ((size_t)y0 * w + x0) * DP + d0;
+        }
+        hst[c] = Hp + e0; hld[c] = hst[c]; cld[c] = Cp + e0 * CE;
+    }
 
-    // Prefetch: row y+PFS-1 of both columns is copied global -> shared (asynchronously, no registers) while row y
-    // is computed.  Every lane copies and later reads its own bytes; only the intensity (lane 0) needs a __syncwarp.
-    const unsigned pfA = (unsigned)__cvta_generic_to_shared(s_pf) + (warp * 2) * PFS * STAGE_B;
-    const unsigned pfB = pfA + PFS * STAGE_B;
-    auto issue_px = [&](unsigned base, int yl, const float*& hld, const char*& cld, const float*& ild) {
+    // Prefetch: row y+PFS-1 of every column is copied global -> shared (asynchronously, no registers) while row y
+    // is computed.  Every lane copies and later reads its own bytes, so no barrier is needed.
+    const unsigned pf0 = (unsigned)__cvta_generic_to_shared(s_pf) + (warp * NCW) * PFS * STAGE_B;
+    auto issue_px = [&](unsigned base, int yl, const float*& hl, const char*& cl) {
         const unsigned dst = base + ((unsigned)yl & (PFS - 1)) * STAGE_B;
-        if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hld);
-        cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cld);
-        if (lane == 0) cp_async_bytes<4>(dst + DP * 4 + DP * CE, ild);
-        hld += estep; cld += estep * CE; ild += pstep;
+        if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hl);
+        cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cl);
+        hl += estep; cl += estep * CE;
     };
+    int aLo = yin[0], aHi = yout[NCW - 1];   // rows in which every column is active
     auto issue_row = [&](int yl) {
-        if (yl >= yinA && yl <= youtA) issue_px(pfA, yl, hldA, cldA, ildA);
-        if (yl >= yinB && yl <= youtB) issue_px(pfB, yl, hldB, cldB, ildB);
+        if (yl >= aLo && yl <= aHi) {
+#pragma unroll
+            for (int c = 0; c < NCW; ++c) issue_px(pf0 + c * PFS * STAGE_B, yl, hld[c], cld[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+                if (yl >= yin[c] && yl <= yout[c]) issue_px(pf0 + c * PFS * STAGE_B, yl, hld[c], cld[c]);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     for (int k = 0; k < PFS - 1; ++k) issue_row(y_in + k);
+
+    // Intensities: lane k keeps the pixel of row 32*blk + k of every column (one gather per 32 rows, the next
+    // block already in flight), and a row takes its value with one shuffle -- nothing per row goes to memory.
+    auto gather = [&](int c, int blk) {
+        const int r = 32 * blk + lane;
+        float v = 0.0f;
+        if (r >= yin[c] && r <= yout[c]) {
+            const int xp = u0 + c + r;
+            const int x = fwd ? xp : w - 1 - xp, yy = fwd ? r : h - 1 - r;
+            v = __ldg(Ip + (size_t)yy * w + x);
+        }
+        return v;
+    };
+    int iblk = y_in >> 5;
+    float icur[NCW], inxt[NCW];
+#pragma unroll
+    for (int c = 0; c < NCW; ++c) { icur[c] = gather(c, iblk); inxt[c] = gather(c, iblk + 1); }
 
     // ---- shared-memory addressing, resolved once per warp (32-bit shared-window addresses) ----
     // The three state rows of "the warp above" for image row y-1 come either from the in-band ring (slot
@@ -354,20 +379,28 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     const unsigned eBase = sh_edge + lane * DPL * 4;
     // hand-off flags: rows < *flag of the producer are done
     // (32-bit shared-window addresses: the polling loops below are then LDS / ISETP / BRA / NANOSLEEP only)
-    const unsigned fUp = (unsigned)__cvta_generic_to_shared(upIn ? (const void*)(const_cast<int*>(prog) + warp + 1)
+    unsigned fUp = (unsigned)__cvta_generic_to_shared(upIn ? (const void*)(const_cast<int*>(prog) + warp + 1)
                                                                  : (const void*)const_cast<int*>(&ctl->halo_ready));
-    const unsigned fDn = warp >= 1 ? (unsigned)__cvta_generic_to_shared(const_cast<int*>(prog) + warp - 1)
+    unsigned fDn = warp >= 1 ? (unsigned)__cvta_generic_to_shared(const_cast<int*>(prog) + warp - 1)
                                    : fUp;   // no consumer: alias a flag that is already waited on
-    const unsigned fCp = (unsigned)__cvta_generic_to_shared(const_cast<int*>(&ctl->copied));
+    unsigned fCp = (unsigned)__cvta_generic_to_shared(const_cast<int*>(&ctl->copied));
+    fUp = __shfl_sync(0xffffffffu, fUp, 0); fDn = __shfl_sync(0xffffffffu, fDn, 0); fCp = __shfl_sync(0xffffffffu, fCp, 0);
+    aLo = __shfl_sync(0xffffffffu, aLo, 0); aHi = __shfl_sync(0xffffffffu, aHi, 0);
     const int upCap = upIn ? 0x7fffffff : hend;   // an upstream band only publishes rows < hend
     const int wOff = S - 2;            // the consumer must have finished row y-S+1  <=>  prog >= y-S+2
     const int cOff = RING - 1;         // downstream ring slot free once rows < y-RING+1 were copied out
 
-    // register state: diagonal path of both columns; A's vertical state of the previous row (input of B's vertical path)
-    float dA[DPL], dB[DPL], vA[DPL];
+    // register state of the previous row: the diagonal path of every column (it stays in its column), the
+    // vertical path of columns 1.. (input of the column below: c-1) and the anti-diagonal path of columns 2..
+    // (input of column c-2); columns 0 and 1 hand theirs to the warp below through shared memory instead.
+    float Dr[NCW][DPL], Vr[NCW][DPL], Ar[NCW][DPL];
+    float lbD[NCW], pixD[NCW], lbVr[NCW], lbAr[NCW], pxr[NCW];
 #pragma unroll
-    for (int j = 0; j < DPL; ++j) { dA[j] = ROO_INF; dB[j] = ROO_INF; vA[j] = ROO_INF; }
-    float lbDA = 0.0f, pixDA = 0.0f, lbDB = 0.0f, pixDB = 0.0f, lbVA = 0.0f, pixA = 0.0f;
+    for (int c = 0; c < NCW; ++c) {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) { Dr[c][j] = ROO_INF; Vr[c][j] = ROO_INF; Ar[c][j] = ROO_INF; }
+        lbD[c] = 0.0f; pixD[c] = 0.0f; lbVr[c] = 0.0f; lbAr[c] = 0.0f; pxr[c] = 0.0f;
+    }
 
     auto tick = [&](auto masked_tag, auto edge_tag, int y) {
         constexpr bool MASKED = decltype(masked_tag)::value;
@@ -377,63 +410,82 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         const unsigned upsc = upScBase + (ym1 & upMask) * upScStride;
         const unsigned slot = (unsigned)y & (S - 1);
         const unsigned mine = myBase + slot * SLOT_B;
-        const bool actA = !EDGE || (y >= yinA && y <= youtA);
-        const bool actB = !EDGE || (y >= yinB && y <= youtB);
-        const float4 scUpB = lds_f4(upsc);        // upper warp's B: {lastBest(V), lastBest(A), pix, -}
-        const float4 scUpA = lds_f4(upsc + 16);   // upper warp's A: {-, lastBest(A), pix, -}
-        float bBV = 0.0f, bBA = 0.0f, pixB = 0.0f, bAA = 0.0f;
-        // ---- column B (lower): vertical continues from A's previous row (registers), anti-diagonal from upper B
-        if (actB) {
-            const int xp = uB + y, x = fwd ? xp : w - 1 - xp;
-            float hv[DPL], ha[DPL];
+        const unsigned stg0 = pf0 + ((unsigned)y & (PFS - 1)) * STAGE_B;
+        const unsigned er = eBase + ((unsigned)y & (RING - 1)) * HROW_B;
+        const float4 scUp0 = lds_f4(upsc);        // upper warp's c0: {lastBest(V), lastBest(A), pix, -}
+        const float4 scUp1 = lds_f4(upsc + 16);   // upper warp's c1: {-, lastBest(A), pix, -}
+        float4 sc0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sc1 = sc0;
+        // ascending c: column c reads the previous-row registers of c+1 and c+2 before those columns overwrite them
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) hv[j] = vA[j];
-            lds_vec<DPL>(ha, up + REC_B);
-            float lbV = lbVA, lbA = scUpB.y;
-            vg_pixel<DPL, COST, MASKED, EDGE, FIRST, IEEE>(pfB + ((unsigned)y & (PFS - 1)) * STAGE_B, lane, y, xp, x, w, M, P1, P2,
-                                                           cscale, hv, lbV, pixA, dB, lbDB, pixDB, ha, lbA, scUpB.z, pixB, hstB);
-            hstB += estep;
-            sts_vec<DPL>(mine, hv);
-            sts_vec<DPL>(mine + REC_B, ha);
-            if (edge_out) {
-                const unsigned er = eBase + ((unsigned)y & (RING - 1)) * HROW_B;
-                sts_vec<DPL>(er, hv);
-                sts_vec<DPL>(er + REC_B, ha);
+        for (int c = 0; c < NCW; ++c) {
+            const bool act = !EDGE || (y >= yin[c] && y <= yout[c]);
+            if (act) {
+                const int xp = u0 + c + y, x = fwd ? xp : w - 1 - xp;
+                const float pix = __shfl_sync(0xffffffffu, icur[c], y & 31);
+                float hv[DPL], ha[DPL], lbV, lbA, ppV, ppA;
+                if (c < NCW - 1) {
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) hv[j] = Vr[c + 1][j];
+                    lbV = lbVr[c + 1]; ppV = pxr[c + 1];
+                } else {
+                    lds_vec<DPL>(hv, up);
+                    lbV = scUp0.x; ppV = scUp0.z;
+                }
+                if (c < NCW - 2) {
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) ha[j] = Ar[c + 2][j];
+                    lbA = lbAr[c + 2]; ppA = pxr[c + 2];
+                } else if (c == NCW - 2) {
+                    lds_vec<DPL>(ha, up + REC_B);
+                    lbA = scUp0.y; ppA = scUp0.z;
+                } else {
+                    lds_vec<DPL>(ha, up + 2 * REC_B);
+                    lbA = scUp1.y; ppA = scUp1.z;
+                }
+                vg_pixel<DPL, COST, MASKED, EDGE, FIRST, IEEE>(stg0 + c * PFS * STAGE_B, lane, y, xp, x, w, M, P1, P2, cscale, pix,
+                                                               hv, lbV, ppV, Dr[c], lbD[c], pixD[c], ha, lbA, ppA, hst[c]);
+                hst[c] += estep;
+                if (c == 0) {
+                    sts_vec<DPL>(mine, hv);
+                    sts_vec<DPL>(mine + REC_B, ha);
+                    if (edge_out) { sts_vec<DPL>(er, hv); sts_vec<DPL>(er + REC_B, ha); }
+                    sc0 = make_float4(lbV, lbA, pix, 0.0f);
+                } else {
+                    if (c == 1) {
+                        sts_vec<DPL>(mine + 2 * REC_B, ha);
+                        if (edge_out) sts_vec<DPL>(er + 2 * REC_B, ha);
+                        sc1 = make_float4(0.0f, lbA, pix, 0.0f);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < DPL; ++j) Ar[c][j] = ha[j];
+                        lbAr[c] = lbA;
+                    }
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) Vr[c][j] = hv[j];
+                    lbVr[c] = lbV; pxr[c] = pix;
+                }
             }
-            bBV = lbV; bBA = lbA;
-        }
-        // ---- column A (upper): vertical from upper B, anti-diagonal from upper A; its vertical state stays in registers
-        if (actA) {
-            const int xp = uA + y, x = fwd ? xp : w - 1 - xp;
-            float ha[DPL];
-            lds_vec<DPL>(vA, up);
-            lds_vec<DPL>(ha, up + 2 * REC_B);
-            lbVA = scUpB.x;
-            float lbA = scUpA.y;
-            vg_pixel<DPL, COST, MASKED, EDGE, FIRST, IEEE>(pfA + ((unsigned)y & (PFS - 1)) * STAGE_B, lane, y, xp, x, w, M, P1, P2,
-                                                           cscale, vA, lbVA, scUpB.z, dA, lbDA, pixDA, ha, lbA, scUpA.z, pixA, hstA);
-            hstA += estep;
-            sts_vec<DPL>(mine + 2 * REC_B, ha);
-            if (edge_out) sts_vec<DPL>(eBase + ((unsigned)y & (RING - 1)) * HROW_B + 2 * REC_B, ha);
-            bAA = lbA;
         }
         if (lane == 0) {
-            sts_f4(myScBase + slot * SLOTSC_B, make_float4(bBV, bBA, pixB, 0.0f));
-            sts_f4(myScBase + slot * SLOTSC_B + 16, make_float4(0.0f, bAA, pixA, 0.0f));
+            sts_f4(myScBase + slot * SLOTSC_B, sc0);
+            sts_f4(myScBase + slot * SLOTSC_B + 16, sc1);
             if (edge_out) {
                 const unsigned esc = sh_esc + ((unsigned)y & (RING - 1)) * HSC_B;
-                sts_f4(esc, make_float4(bBV, bBA, pixB, 0.0f));
-                sts_f4(esc + 16, make_float4(0.0f, bAA, pixA, 0.0f));
+                sts_f4(esc, sc0);
+                sts_f4(esc + 16, sc1);
             }
         }
     };
 
-    // Row classes, resolved once per warp.  With x'_B = uB + y (B is the leftmost of the two columns, x'_A = x'_B + 1):
-    //   interior rows [eLo, eHi]: y >= 1, x'_B >= 1, x'_A <= w-2 and both columns active -- no path starts or ends;
-    //   unmasked rows [mLo, mHi]: the smaller true x of the two pixels (x'_B forward, w-2-x'_B backward) is >= xf.
-    int eLo = max(max(1, 1 - uB), max(yinA, yinB)), eHi = min(w - 3 - uB, min(youtA, youtB));
-    int mLo = fwd ? xf - uB : -0x3fffffff, mHi = fwd ? 0x3fffffff : (xf > w ? -0x3fffffff : w - 2 - uB - xf);
-    asm volatile("" : "+r"(eLo), "+r"(eHi), "+r"(mLo), "+r"(mHi));   // keep them in registers: no per-row rematerialisation
+    // Row classes, resolved once per warp.  With x'_c = u0 + c + y (c0 is the leftmost column):
+    //   interior rows [eLo, eHi]: y >= 1, x'_0 >= 1, x'_{NCW-1} <= w-2 and every column active -- no path starts or ends;
+    //   unmasked rows [mLo, mHi]: the smallest true x of the NCW pixels (x'_0 forward, w-1-x'_{NCW-1} backward) is >= xf.
+    int eLo = max(max(1, 1 - u0), yin[0]), eHi = min(w - 1 - NCW - u0, yout[NCW - 1]);
+    int mLo = fwd ? xf - u0 : -0x3fffffff, mHi = fwd ? 0x3fffffff : (xf > w ? -0x3fffffff : w - NCW - u0 - xf);
+    // through a shuffle: ptxas cannot rematerialise that, so the bounds stay in registers instead of being
+    // recomputed (6-10 instructions each) in every row
+    eLo = __shfl_sync(0xffffffffu, eLo, 0); eHi = __shfl_sync(0xffffffffu, eHi, 0);
+    mLo = __shfl_sync(0xffffffffu, mLo, 0); mHi = __shfl_sync(0xffffffffu, mHi, 0);
 
     // No CTA-wide barrier: the warps of a band form a dataflow pipeline through shared memory.  Warp v may start
     // row y once warp v+1 has finished row y-1 (read-after-write) and warp v-1 has finished row y-S+1 (so the
@@ -447,8 +499,12 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         long long t0 = clock64();
 #endif
         issue_row(y + PFS - 1);
+        if ((y & 31) == 0 && y != y_in) {   // next block of 32 rows of intensities: in flight since 32 rows ago
+            ++iblk;
+#pragma unroll
+            for (int c = 0; c < NCW; ++c) { icur[c] = inxt[c]; inxt[c] = gather(c, iblk + 1); }
+        }
         asm volatile("cp.async.wait_group %0;" ::"n"(PFS - 1) : "memory");   // row y's stages have landed
-        __syncwarp();
 #ifdef VG_TIMING
         long long t1 = clock64(); tcp += t1 - t0;
         spin_until(fUp, min(y, upCap));
@@ -499,15 +555,15 @@ size_t vgroup_edge_floats(int w, int h, int DP) { return (size_t)vgroup_bands(w,
 template <int DPL, int COST>
 static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     constexpr int DP = 32 * DPL;
-    constexpr int NWW = vg_nww(DPL);
+    constexpr int NWW = vg_nww(DPL), NCW = vg_ncw(DPL);
     constexpr int CE = RawCost<DPL, COST>::ELEM;
     const size_t smem = (size_t)(VG_S * NWW * 3 * DP + VG_S * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
-                        sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * 2 * vg_pfs(DPL, CE) * (DP * 4 + DP * CE + 16);
+                        sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * NCW * vg_pfs(DPL, CE) * (DP * 4 + DP * CE);
     dim3 grid(a.n_bands * a.batch), block((NWW + 1) * 32);
     const bool ieee = g_ieee_div.load() != 0;
 #define ROO_VG(F, I)                                                                                          \
     do {                                                                                                      \
-        auto kern = sgm_vgroup_kernel<DPL, COST, F, I, NWW>;                                                  \
+        auto kern = sgm_vgroup_kernel<DPL, COST, F, I, NWW, NCW>;                                                  \
         if (smem > 48 * 1024) {                                                                               \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                              \

@@ -93,6 +93,12 @@ __device__ __forceinline__ void cp_async_bytes(unsigned sdst, const void* gsrc) 
     }
 }
 
+// 4-byte copy issued by the lanes with pred != 0 only -- a predicated instruction, not a divergent branch
+__device__ __forceinline__ void cp_async_4_if(int pred, unsigned sdst, const void* gsrc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p cp.async.ca.shared.global [%1], [%2], 4;\n\t}"
+                 ::"r"(pred), "r"(sdst), "l"(gsrc) : "memory");
+}
+
 // raw matching cost of one pixel as loaded; converted to float at use
 enum CostKind { COST_F32 = 0, COST_U8 = 1 };
 template <int DPL, int COST> struct RawCost;
@@ -197,6 +203,7 @@ __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float de
     const float baseD = sgm_p2_base<IEEE>(lbD, p2D, denD);
     const float baseA = sgm_p2_base<IEEE>(lbA, p2A, denA);
     float mV = SGM_MAX_ERROR, mD = SGM_MAX_ERROR, mA = SGM_MAX_ERROR;
+    float tV = 0.0f, tD = 0.0f, tA = 0.0f;
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
         const float cmV = fminf(fminf(baseV, hpV[j]), fminf(j > 0 ? pV[j - 1] : upV, j < DPL - 1 ? pV[j + 1] : dnV));
@@ -218,7 +225,14 @@ __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float de
             hpA[j] = in ? h3 : ROO_INF;
             H3[j] = in ? h3 : (FIRST ? 0.0f : hin[j]);
         } else {
-            mV = fminf(mV, crV); mD = fminf(mD, crD); mA = fminf(mA, crA);
+            // pairs first, so that every second min is a three-input FMNMX3 (min is exact: any grouping agrees)
+            if (j & 1) {
+                mV = fminf(mV, fminf(tV, crV)); mD = fminf(mD, fminf(tD, crD)); mA = fminf(mA, fminf(tA, crA));
+            } else if (j == DPL - 1) {
+                mV = fminf(mV, crV); mD = fminf(mD, crD); mA = fminf(mA, crA);
+            } else {
+                tV = crV; tD = crD; tA = crA;
+            }
             hpV[j] = h1; hpD[j] = h2; hpA[j] = h3;
             H3[j] = h3;
         }

@@ -37,13 +37,20 @@ namespace roo_b200 {
 // rows of prefetch per column, staged in shared memory by cp.async (LDGSTS): under load a DRAM access takes
 // ~3000 SM cycles on B200, so a band needs ~60-80 KB in flight per SM to stream at HBM speed -- far more
 // than a register ring can hold, and without unrolling the row loop.  (227 KB of shared memory per CTA.)
-__host__ __device__ constexpr int vg_pfs(int DPL, int CE) { return DPL >= 8 ? 2 : (DPL == 4 ? (CE == 4 ? 2 : 4) : 8); }
+__host__ __device__ constexpr int vg_pfs(int DPL, int CE) {
+    return DPL >= 8 ? 2 : (DPL == 4 ? (CE == 4 ? 2 : 4) : (DPL == 2 && CE == 4 ? 4 : 8));
+}
 // skewed columns per compute warp, and compute warps per band (+ 1 communication warp)
 #ifndef VG_NCW
 #define VG_NCW 4
 #endif
 __host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? 2 : VG_NCW; }
-__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : 32 / vg_ncw(DPL); }
+// 12 warps x 4 columns: 13 warps of <= 152 registers fill the register file, and ring + prefetch stages fill
+// the 227 KB of shared memory (measured on B200 at 128 disparities: 8 warps 6.6 ms, 10: 6.5 ms, 12: 6.1 ms per 16 pairs)
+#ifndef VG_NWW
+#define VG_NWW 12
+#endif
+__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : VG_NWW; }
 inline int vg_cols_of_dp(int DP) { return vg_ncw(DP / 32) * vg_nww(DP / 32); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -121,8 +128,14 @@ __device__ __forceinline__ void spin_until(unsigned flag_addr, int need) {
 struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 
 
-__host__ __device__ constexpr int vg_r(int DPL) { return 4; }   // max rows per hand-off batch between bands (ring = 2x)
-constexpr int VG_S = 4;   // depth (rows) of the in-band state ring in shared memory
+#ifndef VG_R
+#define VG_R 4
+#endif
+__host__ __device__ constexpr int vg_r(int DPL) { return VG_R; }   // max rows per hand-off batch between bands (ring = 2x)
+#ifndef VG_S_DEPTH
+#define VG_S_DEPTH 4
+#endif
+constexpr int VG_S = VG_S_DEPTH;   // depth (rows) of the in-band state ring in shared memory
 
 // One pixel of the three paths.  V/D/A = vertical / diagonal / anti-diagonal.  hpV, hpD, hpA: previous pixel's
 // state rows on entry, this pixel's on exit.  Handles path starts when EDGE.
@@ -557,8 +570,9 @@ static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     constexpr int DP = 32 * DPL;
     constexpr int NWW = vg_nww(DPL), NCW = vg_ncw(DPL);
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    const size_t smem = (size_t)(VG_S * NWW * 3 * DP + VG_S * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
-                        sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * NCW * vg_pfs(DPL, CE) * (DP * 4 + DP * CE);
+    constexpr size_t smem = (size_t)(VG_S * NWW * 3 * DP + VG_S * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
+                            sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * NCW * vg_pfs(DPL, CE) * (DP * 4 + DP * CE);
+    static_assert(smem <= 227 * 1024, "vertical-group kernel: shared memory budget of one sm_100 CTA exceeded");
     dim3 grid(a.n_bands * a.batch), block((NWW + 1) * 32);
     const bool ieee = g_ieee_div.load() != 0;
 #define ROO_VG(F, I)                                                                                          \

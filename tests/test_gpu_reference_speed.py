@@ -1,0 +1,109 @@
+"""The "beat THAT kernel" row: the reference's own CUDA kernels, recompiled unmodified for
+sm_100a (oracle/_ref), timed on the same B200 next to this engine on the same stereo pair.
+
+Sequence timed for the reference = applications/stereo2/main.cpp:380-431 with device-resident inputs:
+Census x2 -> CensusStereoVolume<float, unsigned long> -> SemiGlobalMatching<float,float,float> (4 paths)
+-> CostVolMinimumSubpix.  The reference launches one block per sweep and is limited to w, h <= 1024, so the
+shapes are BASELINE config 1 (640x480x64) and 1024x720x128 (config 2 cropped to the reference's limit).
+
+The numbers go to gpurun_out/ref_gpu_speed.json (copied to profiles/ by hand); the assertions are that both
+produce the same disparities and that the engine is faster.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from kangaroo_b200.synth import stereo_pair
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from kangaroo_b200 import roo  # noqa: E402
+from oracle import ref_gpu  # noqa: E402
+
+if not ref_gpu.available():  # pragma: no cover
+    pytest.skip("oracle/_ref/libkangaroo_ref.so not built", allow_module_level=True)
+
+
+def _events(fn, reps):
+    fn()  # warm-up
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(reps):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) / reps
+
+
+def _reference_step(L, R, D):
+    """Device buffers + a closure that runs the reference's kernels once (legacy default stream)."""
+    h, w = L.shape
+    lib = ref_gpu.lib()
+    u8 = lambda n: torch.zeros(n, dtype=torch.uint8, device="cuda")  # noqa: E731
+    dL, dR = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    fL = (dL.float() / 255.0).contiguous()   # stereo2/main.cpp:376 -- ElementwiseScaleBias, outside the path
+    cL, cR = u8(h * w * 8), u8(h * w * 8)
+    # one slice of slack: CostVolMinimumSubpix reads slice bestd+1 == maxDisp where the minimum is the last one (Q7)
+    volC, volH = u8(D * h * w * 4), u8((D + 1) * h * w * 4)
+    disp = torch.zeros((h, w), dtype=torch.float32, device="cuda")
+
+    def step():
+        rc = lib.kref_census(cL.data_ptr(), w * 8, dL.data_ptr(), w, w, h, 0, 0)
+        rc |= lib.kref_census(cR.data_ptr(), w * 8, dR.data_ptr(), w, w, h, 0, 0)
+        rc |= lib.kref_census_stereo_volume(volC.data_ptr(), w * 4, w * h * 4, D, cL.data_ptr(), cR.data_ptr(), w * 8,
+                                            w, h, 1, 1, D, -1.0)
+        rc |= lib.kref_sgm(volH.data_ptr(), volC.data_ptr(), w * 4, w * h * 4, w * 4, w * h * 4, fL.data_ptr(), w * 4,
+                           w, h, D, 0, D, 0.01, 0.02, 1, 1, 1)
+        rc |= lib.kref_costvol_minimum_subpix(disp.data_ptr(), w * 4, volH.data_ptr(), w * 4, w * h * 4, w, h, D, D,
+                                              -1.0)
+        assert rc == 0
+    return step, disp
+
+
+@pytest.mark.parametrize("w,h,D,cfg", [(640, 480, 64, 1), (1024, 720, 128, 2)])
+def test_engine_beats_reference_kernels_on_the_same_gpu(w, h, D, cfg):
+    L, R, _ = stereo_pair(w, h, D, config=cfg)
+    ref_step, ref_disp = _reference_step(L, R, D)
+    ref_ms = _events(ref_step, 3)
+
+    B = 8
+    dL = torch.from_numpy(np.repeat(L[None], B, 0)).cuda()
+    dR = torch.from_numpy(np.repeat(R[None], B, 0)).cuda()
+    out = {}
+    for name, batch in (("engine_1pair", 1), ("engine_batch8", B)):
+        eng = roo.StereoEngine(w, h, D, subpix=True, max_batch=batch)   # the reference's 4 paths
+        disp = torch.empty((batch, h, w), dtype=torch.float32, device="cuda")
+        ms = _events(lambda: eng.run_device(dL[:batch], dR[:batch], disp), 20)
+        out[name] = {"ms_per_call": ms, "pairs_per_s": batch / ms * 1e3}
+        mine = disp[0].cpu().numpy()
+        eng.close()
+
+    # same answer (the aggregate is bit-identical -- test_gpu_parity -- so only the Q7 top-slice pixels may differ)
+    ref = ref_disp.cpu().numpy()
+    top = np.rint(ref) >= D - 1
+    assert (np.abs(ref - mine)[~top] <= 0.01).mean() >= 0.999
+
+    res = {"shape": [w, h, D], "paths": 4, "wta": "CostVolMinimumSubpix",
+           "reference_kernels": {"ms_per_pair": ref_ms, "pairs_per_s": 1e3 / ref_ms,
+                                 "build": "oracle/_ref: nvcc -O2 -use_fast_math sm_100a, unmodified sources"},
+           **out,
+           "speedup_1pair": ref_ms / out["engine_1pair"]["ms_per_call"],
+           "speedup_batch8": ref_ms / (out["engine_batch8"]["ms_per_call"] / B),
+           "gpu": torch.cuda.get_device_name(0)}
+    print("\nREF_GPU_SPEED " + json.dumps(res))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        path = "gpurun_out/ref_gpu_speed.json"
+        prev = json.load(open(path)) if os.path.exists(path) else {}
+        prev[f"{w}x{h}x{D}"] = res
+        json.dump(prev, open(path, "w"), indent=1)
+    except OSError:
+        pass
+    assert res["speedup_1pair"] > 1.0

@@ -302,10 +302,13 @@ def main():
         if e2e:
             out["e2e"] = e2e
         if not args.no_cpu_baseline:
-            rows = min(h, 240)  # bounded sample: ~10-30 s of CPU work
-            v, dt, cores, rows = cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, rows)
+            # bounded sample: whole pairs, about 10-20 s of wall time on all host cores
+            _, dt1, _, _ = cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, h)
+            reps = max(1, min(8, int(10.0 / dt1)))
+            v, dt, cores, rows = cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, h, reps)
             out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                   "sample": f"{rows} of {h} rows of one {w}x{h}x{D} pair, {paths}-path, {dt:.1f} s"}
+                                   "sample": f"{reps} whole {w}x{h}x{D} pair(s), {paths}-path, {dt:.2f} s each "
+                                             f"on {cores} threads (after 1 warm-up pair)"}
         print(json.dumps(out), flush=True)
     eng.close()
     if world > 1:

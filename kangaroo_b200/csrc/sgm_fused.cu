@@ -14,17 +14,18 @@
 //   * the diagonal path (+1,+1) stays inside the warp: its state never leaves registers;
 //   * the vertical path needs the state of column u+1, the anti-diagonal path that of column u+2, both of
 //     the previous row -> every dependency points towards HIGHER u.  Inside a CTA (a band of NW columns)
-//     the states go through shared memory (double-buffered by row parity, one __syncthreads per row);
+//     the states go through a shared-memory ring guarded by per-warp progress words (no CTA barrier);
 //     between CTAs they flow one way only, from band b-1 to band b, through a small L2-resident edge
 //     buffer guarded by a monotonic progress flag.  One-way dependencies make the bands a pipeline, not a
 //     ping-pong: a band never waits for a band that waits for it, and lower block indices (scheduled
 //     first) never wait for higher ones.
 //   * a dedicated communication warp per CTA polls the upstream flag, stages the upstream edge rows into
 //     shared memory and publishes this band's flag, so the compute warps never touch the global flags.
-//   * every compute warp owns TWO adjacent skewed columns (B = u, A = u+1) and advances both by one row per
-//     tick: the vertical path of B continues from A's state of the previous tick (registers), so only three
-//     state rows per tick go through shared memory, and the per-tick bookkeeping (hand-off flags, prefetch
-//     issue, addressing) is paid once for two pixels.
+//   * every compute warp owns NCW (four; two at 256 disparities) adjacent skewed columns c0 = u .. and advances
+//     all of them by one row per tick: the vertical path of column c continues from column c+1's state of the
+//     previous tick and the anti-diagonal path from column c+2's (registers), so only three state rows per tick
+//     (c0.vertical, c0.anti-diagonal, c1.anti-diagonal) go through shared memory, and the per-tick bookkeeping
+//     (hand-off flags, prefetch issue, addressing) is paid once for NCW pixels.
 // HBM traffic of the pass: read H (unless first) + read cost + write H -- the same as ONE single-path sweep.
 #include <type_traits>
 

@@ -177,6 +177,39 @@ inline void LeftRightCheck(Image<float> dispL, Image<float> dispR, float sd = -1
     b200::done(roo_left_right_check_f32(&l, &r, sd, maxDiff, b200::stream_slot()), "LeftRightCheck");
 }
 
+// ---- callers either side of the path: cu_operations.h:14-15, reduce.h:7-8, cu_depth_tools.h:11,
+//      cu_dense_stereo.h (DisparityImageToVbo) -- same names, template parameters and defaults as the reference
+namespace b200 {
+template <typename T> struct pix_type;
+template <> struct pix_type<unsigned char> { static constexpr int value = ROO_PIX_U8; };
+template <> struct pix_type<unsigned short> { static constexpr int value = ROO_PIX_U16; };
+template <> struct pix_type<float> { static constexpr int value = ROO_PIX_F32; };
+}  // namespace b200
+template <typename Tout, typename Tin, typename Tup>
+inline void ElementwiseScaleBias(Image<Tout> b, const Image<Tin> a, float s, Tup offset = 0) {
+    static_assert(std::is_same<Tout, float>::value && std::is_same<Tup, float>::value,
+                  "ElementwiseScaleBias: <float, {unsigned char, unsigned short, float}, float> (cu_operations.cu:260-262)");
+    auto cb = b200::c(b), ca = b200::c(a);
+    b200::done(roo_elementwise_scale_bias(&cb, &ca, b200::pix_type<Tin>::value, s, offset, b200::stream_slot()),
+               "ElementwiseScaleBias");
+}
+template <typename To, typename UpType, typename Ti>
+inline void BoxHalf(Image<To> out, const Image<Ti> in) {
+    static_assert(std::is_same<To, Ti>::value && (std::is_same<Ti, unsigned char>::value || std::is_same<Ti, float>::value),
+                  "BoxHalf: <unsigned char, unsigned int, unsigned char> or <float, float, float> (cu_resample.cu:80-81)");
+    auto co = b200::c(out), ci = b200::c(in);
+    b200::done(roo_box_half(&co, &ci, b200::pix_type<Ti>::value, b200::stream_slot()), "BoxHalf");
+}
+inline void Disp2Depth(Image<float> dIn, const Image<float> dOut, float fu, float fBaseline, float fMinDisp = 0.0) {
+    auto ci = b200::c(dIn), co = b200::c(dOut);
+    b200::done(roo_disp2depth(&ci, &co, fu, fBaseline, fMinDisp, b200::stream_slot()), "Disp2Depth");
+}
+inline void DisparityImageToVbo(Image<float4> dVbo, const Image<float> dDisp, float baseline, float fu, float fv,
+                                float u0, float v0) {
+    auto cv = b200::c(dVbo), cd = b200::c(dDisp);
+    b200::done(roo_disparity_image_to_vbo(&cv, &cd, baseline, fu, fv, u0, v0, b200::stream_slot()), "DisparityImageToVbo");
+}
+
 // ---- extension: the fused per-frame engine (census -> cost -> SGM -> WTA/subpixel -> LR check) --------
 class StereoEngine {
 public:

@@ -103,6 +103,30 @@ int roo_dense_stereo_subpixel_refine(const roo_image_t* out_f32, const roo_image
 int roo_left_right_check_f32(const roo_image_t* dispL, const roo_image_t* dispR, float sd, float maxDiff, void* stream);
 int roo_left_right_check_i8(const roo_image_t* dispL, const roo_image_t* dispR, int sd, int maxDiff, void* stream);
 
+/* ---- callers either side of the path (N3 front end, N2 back end) ------------------------------- */
+
+enum roo_pix_type { ROO_PIX_U8 = 0, ROO_PIX_F32 = 1, ROO_PIX_U16 = 2 };
+
+/* roo::ElementwiseScaleBias<float, {unsigned char, unsigned short, float}, float> (cu_operations.h:14-15;
+ * cu_operations.cu:39-57,260-262): b = s*a + offset (one fused multiply-add, as in the reference build).
+ * applications/stereo2/main.cpp:376 calls it with s = 1/255 to feed Census / SemiGlobalMatching. */
+int roo_elementwise_scale_bias(const roo_image_t* b_f32, const roo_image_t* a, int in_type, float s, float offset,
+                               void* stream);
+
+/* roo::BoxHalf<unsigned char,unsigned int,unsigned char> / <float,float,float> (reduce.h:7-8;
+ * cu_resample.cu:53-83): out(x,y) = mean of in(2x..2x+1, 2y..2y+1); one level of BoxReduce (reduce.h:35-46).
+ * `in` must cover 2*out.w x 2*out.h (the reference reads it unguarded). */
+int roo_box_half(const roo_image_t* out, const roo_image_t* in, int pix_type, void* stream);
+
+/* roo::Disp2Depth (cu_depth_tools.h:11; cu_depth_tools.cu:15-30): out = in >= minDisp ? fu*baseline/in : NaN. */
+int roo_disp2depth(const roo_image_t* in_f32, const roo_image_t* out_f32, float fu, float baseline, float minDisp,
+                   void* stream);
+
+/* roo::DisparityImageToVbo (cu_dense_stereo.h; cu_dense_stereo.cu:633-646; disparity.h:9-20): vbo = float4
+ * {z*(u-u0)/fu, z*(v-v0)/fv, z, 1} with z = disp >= 0 ? fu*baseline/disp : NaN.  vbo rows must be 16-byte aligned. */
+int roo_disparity_image_to_vbo(const roo_image_t* vbo_f32x4, const roo_image_t* disp_f32, float baseline, float fu,
+                               float fv, float u0, float v0, void* stream);
+
 /* ---- fused engine: the whole per-frame path of applications/stereo2/main.cpp:375-454 ------- */
 
 typedef struct roo_engine roo_engine_t;

@@ -202,6 +202,45 @@ def LeftRightCheck(dispL: Image, dispR: Image, sd=-1, maxDiff=None, stream=None)
               "LeftRightCheck")
 
 
+# ---- callers either side of the path: front end (N3) and back end (N2) of SURVEY.md section 8f
+
+FLOAT4 = np.dtype((np.float32, (4,)))   # float4
+PIX_U8, PIX_F32, PIX_U16 = 0, 1, 2
+_PIX_TYPES = {np.dtype(np.uint8): PIX_U8, np.dtype(np.float32): PIX_F32, np.dtype(np.uint16): PIX_U16}
+
+
+def ElementwiseScaleBias(b: Image, a: Image, s: float, offset: float = 0.0, stream=None) -> None:
+    """roo::ElementwiseScaleBias<float,{uchar,ushort,float},float> (cu_operations.h:14-15): b = s*a + offset."""
+    check(lib().roo_elementwise_scale_bias(C.byref(b.c()), C.byref(a.c()), _PIX_TYPES[a.dtype], s, offset,
+                                           _stream(stream)), "ElementwiseScaleBias")
+
+
+def BoxHalf(out: Image, in_: Image, stream=None) -> None:
+    """roo::BoxHalf<uchar,uint,uchar> / <float,float,float> (reduce.h:7-8)."""
+    if out.dtype != in_.dtype or in_.dtype not in (np.dtype(np.uint8), np.dtype(np.float32)):
+        raise TypeError("BoxHalf: unsigned char or float images of the same type (reduce.h:7-8 instantiations)")
+    check(lib().roo_box_half(C.byref(out.c()), C.byref(in_.c()), _PIX_TYPES[in_.dtype], _stream(stream)), "BoxHalf")
+
+
+def BoxReduce(pyramid, stream=None) -> None:
+    """roo::BoxReduce(Pyramid) (reduce.h:35-46): level l = BoxHalf(level l-1); `pyramid` is a list of Images."""
+    for lvl in range(1, len(pyramid)):
+        BoxHalf(pyramid[lvl], pyramid[lvl - 1], stream)
+
+
+def Disp2Depth(dIn: Image, dOut: Image, fu: float, fBaseline: float, fMinDisp: float = 0.0, stream=None) -> None:
+    """roo::Disp2Depth (cu_depth_tools.h:11)."""
+    check(lib().roo_disp2depth(C.byref(dIn.c()), C.byref(dOut.c()), fu, fBaseline, fMinDisp, _stream(stream)),
+          "Disp2Depth")
+
+
+def DisparityImageToVbo(dVbo: Image, dDisp: Image, baseline: float, fu: float, fv: float, u0: float, v0: float,
+                        stream=None) -> None:
+    """roo::DisparityImageToVbo (cu_dense_stereo.cu:633-646); dVbo is an Image of FLOAT4."""
+    check(lib().roo_disparity_image_to_vbo(C.byref(dVbo.c()), C.byref(dDisp.c()), baseline, fu, fv, u0, v0,
+                                           _stream(stream)), "DisparityImageToVbo")
+
+
 def set_ieee_division(on: bool) -> None:
     lib().roo_set_ieee_division(int(on))
 

@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
         L.ko_dense_stereo_subpixel_refine.argtypes = [P(KoImage)] * 5
         L.ko_left_right_check_f32.argtypes = [P(KoImage), P(KoImage), C.c_float, C.c_float]
         L.ko_left_right_check_i8.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
+        L.ko_elementwise_scale_bias.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_float, C.c_float]
+        L.ko_box_half.argtypes = [P(KoImage), P(KoImage), C.c_int]
+        L.ko_disp2depth.argtypes = [P(KoImage), P(KoImage), C.c_float, C.c_float, C.c_float]
+        L.ko_disparity_image_to_vbo.argtypes = [P(KoImage), P(KoImage)] + [C.c_float] * 5
         L.ko_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ko_hamming.restype = C.c_uint
         L.ko_pipeline_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -203,6 +207,36 @@ def left_right_check_i8(disp_l: np.ndarray, disp_r: np.ndarray, sd: int = -1, ma
     out = np.array(disp_l, np.int8, copy=True)
     lib().ko_left_right_check_i8(C.byref(_img(out)), C.byref(_img(disp_r)), sd, max_diff)
     return out
+
+
+PIX_U8, PIX_F32, PIX_U16 = 0, 1, 2
+_PIX = {np.dtype(np.uint8): PIX_U8, np.dtype(np.float32): PIX_F32, np.dtype(np.uint16): PIX_U16}
+
+
+def elementwise_scale_bias(a: np.ndarray, s: float, offset: float = 0.0) -> np.ndarray:
+    b = np.zeros(a.shape, np.float32)
+    lib().ko_elementwise_scale_bias(C.byref(_img(b)), C.byref(_img(a)), _PIX[a.dtype], s, offset)
+    return b
+
+
+def box_half(img: np.ndarray) -> np.ndarray:
+    h, w = img.shape
+    out = np.zeros((h // 2, w // 2), img.dtype)
+    lib().ko_box_half(C.byref(_img(out)), C.byref(_img(img)), _PIX[img.dtype])
+    return out
+
+
+def disp2depth(disp: np.ndarray, fu: float, baseline: float, min_disp: float = 0.0) -> np.ndarray:
+    out = np.zeros(disp.shape, np.float32)
+    lib().ko_disp2depth(C.byref(_img(disp)), C.byref(_img(out)), fu, baseline, min_disp)
+    return out
+
+
+def disparity_image_to_vbo(disp: np.ndarray, baseline: float, fu: float, fv: float, u0: float, v0: float) -> np.ndarray:
+    h, w = disp.shape
+    vbo = np.zeros((h, w, 4), np.float32)
+    lib().ko_disparity_image_to_vbo(C.byref(_img(vbo)), C.byref(_img(disp)), baseline, fu, fv, u0, v0)
+    return vbo
 
 
 def pipeline_u8(left: np.ndarray, right: np.ndarray, max_disp: int, window: int = WIN_9x7,

@@ -422,6 +422,71 @@ void ko_dense_stereo_subpixel_refine(const ko_image* out, const ko_image* disp, 
         }
 }
 
+/* ---------------------------------------------------------------- front end / back end ---- */
+
+/* cu_operations.cu:39-49: v1 = ConvertPixel<float,Tin>(a(x,y)) (plain conversion, pixel_convert.h);
+ * b(x,y) = s*v1 + offset -- one FFMA in the reference's SASS (nvcc -fmad=true), fmaf here. */
+void ko_elementwise_scale_bias(const ko_image* b, const ko_image* a, int in_type, float s, float offset) {
+    const int w = (int)b->w, h = (int)b->h;
+    const size_t es = in_type == KO_PIX_U8 ? 1 : (in_type == KO_PIX_U16 ? 2 : 4);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const void* pa = img_at(a, (size_t)x, (size_t)y, es);
+            const float v1 = in_type == KO_PIX_U8 ? (float)*(const uint8_t*)pa
+                           : in_type == KO_PIX_U16 ? (float)*(const uint16_t*)pa : *(const float*)pa;
+            *(float*)img_at(b, (size_t)x, (size_t)y, 4) = fmaf(s, v1, offset);
+        }
+}
+
+/* cu_resample.cu:53-68.  The sum runs tl, tl+1, bl, bl+1 in that order (it matters for float); the division
+ * by 4.0f is exact; ConvertPixel<unsigned char>(float) truncates. */
+void ko_box_half(const ko_image* out, const ko_image* in, int pix_type) {
+    const int w = (int)out->w, h = (int)out->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            if (pix_type == KO_PIX_U8) {
+                const uint8_t* tl = (const uint8_t*)img_at(in, (size_t)(2 * x), (size_t)(2 * y), 1);
+                const uint8_t* bl = (const uint8_t*)img_at(in, (size_t)(2 * x), (size_t)(2 * y + 1), 1);
+                const unsigned sum = (unsigned)tl[0] + (unsigned)tl[1] + (unsigned)bl[0] + (unsigned)bl[1];
+                *(uint8_t*)img_at(out, (size_t)x, (size_t)y, 1) = (uint8_t)((float)sum / 4.0f);
+            } else {
+                const float* tl = (const float*)img_at(in, (size_t)(2 * x), (size_t)(2 * y), 4);
+                const float* bl = (const float*)img_at(in, (size_t)(2 * x), (size_t)(2 * y + 1), 4);
+                *(float*)img_at(out, (size_t)x, (size_t)y, 4) = (((tl[0] + tl[1]) + bl[0]) + bl[1]) / 4.0f;
+            }
+        }
+}
+
+/* cu_depth_tools.cu:15-23 (IEEE division here; the reference build uses div.approx) */
+void ko_disp2depth(const ko_image* in, const ko_image* out, float fu, float baseline, float minDisp) {
+    const int w = (int)out->w, h = (int)out->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float d = *(const float*)img_at(in, (size_t)x, (size_t)y, 4);
+            *(float*)img_at(out, (size_t)x, (size_t)y, 4) = d >= minDisp ? fu * baseline / d : NAN;
+        }
+}
+
+/* disparity.h:9-20 called from cu_dense_stereo.cu:633-639 with minDisp = MinDisparity = 0 */
+void ko_disparity_image_to_vbo(const ko_image* vbo, const ko_image* disp, float baseline, float fu, float fv, float u0,
+                               float v0) {
+    const int w = (int)vbo->w, h = (int)vbo->h;
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < h; ++v)
+        for (int u = 0; u < w; ++u) {
+            const float d = *(const float*)img_at(disp, (size_t)u, (size_t)v, 4);
+            float* P = (float*)img_at(vbo, (size_t)u, (size_t)v, 16);
+            const float z = d >= 0.0f ? fu * baseline / d : NAN;
+            P[0] = z * ((float)u - u0) / fu;
+            P[1] = z * ((float)v - v0) / fv;
+            P[2] = z;
+            P[3] = 1.0f;
+        }
+}
+
 /* ---------------------------------------------------------------- left-right check ---- */
 
 /* cu_dense_stereo.cu:512-532 with TD=float; InvalidValue<float>: NaN / isfinite (InvalidValue.h:18-47) */

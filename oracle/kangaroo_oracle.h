@@ -76,6 +76,26 @@ void ko_costvol_minimum_subpix(const ko_image* disp_f32, const ko_volume* vol_f3
 void ko_dense_stereo_subpixel_refine(const ko_image* out_f32, const ko_image* disp_u8, const ko_image* left_u8,
                                      const ko_image* right_u8, const ko_image* mask_u8);
 
+/* ---- callers either side of the path (N3 front end, N2 back end) ---- */
+
+enum { KO_PIX_U8 = 0, KO_PIX_F32 = 1, KO_PIX_U16 = 2 };
+
+/* src/cu_operations.cu:39-57,260-262: b = s*a + offset, Tout = Tup = float, Tin = in_type.  The
+ * reference build (nvcc default -fmad=true) contracts s*a+offset into one fused multiply-add; so does this. */
+void ko_elementwise_scale_bias(const ko_image* b_f32, const ko_image* a, int in_type, float s, float offset);
+
+/* src/cu_resample.cu:53-83: out(x,y) = (in(2x,2y) + in(2x+1,2y) + in(2x,2y+1) + in(2x+1,2y+1)) / 4.0f, summed
+ * in unsigned int (u8, result truncated back to u8) or float (f32); pix_type in {KO_PIX_U8, KO_PIX_F32} */
+void ko_box_half(const ko_image* out, const ko_image* in, int pix_type);
+
+/* src/cu_depth_tools.cu:15-30: out = in >= minDisp ? fu*baseline / in : NaN */
+void ko_disp2depth(const ko_image* in_f32, const ko_image* out_f32, float fu, float baseline, float minDisp);
+
+/* src/cu_dense_stereo.cu:633-646 + include/kangaroo/disparity.h:9-20 (MinDisparity = 0, cu_dense_stereo.cu:15);
+ * vbo holds float4 {x, y, z, 1} per pixel */
+void ko_disparity_image_to_vbo(const ko_image* vbo_f32x4, const ko_image* disp_f32, float baseline, float fu, float fv,
+                               float u0, float v0);
+
 /* src/cu_dense_stereo.cu:512-546 */
 void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff);
 void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd, int maxDiff);

@@ -36,6 +36,10 @@ def lib() -> C.CDLL:
         L.kref_dense_stereo_subpixel_refine.argtypes = [p, z, p, p, p, z, z, z]
         L.kref_left_right_check_f32.argtypes = [p, p, z, z, z, f, f]
         L.kref_left_right_check_i8.argtypes = [p, p, z, z, z, i, i]
+        L.kref_elementwise_scale_bias.argtypes = [p, z, p, z, z, z, i, f, f]
+        L.kref_box_half.argtypes = [p, z, p, z, z, z, i]
+        L.kref_disp2depth.argtypes = [p, p, z, z, z, f, f, f]
+        L.kref_disparity_image_to_vbo.argtypes = [p, z, p, z, z, z, f, f, f, f, f]
         _lib = L
     return _lib
 
@@ -170,3 +174,48 @@ def left_right_check_i8(disp_l, disp_r, sd=-1, max_diff=0) -> np.ndarray:
     dl, dr = _dev(disp_l.astype(np.int8)), _dev(disp_r.astype(np.int8))
     _ck(lib().kref_left_right_check_i8(dl.data_ptr(), dr.data_ptr(), w, w, h, sd, max_diff), "LeftRightCheck<char>")
     return _back(dl, np.int8, (h, w))
+
+
+# ---- callers either side of the path (front end / back end)
+
+_PIX = {np.dtype(np.uint8): 0, np.dtype(np.float32): 1, np.dtype(np.uint16): 2}
+
+
+def elementwise_scale_bias(a: np.ndarray, s: float, offset: float = 0.0) -> np.ndarray:
+    import torch
+    h, w = a.shape
+    da = _dev(a)
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_elementwise_scale_bias(out.data_ptr(), w * 4, da.data_ptr(), w * a.itemsize, w, h, _PIX[a.dtype], s,
+                                          offset), "ElementwiseScaleBias")
+    return _back(out, np.float32, (h, w))
+
+
+def box_half(img: np.ndarray) -> np.ndarray:
+    import torch
+    h, w = img.shape
+    assert h % 2 == 0 and w % 2 == 0
+    di = _dev(img)
+    out = torch.zeros((h // 2) * (w // 2) * img.itemsize, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_box_half(out.data_ptr(), (w // 2) * img.itemsize, di.data_ptr(), w * img.itemsize, w // 2, h // 2,
+                            _PIX[img.dtype]), "BoxHalf")
+    return _back(out, img.dtype, (h // 2, w // 2))
+
+
+def disp2depth(disp: np.ndarray, fu: float, baseline: float, min_disp: float = 0.0) -> np.ndarray:
+    import torch
+    h, w = disp.shape
+    di = _dev(disp)
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_disp2depth(di.data_ptr(), out.data_ptr(), w * 4, w, h, fu, baseline, min_disp), "Disp2Depth")
+    return _back(out, np.float32, (h, w))
+
+
+def disparity_image_to_vbo(disp: np.ndarray, baseline: float, fu: float, fv: float, u0: float, v0: float) -> np.ndarray:
+    import torch
+    h, w = disp.shape
+    di = _dev(disp)
+    out = torch.zeros(h * w * 16, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_disparity_image_to_vbo(out.data_ptr(), w * 16, di.data_ptr(), w * 4, w, h, baseline, fu, fv, u0, v0),
+        "DisparityImageToVbo")
+    return _back(out, np.float32, (h, w, 4))

@@ -5,8 +5,9 @@
 // reference code: it only includes the reference's public headers
 // (include/kangaroo/cu_census.h, cu_semi_global_matching.h, cu_dense_stereo.h) and
 // forwards plain pointers to the roo:: free functions.  It is compiled together
-// with /root/reference/src/{cu_census,cu_semi_global_matching,cu_dense_stereo}.cu
-// (from where they lie) into oracle/_ref/libkangaroo_ref.so by oracle/Makefile.
+// with /root/reference/src/{cu_census,cu_semi_global_matching,cu_dense_stereo,cu_operations,
+// cu_resample,cu_depth_tools}.cu (from where they lie) into oracle/_ref/libkangaroo_ref.so
+// by oracle/Makefile.
 //
 // The reference kernels launch one thread per pixel of a row/column in ONE block
 // (cu_census.cu:304-306, cu_semi_global_matching.cu:69-83), so every entry point
@@ -15,6 +16,10 @@
 #include <kangaroo/cu_census.h>
 #include <kangaroo/cu_semi_global_matching.h>
 #include <kangaroo/cu_dense_stereo.h>
+#include <kangaroo/cu_operations.h>
+#include <kangaroo/Pyramid.h>
+#include <kangaroo/reduce.h>
+#include <kangaroo/cu_depth_tools.h>
 
 namespace {
 template <typename T>
@@ -158,6 +163,36 @@ int kref_left_right_check_f32(void* dl, void* dr, size_t pitch, size_t w, size_t
 
 int kref_left_right_check_i8(void* dl, void* dr, size_t pitch, size_t w, size_t h, int sd, int maxDiff) {
     roo::LeftRightCheck(img<char>(dl, pitch, w, h), img<char>(dr, pitch, w, h), sd, maxDiff);
+    return finish();
+}
+
+// ---- callers either side of the path (front end / back end)
+// in_type: 0 = unsigned char, 1 = float, 2 = unsigned short
+int kref_elementwise_scale_bias(void* b, size_t b_pitch, void* a, size_t a_pitch, size_t w, size_t h, int in_type,
+                                float s, float offset) {
+    if (in_type == 0) roo::ElementwiseScaleBias<float, unsigned char, float>(img<float>(b, b_pitch, w, h), img<unsigned char>(a, a_pitch, w, h), s, offset);
+    else if (in_type == 1) roo::ElementwiseScaleBias<float, float, float>(img<float>(b, b_pitch, w, h), img<float>(a, a_pitch, w, h), s, offset);
+    else if (in_type == 2) roo::ElementwiseScaleBias<float, unsigned short, float>(img<float>(b, b_pitch, w, h), img<unsigned short>(a, a_pitch, w, h), s, offset);
+    else return -1;
+    return finish();
+}
+
+// pix_type: 0 = unsigned char, 1 = float; (w, h) = size of the OUTPUT image, the input is (2w, 2h)
+int kref_box_half(void* out, size_t out_pitch, void* in, size_t in_pitch, size_t w, size_t h, int pix_type) {
+    if (pix_type == 0) roo::BoxHalf<unsigned char, unsigned int, unsigned char>(img<unsigned char>(out, out_pitch, w, h), img<unsigned char>(in, in_pitch, 2 * w, 2 * h));
+    else if (pix_type == 1) roo::BoxHalf<float, float, float>(img<float>(out, out_pitch, w, h), img<float>(in, in_pitch, 2 * w, 2 * h));
+    else return -1;
+    return finish();
+}
+
+int kref_disp2depth(void* in, void* out, size_t pitch, size_t w, size_t h, float fu, float baseline, float minDisp) {
+    roo::Disp2Depth(img<float>(in, pitch, w, h), img<float>(out, pitch, w, h), fu, baseline, minDisp);
+    return finish();
+}
+
+int kref_disparity_image_to_vbo(void* vbo, size_t vbo_pitch, void* disp, size_t disp_pitch, size_t w, size_t h,
+                                float baseline, float fu, float fv, float u0, float v0) {
+    roo::DisparityImageToVbo(img<float4>(vbo, vbo_pitch, w, h), img<float>(disp, disp_pitch, w, h), baseline, fu, fv, u0, v0);
     return finish();
 }
 

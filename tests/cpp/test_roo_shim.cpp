@@ -55,6 +55,42 @@ int main() {
     std::printf("shim: %d / %d interior pixels at the true disparity\n", good, total);
     if (good < total * 0.95) return 1;
 
+    // front end / back end operators, as the applications call them (stereo2/main.cpp:360-376, stereo/main.cpp:476)
+    {
+        auto imgf = alloc_image<float>(w, h), half = alloc_image<float>(w / 2, h / 2), depth = alloc_image<float>(w, h);
+        auto half8 = alloc_image<unsigned char>(w / 2, h / 2);
+        auto vbo = alloc_image<float4>(w, h);
+        roo::ElementwiseScaleBias<float, unsigned char, float>(imgf, imgL, 1.0f / 255.0f);
+        roo::BoxHalf<float, float, float>(half, imgf);
+        roo::BoxHalf<unsigned char, unsigned int, unsigned char>(half8, imgL);
+        roo::Disp2Depth(disp, depth, 500.0f, 0.1f);
+        roo::DisparityImageToVbo(vbo, disp, 0.1f, 500.0f, 500.0f, w / 2.0f, h / 2.0f);
+        CK(cudaDeviceSynchronize());
+        std::vector<float> f(w * h), hf((w / 2) * (h / 2)), z(w * h);
+        std::vector<float4> P(w * h);
+        std::vector<unsigned char> h8((w / 2) * (h / 2));
+        CK(cudaMemcpy2D(f.data(), w * 4, imgf.ptr, imgf.pitch, w * 4, h, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2D(hf.data(), (w / 2) * 4, half.ptr, half.pitch, (w / 2) * 4, h / 2, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2D(h8.data(), w / 2, half8.ptr, half8.pitch, w / 2, h / 2, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2D(z.data(), w * 4, depth.ptr, depth.pitch, w * 4, h, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2D(P.data(), w * 16, vbo.ptr, vbo.pitch, w * 16, h, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int y = 0; y < h / 2; ++y)
+            for (int x = 0; x < w / 2; ++x) {
+                const int a = L[2 * y * w + 2 * x], b = L[2 * y * w + 2 * x + 1], c = L[(2 * y + 1) * w + 2 * x], d = L[(2 * y + 1) * w + 2 * x + 1];
+                if (h8[y * (w / 2) + x] != (unsigned char)((a + b + c + d) / 4)) ++bad;
+                if (std::fabs(hf[y * (w / 2) + x] - (a + b + c + d) / (4.0f * 255.0f)) > 1e-6f) ++bad;
+            }
+        for (int i = 0; i < w * h; ++i) {
+            if (f[i] != L[i] * (1.0f / 255.0f)) ++bad;
+            const float d = out[i];
+            if (std::isnan(d)) { if (!std::isnan(z[i]) || !std::isnan(P[i].z)) ++bad; continue; }
+            if (d > 0 && (std::fabs(z[i] - 50.0f / d) > 1e-4f * z[i] || P[i].z != z[i] || P[i].w != 1.0f)) ++bad;
+        }
+        std::printf("shim: front/back end operators, %d mismatches\n", bad);
+        if (bad) return 1;
+    }
+
     // invalid arguments raise under ROO_B200_THROW
     bool threw = false;
     try { roo::CensusStereoVolume<float, unsigned long>(volC, cenL, cenR, D, 0.5f); } catch (const std::exception&) { threw = true; }

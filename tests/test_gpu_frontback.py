@@ -1,0 +1,162 @@
+"""GPU parity of the operators either side of the stereo path through the C ABI:
+ElementwiseScaleBias, BoxHalf / BoxReduce, Disp2Depth, DisparityImageToVbo.
+
+Bars: bit-exact against the committed outputs of the reference kernels (default fp mode reproduces the
+reference's fast-math SASS) and bit-exact against the CPU oracle under roo_set_ieee_division(1)."""
+import numpy as np
+import pytest
+
+import oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from kangaroo_b200 import roo  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _default_fp_mode():
+    roo.set_ieee_division(False)
+    yield
+    roo.set_ieee_division(False)
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32) if a.dtype == np.float32 else a,
+                          np.ascontiguousarray(b).view(np.uint32) if b.dtype == np.float32 else b)
+
+
+def same_float(a, b):
+    """bit-identical except that any NaN matches any NaN"""
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and same_bits(np.where(na, 0, a).astype(np.float32), np.where(nb, 0, b).astype(np.float32))
+
+
+def scale_bias(a, s, off, pitch=None):
+    h, w = a.shape
+    b = roo.Image(w, h, np.float32)
+    roo.ElementwiseScaleBias(b, roo.Image.from_numpy(a, pitch=pitch), s, off)
+    return b.numpy()
+
+
+def box_half(a):
+    h, w = a.shape
+    out = roo.Image(w // 2, h // 2, a.dtype)
+    roo.BoxHalf(out, roo.Image.from_numpy(a))
+    return out.numpy()
+
+
+def depth(d, fu, b, md):
+    h, w = d.shape
+    out = roo.Image(w, h, np.float32)
+    roo.Disp2Depth(roo.Image.from_numpy(d), out, fu, b, md)
+    return out.numpy()
+
+
+def vbo(d, *cam):
+    h, w = d.shape
+    out = roo.Image(w, h, roo.FLOAT4)
+    roo.DisparityImageToVbo(out, roo.Image.from_numpy(d), *cam)
+    return out.numpy()
+
+
+@pytest.mark.parametrize("nm", ["u8", "u16", "f32"])
+def test_scale_bias_bitexact_vs_reference_and_oracle(golden, nm):
+    g = golden("frontback")
+    a = g["sb_" + nm]
+    assert same_bits(scale_bias(a, 1.0 / 255.0, 0.0), g[f"sb_{nm}_app"])
+    assert same_bits(scale_bias(a, 0.37, -1.25, pitch=a.shape[1] * a.itemsize + 12), g[f"sb_{nm}_bias"])
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, (375, 1242), dtype=np.uint8)
+    assert same_bits(scale_bias(big, 1.0 / 255.0, 0.0), ko.elementwise_scale_bias(big, 1.0 / 255.0, 0.0))
+
+
+@pytest.mark.parametrize("nm", ["u8", "f32"])
+def test_box_half_bitexact_vs_reference_and_oracle(golden, nm):
+    g = golden("frontback")
+    l1 = box_half(g["bh_" + nm])
+    assert same_bits(l1, g[f"bh_{nm}_l1"])
+    assert same_bits(box_half(l1), g[f"bh_{nm}_l2"])
+    rng = np.random.default_rng(4)
+    big = rng.integers(0, 256, (720, 1280)).astype(g["bh_" + nm].dtype)
+    assert same_bits(box_half(big), ko.box_half(big))
+    odd = rng.integers(0, 256, (7, 11)).astype(g["bh_" + nm].dtype)   # odd sizes: the last row / column is dropped
+    assert same_bits(box_half(odd), ko.box_half(odd))
+
+
+def test_box_reduce_pyramid_matches_repeated_oracle():
+    rng = np.random.default_rng(5)
+    img = rng.random((96, 160), dtype=np.float32)
+    pyr = [roo.Image.from_numpy(img)] + [roo.Image(160 >> l, 96 >> l, np.float32) for l in (1, 2, 3)]
+    roo.BoxReduce(pyr)
+    ref = img
+    for l in (1, 2, 3):
+        ref = ko.box_half(ref)
+        assert same_bits(pyr[l].numpy(), ref)
+
+
+def test_disp2depth_and_vbo_bitexact_vs_reference_kernels(golden):
+    g = golden("frontback")
+    d = g["disp"]
+    assert same_float(depth(d, 570.3, 0.12, 0.0), g["depth_min0"])
+    assert same_float(depth(d, 570.3, 0.12, 2.0), g["depth_min2"])
+    assert same_float(vbo(d, 0.12, 570.3, 568.9, 23.4, 15.7), g["vbo"])
+
+
+def test_disp2depth_and_vbo_ieee_mode_bitexact_vs_oracle():
+    rng = np.random.default_rng(6)
+    d = (rng.random((375, 1242), dtype=np.float32) * 128).astype(np.float32)
+    d[rng.random(d.shape) < 0.05] = np.nan
+    d[rng.random(d.shape) < 0.02] = 0.0
+    d[rng.random(d.shape) < 0.02] = -3.0
+    roo.set_ieee_division(True)
+    assert same_float(depth(d, 718.9, 0.54, 0.5), ko.disp2depth(d, 718.9, 0.54, 0.5))
+    assert same_float(vbo(d, 0.54, 718.9, 718.3, 607.2, 185.2), ko.disparity_image_to_vbo(d, 0.54, 718.9, 718.3, 607.2, 185.2))
+
+
+def test_front_end_feeds_the_path_like_the_application():
+    """stereo2/main.cpp:360-384: BoxReduce pyramid level -> ElementwiseScaleBias(1/255) -> Census on the float image
+    gives the same descriptors as Census on the u8 level (the scale is monotonic)."""
+    rng = np.random.default_rng(7)
+    raw = rng.integers(0, 256, (96, 128), dtype=np.uint8)
+    pyr = [roo.Image.from_numpy(raw), roo.Image(64, 48, np.uint8)]
+    roo.BoxReduce(pyr)
+    imgf = roo.Image(64, 48, np.float32)
+    roo.ElementwiseScaleBias(imgf, pyr[1], 1.0 / 255.0)
+    cf, c8 = roo.Image(64, 48, roo.ULONG), roo.Image(64, 48, roo.ULONG)
+    roo.Census(cf, imgf)
+    roo.Census(c8, pyr[1])
+    assert np.array_equal(cf.numpy(), c8.numpy())
+    assert np.array_equal(c8.numpy().reshape(48, 64), ko.census(ko.box_half(raw), 0).reshape(48, 64))
+
+
+def test_invalid_arguments():
+    a = roo.Image(8, 8, np.uint8)
+    small = roo.Image(8, 8, np.uint8)
+    from kangaroo_b200.capi import RooError
+    with pytest.raises(RooError):
+        roo.BoxHalf(small, a)   # input must cover 2w x 2h
+
+
+def test_unaligned_subimage_views_take_the_scalar_path():
+    """SubImage keeps the parent pitch and may start at any pixel (Image.h SubImage): results must not depend on alignment."""
+    rng = np.random.default_rng(8)
+    raw = rng.integers(0, 256, (40, 70), dtype=np.uint8)
+    f = rng.random((40, 70), dtype=np.float32) * 50
+    praw, pf = roo.Image.from_numpy(raw), roo.Image.from_numpy(f)
+    # scale/bias on a view starting at x = 1 (u8) and into an output view starting at x = 3
+    dst = roo.Image(70, 40, np.float32)
+    roo.ElementwiseScaleBias(dst.sub_image(3, 2, 41, 30), praw.sub_image(1, 5, 41, 30), 0.5, 1.0)
+    assert same_bits(dst.numpy()[2:32, 3:44], ko.elementwise_scale_bias(np.ascontiguousarray(raw[5:35, 1:42]), 0.5, 1.0))
+    # box half of a view starting at an odd pixel
+    for parent, src in ((praw, raw), (pf, f)):
+        out = roo.Image(17, 12, src.dtype)
+        roo.BoxHalf(out, parent.sub_image(3, 1, 34, 24))
+        assert same_bits(out.numpy(), ko.box_half(np.ascontiguousarray(src[1:25, 3:37])))
+    roo.set_ieee_division(True)
+    out = roo.Image(37, 20, np.float32)
+    roo.Disp2Depth(pf.sub_image(5, 3, 37, 20), out, 300.0, 0.2, 1.0)
+    assert same_float(out.numpy(), ko.disp2depth(np.ascontiguousarray(f[3:23, 5:42]), 300.0, 0.2, 1.0))

@@ -266,3 +266,54 @@ def test_diagonal_extension_reduces_to_reference_without_dodiag(golden):
     assert relerr(g["H_h1v1r1"], a).max() <= 1e-5
     assert not np.array_equal(a, b)
     assert (b >= a - 1e-6).all()  # four more non-negative path costs
+
+
+# ---------------------------------------------------------------- front end / back end
+
+@pytest.mark.parametrize("nm", ["u8", "u16", "f32"])
+def test_elementwise_scale_bias_matches_reference(golden, nm):
+    g = golden("frontback")
+    assert np.array_equal(ko.elementwise_scale_bias(g["sb_" + nm], 1.0 / 255.0, 0.0), g[f"sb_{nm}_app"])
+    assert np.array_equal(ko.elementwise_scale_bias(g["sb_" + nm], 0.37, -1.25), g[f"sb_{nm}_bias"])
+
+
+@pytest.mark.parametrize("nm", ["u8", "f32"])
+def test_box_half_matches_reference_two_levels(golden, nm):
+    g = golden("frontback")
+    l1 = ko.box_half(g["bh_" + nm])
+    assert np.array_equal(l1, g[f"bh_{nm}_l1"])
+    assert np.array_equal(ko.box_half(l1), g[f"bh_{nm}_l2"])
+
+
+def _same_special(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b)) and \
+        np.array_equal(np.signbit(a[~np.isnan(a)]), np.signbit(b[~np.isnan(b)]))
+
+
+def test_disp2depth_and_vbo_match_reference_within_fast_math(golden):
+    """The reference build divides with div.approx: NaN / inf / sign patterns must agree exactly,
+    finite values to 2 ulp (3e-7 relative)."""
+    g = golden("frontback")
+    d = g["disp"]
+    for tag, md in (("depth_min0", 0.0), ("depth_min2", 2.0)):
+        out = ko.disp2depth(d, 570.3, 0.12, md)
+        assert _same_special(out, g[tag])
+        fin = np.isfinite(out) & (out != 0)
+        assert relerr(g[tag][fin], out[fin]).max() <= 3e-7
+    vbo = ko.disparity_image_to_vbo(d, 0.12, 570.3, 568.9, 23.4, 15.7)
+    assert _same_special(vbo, g["vbo"])
+    fin = np.isfinite(vbo) & (vbo != 0)
+    assert relerr(g["vbo"][fin], vbo[fin]).max() <= 6e-7
+    assert (vbo[..., 3] == 1.0).all()
+
+
+def test_kat_box_half_and_depth():
+    a = np.array([[1, 2, 5, 6], [3, 4, 7, 9]], np.uint8)
+    assert ko.box_half(a).tolist() == [[2, 6]]  # (1+2+3+4)/4 = 2.5 -> 2 (truncation), (5+6+7+9)/4 = 6.75 -> 6
+    assert ko.box_half(a.astype(np.float32)).tolist() == [[2.5, 6.75]]
+    z = ko.disp2depth(np.array([[4.0, 0.5, -1.0]], np.float32), 100.0, 0.2, 1.0)
+    assert z[0, 0] == 5.0 and np.isnan(z[0, 1]) and np.isnan(z[0, 2])
+    P = ko.disparity_image_to_vbo(np.array([[4.0, 4.0]], np.float32), 0.2, 100.0, 50.0, 1.0, 2.0)
+    f = np.float32
+    assert np.array_equal(P[0, 0], np.array([f(-5.0) / f(100.0), f(-10.0) / f(50.0), 5.0, 1.0], f))
+    assert np.array_equal(P[0, 1], np.array([0.0, f(-10.0) / f(50.0), 5.0, 1.0], f))

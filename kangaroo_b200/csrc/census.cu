@@ -325,50 +325,59 @@ template <int WORDS, bool POPC64, bool IEEE>
 __global__ void __launch_bounds__(128)
 census_wta_kernel(float* __restrict__ disp, const unsigned long long* __restrict__ cself,
                   const unsigned long long* __restrict__ cother, int w, int h, int maxDisp, int subpix, int sdi) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
+    // The 128 pixels of a block compare against 128 + maxDisp - 1 consecutive descriptors of the other image's
+    // row: staged once in shared memory (taps outside the image are never read).  The search runs on integers:
+    // cost = count / bits is monotonic in the count and the out-of-image value 0.5 is exactly bits/2 counts, so
+    // "first strict minimum" = min over (count << 9 | d) -- five instructions per candidate.
+    extern __shared__ unsigned long long s_o[];
+    const int x0 = blockIdx.x * 128, x = x0 + threadIdx.x, y = blockIdx.y;
     const size_t rowoff = ((size_t)blockIdx.z * h + y) * (size_t)w;
-    const unsigned long long* sp = cself + (rowoff + x) * WORDS;
     const unsigned long long* orow = cother + rowoff * WORDS;
+    const int span = 128 + maxDisp - 1;
+    const int base = sdi > 0 ? x0 : x0 - (maxDisp - 1);   // image x of s_o[0]
+    for (int i = threadIdx.x; i < span * WORDS; i += 128) {
+        const int xi = base + i / WORDS;
+        s_o[i] = (xi >= 0 && xi < w) ? orow[(size_t)xi * WORDS + i % WORDS] : 0ull;
+    }
+    __syncthreads();
+    if (x >= w) return;
+    const unsigned long long* sp = cself + (rowoff + x) * WORDS;
     unsigned long long p[WORDS];
 #pragma unroll
     for (int k = 0; k < WORDS; ++k) p[k] = sp[k];
+    constexpr int HALF = WORDS * 32;                      // 0.5 * bits
     const float inv_bits = 1.0f / (float)(WORDS * 64);
-    auto cost = [&](int d) -> float {
+    auto count = [&](int d) -> int {                      // Hamming count of candidate d; bits/2 outside the image
         const int xd = x + sdi * d;
-        if (xd < 0 || xd >= w) return 0.5f;
+        if (xd < 0 || xd >= w) return HALF;
+        const unsigned long long* q = s_o + (size_t)(xd - base) * WORDS;
         unsigned hd = 0;
 #pragma unroll
-        for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], orow[(size_t)xd * WORDS + k]);
-        return (float)hd * inv_bits;
+        for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], q[k]);
+        return (int)hd;
     };
-    float out;
-    if (!subpix) {
-        // CostVolMinimum (cu_dense_stereo.cu:25-43): d < min(maxDisp, x+1), slices beyond x+sd*d range hold 0.5
-        int bestd = 0;
-        float bestc = cost(0);
-        const int md = min(maxDisp, x + 1);
-        for (int d = 1; d < md; ++d) {
-            const float c = cost(d);
-            if (c < bestc) { bestc = c; bestd = d; }
-        }
-        out = (float)bestd;
-    } else {
-        // CostVolMinimumSubpix (cu_dense_stereo.cu:66-109)
-        int bestd = 0;
-        float bestc = 1E10f;
-        for (int d = 0; d < maxDisp; ++d) {
-            const int xr = x + sdi * d;
-            if (0 <= xr && xr < w) {
-                const float c = cost(d);
-                if (c < bestc) { bestc = c; bestd = d; }
-            }
-        }
-        out = (float)bestd;
+    const int dvalid = sdi < 0 ? x + 1 : w - x;            // candidates d < dvalid have their tap inside the image
+    // CostVolMinimum (cu_dense_stereo.cu:25-43) searches d < min(maxDisp, x+1), slices whose tap is outside hold 0.5;
+    // CostVolMinimumSubpix (cu_dense_stereo.cu:66-109) searches the d < maxDisp whose tap is inside.
+    const int md = subpix ? min(maxDisp, dvalid) : min(maxDisp, x + 1);
+    const int din = min(md, dvalid);
+    unsigned best = 0xffffffffu;
+    const unsigned long long* q = s_o + (size_t)(x - base) * WORDS;
+    for (int d = 0; d < din; ++d, q += sdi * WORDS) {
+        unsigned hd = 0;
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k) hd += hamming_word<POPC64>(p[k], q[k]);
+        best = min(best, (hd << 9) | (unsigned)d);
+    }
+    if (din < md) best = min(best, ((unsigned)HALF << 9) | (unsigned)din);   // the first out-of-image slice (0.5)
+    const int bestd = (int)(best & 511u);
+    float out = (float)bestd;
+    if (subpix) {
+        const float bestc = (float)(best >> 9) * inv_bits;
         const int bestxr = x + sdi * bestd;
         if (0 < bestxr && bestxr < w - 1 && bestd + 1 < maxDisp) {
-            const float sl = cost(max(bestd - 1, 0));  // GPU float->unsigned saturation of bestd-1 (Q7)
-            const float sr = cost(bestd + 1);
+            const float sl = (float)count(max(bestd - 1, 0)) * inv_bits;  // GPU float->unsigned saturation of bestd-1 (Q7)
+            const float sr = (float)count(bestd + 1) * inv_bits;
             const float sub = parabola_vertex<IEEE>((float)bestd, bestc, sl, sr);
             if ((float)(bestd - 1) < sub && sub < (float)(bestd + 1)) out = sub;
         }
@@ -382,7 +391,8 @@ int launch_census_wta(float* disp, const void* cself, const void* cother, int w,
     const auto* a = (const unsigned long long*)cself;
     const auto* b = (const unsigned long long*)cother;
     const bool p64 = popc_mode == ROO_POPC64, ieee = g_ieee_div.load() != 0;
-#define ROO_RW(W, P, I) census_wta_kernel<W, P, I><<<grid, block, 0, st>>>(disp, a, b, w, h, maxDisp, subpix, sdi)
+    const size_t smem = (size_t)(128 + maxDisp - 1) * words * 8;
+#define ROO_RW(W, P, I) census_wta_kernel<W, P, I><<<grid, block, smem, st>>>(disp, a, b, w, h, maxDisp, subpix, sdi)
 #define ROO_RW2(W)                                                                 \
     if (p64) { if (ieee) ROO_RW(W, true, true); else ROO_RW(W, true, false); }     \
     else { if (ieee) ROO_RW(W, false, true); else ROO_RW(W, false, false); }

@@ -21,7 +21,7 @@
 //     first) never wait for higher ones.
 //   * a dedicated communication warp per CTA polls the upstream flag, stages the upstream edge rows into
 //     shared memory and publishes this band's flag, so the compute warps never touch the global flags.
-//   * every compute warp owns NCW (four; two at 256 disparities) adjacent skewed columns c0 = u .. and advances
+//   * every compute warp owns NCW = four adjacent skewed columns c0 = u .. and advances
 //     all of them by one row per tick: the vertical path of column c continues from column c+1's state of the
 //     previous tick and the anti-diagonal path from column c+2's (registers), so only three state rows per tick
 //     (c0.vertical, c0.anti-diagonal, c1.anti-diagonal) go through shared memory, and the per-tick bookkeeping
@@ -45,13 +45,19 @@ __host__ __device__ constexpr int vg_pfs(int DPL, int CE) {
 #ifndef VG_NCW
 #define VG_NCW 4
 #endif
-__host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? 2 : VG_NCW; }
+#ifndef VG_NCW8
+#define VG_NCW8 4
+#endif
+#ifndef VG_NWW8
+#define VG_NWW8 6
+#endif
+__host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? VG_NCW8 : VG_NCW; }
 // 12 warps x 4 columns: 13 warps of <= 152 registers fill the register file, and ring + prefetch stages fill
 // the 227 KB of shared memory (measured on B200 at 128 disparities: 8 warps 6.6 ms, 10: 6.5 ms, 12: 6.1 ms per 16 pairs)
 #ifndef VG_NWW
 #define VG_NWW 12
 #endif
-__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? 8 : VG_NWW; }
+__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? VG_NWW8 : VG_NWW; }
 inline int vg_cols_of_dp(int DP) { return vg_ncw(DP / 32) * vg_nww(DP / 32); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {

@@ -185,7 +185,7 @@ __device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, 
     store_f<DPL>(hst, H3);
 }
 
-template <int DPL, int COST, bool FIRST, bool IEEE, int NWW, int NCW>
+template <int DPL, int COST, bool FIRST, bool IEEE, int NWW, int NCW, bool FWD>
 __global__ void __launch_bounds__((NWW + 1) * 32, 1)
 sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int DP = 32 * DPL;
@@ -215,7 +215,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     // band-to-band pipeline of each pair has only a short ramp
     const int pair = blockIdx.x % a.batch, band = blockIdx.x / a.batch;
     const int w = a.w, h = a.h, M = a.maxDisp;
-    const bool fwd = a.fwd != 0;
+    constexpr bool fwd = FWD;   // travel direction in y: compile-time, so that the columns' address offsets are immediates
     const float P1 = a.P1, P2 = a.P2, cscale = a.cost_scale;
 
     const int ulo = w - (band + 1) * NC;                 // lowest skewed column of this band
@@ -234,10 +234,9 @@ sgm_vgroup_kernel(const VGroupArgs a) {
 
     // this warp's skewed columns u0 .. u0+NCW-1 (c0 = lowest u) and their active rows (x' = u + y' in [0, w))
     const int u0 = ulo + NCW * warp;
-    int yin[NCW], yout[NCW];
-#pragma unroll
-    for (int c = 0; c < NCW; ++c) { yin[c] = max(0, -(u0 + c)); yout[c] = min(h - 1, w - 1 - (u0 + c)); }
-    const int y_in = yin[NCW - 1], y_out = yout[0];   // the highest column enters first, the lowest leaves last
+    // column c is active in row y (>= 0) iff 0 <= u0 + c + y < w and y < h: rows [max(0, -(u0+c)), min(h-1, w-1-u0-c)]
+    auto col_active = [&](int c, int y) { return (unsigned)(u0 + c + y) < (unsigned)w && y < h; };
+    const int y_in = max(0, -(u0 + NCW - 1)), y_out = min(h - 1, w - 1 - u0);   // the highest column enters first, the lowest leaves last
     const bool any = warp < NWW && y_in <= y_out;
     if (threadIdx.x == 0) { ctl->halo_ready = hbeg; ctl->copied = ymin; }
     if (warp < NWW && lane == 0) prog[warp] = any ? y_in : 0x7fffffff;   // rows before y_in never happen
@@ -323,44 +322,41 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     // -------------------------------------------------------------------- compute warps
     const int xf = (M == DP) ? DP - 1 : 0x3fffffff;               // all lanes in range iff true x >= xf
     const int d0 = lane * DPL;
-    const ptrdiff_t pstep = fwd ? (ptrdiff_t)(w + 1) : -(ptrdiff_t)(w + 1);   // one row down the travel direction
-    const ptrdiff_t estep = pstep * DP;
+    const ptrdiff_t estep = (fwd ? (ptrdiff_t)(w + 1) : -(ptrdiff_t)(w + 1)) * DP;   // one row down the travel direction
 
-    // per-column cursors at the column's first active pixel
+    // One cursor for all NCW columns: in a given row their pixels are adjacent in x, i.e. DP elements apart, so
+    // column c lives at a compile-time offset from the column with the lowest address (c0 forward, the last one
+    // backward).  The cursor is a linear function of the row; it may point outside the image while that column is
+    // inactive, and is only dereferenced at offsets of active columns.
     float* const Hp = a.H + (size_t)pair * a.h_pair;
     const char* const Cp = (const char*)a.C + (size_t)pair * a.c_pair * CE;
     const float* const Ip = a.img + (size_t)pair * a.img_pair;
-    float* hst[NCW]; const float* hld[NCW]; const char* cld[NCW];
-#pragma unroll
-    for (int c = 0; c < NCW; ++c) {
-        size_t e0 = 0;
-        if (yin[c] <= yout[c]) {
-            const int xp0 = u0 + c + yin[c];
-            const int x0 = fwd ? xp0 : w - 1 - xp0, y0 = fwd ? yin[c] : h - 1 - yin[c];
-            e0 = ((size_t)y0 * w + x0) * DP + d0;
-        }
-        hst[c] = Hp + e0; hld[c] = hst[c]; cld[c] = Cp + e0 * CE;
-    }
+    auto coff = [](int c) { return (fwd ? c : NCW - 1 - c) * DP; };   // element offset of column c from the cursor
+    const ptrdiff_t e_in = fwd ? ((ptrdiff_t)y_in * w + (u0 + y_in)) * DP + d0
+                               : ((ptrdiff_t)(h - 1 - y_in) * w + (w - 1 - (u0 + NCW - 1) - y_in)) * DP + d0;
+    float* hst = Hp + e_in;                          // row being computed
+    const float* hld = hst;                          // row being prefetched
+    const char* cld = Cp + e_in * CE;
 
     // Prefetch: row y+PFS-1 of every column is copied global -> shared (asynchronously, no registers) while row y
     // is computed.  Every lane copies and later reads its own bytes, so no barrier is needed.
     const unsigned pf0 = (unsigned)__cvta_generic_to_shared(s_pf) + (warp * NCW) * PFS * STAGE_B;
-    auto issue_px = [&](unsigned base, int yl, const float*& hl, const char*& cl) {
-        const unsigned dst = base + ((unsigned)yl & (PFS - 1)) * STAGE_B;
-        if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hl);
-        cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cl);
-        hl += estep; cl += estep * CE;
+    auto issue_px = [&](int c, int yl) {
+        const unsigned dst = pf0 + c * PFS * STAGE_B + ((unsigned)yl & (PFS - 1)) * STAGE_B;
+        if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hld + coff(c));
+        cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cld + coff(c) * CE);
     };
-    int aLo = yin[0], aHi = yout[NCW - 1];   // rows in which every column is active
+    int aLo = max(0, -u0), aHi = min(h - 1, w - 1 - (u0 + NCW - 1));   // rows in which every column is active
     auto issue_row = [&](int yl) {
         if (yl >= aLo && yl <= aHi) {
 #pragma unroll
-            for (int c = 0; c < NCW; ++c) issue_px(pf0 + c * PFS * STAGE_B, yl, hld[c], cld[c]);
+            for (int c = 0; c < NCW; ++c) issue_px(c, yl);
         } else {
 #pragma unroll
             for (int c = 0; c < NCW; ++c)
-                if (yl >= yin[c] && yl <= yout[c]) issue_px(pf0 + c * PFS * STAGE_B, yl, hld[c], cld[c]);
+                if (col_active(c, yl)) issue_px(c, yl);
         }
+        hld += estep; cld += estep * CE;
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     for (int k = 0; k < PFS - 1; ++k) issue_row(y_in + k);
@@ -370,7 +366,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     auto gather = [&](int c, int blk) {
         const int r = 32 * blk + lane;
         float v = 0.0f;
-        if (r >= yin[c] && r <= yout[c]) {
+        if (col_active(c, r)) {
             const int xp = u0 + c + r;
             const int x = fwd ? xp : w - 1 - xp, yy = fwd ? r : h - 1 - r;
             v = __ldg(Ip + (size_t)yy * w + x);
@@ -438,7 +434,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         // ascending c: column c reads the previous-row registers of c+1 and c+2 before those columns overwrite them
 #pragma unroll
         for (int c = 0; c < NCW; ++c) {
-            const bool act = !EDGE || (y >= yin[c] && y <= yout[c]);
+            const bool act = !EDGE || col_active(c, y);
             if (act) {
                 const int xp = u0 + c + y, x = fwd ? xp : w - 1 - xp;
                 const float pix = __shfl_sync(0xffffffffu, icur[c], y & 31);
@@ -463,8 +459,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
                     lbA = scUp1.y; ppA = scUp1.z;
                 }
                 vg_pixel<DPL, COST, MASKED, EDGE, FIRST, IEEE>(stg0 + c * PFS * STAGE_B, lane, y, xp, x, w, M, P1, P2, cscale, pix,
-                                                               hv, lbV, ppV, Dr[c], lbD[c], pixD[c], ha, lbA, ppA, hst[c]);
-                hst[c] += estep;
+                                                               hv, lbV, ppV, Dr[c], lbD[c], pixD[c], ha, lbA, ppA, hst + coff(c));
                 if (c == 0) {
                     sts_vec<DPL>(mine, hv);
                     sts_vec<DPL>(mine + REC_B, ha);
@@ -500,7 +495,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     // Row classes, resolved once per warp.  With x'_c = u0 + c + y (c0 is the leftmost column):
     //   interior rows [eLo, eHi]: y >= 1, x'_0 >= 1, x'_{NCW-1} <= w-2 and every column active -- no path starts or ends;
     //   unmasked rows [mLo, mHi]: the smallest true x of the NCW pixels (x'_0 forward, w-1-x'_{NCW-1} backward) is >= xf.
-    int eLo = max(max(1, 1 - u0), yin[0]), eHi = min(w - 1 - NCW - u0, yout[NCW - 1]);
+    int eLo = max(1, 1 - u0), eHi = min(w - 1 - NCW - u0, h - 1);
     int mLo = fwd ? xf - u0 : -0x3fffffff, mHi = fwd ? 0x3fffffff : (xf > w ? -0x3fffffff : w - NCW - u0 - xf);
     // through a shuffle: ptxas cannot rematerialise that, so the bounds stay in registers instead of being
     // recomputed (6-10 instructions each) in every row
@@ -549,6 +544,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
             if (unmasked) tick(std::false_type{}, std::false_type{}, y);
             else tick(std::true_type{}, std::false_type{}, y);
         }
+        hst += estep;
         __syncwarp();
         smem_order();
         if (lane == 0) prog[warp] = (y == y_out) ? 0x7fffffff : y + 1;
@@ -584,7 +580,8 @@ static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     const bool ieee = g_ieee_div.load() != 0;
 #define ROO_VG(F, I)                                                                                          \
     do {                                                                                                      \
-        auto kern = sgm_vgroup_kernel<DPL, COST, F, I, NWW, NCW>;                                                  \
+        auto kern = a.fwd ? sgm_vgroup_kernel<DPL, COST, F, I, NWW, NCW, true>                                \
+                          : sgm_vgroup_kernel<DPL, COST, F, I, NWW, NCW, false>;                              \
         if (smem > 48 * 1024) {                                                                               \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                              \

@@ -228,6 +228,14 @@ public:
     void RunHost(const uint8_t* left, const uint8_t* right, float* disp, int n) {
         b200::done(roo_engine_run_host(e_, left, right, disp, n), "roo_engine_run_host");
     }
+    // streaming form: enqueue one group (n <= max_batch) and return a ticket; Wait(ticket) blocks until its
+    // disparities are in `disp`.  Two groups may be in flight (copies overlap the other group's kernels).
+    long long SubmitHost(const uint8_t* left, const uint8_t* right, float* disp, int n) {
+        long long t = -1;
+        b200::done(roo_engine_submit_host(e_, left, right, disp, n, &t), "roo_engine_submit_host");
+        return t;
+    }
+    void Wait(long long ticket) { b200::done(roo_engine_wait(e_, ticket), "roo_engine_wait"); }
     roo_engine_t* handle() { return e_; }
 private:
     roo_engine_t* e_;

@@ -158,6 +158,14 @@ int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const uint8_t* r
 /* Same with HOST buffers (pinned memory recommended): uploads, runs, downloads, and synchronises. */
 int roo_engine_run_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
                         int n_pairs);
+/* Asynchronous form of roo_engine_run_host for callers that stream frames: enqueue one group (n_pairs <= max_batch)
+ * and return; roo_engine_wait(ticket) blocks until that group's disparities are in disp_host.  Two groups may be in
+ * flight: the upload of group t+1 and the download of group t-1 overlap the computation of group t (a third submit
+ * first waits, on the host, for the group two tickets back).  The host buffers must stay valid (and should be
+ * pinned) until the wait returns.  Not thread-safe per engine, like the rest of the engine API. */
+int roo_engine_submit_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
+                           int n_pairs, long long* ticket);
+int roo_engine_wait(roo_engine_t* e, long long ticket);
 /* Copies the aggregated volume of batch slot `slot` from the last run into a roo::Volume<float>
  * (d >= max_disp slices are left untouched); for parity tests. */
 int roo_engine_export_volume(roo_engine_t* e, int slot, const roo_volume_t* volH, void* stream);

@@ -67,6 +67,8 @@ SYMBOLS = {
     "roo_engine_scratch_bytes": (C.c_size_t, [C.c_void_p]),
     "roo_engine_run_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _S]),
     "roo_engine_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "roo_engine_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _P(C.c_longlong)]),
+    "roo_engine_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
     "roo_engine_export_volume": (C.c_int, [C.c_void_p, C.c_int, _VOL, _S]),
     "roo_engine_export_census": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _IMG, _S]),
     "roo_multi_engine_create": (C.c_int, [_P(C.c_void_p), _P(PipelineParams), _P(C.c_int), C.c_int]),

@@ -36,6 +36,7 @@ struct roo_engine {
     unsigned char* in_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][side]
     float* out_dev[2] = {nullptr, nullptr};
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    long long ticket = 0;   // groups submitted through the host-buffer path so far
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     size_t scratch_bytes = 0;
     int last_batch = 0;
@@ -196,42 +197,75 @@ extern "C" int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const
 
 // Host buffers: upload group g+1 and download group g-1 while group g computes (three streams, two
 // staging buffers).  Pinned host memory makes the copies truly asynchronous.
+static int host_streams_init(roo_engine_t* e) {
+    if (e->s_compute) return ROO_OK;
+    const size_t npx = e->npx, B = (size_t)e->p.max_batch;
+    ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+    ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][0], B * npx));
+        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][1], B * npx));
+        ROO_CUDA_TRY(cudaMalloc((void**)&e->out_dev[b], B * npx * 4));
+        e->scratch_bytes += 2 * B * npx + B * npx * 4;
+        ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[b], cudaEventDisableTiming));
+        ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
+        ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[b], cudaEventDisableTiming));
+    }
+    return ROO_OK;
+}
+
+// One group (<= max_batch pairs) through staging slot ticket & 1: H2D on s_in, the path on s_compute, D2H on s_out.
+// The slot's previous user (ticket - 2) is waited for on the HOST first, so its events are never re-recorded
+// while somebody may still wait on them and its staging buffers are free.
+static int submit_group(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host, int batch) {
+    const size_t npx = e->npx;
+    const int b = (int)(e->ticket & 1);
+    if (e->ticket >= 2) ROO_CUDA_TRY(cudaEventSynchronize(e->ev_out[b]));
+    ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][0], left_host, (size_t)batch * npx, cudaMemcpyHostToDevice, e->s_in));
+    ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][1], right_host, (size_t)batch * npx, cudaMemcpyHostToDevice, e->s_in));
+    ROO_CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
+    ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_compute, e->ev_in[b], 0));
+    const int rc = engine_group(e, e->in_dev[b][0], e->in_dev[b][1], e->out_dev[b], batch, e->s_compute);
+    if (rc) return rc;
+    ROO_CUDA_TRY(cudaEventRecord(e->ev_done[b], e->s_compute));
+    ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_done[b], 0));
+    ROO_CUDA_TRY(cudaMemcpyAsync(disp_host, e->out_dev[b], (size_t)batch * npx * 4, cudaMemcpyDeviceToHost, e->s_out));
+    ROO_CUDA_TRY(cudaEventRecord(e->ev_out[b], e->s_out));
+    ++e->ticket;
+    return ROO_OK;
+}
+
+extern "C" int roo_engine_submit_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
+                                      int n_pairs, long long* ticket) {
+    if (!e || !left_host || !right_host || !disp_host || !ticket || n_pairs <= 0 || n_pairs > e->p.max_batch)
+        return ROO_ERR_INVALID_ARGUMENT;
+    const int rc0 = host_streams_init(e);
+    if (rc0) return rc0;
+    const int rc = submit_group(e, left_host, right_host, disp_host, n_pairs);
+    if (rc) return rc;
+    *ticket = e->ticket - 1;
+    return ROO_OK;
+}
+
+extern "C" int roo_engine_wait(roo_engine_t* e, long long ticket) {
+    if (!e || ticket < 0 || ticket >= e->ticket) return ROO_ERR_INVALID_ARGUMENT;
+    if (ticket + 2 < e->ticket) return ROO_OK;   // its slot was reused: submit_group already waited for it
+    ROO_CUDA_TRY(cudaEventSynchronize(e->ev_out[ticket & 1]));
+    return ROO_OK;
+}
+
 extern "C" int roo_engine_run_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
                                    int n_pairs) {
     if (!e || !left_host || !right_host || !disp_host || n_pairs < 0) return ROO_ERR_INVALID_ARGUMENT;
-    const size_t npx = e->npx, B = (size_t)e->p.max_batch;
-    if (!e->s_compute) {
-        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
-        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
-        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
-            ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][0], B * npx));
-            ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][1], B * npx));
-            ROO_CUDA_TRY(cudaMalloc((void**)&e->out_dev[b], B * npx * 4));
-            e->scratch_bytes += 2 * B * npx + B * npx * 4;
-            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[b], cudaEventDisableTiming));
-            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
-            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[b], cudaEventDisableTiming));
-        }
-    }
-    int gi = 0;
-    for (int g = 0; g < n_pairs; g += (int)B, ++gi) {
-        const int b = gi & 1;
-        const size_t batch = (size_t)(n_pairs - g) < B ? (size_t)(n_pairs - g) : B;
-        if (gi >= 2) {
-            ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_in, e->ev_done[b], 0));      // inputs of group gi-2 consumed
-            ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_compute, e->ev_out[b], 0));  // output of group gi-2 downloaded
-        }
-        ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][0], left_host + (size_t)g * npx, batch * npx, cudaMemcpyHostToDevice, e->s_in));
-        ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][1], right_host + (size_t)g * npx, batch * npx, cudaMemcpyHostToDevice, e->s_in));
-        ROO_CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
-        ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_compute, e->ev_in[b], 0));
-        const int rc = engine_group(e, e->in_dev[b][0], e->in_dev[b][1], e->out_dev[b], (int)batch, e->s_compute);
+    const int rc0 = host_streams_init(e);
+    if (rc0) return rc0;
+    const size_t npx = e->npx;
+    const int B = e->p.max_batch;
+    for (int g = 0; g < n_pairs; g += B) {
+        const int batch = n_pairs - g < B ? n_pairs - g : B;
+        const int rc = submit_group(e, left_host + (size_t)g * npx, right_host + (size_t)g * npx, disp_host + (size_t)g * npx, batch);
         if (rc) return rc;
-        ROO_CUDA_TRY(cudaEventRecord(e->ev_done[b], e->s_compute));
-        ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_done[b], 0));
-        ROO_CUDA_TRY(cudaMemcpyAsync(disp_host + (size_t)g * npx, e->out_dev[b], batch * npx * 4, cudaMemcpyDeviceToHost, e->s_out));
-        ROO_CUDA_TRY(cudaEventRecord(e->ev_out[b], e->s_out));
     }
     ROO_CUDA_TRY(cudaStreamSynchronize(e->s_out));
     ROO_CUDA_TRY(cudaStreamSynchronize(e->s_compute));

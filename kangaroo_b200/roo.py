@@ -296,6 +296,18 @@ class StereoEngine:
               "roo_engine_run_host")
         return disp
 
+    def submit_host(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor) -> int:
+        """Asynchronous run_host for one group (<= max_batch pairs): returns a ticket for wait().  The tensors must
+        stay alive (and should be pinned) until wait(ticket) returns."""
+        assert not left.is_cuda and left.dtype == torch.uint8 and disp.dtype == torch.float32
+        t = C.c_longlong(-1)
+        check(lib().roo_engine_submit_host(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(), left.shape[0],
+                                           C.byref(t)), "roo_engine_submit_host")
+        return int(t.value)
+
+    def wait(self, ticket: int) -> None:
+        check(lib().roo_engine_wait(self._h, ticket), "roo_engine_wait")
+
     def set_profiling(self, on: bool) -> None:
         check(lib().roo_engine_set_profiling(self._h, int(on)), "roo_engine_set_profiling")
 

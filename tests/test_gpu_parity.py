@@ -458,6 +458,34 @@ def test_engine_run_host_equals_run_device():
     eng.close()
 
 
+def test_engine_submit_host_pipeline_equals_run_device():
+    """roo_engine_submit_host / roo_engine_wait: five groups streamed with two in flight, different inputs each."""
+    w, h, D, B = 160, 64, 32, 2
+    eng = roo.StereoEngine(w, h, D, dodiag=True, subpix=True, max_batch=B)
+    groups = []
+    for k in range(5):
+        n = B if k != 3 else 1   # a short group in the middle
+        prs = [stereo_pair(w, h, D, config=60 + 2 * k + i) for i in range(n)]
+        L = torch.from_numpy(np.stack([p[0] for p in prs])).pin_memory()
+        R = torch.from_numpy(np.stack([p[1] for p in prs])).pin_memory()
+        groups.append((L, R, torch.empty((n, h, w), dtype=torch.float32).pin_memory()))
+    tickets = []
+    for k, (L, R, Dh) in enumerate(groups):
+        tickets.append(eng.submit_host(L, R, Dh))
+        if k >= 1:
+            eng.wait(tickets[k - 1])
+    eng.wait(tickets[-1])
+    eng.wait(tickets[0])   # waiting again for a long-finished ticket is fine
+    for L, R, Dh in groups:
+        ref = eng.run_device(L.cuda(), R.cuda()).cpu().numpy()
+        got = Dh.numpy()
+        assert np.array_equal(np.isnan(ref), np.isnan(got)) and np.array_equal(ref[~np.isnan(ref)], got[~np.isnan(got)])
+    from kangaroo_b200.capi import RooError
+    with pytest.raises(RooError):
+        eng.wait(99)
+    eng.close()
+
+
 def test_multi_gpu_engine_shards_pairs_across_all_devices():
     """In-library sharding (one engine + host thread per device, no collective): identical disparities whatever
     the device count -- runs on however many GPUs are visible (1 on the default test box)."""

@@ -245,50 +245,45 @@ cost_u8_kernel(unsigned char* __restrict__ c8, const unsigned long long* __restr
         s_l[k * COST_TX + px] = (x0 + px < w) ? (WT)cl[(rowoff + x0 + px) * WORDS + k] : (WT)0;
     }
     __syncthreads();
-    // lanes run over pixels (consecutive descriptors in shared memory: conflict-free), each thread packs 4
-    // consecutive disparities into one word of a padded output tile; the tile then leaves coalesced
-    const int groups = DP >> 2;                           // 32-bit words per pixel
+    // lanes run over pixels (consecutive descriptors in shared memory: conflict-free); a thread keeps ONE pixel
+    // (its left descriptor stays in registers) and walks the disparity groups, packing 4 consecutive disparities
+    // into one word of a padded output tile; the tile then leaves coalesced in 16-byte stores
+    const int groups = DP >> 2;                           // 32-bit words per pixel (8, 16, 32 or 64)
+    const int lg = 31 - __clz(groups);
     const int gpad = groups + 1;
     auto popc = [](WT v) -> unsigned { return POPC64 ? (unsigned)__popcll((unsigned long long)v) : (unsigned)__popc((unsigned)v); };
     // every pixel of the segment sees its whole disparity range: no per-disparity tests
     const bool full = x0 >= DP - 1 && maxDisp == DP;
-    for (int i = threadIdx.x; i < COST_TX * groups; i += 256) {
-        const int px = i % COST_TX, g = i / COST_TX;
+    {
+        const int px = threadIdx.x & (COST_TX - 1);
         WT p[WORDS];
 #pragma unroll
         for (int k = 0; k < WORDS; ++k) p[k] = s_l[k * COST_TX + px];
-        const int r0 = px + (DP - 1) - g * 4;             // index of x-d in s_r for d = 4g
-        unsigned packed = 0;
-        if (full) {
+        const int x = x0 + px;
+        unsigned* orow = s_out + px * gpad;
+        for (int g = threadIdx.x / COST_TX; g < groups; g += 256 / COST_TX) {
+            const WT* q = s_r + px + (DP - 1) - g * 4;     // x-d in s_r for d = 4g; d+1 is one element lower
+            unsigned hd[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                unsigned hd = 0;
+                hd[j] = 0;
 #pragma unroll
-                for (int k = 0; k < WORDS; ++k) hd += popc(p[k] ^ s_r[k * span + r0 - j]);
-                packed |= hd << (8 * j);
-            }
-        } else {
-            const int x = x0 + px;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int d = g * 4 + j;
-                unsigned hd = WORDS * 32;                 // 0.5 * bits: no right pixel (the reference's 0.5)
-                if (d < maxDisp && d <= x) {
-                    hd = 0;
-#pragma unroll
-                    for (int k = 0; k < WORDS; ++k) hd += popc(p[k] ^ s_r[k * span + r0 - j]);
+                for (int k = 0; k < WORDS; ++k) hd[j] += popc(p[k] ^ q[k * span - j]);
+                if (!full) {
+                    const int d = g * 4 + j;
+                    if (!(d < maxDisp && d <= x)) hd[j] = WORDS * 32;   // 0.5 * bits: no right pixel (the reference's 0.5)
                 }
-                packed |= hd << (8 * j);
             }
+            orow[g] = hd[0] | (hd[1] << 8) | (hd[2] << 16) | (hd[3] << 24);
         }
-        s_out[px * gpad + g] = packed;
     }
     __syncthreads();
-    unsigned* out = reinterpret_cast<unsigned*>(c8 + (rowoff + x0) * DP);
+    uint4* out = reinterpret_cast<uint4*>(c8 + (rowoff + x0) * DP);   // DP bytes per pixel: 16-byte aligned
     const int npx = min(COST_TX, w - x0);
-    for (int i = threadIdx.x; i < npx * groups; i += 256) {   // consecutive threads -> consecutive 4-byte words
-        const int px = i / groups, g = i - px * groups;
-        out[i] = s_out[px * gpad + g];
+    for (int i = threadIdx.x; i < npx * (groups >> 2); i += 256) {   // consecutive threads -> consecutive 16 bytes
+        const int px = i >> (lg - 2), g = (i & ((groups >> 2) - 1)) << 2;
+        const unsigned* t = s_out + px * gpad + g;
+        out[i] = make_uint4(t[0], t[1], t[2], t[3]);
     }
 }
 

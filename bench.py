@@ -33,6 +33,7 @@ WORKLOADS = {
     "c2_1280x720x128_8path_wta": (1280, 720, 128, 8, 0, 0, 16, 2),
     "c3_kitti_1242x375x128_4path": (1242, 375, 128, 4, 0, 0, 16, 3),
     "c4_1920x1080x256_8path_subpix_lr": (1920, 1080, 256, 8, 1, 1, 4, 4),
+    "c5_3840x2160x256_8path_subpix_lr_single_gpu": (3840, 2160, 256, 8, 1, 1, 1, 5),
 }
 DEFAULT_WORKLOAD = "c2_1280x720x128_8path_wta"
 P1, P2 = 0.01, 0.02  # applications/stereo2/main.cpp:246-247

@@ -359,6 +359,40 @@ def test_engine_c2_full_size_properties_and_oracle():
     assert np.array_equal(dhf[0][::-1], dh[0])
 
 
+def test_engine_c5_maximum_size_3840x2160x256():
+    """BASELINE config 5 on ONE GPU: 3840x2160, 256 disparities (8.5 GB aggregate, 2.1e9 elements -- past 2^31).
+    Size-independent checks: the fused passes equal the separate sweeps bit for bit; rows are independent under
+    horizontal-only aggregation and columns under plain vertical aggregation, so crops run through the CPU oracle
+    must reproduce the same pixels exactly (IEEE mode)."""
+    w, h, D = 3840, 2160, 256
+    L, R, gt = stereo_pair(w, h, D, config=5)
+    roo.set_ieee_division(True)
+
+    def run(**kw):
+        eng = roo.StereoEngine(w, h, D, max_batch=1, **kw)
+        d = eng.run_device(torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda())[0].cpu().numpy()
+        eng.close()
+        torch.cuda.empty_cache()
+        return d
+
+    fused = run(dodiag=True, subpix=True)
+    plain = run(dodiag=True, subpix=True, fuse_vertical=False)
+    assert np.array_equal(np.isnan(fused), np.isnan(plain)) and np.array_equal(fused[~np.isnan(fused)], plain[~np.isnan(plain)])
+    valid = np.arange(w)[None, :] >= gt
+    assert (np.abs(fused - gt)[valid & np.isfinite(fused)] <= 1).mean() > 0.8   # and it is a sensible disparity map
+
+    # rows are independent without vertical paths: the last 48 rows (the highest addresses of the volume)
+    dh = run(dovert=False)
+    y0 = h - 48 - 7                                       # 7 rows of census support above the checked band
+    oh = ko.pipeline_u8(L[y0:], R[y0:], D, dovert=False)
+    assert np.array_equal(dh[y0 + 7:], oh[7:])
+    # columns are independent with plain vertical paths only: the last 256 columns see the full disparity range
+    dv = run(dohoriz=False)
+    x0 = w - 256 - D - 8                                  # disparity reach + census support to the left
+    ov = ko.pipeline_u8(np.ascontiguousarray(L[:, x0:]), np.ascontiguousarray(R[:, x0:]), D, dohoriz=False)
+    assert np.array_equal(dv[:, w - 256:], ov[:, -256:])
+
+
 @pytest.mark.parametrize("shape", [(20, 90, 32), (257, 130, 64), (33, 17, 40), (500, 64, 128), (96, 40, 256)])
 def test_fused_vertical_group_equals_separate_sweeps_and_oracle(shape):
     """The fused pass (vertical path + its two diagonals, sgm_fused.cu) must be bit-identical to three

@@ -210,6 +210,20 @@ inline void DisparityImageToVbo(Image<float4> dVbo, const Image<float> dDisp, fl
     b200::done(roo_disparity_image_to_vbo(&cv, &cd, baseline, fu, fv, u0, v0, b200::stream_slot()), "DisparityImageToVbo");
 }
 
+// ---- cu_median.h:19-32 (out of place only: the reference races when dOut aliases dIn)
+inline void MedianFilterRejectNegative5x5(Image<float> dOut, Image<float> dIn, int maxbad = 100) {
+    auto o = b200::c(dOut), i = b200::c(dIn);
+    b200::done(roo_median_filter_reject_negative(&o, &i, 5, maxbad, b200::stream_slot()), "MedianFilterRejectNegative5x5");
+}
+inline void MedianFilterRejectNegative7x7(Image<float> dOut, Image<float> dIn, int maxbad) {
+    auto o = b200::c(dOut), i = b200::c(dIn);
+    b200::done(roo_median_filter_reject_negative(&o, &i, 7, maxbad, b200::stream_slot()), "MedianFilterRejectNegative7x7");
+}
+inline void MedianFilterRejectNegative9x9(Image<float> dOut, Image<float> dIn, int maxbad) {
+    auto o = b200::c(dOut), i = b200::c(dIn);
+    b200::done(roo_median_filter_reject_negative(&o, &i, 9, maxbad, b200::stream_slot()), "MedianFilterRejectNegative9x9");
+}
+
 // ---- extension: the fused per-frame engine (census -> cost -> SGM -> WTA/subpixel -> LR check) --------
 class StereoEngine {
 public:

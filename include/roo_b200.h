@@ -127,6 +127,14 @@ int roo_disp2depth(const roo_image_t* in_f32, const roo_image_t* out_f32, float 
 int roo_disparity_image_to_vbo(const roo_image_t* vbo_f32x4, const roo_image_t* disp_f32, float baseline, float fu,
                                float fv, float u0, float v0, void* stream);
 
+/* roo::MedianFilterRejectNegative5x5 / 7x7 / 9x9 (cu_median.h:19-32; cu_median.cu:160-350), size in {5,7,9}: NaN unless
+ * fewer than maxbad (and not all) samples of the clamp-to-edge window are non-finite, else the median of the valid
+ * samples.  Bit-identical to the reference for windows without invalid samples; with invalid samples the reference
+ * returns a comparator-order-dependent near-median, this returns the true median of the valid
+ * ones.  `out` must not overlap `in` (the reference races when called in place, as its applications do). */
+int roo_median_filter_reject_negative(const roo_image_t* out_f32, const roo_image_t* in_f32, int size, int maxbad,
+                                      void* stream);
+
 /* ---- fused engine: the whole per-frame path of applications/stereo2/main.cpp:375-454 ------- */
 
 typedef struct roo_engine roo_engine_t;

@@ -62,6 +62,7 @@ SYMBOLS = {
     "roo_box_half": (C.c_int, [_IMG, _IMG, C.c_int, _S]),
     "roo_disp2depth": (C.c_int, [_IMG, _IMG, C.c_float, C.c_float, C.c_float, _S]),
     "roo_disparity_image_to_vbo": (C.c_int, [_IMG, _IMG, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _S]),
+    "roo_median_filter_reject_negative": (C.c_int, [_IMG, _IMG, C.c_int, C.c_int, _S]),
     "roo_engine_create": (C.c_int, [_P(C.c_void_p), _P(PipelineParams)]),
     "roo_engine_destroy": (C.c_int, [C.c_void_p]),
     "roo_engine_scratch_bytes": (C.c_size_t, [C.c_void_p]),

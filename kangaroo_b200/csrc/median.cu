@@ -1,0 +1,88 @@
+// MedianFilterRejectNegative{5x5,7x7,9x9} (src/cu_median.cu:160-350) -- the step between winner-takes-all and the
+// left-right check in both applications (stereo2/main.cpp:438-444).  SURVEY.md section 8f, N1.
+//
+// Semantics (out of place): window = clamp-to-edge neighbourhood, bad = number of non-finite samples, output NaN
+// unless bad < maxbad && bad < size^2, else the median of the valid samples: sorted valid samples, element
+// (size^2 + bad)/2 - bad.  For windows without invalid samples this is bit-identical to the reference (its exchange
+// network then returns the exact median); with invalid samples the reference's result depends on its comparator
+// order (fminf/fmaxf overwrite NaNs with copies of their partners) and is NOT reproduced -- see oracle header and
+// tests/golden/median.npz.  Calling it in place (as the applications do) races in the reference; here in == out is
+// refused.
+//
+// Kernel: a 32x8 tile (+ apron) staged in shared memory with clamp-to-edge; every thread keeps its size^2 samples in
+// registers as order-preserving integer keys and finds the k-th smallest by a bitwise binary search over the key
+// (32 x size^2 compare-and-count steps, branch-free) -- no sorting network, exact for any input.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace roo_b200 {
+
+constexpr int MED_TX = 32, MED_TY = 8;
+
+__device__ __forceinline__ unsigned float_key(float f) {   // monotonic: a < b  <=>  key(a) < key(b)
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <int SIZE>
+__global__ void __launch_bounds__(MED_TX* MED_TY) median_reject_kernel(Img<float> out, Img<float> in, int maxbad) {
+    constexpr int R = SIZE / 2, K = SIZE * SIZE, TW = MED_TX + 2 * R, TH = MED_TY + 2 * R;
+    __shared__ float tile[TH][TW + 1];
+    const int x0 = blockIdx.x * MED_TX, y0 = blockIdx.y * MED_TY;
+    for (int i = threadIdx.y * MED_TX + threadIdx.x; i < TW * TH; i += MED_TX * MED_TY) {
+        const int ty = i / TW, tx = i - ty * TW;
+        tile[ty][tx] = in(clampi(x0 + tx - R, 0, in.w - 1), clampi(y0 + ty - R, 0, in.h - 1));
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    unsigned key[K];
+    int bad = 0;
+#pragma unroll
+    for (int dy = 0; dy < SIZE; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < SIZE; ++dx) {
+            const float v = tile[threadIdx.y + dy][threadIdx.x + dx];
+            const bool ok = isfinite(v);            // InvalidValue<float>::IsValid (InvalidValue.h:18-47)
+            bad += ok ? 0 : 1;
+            key[dy * SIZE + dx] = ok ? float_key(v) : 0xffffffffu;   // invalid samples sort last
+        }
+    float r = __int_as_float(0x7fffffff);
+    if (bad < maxbad && bad < K) {
+        const int want = (K + bad) / 2 - bad + 1;   // the result is the smallest key with at least `want` keys <= it
+        unsigned prefix = 0;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned trial = prefix | ((1u << bit) - 1u);
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) cnt += key[i] <= trial ? 1 : 0;
+            if (cnt < want) prefix |= 1u << bit;
+        }
+        r = key_float(prefix);
+    }
+    out(x, y) = r;
+}
+
+}  // namespace roo_b200
+
+using namespace roo_b200;
+
+extern "C" int roo_median_filter_reject_negative(const roo_image_t* out, const roo_image_t* in, int size, int maxbad,
+                                                 void* stream) {
+    if (size != 5 && size != 7 && size != 9) return ROO_ERR_UNSUPPORTED;
+    if (!valid_image(out, 4) || !valid_image(in, 4) || in->w != out->w || in->h != out->h) return ROO_ERR_INVALID_ARGUMENT;
+    // in place = a data race in the reference (neighbours are read while other blocks overwrite them): refuse overlap
+    const char *ob = (const char*)out->ptr, *ib = (const char*)in->ptr;
+    if (ob < ib + in->pitch * in->h && ib < ob + out->pitch * out->h) return ROO_ERR_INVALID_ARGUMENT;
+    const dim3 grid(cdiv((long long)out->w, MED_TX), cdiv((long long)out->h, MED_TY)), block(MED_TX, MED_TY);
+    cudaStream_t st = as_stream(stream);
+    if (size == 5) median_reject_kernel<5><<<grid, block, 0, st>>>(Img<float>(*out), Img<float>(*in), maxbad);
+    else if (size == 7) median_reject_kernel<7><<<grid, block, 0, st>>>(Img<float>(*out), Img<float>(*in), maxbad);
+    else median_reject_kernel<9><<<grid, block, 0, st>>>(Img<float>(*out), Img<float>(*in), maxbad);
+    count_launch();
+    return launch_status();
+}

@@ -241,6 +241,19 @@ def DisparityImageToVbo(dVbo: Image, dDisp: Image, baseline: float, fu: float, f
                                            _stream(stream)), "DisparityImageToVbo")
 
 
+def _median(size):
+    def f(dOut: Image, dIn: Image, maxbad: int = 100, stream=None) -> None:
+        check(lib().roo_median_filter_reject_negative(C.byref(dOut.c()), C.byref(dIn.c()), size, maxbad, _stream(stream)),
+              f"MedianFilterRejectNegative{size}x{size}")
+    f.__doc__ = f"roo::MedianFilterRejectNegative{size}x{size} (cu_median.h:19-32), out of place."
+    return f
+
+
+MedianFilterRejectNegative5x5 = _median(5)
+MedianFilterRejectNegative7x7 = _median(7)
+MedianFilterRejectNegative9x9 = _median(9)
+
+
 def set_ieee_division(on: bool) -> None:
     lib().roo_set_ieee_division(int(on))
 

@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         L.ko_box_half.argtypes = [P(KoImage), P(KoImage), C.c_int]
         L.ko_disp2depth.argtypes = [P(KoImage), P(KoImage), C.c_float, C.c_float, C.c_float]
         L.ko_disparity_image_to_vbo.argtypes = [P(KoImage), P(KoImage)] + [C.c_float] * 5
+        L.ko_median_filter_reject_negative.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
         L.ko_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ko_hamming.restype = C.c_uint
         L.ko_pipeline_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -237,6 +238,12 @@ def disparity_image_to_vbo(disp: np.ndarray, baseline: float, fu: float, fv: flo
     vbo = np.zeros((h, w, 4), np.float32)
     lib().ko_disparity_image_to_vbo(C.byref(_img(vbo)), C.byref(_img(disp)), baseline, fu, fv, u0, v0)
     return vbo
+
+
+def median_filter_reject_negative(img: np.ndarray, size: int, maxbad: int) -> np.ndarray:
+    out = np.zeros(img.shape, np.float32)
+    lib().ko_median_filter_reject_negative(C.byref(_img(out)), C.byref(_img(img)), size, maxbad)
+    return out
 
 
 def pipeline_u8(left: np.ndarray, right: np.ndarray, max_disp: int, window: int = WIN_9x7,

@@ -487,6 +487,39 @@ void ko_disparity_image_to_vbo(const ko_image* vbo, const ko_image* disp, float 
         }
 }
 
+/* ---------------------------------------------------------------- median (N1) ---- */
+
+static int cmp_float(const void* a, const void* b) {
+    const float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+/* cu_median.cu:160-207 (5x5), :217-273 (7x7), :283-342 (9x9): gather with GetWithClampedRange, count invalid
+ * samples, output the median of the valid ones (see the header for the exact relation to the reference). */
+void ko_median_filter_reject_negative(const ko_image* out, const ko_image* in, int size, int maxbad) {
+    const int w = (int)out->w, h = (int)out->h, krad = size / 2, kpix = size * size;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float v[81];
+            int n = 0;
+            for (int dx = -krad; dx <= krad; ++dx)
+                for (int dy = -krad; dy <= krad; ++dy) {
+                    const int xx = x + dx < 0 ? 0 : (x + dx > w - 1 ? w - 1 : x + dx);
+                    const int yy = y + dy < 0 ? 0 : (y + dy > h - 1 ? h - 1 : y + dy);
+                    const float s = *(const float*)img_at(in, (size_t)xx, (size_t)yy, 4);
+                    if (isfinite(s)) v[n++] = s;
+                }
+            const int bad = kpix - n;
+            float r = NAN;
+            if (bad < maxbad && bad < kpix) {
+                qsort(v, (size_t)n, sizeof(float), cmp_float);
+                r = v[(kpix + bad) / 2 - bad];
+            }
+            *(float*)img_at(out, (size_t)x, (size_t)y, 4) = r;
+        }
+}
+
 /* ---------------------------------------------------------------- left-right check ---- */
 
 /* cu_dense_stereo.cu:512-532 with TD=float; InvalidValue<float>: NaN / isfinite (InvalidValue.h:18-47) */

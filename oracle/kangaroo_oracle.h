@@ -96,6 +96,16 @@ void ko_disp2depth(const ko_image* in_f32, const ko_image* out_f32, float fu, fl
 void ko_disparity_image_to_vbo(const ko_image* vbo_f32x4, const ko_image* disp_f32, float baseline, float fu, float fv,
                                float u0, float v0);
 
+/* src/cu_median.cu:160-350 (MedianFilterRejectNegative5x5 / 7x7 / 9x9), OUT OF PLACE.  size in {5,7,9}.
+ * Window = clamp-to-edge neighbourhood (Image.h:298-303); bad = number of non-finite samples
+ * (InvalidValue<float>::IsValid = isfinite, InvalidValue.h:18-47); out = NaN unless bad < maxbad && bad < size^2.
+ * For windows WITHOUT invalid samples the reference's exchange network returns the exact median v[size^2/2] and so
+ * does this.  With invalid samples the reference returns v[(size^2+bad)/2] of a PARTIALLY sorted array in which
+ * fminf/fmaxf have overwritten NaNs with copies of their partners -- a near-median sample that depends on the
+ * comparator order; this restatement returns what the code says it means ("select median, ignoring bad values"):
+ * the valid samples sorted, element (size^2+bad)/2 - bad.  tests/golden/median.npz pins both facts. */
+void ko_median_filter_reject_negative(const ko_image* out_f32, const ko_image* in_f32, int size, int maxbad);
+
 /* src/cu_dense_stereo.cu:512-546 */
 void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff);
 void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd, int maxDiff);

@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         L.kref_box_half.argtypes = [p, z, p, z, z, z, i]
         L.kref_disp2depth.argtypes = [p, p, z, z, z, f, f, f]
         L.kref_disparity_image_to_vbo.argtypes = [p, z, p, z, z, z, f, f, f, f, f]
+        L.kref_median_reject_negative.argtypes = [p, p, z, z, z, i, i]
         _lib = L
     return _lib
 
@@ -219,3 +220,14 @@ def disparity_image_to_vbo(disp: np.ndarray, baseline: float, fu: float, fv: flo
     _ck(lib().kref_disparity_image_to_vbo(out.data_ptr(), w * 16, di.data_ptr(), w * 4, w, h, baseline, fu, fv, u0, v0),
         "DisparityImageToVbo")
     return _back(out, np.float32, (h, w, 4))
+
+
+def median_filter_reject_negative(img: np.ndarray, size: int, maxbad: int) -> np.ndarray:
+    """MedianFilterRejectNegative{5x5,7x7,9x9}, out of place (the applications call it in place, which races)."""
+    import torch
+    h, w = img.shape
+    di = _dev(img)
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_median_reject_negative(out.data_ptr(), di.data_ptr(), w * 4, w, h, size, maxbad),
+        "MedianFilterRejectNegative")
+    return _back(out, np.float32, (h, w))

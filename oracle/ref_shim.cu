@@ -6,7 +6,7 @@
 // (include/kangaroo/cu_census.h, cu_semi_global_matching.h, cu_dense_stereo.h) and
 // forwards plain pointers to the roo:: free functions.  It is compiled together
 // with /root/reference/src/{cu_census,cu_semi_global_matching,cu_dense_stereo,cu_operations,
-// cu_resample,cu_depth_tools}.cu (from where they lie) into oracle/_ref/libkangaroo_ref.so
+// cu_resample,cu_depth_tools,cu_median}.cu (from where they lie) into oracle/_ref/libkangaroo_ref.so
 // by oracle/Makefile.
 //
 // The reference kernels launch one thread per pixel of a row/column in ONE block
@@ -20,6 +20,7 @@
 #include <kangaroo/Pyramid.h>
 #include <kangaroo/reduce.h>
 #include <kangaroo/cu_depth_tools.h>
+#include <kangaroo/cu_median.h>
 
 namespace {
 template <typename T>
@@ -193,6 +194,17 @@ int kref_disp2depth(void* in, void* out, size_t pitch, size_t w, size_t h, float
 int kref_disparity_image_to_vbo(void* vbo, size_t vbo_pitch, void* disp, size_t disp_pitch, size_t w, size_t h,
                                 float baseline, float fu, float fv, float u0, float v0) {
     roo::DisparityImageToVbo(img<float4>(vbo, vbo_pitch, w, h), img<float>(disp, disp_pitch, w, h), baseline, fu, fv, u0, v0);
+    return finish();
+}
+
+// size: 5, 7 or 9 (MedianFilterRejectNegative{5x5,7x7,9x9}); out and in must be different images (the kernels read
+// neighbours that other blocks write when called in place)
+int kref_median_reject_negative(void* out, void* in, size_t pitch, size_t w, size_t h, int size, int maxbad) {
+    if (out == in) return -3;
+    if (size == 5) roo::MedianFilterRejectNegative5x5(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), maxbad);
+    else if (size == 7) roo::MedianFilterRejectNegative7x7(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), maxbad);
+    else if (size == 9) roo::MedianFilterRejectNegative9x9(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), maxbad);
+    else return -1;
     return finish();
 }
 

@@ -56,6 +56,10 @@ def main():
             ("Disp2Depth", lambda: roo.Disp2Depth(disp, depth, 500.0, 0.1), px * 8),
             ("DisparityImageToVbo", lambda: roo.DisparityImageToVbo(vbo, disp, 0.1, 500.0, 500.0, w / 2, h / 2), px * 20),
         ]
+        med = roo.Image(w, h, np.float32)
+        for size in (5, 7, 9):
+            cases.append((f"MedianFilterRejectNegative{size}x{size}",
+                          (lambda f: (lambda: f(med, disp, 50)))(getattr(roo, f"MedianFilterRejectNegative{size}x{size}")), px * 8))
         for name, fn, nbytes in cases:
             ms = timed(fn, flush)
             gbs = nbytes / (ms * 1e-3) / 1e9

@@ -160,3 +160,39 @@ def test_unaligned_subimage_views_take_the_scalar_path():
     out = roo.Image(37, 20, np.float32)
     roo.Disp2Depth(pf.sub_image(5, 3, 37, 20), out, 300.0, 0.2, 1.0)
     assert same_float(out.numpy(), ko.disp2depth(np.ascontiguousarray(f[3:23, 5:42]), 300.0, 0.2, 1.0))
+
+
+# ---------------------------------------------------------------- median filters
+
+def median(img, size, maxbad, pitch=None):
+    h, w = img.shape
+    out = roo.Image(w, h, np.float32)
+    getattr(roo, f"MedianFilterRejectNegative{size}x{size}")(out, roo.Image.from_numpy(img, pitch=pitch), maxbad)
+    return out.numpy()
+
+
+@pytest.mark.parametrize("size", [5, 7, 9])
+def test_median_reject_negative_vs_reference_and_oracle(golden, size):
+    g = golden("median")
+    # no invalid samples: bit-identical to the reference kernels
+    assert same_bits(median(g["clean"], size, 100), g[f"clean_{size}_mb100"])
+    assert np.isnan(median(g["clean"], size, 0)).all()
+    # invalid samples: same valid/NaN pattern as the reference, values = median of the valid samples (oracle)
+    for mb in (1, 4, 100):
+        out = median(g["dirty"], size, mb, pitch=64 * 4 + 16)
+        assert np.array_equal(np.isnan(out), np.isnan(g[f"dirty_{size}_mb{mb}"]))
+        assert same_float(out, ko.median_filter_reject_negative(g["dirty"], size, mb))
+    # full-size frame with ties, negatives and holes; odd size so that the last tiles are partial
+    rng = np.random.default_rng(size)
+    big = np.round(rng.normal(40, 20, (375, 1242)), 1).astype(np.float32)
+    big[rng.random(big.shape) < 0.03] = np.nan
+    assert same_float(median(big, size, 10), ko.median_filter_reject_negative(big, size, 10))
+
+
+def test_median_refuses_in_place():
+    from kangaroo_b200.capi import RooError
+    img = roo.Image(32, 32, np.float32)
+    with pytest.raises(RooError):
+        roo.MedianFilterRejectNegative5x5(img, img, 100)
+    with pytest.raises(RooError):
+        roo.MedianFilterRejectNegative5x5(img.sub_image(0, 0, 16, 16), img.sub_image(8, 8, 16, 16), 100)

@@ -317,3 +317,34 @@ def test_kat_box_half_and_depth():
     f = np.float32
     assert np.array_equal(P[0, 0], np.array([f(-5.0) / f(100.0), f(-10.0) / f(50.0), 5.0, 1.0], f))
     assert np.array_equal(P[0, 1], np.array([0.0, f(-10.0) / f(50.0), 5.0, 1.0], f))
+
+
+# ---------------------------------------------------------------- median filters
+
+@pytest.mark.parametrize("size", [5, 7, 9])
+def test_median_reject_negative_matches_reference(golden, size):
+    """Windows without invalid samples: the reference's exchange network returns the exact median, bit for bit.
+    With invalid samples: the valid/NaN pattern (the bad < maxbad rule) matches exactly; the value the reference
+    picks is comparator-order dependent (see oracle header) and is compared only where no sample is invalid."""
+    g = golden("median")
+    assert np.array_equal(ko.median_filter_reject_negative(g["clean"], size, 100), g[f"clean_{size}_mb100"])
+    assert np.isnan(ko.median_filter_reject_negative(g["clean"], size, 0)).all() and np.isnan(g[f"clean_{size}_mb0"]).all()
+    dirty = g["dirty"]
+    r = size // 2
+    pad = np.pad(~np.isfinite(dirty), r, mode="edge")
+    nbad = sum(pad[dy:dy + dirty.shape[0], dx:dx + dirty.shape[1]].astype(int) for dy in range(size) for dx in range(size))
+    for mb in (1, 4, 100):
+        out, ref = ko.median_filter_reject_negative(dirty, size, mb), g[f"dirty_{size}_mb{mb}"]
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.array_equal(np.isnan(out), ~((nbad < mb) & (nbad < size * size)))
+        assert np.array_equal(out[nbad == 0], ref[nbad == 0])
+
+
+def test_kat_median_ignores_invalid_samples():
+    img = np.arange(25, dtype=np.float32).reshape(5, 5)
+    assert ko.median_filter_reject_negative(img, 5, 100)[2, 2] == 12.0
+    img[0, 0] = np.nan   # valid samples 1..24, bad = 1: sorted valid, index (25+1)//2 - 1 = 12 -> 13
+    assert ko.median_filter_reject_negative(img, 5, 100)[2, 2] == 13.0
+    img[4, 4] = np.inf   # valid samples 1..23, bad = 2: index (25+2)//2 - 2 = 11 -> 12
+    assert ko.median_filter_reject_negative(img, 5, 100)[2, 2] == 12.0
+    assert np.isnan(ko.median_filter_reject_negative(img, 5, 2)[2, 2])   # bad < maxbad fails

@@ -316,7 +316,7 @@ def main():
         }
         if e2e:
             out["e2e"] = e2e
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU port is timed at N=1 only (rank 0)
             # bounded sample: whole pairs, about 10-20 s of wall time on all host cores
             _, dt1, _, _ = cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, h)
             reps = max(1, min(8, int(10.0 / dt1)))

@@ -9,7 +9,7 @@
 // A pixel therefore needs, besides its own H, only the state of three pixels of the previous image row.
 //
 // Mapping.  Work in travel coordinates (x', y') (reverse group = image rotated by 180 degrees) and skewed
-// columns u = x' - y'.  One warp owns one skewed column and walks it row by row, lane l holding disparities
+// columns u = x' - y'.  A skewed column is walked row by row by one warp, lane l holding disparities
 // [l*DPL, (l+1)*DPL):
 //   * the diagonal path (+1,+1) stays inside the warp: its state never leaves registers;
 //   * the vertical path needs the state of column u+1, the anti-diagonal path that of column u+2, both of

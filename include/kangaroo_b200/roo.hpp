@@ -19,6 +19,7 @@
 #pragma once
 
 #include <cstddef>
+#include <cstdio>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -222,6 +223,24 @@ inline void MedianFilterRejectNegative7x7(Image<float> dOut, Image<float> dIn, i
 inline void MedianFilterRejectNegative9x9(Image<float> dOut, Image<float> dIn, int maxbad) {
     auto o = b200::c(dOut), i = b200::c(dIn);
     b200::done(roo_median_filter_reject_negative(&o, &i, 9, maxbad, b200::stream_slot()), "MedianFilterRejectNegative9x9");
+}
+
+// ---- on-disk outputs (extra/SavePPM.h:20-39; applications/stereo/main.cpp:400-410): host pointers, tightly packed rows
+template <typename T>
+inline bool SavePXM(const std::string& filename, const T* host, size_t w, size_t h, size_t pitch_bytes,
+                    const std::string& ppm_type = "P5", int num_colors = 255) {
+    FILE* f = std::fopen(filename.c_str(), "wb");
+    if (!f) return false;
+    std::fprintf(f, "%s\n%zu %zu\n%d\n", ppm_type.c_str(), w, h, num_colors);
+    for (size_t r = 0; r < h; ++r) std::fwrite(reinterpret_cast<const char*>(host) + r * pitch_bytes, sizeof(T), w, f);
+    return std::fclose(f) == 0;
+}
+inline bool SavePDM(const std::string& filename, const float* host, size_t cols, size_t rows) {
+    FILE* f = std::fopen(filename.c_str(), "wb");
+    if (!f) return false;
+    std::fprintf(f, "P7\n%zu %zu\n4294967295\n", cols, rows);
+    std::fwrite(host, sizeof(float), cols * rows, f);
+    return std::fclose(f) == 0;
 }
 
 // ---- extension: the fused per-frame engine (census -> cost -> SGM -> WTA/subpixel -> LR check) --------

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
 #define ROO_B200_THROW
@@ -86,6 +87,17 @@ int main() {
             const float d = out[i];
             if (std::isnan(d)) { if (!std::isnan(z[i]) || !std::isnan(P[i].z)) ++bad; continue; }
             if (d > 0 && (std::fabs(z[i] - 50.0f / d) > 1e-4f * z[i] || P[i].z != z[i] || P[i].w != 1.0f)) ++bad;
+        }
+        // on-disk outputs: header + tightly packed payload (extra/SavePPM.h:20-39, stereo/main.cpp:400-410)
+        if (!roo::SavePDM("/tmp/roo_shim_test.pdm", z.data(), w, h) || !roo::SavePXM<unsigned char>("/tmp/roo_shim_test.pgm", L.data(), w, h, w)) ++bad;
+        {
+            FILE* fp = std::fopen("/tmp/roo_shim_test.pdm", "rb");
+            char hdr[64] = {0};
+            const size_t n = fp ? std::fread(hdr, 1, 24, fp) : 0;
+            if (fp) std::fclose(fp);
+            char want[64];
+            const int wl = std::snprintf(want, sizeof(want), "P7\n%d %d\n4294967295\n", w, h);
+            if (n < (size_t)wl || std::memcmp(hdr, want, wl) != 0) ++bad;
         }
         std::printf("shim: front/back end operators, %d mismatches\n", bad);
         if (bad) return 1;

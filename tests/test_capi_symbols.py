@@ -50,3 +50,16 @@ def test_product_never_imports_the_oracle():
                     if re.search(r"\bimport oracle\b|from oracle\b|kangaroo_oracle|libkangaroo_ref|oracle/", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_cpp_shim_program_compiles_and_links(tmp_path):
+    """The C++ drop-in shim (include/kangaroo_b200/roo.hpp) and its test program build against the library on CPU;
+    tests/test_gpu_cpp_shim.py runs it on the GPU box."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("no nvcc")
+    lib_dir = os.path.join(ROOT, "kangaroo_b200", "lib")
+    subprocess.check_call(["nvcc", "-std=c++17", "-O0", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_roo_shim.cpp"), "-o", str(tmp_path / "shim"),
+                           "-L", lib_dir, "-lroo_b200"])

@@ -5,6 +5,8 @@ import ctypes as C
 import os
 import re
 
+import pytest
+
 from kangaroo_b200 import capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -201,6 +201,10 @@ inline void BoxHalf(Image<To> out, const Image<Ti> in) {
     auto co = b200::c(out), ci = b200::c(in);
     b200::done(roo_box_half(&co, &ci, b200::pix_type<Ti>::value, b200::stream_slot()), "BoxHalf");
 }
+inline void Warp(Image<unsigned char> out, const Image<unsigned char> in, const Image<float2> lookup) {
+    auto co = b200::c(out), ci = b200::c(in), cl = b200::c(lookup);
+    b200::done(roo_warp(&co, &ci, &cl, b200::stream_slot()), "Warp");
+}
 inline void Disp2Depth(Image<float> dIn, const Image<float> dOut, float fu, float fBaseline, float fMinDisp = 0.0) {
     auto ci = b200::c(dIn), co = b200::c(dOut);
     b200::done(roo_disp2depth(&ci, &co, fu, fBaseline, fMinDisp, b200::stream_slot()), "Disp2Depth");

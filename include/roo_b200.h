@@ -118,6 +118,11 @@ int roo_elementwise_scale_bias(const roo_image_t* b_f32, const roo_image_t* a, i
  * `in` must cover 2*out.w x 2*out.h (the reference reads it unguarded). */
 int roo_box_half(const roo_image_t* out, const roo_image_t* in, int pix_type, void* stream);
 
+/* roo::Warp (cu_lookup_warp.h; cu_lookup_warp.cu:85-106): out(x,y) = bilinear sample of `in` at lookup(x,y) (float2
+ * pixel coordinates), the rectification step of applications/stereo2/main.cpp:362-365.  Taps outside `in` are clamped
+ * (the reference reads them unguarded). */
+int roo_warp(const roo_image_t* out_u8, const roo_image_t* in_u8, const roo_image_t* lookup_f32x2, void* stream);
+
 /* roo::Disp2Depth (cu_depth_tools.h:11; cu_depth_tools.cu:15-30): out = in >= minDisp ? fu*baseline/in : NaN. */
 int roo_disp2depth(const roo_image_t* in_f32, const roo_image_t* out_f32, float fu, float baseline, float minDisp,
                    void* stream);

@@ -228,6 +228,14 @@ def BoxReduce(pyramid, stream=None) -> None:
         BoxHalf(pyramid[lvl], pyramid[lvl - 1], stream)
 
 
+FLOAT2 = np.dtype((np.float32, (2,)))   # float2
+
+
+def Warp(out: Image, in_: Image, lookup: Image, stream=None) -> None:
+    """roo::Warp (cu_lookup_warp.cu:96-106): rectify `in_` through a FLOAT2 lookup table (bilinear)."""
+    check(lib().roo_warp(C.byref(out.c()), C.byref(in_.c()), C.byref(lookup.c()), _stream(stream)), "Warp")
+
+
 def Disp2Depth(dIn: Image, dOut: Image, fu: float, fBaseline: float, fMinDisp: float = 0.0, stream=None) -> None:
     """roo::Disp2Depth (cu_depth_tools.h:11)."""
     check(lib().roo_disp2depth(C.byref(dIn.c()), C.byref(dOut.c()), fu, fBaseline, fMinDisp, _stream(stream)),

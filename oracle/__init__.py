@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         L.ko_disp2depth.argtypes = [P(KoImage), P(KoImage), C.c_float, C.c_float, C.c_float]
         L.ko_disparity_image_to_vbo.argtypes = [P(KoImage), P(KoImage)] + [C.c_float] * 5
         L.ko_median_filter_reject_negative.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
+        L.ko_warp.argtypes = [P(KoImage), P(KoImage), P(KoImage)]
         L.ko_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ko_hamming.restype = C.c_uint
         L.ko_pipeline_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -238,6 +239,13 @@ def disparity_image_to_vbo(disp: np.ndarray, baseline: float, fu: float, fv: flo
     vbo = np.zeros((h, w, 4), np.float32)
     lib().ko_disparity_image_to_vbo(C.byref(_img(vbo)), C.byref(_img(disp)), baseline, fu, fv, u0, v0)
     return vbo
+
+
+def warp(img: np.ndarray, lookup: np.ndarray) -> np.ndarray:
+    h, w = lookup.shape[:2]
+    out = np.zeros((h, w), np.uint8)
+    lib().ko_warp(C.byref(_img(out)), C.byref(_img(img)), C.byref(_img(np.ascontiguousarray(lookup, np.float32))))
+    return out
 
 
 def median_filter_reject_negative(img: np.ndarray, size: int, maxbad: int) -> np.ndarray:

@@ -487,6 +487,39 @@ void ko_disparity_image_to_vbo(const ko_image* vbo, const ko_image* disp, float 
         }
 }
 
+/* ---------------------------------------------------------------- rectification warp (N3) ---- */
+
+static inline size_t f2size_floor(float v) {   /* cvt.rmi.u64.f32: floor, negative and NaN -> 0 */
+    if (!(v >= 0.0f)) return 0;
+    return (size_t)floorf(v);
+}
+
+/* cu_lookup_warp.cu:85-94, Image.h:317-334 */
+void ko_warp(const ko_image* out, const ko_image* in, const ko_image* lookup) {
+    const int w = (int)out->w, h = (int)out->h;
+    const size_t xmax = in->w - 1, ymax = in->h - 1;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float* lu = (const float*)img_at(lookup, (size_t)x, (size_t)y, 8);
+            const float u = lu[0], v = lu[1];
+            const float ix = floorf(u), iy = floorf(v);
+            const float fx = u - ix, fy = v - iy;
+            size_t x0 = f2size_floor(u), y0 = f2size_floor(v), y1 = f2size_floor(iy + 1.0f);
+            size_t x1 = x0 + 1;
+            if (x0 > xmax) x0 = xmax;
+            if (x1 > xmax) x1 = xmax;
+            if (y0 > ymax) y0 = ymax;
+            if (y1 > ymax) y1 = ymax;
+            const float b0 = (float)*(const uint8_t*)img_at(in, x0, y0, 1), b1 = (float)*(const uint8_t*)img_at(in, x1, y0, 1);
+            const float t0 = (float)*(const uint8_t*)img_at(in, x0, y1, 1), t1 = (float)*(const uint8_t*)img_at(in, x1, y1, 1);
+            const float l0 = fmaf(fx, b1 - b0, b0), l1 = fmaf(fx, t1 - t0, t0);
+            const float r = fmaf(fy, l1 - l0, l0);
+            uint32_t q = !(r > 0.0f) ? 0u : (r >= 4294967296.0f ? 0xffffffffu : (uint32_t)r);   /* cvt.rzi.u32.f32 */
+            *(uint8_t*)img_at(out, (size_t)x, (size_t)y, 1) = (uint8_t)(q & 0xffu);
+        }
+}
+
 /* ---------------------------------------------------------------- median (N1) ---- */
 
 static int cmp_float(const void* a, const void* b) {

@@ -96,6 +96,12 @@ void ko_disp2depth(const ko_image* in_f32, const ko_image* out_f32, float fu, fl
 void ko_disparity_image_to_vbo(const ko_image* vbo_f32x4, const ko_image* disp_f32, float baseline, float fu, float fv,
                                float u0, float v0);
 
+/* src/cu_lookup_warp.cu:85-106 + Image.h:317-334 (GetBilinear): out(x,y) = (unsigned char) bilinear sample of `in` at
+ * lookup(x,y) = (u, v).  lerp(a,b,t) = a + t*(b-a), one fused multiply-add each as in the reference build; the float
+ * result is truncated to unsigned 32 bit and its low byte stored.  Row / column indices come from float -> size_t
+ * conversions (negative saturates to 0); the reference reads unguarded, this clamps the taps into the image. */
+void ko_warp(const ko_image* out_u8, const ko_image* in_u8, const ko_image* lookup_f32x2);
+
 /* src/cu_median.cu:160-350 (MedianFilterRejectNegative5x5 / 7x7 / 9x9), OUT OF PLACE.  size in {5,7,9}.
  * Window = clamp-to-edge neighbourhood (Image.h:298-303); bad = number of non-finite samples
  * (InvalidValue<float>::IsValid = isfinite, InvalidValue.h:18-47); out = NaN unless bad < maxbad && bad < size^2.

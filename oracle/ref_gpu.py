@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
         L.kref_disp2depth.argtypes = [p, p, z, z, z, f, f, f]
         L.kref_disparity_image_to_vbo.argtypes = [p, z, p, z, z, z, f, f, f, f, f]
         L.kref_median_reject_negative.argtypes = [p, p, z, z, z, i, i]
+        L.kref_warp.argtypes = [p, z, p, z, z, z, p, z, z, z]
         _lib = L
     return _lib
 
@@ -231,3 +232,14 @@ def median_filter_reject_negative(img: np.ndarray, size: int, maxbad: int) -> np
     _ck(lib().kref_median_reject_negative(out.data_ptr(), di.data_ptr(), w * 4, w, h, size, maxbad),
         "MedianFilterRejectNegative")
     return _back(out, np.float32, (h, w))
+
+
+def warp(img: np.ndarray, lookup: np.ndarray) -> np.ndarray:
+    """roo::Warp: lookup is (h, w, 2) float32 = (x, y) sample positions inside [0, W-2] x [0, H-2] of img."""
+    import torch
+    h, w = lookup.shape[:2]
+    ih, iw = img.shape
+    di, dl = _dev(img), _dev(lookup)
+    out = torch.zeros(h * w, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_warp(out.data_ptr(), w, di.data_ptr(), iw, iw, ih, dl.data_ptr(), w * 8, w, h), "Warp")
+    return _back(out, np.uint8, (h, w))

@@ -6,7 +6,7 @@
 // (include/kangaroo/cu_census.h, cu_semi_global_matching.h, cu_dense_stereo.h) and
 // forwards plain pointers to the roo:: free functions.  It is compiled together
 // with /root/reference/src/{cu_census,cu_semi_global_matching,cu_dense_stereo,cu_operations,
-// cu_resample,cu_depth_tools,cu_median}.cu (from where they lie) into oracle/_ref/libkangaroo_ref.so
+// cu_resample,cu_depth_tools,cu_median,cu_lookup_warp}.cu (from where they lie) into oracle/_ref/libkangaroo_ref.so
 // by oracle/Makefile.
 //
 // The reference kernels launch one thread per pixel of a row/column in ONE block
@@ -21,6 +21,7 @@
 #include <kangaroo/reduce.h>
 #include <kangaroo/cu_depth_tools.h>
 #include <kangaroo/cu_median.h>
+#include <kangaroo/cu_lookup_warp.h>
 
 namespace {
 template <typename T>
@@ -205,6 +206,14 @@ int kref_median_reject_negative(void* out, void* in, size_t pitch, size_t w, siz
     else if (size == 7) roo::MedianFilterRejectNegative7x7(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), maxbad);
     else if (size == 9) roo::MedianFilterRejectNegative9x9(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), maxbad);
     else return -1;
+    return finish();
+}
+
+// rectification warp: out (w x h) = bilinear sample of in (in_w x in_h) at lookup(x, y); lookup holds float2
+int kref_warp(void* out, size_t out_pitch, void* in, size_t in_pitch, size_t in_w, size_t in_h, void* lookup,
+              size_t lookup_pitch, size_t w, size_t h) {
+    roo::Warp(img<unsigned char>(out, out_pitch, w, h), img<unsigned char>(in, in_pitch, in_w, in_h),
+              img<float2>(lookup, lookup_pitch, w, h));
     return finish();
 }
 

@@ -56,6 +56,11 @@ def main():
             ("Disp2Depth", lambda: roo.Disp2Depth(disp, depth, 500.0, 0.1), px * 8),
             ("DisparityImageToVbo", lambda: roo.DisparityImageToVbo(vbo, disp, 0.1, 500.0, 500.0, w / 2, h / 2), px * 20),
         ]
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        lut = roo.Image.from_numpy(np.ascontiguousarray(np.stack([np.clip(xx * 0.98 + 3.3, 1, w - 2),
+                                                                    np.clip(yy * 0.98 + 2.7, 1, h - 2)], -1).astype(np.float32)))
+        rect = roo.Image(w, h, np.uint8)
+        cases.append(("Warp (rectification lookup)", lambda: roo.Warp(rect, raw, lut), px * (8 + 1 + 1)))
         med = roo.Image(w, h, np.float32)
         for size in (5, 7, 9):
             cases.append((f"MedianFilterRejectNegative{size}x{size}",

@@ -196,3 +196,24 @@ def test_median_refuses_in_place():
         roo.MedianFilterRejectNegative5x5(img, img, 100)
     with pytest.raises(RooError):
         roo.MedianFilterRejectNegative5x5(img.sub_image(0, 0, 16, 16), img.sub_image(8, 8, 16, 16), 100)
+
+
+# ---------------------------------------------------------------- rectification warp
+
+def warp(img, lut, pitch=None):
+    h, w = lut.shape[:2]
+    out = roo.Image(w, h, np.uint8)
+    roo.Warp(out, roo.Image.from_numpy(img, pitch=pitch), roo.Image.from_numpy(np.ascontiguousarray(lut)))
+    return out.numpy()
+
+
+def test_warp_bitexact_vs_reference_and_oracle(golden):
+    g = golden("warp")
+    for nm in ("radial", "ident", "half"):
+        assert np.array_equal(warp(g["img"], g[nm], pitch=64 + 3), g["out_" + nm])
+    # full frame, random sub-pixel positions incl. positions outside the image (clamped taps, as the oracle)
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (375, 1242), dtype=np.uint8)
+    yy, xx = np.mgrid[0:375, 0:1242].astype(np.float32)
+    lut = np.stack([xx + rng.normal(0, 3, xx.shape), yy + rng.normal(0, 3, yy.shape)], -1).astype(np.float32)
+    assert np.array_equal(warp(img, lut), ko.warp(img, lut))

@@ -348,3 +348,10 @@ def test_kat_median_ignores_invalid_samples():
     img[4, 4] = np.inf   # valid samples 1..23, bad = 2: index (25+2)//2 - 2 = 11 -> 12
     assert ko.median_filter_reject_negative(img, 5, 100)[2, 2] == 12.0
     assert np.isnan(ko.median_filter_reject_negative(img, 5, 2)[2, 2])   # bad < maxbad fails
+
+
+def test_warp_matches_reference(golden):
+    g = golden("warp")
+    for nm in ("radial", "ident", "half"):
+        assert np.array_equal(ko.warp(g["img"], g[nm]), g["out_" + nm])
+    assert np.array_equal(g["out_ident"][:-1, :-1], g["img"][:-1, :-1])   # KAT: integer positions copy the pixel

@@ -85,15 +85,35 @@ def test_engine_beats_reference_kernels_on_the_same_gpu(w, h, D, cfg):
         mine = disp[0].cpu().numpy()
         eng.close()
 
+    # the same call sequence through the drop-in operators (reference layouts, no application change)
+    imgL, imgR = roo.Image.from_numpy(L), roo.Image.from_numpy(R)
+    imgf = roo.Image(w, h, np.float32)
+    cenL, cenR = roo.Image(w, h, roo.ULONG), roo.Image(w, h, roo.ULONG)
+    volC, volH = roo.Volume(w, h, D, np.float32), roo.Volume(w, h, D + 1, np.float32)
+    dispg = roo.Image(w, h, np.float32)
+
+    def granular():
+        roo.ElementwiseScaleBias(imgf, imgL, 1.0 / 255.0)
+        roo.Census(cenL, imgL)
+        roo.Census(cenR, imgR)
+        roo.CensusStereoVolume(volC, cenL, cenR, D, -1.0)
+        roo.SemiGlobalMatching(volH, volC, imgf, D, 0.01, 0.02, True, True, True)
+        roo.CostVolMinimumSubpix(dispg, volH, D, -1.0)
+    ms = _events(granular, 10)
+    out["dropin_operators"] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms}
+    gran = dispg.numpy()
+
     # same answer (the aggregate is bit-identical -- test_gpu_parity -- so only the Q7 top-slice pixels may differ)
     ref = ref_disp.cpu().numpy()
     top = np.rint(ref) >= D - 1
     assert (np.abs(ref - mine)[~top] <= 0.01).mean() >= 0.999
+    assert (np.abs(ref - gran)[~top] <= 0.01).mean() >= 0.999
 
     res = {"shape": [w, h, D], "paths": 4, "wta": "CostVolMinimumSubpix",
            "reference_kernels": {"ms_per_pair": ref_ms, "pairs_per_s": 1e3 / ref_ms,
                                  "build": "oracle/_ref: nvcc -O2 -use_fast_math sm_100a, unmodified sources"},
            **out,
+           "speedup_dropin_operators": ref_ms / out["dropin_operators"]["ms_per_pair"],
            "speedup_1pair": ref_ms / out["engine_1pair"]["ms_per_call"],
            "speedup_batch8": ref_ms / (out["engine_batch8"]["ms_per_call"] / B),
            "gpu": torch.cuda.get_device_name(0)}

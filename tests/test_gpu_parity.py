@@ -446,6 +446,32 @@ def test_engine_degenerate_shapes(shape, dodiag):
         assert np.array_equal(disp[0], od) and np.array_equal(disp[1], od)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_engine_random_shapes_and_flags_bitexact_vs_oracle(seed):
+    """Seeded sweep over shapes around the kernels' internal sizes (32 lanes, 4 columns per warp, 48/24-column bands,
+    128-pixel cost segments, 32-row intensity blocks) with random flag combinations; IEEE mode, bit-exact."""
+    rng = np.random.default_rng(1000 + seed)
+    roo.set_ieee_division(True)
+    for _ in range(5):
+        w = int(rng.choice([2, 3, 4, 5, 23, 24, 25, 47, 48, 49, 95, 97, 127, 129, 200]))
+        h = int(rng.choice([1, 2, 3, 4, 7, 31, 32, 33, 63, 65, 100]))
+        D = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 100, 128, 129, 255, 256]))
+        kw = dict(window=int(rng.choice([0, 1, 2])), dohoriz=bool(rng.integers(2)), dovert=bool(rng.integers(2)),
+                  doreverse=bool(rng.integers(2)), dodiag=bool(rng.integers(2)), subpix=bool(rng.integers(2)),
+                  lrcheck=bool(rng.integers(2)), popc_mode=int(rng.choice([ko.POPC32_COMPAT, ko.POPC64])))
+        batch = int(rng.choice([1, 2, 3]))
+        L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        R = np.roll(L, -int(rng.integers(0, 4)), axis=1) if rng.integers(2) else rng.integers(0, 8, (h, w), dtype=np.uint8)
+        disp, H, cen = run_engine(L, R, D, batch=batch, **kw)
+        od, oH = ko.pipeline_u8(L, R, D, want_volume=True, **kw)
+        tag = f"{w}x{h}x{D} batch {batch} {kw}"
+        if H is not None:
+            assert np.array_equal(H, oH), tag
+        for b in range(batch):
+            assert np.array_equal(np.isnan(disp[b]), np.isnan(od)), tag
+            assert np.array_equal(disp[b][~np.isnan(od)], od[~np.isnan(od)]), tag
+
+
 def test_engine_kitti_shape_4path_bitexact_vs_oracle():
     """BASELINE config 3 shape (1242x375, 128 disparities): wider than the reference's 1024 limit, 4 reference paths."""
     L, R, gt = stereo_pair(1242, 375, 128, config=3)

@@ -10,8 +10,12 @@
 // refused.
 //
 // Kernel: a 32x8 tile (+ apron) staged in shared memory with clamp-to-edge; every thread keeps its size^2 samples in
-// registers as order-preserving integer keys and finds the k-th smallest by a bitwise binary search over the key
-// (32 x size^2 compare-and-count steps, branch-free) -- no sorting network, exact for any input.
+// registers as order-preserving integer keys (invalid samples = the largest key) and sorts them with Batcher's
+// odd-even merge sort, generated at compile time for exactly size^2 inputs (140 / 394 / 864 compare-exchanges of two
+// integer min/max instructions each) -- a network of this file's own making, exact for any input; the wanted rank
+// (size^2 + bad)/2 - bad is then picked with a select chain.
+#include <utility>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -25,6 +29,34 @@ __device__ __forceinline__ unsigned float_key(float f) {   // monotonic: a < b  
 }
 __device__ __forceinline__ float key_float(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Batcher's odd-even merge sort for exactly K inputs, built at compile time: the comparators that would touch the
+// virtual +inf padding up to the next power of two are dropped (140 / 394 / 864 compare-exchanges for 25 / 49 / 81).
+template <int K> struct SortNet { int a[1024]; int b[1024]; int n; };
+template <int K> __host__ __device__ constexpr SortNet<K> make_sort_net() {
+    SortNet<K> r{};
+    int n = 0;
+    for (int p = 1; p < K; p <<= 1)
+        for (int k = p; k >= 1; k >>= 1)
+            for (int j = k % p; j + k < K; j += 2 * k)
+                for (int i = 0; i < k; ++i)
+                    if (i + j + k < K && (i + j) / (2 * p) == (i + j + k) / (2 * p)) { r.a[n] = i + j; r.b[n] = i + j + k; ++n; }
+    r.n = n;
+    return r;
+}
+template <int K> struct SortNetOf { static constexpr SortNet<K> net = make_sort_net<K>(); };
+
+template <int A, int B, int K>
+__device__ __forceinline__ void compare_exchange(unsigned (&key)[K]) {
+    const unsigned x = key[A], y = key[B];
+    key[A] = min(x, y);
+    key[B] = max(x, y);
+}
+// every register index is a template constant, so the keys never leave registers
+template <int K, int... I>
+__device__ __forceinline__ void sort_keys(unsigned (&key)[K], std::integer_sequence<int, I...>) {
+    (compare_exchange<SortNetOf<K>::net.a[I], SortNetOf<K>::net.b[I], K>(key), ...);
 }
 
 template <int SIZE>
@@ -52,17 +84,12 @@ __global__ void __launch_bounds__(MED_TX* MED_TY) median_reject_kernel(Img<float
         }
     float r = __int_as_float(0x7fffffff);
     if (bad < maxbad && bad < K) {
-        const int want = (K + bad) / 2 - bad + 1;   // the result is the smallest key with at least `want` keys <= it
-        unsigned prefix = 0;
-#pragma unroll 1
-        for (int bit = 31; bit >= 0; --bit) {
-            const unsigned trial = prefix | ((1u << bit) - 1u);
-            int cnt = 0;
+        sort_keys<K>(key, std::make_integer_sequence<int, SortNetOf<K>::net.n>{});
+        const int rank = (K + bad) / 2 - bad;        // valid samples sorted ascending, invalid ones last
+        unsigned sel = key[K / 2];
 #pragma unroll
-            for (int i = 0; i < K; ++i) cnt += key[i] <= trial ? 1 : 0;
-            if (cnt < want) prefix |= 1u << bit;
-        }
-        r = key_float(prefix);
+        for (int i = 0; i < K / 2; ++i) sel = (i == rank) ? key[i] : sel;
+        r = key_float(sel);
     }
     out(x, y) = r;
 }

@@ -215,6 +215,14 @@ inline void DisparityImageToVbo(Image<float4> dVbo, const Image<float> dDisp, fl
     b200::done(roo_disparity_image_to_vbo(&cv, &cd, baseline, fu, fv, u0, v0, b200::stream_slot()), "DisparityImageToVbo");
 }
 
+// ---- cu_dense_stereo.h:66
+inline void CostVolumeFromStereoTruncatedAbsAndGrad(Volume<float> dvol, Image<float> dimgl, Image<float> dimgr, float sd,
+                                                    float alpha, float r1, float r2) {
+    auto v = b200::c(dvol);
+    auto l = b200::c(dimgl), r = b200::c(dimgr);
+    b200::done(roo_costvol_from_stereo_truncated_abs_and_grad(&v, &l, &r, sd, alpha, r1, r2, b200::stream_slot()),
+               "CostVolumeFromStereoTruncatedAbsAndGrad");
+}
 // ---- cu_median.h:19-32 (out of place only: the reference races when dOut aliases dIn)
 inline void MedianFilterRejectNegative5x5(Image<float> dOut, Image<float> dIn, int maxbad = 100) {
     auto o = b200::c(dOut), i = b200::c(dIn);

@@ -132,6 +132,14 @@ int roo_disp2depth(const roo_image_t* in_f32, const roo_image_t* out_f32, float 
 int roo_disparity_image_to_vbo(const roo_image_t* vbo_f32x4, const roo_image_t* disp_f32, float baseline, float fu,
                                float fv, float u0, float v0, void* stream);
 
+/* roo::CostVolumeFromStereoTruncatedAbsAndGrad (cu_dense_stereo.h:66; cu_dense_stereo.cu:820-848), the non-census
+ * matching cost of both applications (stereo2/main.cpp:387-388): a float volume for roo_sgm / roo_costvol_minimum*.
+ * As in the reference, alpha and r1 are ignored (its kernel overwrites them with 0 and 1e37): the cost is the absolute
+ * intensity difference, 1e37 where the right pixel is outside the image.  Bounds-guarded (the reference is not). */
+int roo_costvol_from_stereo_truncated_abs_and_grad(const roo_volume_t* vol_f32, const roo_image_t* left_f32,
+                                                   const roo_image_t* right_f32, float sd, float alpha, float r1, float r2,
+                                                   void* stream);
+
 /* roo::MedianFilterRejectNegative5x5 / 7x7 / 9x9 (cu_median.h:19-32; cu_median.cu:160-350), size in {5,7,9}: NaN unless
  * fewer than maxbad (and not all) samples of the clamp-to-edge window are non-finite, else the median of the valid
  * samples.  Bit-identical to the reference for windows without invalid samples; with invalid samples the reference

@@ -63,6 +63,8 @@ SYMBOLS = {
     "roo_warp": (C.c_int, [_IMG, _IMG, _IMG, _S]),
     "roo_disp2depth": (C.c_int, [_IMG, _IMG, C.c_float, C.c_float, C.c_float, _S]),
     "roo_disparity_image_to_vbo": (C.c_int, [_IMG, _IMG, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _S]),
+    "roo_costvol_from_stereo_truncated_abs_and_grad": (C.c_int, [_VOL, _IMG, _IMG, C.c_float, C.c_float, C.c_float,
+                                                                 C.c_float, _S]),
     "roo_median_filter_reject_negative": (C.c_int, [_IMG, _IMG, C.c_int, C.c_int, _S]),
     "roo_engine_create": (C.c_int, [_P(C.c_void_p), _P(PipelineParams)]),
     "roo_engine_destroy": (C.c_int, [C.c_void_p]),

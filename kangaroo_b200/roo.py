@@ -249,6 +249,14 @@ def DisparityImageToVbo(dVbo: Image, dDisp: Image, baseline: float, fu: float, f
                                            _stream(stream)), "DisparityImageToVbo")
 
 
+def CostVolumeFromStereoTruncatedAbsAndGrad(dvol: Volume, dimgl: Image, dimgr: Image, sd: float, alpha: float, r1: float,
+                                            r2: float, stream=None) -> None:
+    """roo::CostVolumeFromStereoTruncatedAbsAndGrad (cu_dense_stereo.h:66); alpha and r1 are ignored as in the reference."""
+    check(lib().roo_costvol_from_stereo_truncated_abs_and_grad(C.byref(dvol.c()), C.byref(dimgl.c()), C.byref(dimgr.c()),
+                                                               sd, alpha, r1, r2, _stream(stream)),
+          "CostVolumeFromStereoTruncatedAbsAndGrad")
+
+
 def _median(size):
     def f(dOut: Image, dIn: Image, maxbad: int = 100, stream=None) -> None:
         check(lib().roo_median_filter_reject_negative(C.byref(dOut.c()), C.byref(dIn.c()), size, maxbad, _stream(stream)),

@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         L.ko_disparity_image_to_vbo.argtypes = [P(KoImage), P(KoImage)] + [C.c_float] * 5
         L.ko_median_filter_reject_negative.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
         L.ko_warp.argtypes = [P(KoImage), P(KoImage), P(KoImage)]
+        L.ko_costvol_abs_and_grad.argtypes = [P(KoVolume), P(KoImage), P(KoImage), C.c_float, C.c_float, C.c_float, C.c_float]
         L.ko_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ko_hamming.restype = C.c_uint
         L.ko_pipeline_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -239,6 +240,14 @@ def disparity_image_to_vbo(disp: np.ndarray, baseline: float, fu: float, fv: flo
     vbo = np.zeros((h, w, 4), np.float32)
     lib().ko_disparity_image_to_vbo(C.byref(_img(vbo)), C.byref(_img(disp)), baseline, fu, fv, u0, v0)
     return vbo
+
+
+def costvol_abs_and_grad(left: np.ndarray, right: np.ndarray, depth: int, sd: float, alpha: float = 0.9,
+                         r1: float = 0.03, r2: float = 0.008) -> np.ndarray:
+    h, w = left.shape
+    vol = np.zeros((depth, h, w), np.float32)
+    lib().ko_costvol_abs_and_grad(C.byref(_vol(vol)), C.byref(_img(left)), C.byref(_img(right)), sd, alpha, r1, r2)
+    return vol
 
 
 def warp(img: np.ndarray, lookup: np.ndarray) -> np.ndarray:

@@ -487,6 +487,36 @@ void ko_disparity_image_to_vbo(const ko_image* vbo, const ko_image* disp, float 
         }
 }
 
+/* ---------------------------------------------------------------- alternative matching cost (N4) ---- */
+
+/* cu_dense_stereo.cu:820-840; Image.h:367-372 (GetCentralDiffDx) */
+void ko_costvol_abs_and_grad(const ko_volume* vol, const ko_image* left, const ko_image* right, float sd, float alpha,
+                             float r1, float r2) {
+    const int w = (int)vol->w, h = (int)vol->h, dn = (int)vol->d, rw = (int)right->w;
+    (void)alpha; (void)r1;   /* overwritten by the reference kernel: alpha = 0, r1 = 1e37 */
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int d = 0; d < dn; ++d)
+        for (int v = 0; v < h; ++v) {
+            const float* rl = (const float*)img_at(left, 0, (size_t)v, 4);
+            const float* rr = (const float*)img_at(right, 0, (size_t)v, 4);
+            for (int u = 0; u < w; ++u) {
+                const int r = (int)fmaf((float)d, sd, (float)u);   /* u + sd*d: one FFMA in the reference, truncated */
+                float c;
+                if (0 <= r && r < rw) {
+                    const int rm = r > 0 ? r - 1 : 0, rp = r < rw - 1 ? r + 1 : rw - 1;
+                    const int um = u > 0 ? u - 1 : 0, up = u < w - 1 ? u + 1 : w - 1;
+                    const float gr = (rr[rp] - rr[rm]) * 0.5f;
+                    const float grad = fabsf(fmaf(rl[up] - rl[um], -0.5f, gr));
+                    const float absI = fabsf(rr[r] - rl[u]);
+                    c = fmaf(0.0f, fminf(grad, r2), fminf(absI, 1e37f));
+                } else {
+                    c = fmaf(0.0f, r2, 1e37f);
+                }
+                *(float*)vol_at(vol, (size_t)u, (size_t)v, (size_t)d, 4) = c;
+            }
+        }
+}
+
 /* ---------------------------------------------------------------- rectification warp (N3) ---- */
 
 static inline size_t f2size_floor(float v) {   /* cvt.rmi.u64.f32: floor, negative and NaN -> 0 */

@@ -96,6 +96,14 @@ void ko_disp2depth(const ko_image* in_f32, const ko_image* out_f32, float fu, fl
 void ko_disparity_image_to_vbo(const ko_image* vbo_f32x4, const ko_image* disp_f32, float baseline, float fu, float fv,
                                float u0, float v0);
 
+/* src/cu_dense_stereo.cu:820-848 (N4, the non-census matching cost of both applications).  The kernel overrides its
+ * arguments: alpha = 0, r1 = 1e37 (:829-830), so for r = (int)(u + sd*d) inside the right image
+ * vol(u,v,d) = fma(0, min(|grad difference|, r2), min(|R(r,v) - L(u,v)|, 1e37)) -- the absolute difference unless the
+ * gradient term is not finite -- and fma(0, r2, 1e37) outside.  The gradient taps row[x-1], row[x+1] are unguarded in
+ * the reference; here they are clamped into the row (they only matter through 0 * non-finite). */
+void ko_costvol_abs_and_grad(const ko_volume* vol_f32, const ko_image* left_f32, const ko_image* right_f32, float sd,
+                             float alpha, float r1, float r2);
+
 /* src/cu_lookup_warp.cu:85-106 + Image.h:317-334 (GetBilinear): out(x,y) = (unsigned char) bilinear sample of `in` at
  * lookup(x,y) = (u, v).  lerp(a,b,t) = a + t*(b-a), one fused multiply-add each as in the reference build; the float
  * result is truncated to unsigned 32 bit and its low byte stored.  Row / column indices come from float -> size_t

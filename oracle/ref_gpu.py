@@ -42,6 +42,7 @@ def lib() -> C.CDLL:
         L.kref_disparity_image_to_vbo.argtypes = [p, z, p, z, z, z, f, f, f, f, f]
         L.kref_median_reject_negative.argtypes = [p, p, z, z, z, i, i]
         L.kref_warp.argtypes = [p, z, p, z, z, z, p, z, z, z]
+        L.kref_costvol_abs_and_grad.argtypes = [p, z, z, z, p, p, z, z, z, f, f, f, f]
         _lib = L
     return _lib
 
@@ -243,3 +244,24 @@ def warp(img: np.ndarray, lookup: np.ndarray) -> np.ndarray:
     out = torch.zeros(h * w, dtype=torch.uint8, device="cuda")
     _ck(lib().kref_warp(out.data_ptr(), w, di.data_ptr(), iw, iw, ih, dl.data_ptr(), w * 8, w, h), "Warp")
     return _back(out, np.uint8, (h, w))
+
+
+def costvol_abs_and_grad(left: np.ndarray, right: np.ndarray, depth: int, sd: float, alpha: float, r1: float, r2: float,
+                         margin: int = 1):
+    """CostVolumeFromStereoTruncatedAbsAndGrad on float images embedded in a zero margin: the kernel reads row[x-1] /
+    row[x+1] unguarded (Image.h:367-372), so the images are the interior of a larger allocation."""
+    import torch
+    h, w = left.shape
+
+    def emb(a):
+        big = np.zeros((h + 2 * margin, w + 2 * margin), np.float32)
+        big[margin:-margin, margin:-margin] = a
+        return big
+    bl, br = emb(left), emb(right)
+    dl, dr = _dev(bl), _dev(br)
+    pitch = (w + 2 * margin) * 4
+    off = margin * pitch + margin * 4
+    vol = torch.zeros(depth * h * w * 4, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_costvol_abs_and_grad(vol.data_ptr(), w * 4, w * h * 4, depth, dl.data_ptr() + off, dr.data_ptr() + off,
+                                        pitch, w, h, sd, alpha, r1, r2), "CostVolumeFromStereoTruncatedAbsAndGrad")
+    return _back(vol, np.float32, (depth, h, w))

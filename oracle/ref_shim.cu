@@ -217,4 +217,13 @@ int kref_warp(void* out, size_t out_pitch, void* in, size_t in_pitch, size_t in_
     return finish();
 }
 
+// N4: alternative matching cost (cu_dense_stereo.cu:820-848); the kernel has no bounds test: w, h, d multiples of 8 only
+int kref_costvol_abs_and_grad(void* v, size_t v_pitch, size_t v_img_pitch, size_t d, void* l, void* r, size_t i_pitch,
+                              size_t w, size_t h, float sd, float alpha, float r1, float r2) {
+    if (w % 8 || h % 8 || d % 8) return -4;
+    roo::CostVolumeFromStereoTruncatedAbsAndGrad(vol<float>(v, v_pitch, v_img_pitch, w, h, d), img<float>(l, i_pitch, w, h),
+                                                 img<float>(r, i_pitch, w, h), sd, alpha, r1, r2);
+    return finish();
+}
+
 }  // extern "C"

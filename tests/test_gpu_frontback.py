@@ -217,3 +217,27 @@ def test_warp_bitexact_vs_reference_and_oracle(golden):
     yy, xx = np.mgrid[0:375, 0:1242].astype(np.float32)
     lut = np.stack([xx + rng.normal(0, 3, xx.shape), yy + rng.normal(0, 3, yy.shape)], -1).astype(np.float32)
     assert np.array_equal(warp(img, lut), ko.warp(img, lut))
+
+
+# ---------------------------------------------------------------- alternative matching cost
+
+def test_costvol_abs_and_grad_bitexact_and_feeds_sgm(golden):
+    g = golden("absgrad")
+
+    def run(l, r, D, sd, *par):
+        h, w = l.shape
+        vol = roo.Volume(w, h, D, np.float32)
+        roo.CostVolumeFromStereoTruncatedAbsAndGrad(vol, roo.Image.from_numpy(l), roo.Image.from_numpy(r), sd, *par)
+        return vol
+    assert same_bits(run(g["left"], g["right"], 16, -1.0, 0.9, 0.03, 0.008).numpy(), g["vol_sdm1"])
+    assert same_bits(run(g["right"], g["left"], 16, 1.0, 0.5, 0.1, 0.02).numpy(), g["vol_sdp1"])
+    # odd sizes (the reference kernel writes out of bounds there) against the oracle
+    rng = np.random.default_rng(11)
+    l, r = rng.random((37, 101), dtype=np.float32), rng.random((37, 101), dtype=np.float32)
+    vol = run(l, r, 21, -1.0, 0.9, 0.03, 0.008)
+    assert same_bits(vol.numpy(), ko.costvol_abs_and_grad(l, r, 21, -1.0))
+    # ... and the volume goes straight into the aggregation operator (stereo2/main.cpp:387-431 with use_census = false)
+    roo.set_ieee_division(True)
+    volH = roo.Volume(101, 37, 21, np.float32)
+    roo.SemiGlobalMatching(volH, vol, roo.Image.from_numpy(l), 21, 0.01, 0.02, True, True, True)
+    assert same_bits(volH.numpy(), ko.sgm(ko.costvol_abs_and_grad(l, r, 21, -1.0), l, 21, 0.01, 0.02))

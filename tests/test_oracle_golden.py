@@ -355,3 +355,14 @@ def test_warp_matches_reference(golden):
     for nm in ("radial", "ident", "half"):
         assert np.array_equal(ko.warp(g["img"], g[nm]), g["out_" + nm])
     assert np.array_equal(g["out_ident"][:-1, :-1], g["img"][:-1, :-1])   # KAT: integer positions copy the pixel
+
+
+def test_costvol_abs_and_grad_matches_reference(golden):
+    g = golden("absgrad")
+    a = ko.costvol_abs_and_grad(g["left"], g["right"], 16, -1.0, 0.9, 0.03, 0.008)
+    assert np.array_equal(a, g["vol_sdm1"])
+    assert np.array_equal(ko.costvol_abs_and_grad(g["right"], g["left"], 16, 1.0, 0.5, 0.1, 0.02), g["vol_sdp1"])
+    # the kernel's hard override (cu_dense_stereo.cu:829-830): plain absolute difference, 1e37 outside
+    d, x = 5, 20
+    assert a[d, 3, x] == np.abs(g["right"][3, x - d] - g["left"][3, x])
+    assert (a[d, :, :d] == np.float32(1e37)).all()

@@ -168,6 +168,9 @@ typedef struct roo_pipeline_params_t {
     int fuse_vertical;    /* >= 0 (default 0): aggregate a vertical path and its two diagonals in one pass; -1: one pass per path */
 } roo_pipeline_params_t;
 
+/* The engine allocates its scratch on the CURRENT device; later calls must come with that device current (else
+ * ROO_ERR_INVALID_ARGUMENT).  An engine runs one group at a time on its scratch: use it from one host thread, and do
+ * not mix roo_engine_run_device with groups still in flight from roo_engine_submit_host. */
 int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t* params);
 int roo_engine_destroy(roo_engine_t* e);
 size_t roo_engine_scratch_bytes(const roo_engine_t* e);

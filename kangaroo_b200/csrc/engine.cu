@@ -181,11 +181,17 @@ extern "C" int roo_engine_destroy(roo_engine_t* e) {
     return ROO_OK;
 }
 
+// the engine's scratch lives on the device that was current at creation: calls from another device are refused
+static bool on_engine_device(const roo_engine* e) {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess && dev == e->device;
+}
+
 extern "C" size_t roo_engine_scratch_bytes(const roo_engine_t* e) { return e ? e->scratch_bytes : 0; }
 
 extern "C" int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const uint8_t* right, float* disp, int n_pairs,
                                      void* stream) {
-    if (!e || !left || !right || !disp || n_pairs < 0) return ROO_ERR_INVALID_ARGUMENT;
+    if (!e || !left || !right || !disp || n_pairs < 0 || !on_engine_device(e)) return ROO_ERR_INVALID_ARGUMENT;
     cudaStream_t st = as_stream(stream);
     for (int g = 0; g < n_pairs; g += e->p.max_batch) {
         const int batch = n_pairs - g < e->p.max_batch ? n_pairs - g : e->p.max_batch;
@@ -238,7 +244,8 @@ static int submit_group(roo_engine_t* e, const uint8_t* left_host, const uint8_t
 
 extern "C" int roo_engine_submit_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
                                       int n_pairs, long long* ticket) {
-    if (!e || !left_host || !right_host || !disp_host || !ticket || n_pairs <= 0 || n_pairs > e->p.max_batch)
+    if (!e || !left_host || !right_host || !disp_host || !ticket || n_pairs <= 0 || n_pairs > e->p.max_batch ||
+        !on_engine_device(e))
         return ROO_ERR_INVALID_ARGUMENT;
     const int rc0 = host_streams_init(e);
     if (rc0) return rc0;
@@ -257,7 +264,7 @@ extern "C" int roo_engine_wait(roo_engine_t* e, long long ticket) {
 
 extern "C" int roo_engine_run_host(roo_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
                                    int n_pairs) {
-    if (!e || !left_host || !right_host || !disp_host || n_pairs < 0) return ROO_ERR_INVALID_ARGUMENT;
+    if (!e || !left_host || !right_host || !disp_host || n_pairs < 0 || !on_engine_device(e)) return ROO_ERR_INVALID_ARGUMENT;
     const int rc0 = host_streams_init(e);
     if (rc0) return rc0;
     const size_t npx = e->npx;

@@ -166,6 +166,9 @@ typedef struct roo_pipeline_params_t {
     int max_batch;        /* stereo pairs in flight per call (scratch is sized for this many) */
     int keep_volume;      /* 1: the last sweep also writes the aggregate so roo_engine_export_volume() works */
     int fuse_vertical;    /* >= 0 (default 0): aggregate a vertical path and its two diagonals in one pass; -1: one pass per path */
+    int median_size;      /* 0 (none), 5, 7 or 9: MedianFilterRejectNegativeNxN on the disparities between WTA and the */
+    int median_maxbad;    /*   left-right check, median_iters times, on both disparity images when lrcheck is set      */
+    int median_iters;     /*   (main.cpp:438-444; out of place into engine scratch, so without the reference's race)   */
 } roo_pipeline_params_t;
 
 /* The engine allocates its scratch on the CURRENT device; later calls must come with that device current (else

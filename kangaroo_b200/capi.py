@@ -36,7 +36,8 @@ class PipelineParams(C.Structure):
                 ("P1", C.c_float), ("P2", C.c_float), ("img_scale", C.c_float),
                 ("dohoriz", C.c_int), ("dovert", C.c_int), ("doreverse", C.c_int), ("dodiag", C.c_int),
                 ("subpix", C.c_int), ("lrcheck", C.c_int), ("lr_maxdiff", C.c_float),
-                ("max_batch", C.c_int), ("keep_volume", C.c_int), ("fuse_vertical", C.c_int)]
+                ("max_batch", C.c_int), ("keep_volume", C.c_int), ("fuse_vertical", C.c_int),
+                ("median_size", C.c_int), ("median_maxbad", C.c_int), ("median_iters", C.c_int)]
 
 
 # every symbol include/roo_b200.h declares: name -> (restype, argtypes)

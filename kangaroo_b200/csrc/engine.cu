@@ -28,6 +28,7 @@ struct roo_engine {
     unsigned char* c8 = nullptr;                      // [batch][h][w][DP]
     float* H = nullptr;                               // [batch][h][w][DP]
     float* dispR = nullptr;                           // [batch][h][w]
+    float* med = nullptr;                             // [batch][h][w] output of the median stage
     float* imgf = nullptr;                            // [batch][h][w] adaptive-P2 intensity (u8 * img_scale)
     float* edge = nullptr;                            // fused vertical groups: band-to-band state rows
     int* flags = nullptr;                             //                        and their progress flags
@@ -103,6 +104,19 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
             prof_mark(e, e->plan.pass[i].fused ? ROO_PROF_VGROUP : ROO_PROF_SWEEP, st);
         }
     }
+    // MedianFilterRejectNegativeNxN(disp[di], disp[di], maxbad) x iters on every disparity image (main.cpp:438-444),
+    // out of place into scratch and copied back
+    if (p.median_size > 0) {
+        float* imgs[2] = {disp, p.lrcheck ? e->dispR : nullptr};
+        for (int di = 0; di < 2 && imgs[di]; ++di)
+            for (int it = 0; it < p.median_iters; ++it) {
+                rc = launch_median(e->med, (size_t)w * 4, npx * 4, imgs[di], (size_t)w * 4, npx * 4, w, h, batch, p.median_size,
+                                   p.median_maxbad, st);
+                if (rc) return rc;
+                ROO_CUDA_TRY(cudaMemcpyAsync(imgs[di], e->med, (size_t)batch * npx * 4, cudaMemcpyDeviceToDevice, st));
+                prof_mark(e, ROO_PROF_WTA, st);
+            }
+    }
     if (p.lrcheck) {
         // LeftRightCheck(disp[1], disp[0], +1, maxdiff); LeftRightCheck(disp[0], disp[1], -1, maxdiff) (main.cpp:451-454)
         rc = launch_lr_check_f32(e->dispR, (size_t)w * 4, disp, (size_t)w * 4, w, h, batch, npx * 4, npx * 4, +1.0f, p.lr_maxdiff, st);
@@ -117,7 +131,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
 }
 
 static void engine_free(roo_engine* e) {
-    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->imgf); cudaFree(e->edge); cudaFree(e->flags);
+    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->med); cudaFree(e->imgf); cudaFree(e->edge); cudaFree(e->flags);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
         if (e->ev_in[b]) cudaEventDestroy(e->ev_in[b]);
@@ -136,6 +150,8 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     if (p.w <= 0 || p.h <= 0 || p.max_disp <= 0 || p.max_batch <= 0 || p.window < 0 || p.window > 2)
         return ROO_ERR_INVALID_ARGUMENT;
     if (p.max_disp > 256) return ROO_ERR_UNSUPPORTED;
+    if (p.median_size != 0 && p.median_size != 5 && p.median_size != 7 && p.median_size != 9) return ROO_ERR_UNSUPPORTED;
+    if (p.median_size != 0 && p.median_iters < 0) return ROO_ERR_INVALID_ARGUMENT;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ROO_ERR_NO_DEVICE;
     roo_engine* e = new (std::nothrow) roo_engine();
@@ -160,6 +176,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
         ok = alloc((void**)&e->c8, B * npx * e->DP) && alloc((void**)&e->H, B * npx * e->DP * 4) &&
              alloc((void**)&e->imgf, B * npx * 4);
     if (ok && p.lrcheck) ok = alloc((void**)&e->dispR, B * npx * 4);
+    if (ok && p.median_size > 0) ok = alloc((void**)&e->med, B * npx * 4);
     if (ok && fused)
         ok = alloc((void**)&e->edge, B * vgroup_edge_floats(p.w, p.h, e->DP) * 4) &&
              alloc((void**)&e->flags, B * (size_t)vgroup_bands(p.w, p.h, e->DP) * 4 + 256);   // + debug counters (VG_TIMING builds)

@@ -72,6 +72,9 @@ int launch_internal_to_vol(const roo_volume_t* dst, const float* src, int DP, in
 int sgm_directions(int dohoriz, int dovert, int doreverse, int dodiag, int dxs[8], int dys[8]);
 
 // ---- wta.cu ----
+// MedianFilterRejectNegative{5,7,9} over a batch of images (out must not overlap in)
+int launch_median(float* out, size_t out_pitch, size_t out_batch, const float* in, size_t in_pitch, size_t in_batch, int w,
+                  int h, int batch, int size, int maxbad, cudaStream_t st);
 int launch_lr_check_f32(float* dispL, size_t pitchL, const float* dispR, size_t pitchR, int w, int h, int batch,
                         size_t batchL, size_t batchR, float sd, float maxDiff, cudaStream_t st);
 

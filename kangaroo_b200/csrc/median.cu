@@ -60,9 +60,12 @@ __device__ __forceinline__ void sort_keys(unsigned (&key)[K], std::integer_seque
 }
 
 template <int SIZE>
-__global__ void __launch_bounds__(MED_TX* MED_TY) median_reject_kernel(Img<float> out, Img<float> in, int maxbad) {
+__global__ void __launch_bounds__(MED_TX* MED_TY)
+median_reject_kernel(Img<float> out, Img<float> in, int maxbad, size_t out_batch, size_t in_batch) {
     constexpr int R = SIZE / 2, K = SIZE * SIZE, TW = MED_TX + 2 * R, TH = MED_TY + 2 * R;
     __shared__ float tile[TH][TW + 1];
+    out.ptr += (size_t)blockIdx.z * out_batch;   // image blockIdx.z of a batch (clamp-to-edge stays per image)
+    in.ptr += (size_t)blockIdx.z * in_batch;
     const int x0 = blockIdx.x * MED_TX, y0 = blockIdx.y * MED_TY;
     for (int i = threadIdx.y * MED_TX + threadIdx.x; i < TW * TH; i += MED_TX * MED_TY) {
         const int ty = i / TW, tx = i - ty * TW;
@@ -94,6 +97,20 @@ __global__ void __launch_bounds__(MED_TX* MED_TY) median_reject_kernel(Img<float
     out(x, y) = r;
 }
 
+int launch_median(float* out, size_t out_pitch, size_t out_batch, const float* in, size_t in_pitch, size_t in_batch, int w,
+                  int h, int batch, int size, int maxbad, cudaStream_t st) {
+    Img<float> o, i;
+    o.ptr = (char*)out; o.pitch = out_pitch; o.w = w; o.h = h;
+    i.ptr = (char*)in; i.pitch = in_pitch; i.w = w; i.h = h;
+    const dim3 grid(cdiv(w, MED_TX), cdiv(h, MED_TY), batch), block(MED_TX, MED_TY);
+    if (size == 5) median_reject_kernel<5><<<grid, block, 0, st>>>(o, i, maxbad, out_batch, in_batch);
+    else if (size == 7) median_reject_kernel<7><<<grid, block, 0, st>>>(o, i, maxbad, out_batch, in_batch);
+    else if (size == 9) median_reject_kernel<9><<<grid, block, 0, st>>>(o, i, maxbad, out_batch, in_batch);
+    else return ROO_ERR_UNSUPPORTED;
+    count_launch();
+    return launch_status();
+}
+
 }  // namespace roo_b200
 
 using namespace roo_b200;
@@ -105,11 +122,6 @@ extern "C" int roo_median_filter_reject_negative(const roo_image_t* out, const r
     // in place = a data race in the reference (neighbours are read while other blocks overwrite them): refuse overlap
     const char *ob = (const char*)out->ptr, *ib = (const char*)in->ptr;
     if (ob < ib + in->pitch * in->h && ib < ob + out->pitch * out->h) return ROO_ERR_INVALID_ARGUMENT;
-    const dim3 grid(cdiv((long long)out->w, MED_TX), cdiv((long long)out->h, MED_TY)), block(MED_TX, MED_TY);
-    cudaStream_t st = as_stream(stream);
-    if (size == 5) median_reject_kernel<5><<<grid, block, 0, st>>>(Img<float>(*out), Img<float>(*in), maxbad);
-    else if (size == 7) median_reject_kernel<7><<<grid, block, 0, st>>>(Img<float>(*out), Img<float>(*in), maxbad);
-    else median_reject_kernel<9><<<grid, block, 0, st>>>(Img<float>(*out), Img<float>(*in), maxbad);
-    count_launch();
-    return launch_status();
+    return launch_median((float*)out->ptr, out->pitch, 0, (const float*)in->ptr, in->pitch, 0, (int)out->w, (int)out->h, 1,
+                         size, maxbad, as_stream(stream));
 }

@@ -284,11 +284,12 @@ class StereoEngine:
     def __init__(self, w: int, h: int, max_disp: int, window: int = WIN_9x7, popc_mode: int = POPC32_COMPAT,
                  P1: float = 0.01, P2: float = 0.02, img_scale: float = 1.0 / 255.0, dohoriz=True, dovert=True,
                  doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff: float = 1.0,
-                 max_batch: int = 1, keep_volume: bool = False, fuse_vertical: bool = True):
+                 max_batch: int = 1, keep_volume: bool = False, fuse_vertical: bool = True, median_size: int = 0,
+                 median_maxbad: int = 100, median_iters: int = 1):
         self.params = capi.PipelineParams(w, h, max_disp, window, popc_mode, P1, P2, np.float32(img_scale),
                                           int(dohoriz), int(dovert), int(doreverse), int(dodiag), int(subpix),
                                           int(lrcheck), lr_maxdiff, max_batch, int(keep_volume),
-                                          0 if fuse_vertical else -1)
+                                          0 if fuse_vertical else -1, median_size, median_maxbad, median_iters)
         self.w, self.h, self.max_disp = w, h, max_disp
         self._h = C.c_void_p()
         check(lib().roo_engine_create(C.byref(self._h), C.byref(self.params)), "roo_engine_create")
@@ -369,14 +370,16 @@ class MultiGpuStereoEngine:
         proto = StereoEngine.__new__(StereoEngine)
         defaults = dict(window=WIN_9x7, popc_mode=POPC32_COMPAT, P1=0.01, P2=0.02, img_scale=1.0 / 255.0, dohoriz=True,
                         dovert=True, doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff=1.0,
-                        max_batch=1, keep_volume=False, fuse_vertical=True)
+                        max_batch=1, keep_volume=False, fuse_vertical=True, median_size=0, median_maxbad=100,
+                        median_iters=1)
         defaults.update(kw)
         d = defaults
         self.params = capi.PipelineParams(w, h, max_disp, d["window"], d["popc_mode"], d["P1"], d["P2"],
                                           np.float32(d["img_scale"]), int(d["dohoriz"]), int(d["dovert"]),
                                           int(d["doreverse"]), int(d["dodiag"]), int(d["subpix"]), int(d["lrcheck"]),
                                           d["lr_maxdiff"], d["max_batch"], int(d["keep_volume"]),
-                                          0 if d["fuse_vertical"] else -1)
+                                          0 if d["fuse_vertical"] else -1, d["median_size"], d["median_maxbad"],
+                                          d["median_iters"])
         del proto
         self.w, self.h = w, h
         self._h = C.c_void_p()

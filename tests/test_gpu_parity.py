@@ -518,6 +518,36 @@ def test_engine_run_host_equals_run_device():
     eng.close()
 
 
+@pytest.mark.parametrize("size,iters", [(5, 1), (9, 2)])
+def test_engine_median_stage_equals_operator_sequence(size, iters):
+    """stereo2/main.cpp:431-454: WTA -> MedianFilterRejectNegativeNxN x iters (both disparity images) -> LeftRightCheck x2.
+    The engine's fused sequence must equal the same sequence spelled out with the operators."""
+    w, h, D = 190, 70, 64
+    L, R, _ = stereo_pair(w, h, D, config=33)
+    kw = dict(dodiag=True, subpix=True)
+    fused, _, _ = run_engine(L, R, D, lrcheck=True, lr_maxdiff=1.0, median_size=size, median_maxbad=50, median_iters=iters, **kw)
+    # by hand: left disparity from the engine without LR check, right disparity from the raw right-reference volume
+    left, _, cen = run_engine(L, R, D, **kw)
+    cl, cr = roo.Image.from_numpy(ko.census(L, 0).reshape(h, w)), roo.Image.from_numpy(ko.census(R, 0).reshape(h, w))
+    volR = roo.Volume(w, h, D, np.float32)
+    roo.CensusStereoVolume(volR, cr, cl, D, +1.0)
+    dR = roo.Image(w, h, np.float32)
+    roo.CostVolMinimumSubpix(dR, volR, D, +1.0)
+    dL = roo.Image.from_numpy(left[0])
+    med = getattr(roo, f"MedianFilterRejectNegative{size}x{size}")
+    for img in (dL, dR):
+        for _ in range(iters):
+            tmp = roo.Image(w, h, np.float32)
+            med(tmp, img, 50)
+            img.upload(tmp.numpy())
+    roo.LeftRightCheck(dR, dL, +1.0, 1.0)
+    roo.LeftRightCheck(dL, dR, -1.0, 1.0)
+    want = dL.numpy()
+    assert np.array_equal(np.isnan(fused[0]), np.isnan(want))
+    assert np.array_equal(fused[0][~np.isnan(want)], want[~np.isnan(want)])
+    assert np.isnan(want).mean() < 0.5   # the check leaves most of the image valid
+
+
 def test_engine_submit_host_pipeline_equals_run_device():
     """roo_engine_submit_host / roo_engine_wait: five groups streamed with two in flight, different inputs each."""
     w, h, D, B = 160, 64, 32, 2

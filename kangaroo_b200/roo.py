@@ -278,18 +278,23 @@ def set_ieee_division(on: bool) -> None:
 # fused engine
 # ---------------------------------------------------------------------------------------------------
 
+def _fuse_flag(fuse_vertical) -> int:
+    """None: the engine decides per group (roo_pipeline_params_t.fuse_vertical = 0); True: always; False: never."""
+    return 0 if fuse_vertical is None else (1 if fuse_vertical else -1)
+
+
 class StereoEngine:
     """The whole per-frame path (stereo2/main.cpp:375-454) on engine-owned scratch, batched."""
 
     def __init__(self, w: int, h: int, max_disp: int, window: int = WIN_9x7, popc_mode: int = POPC32_COMPAT,
                  P1: float = 0.01, P2: float = 0.02, img_scale: float = 1.0 / 255.0, dohoriz=True, dovert=True,
                  doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff: float = 1.0,
-                 max_batch: int = 1, keep_volume: bool = False, fuse_vertical: bool = True, median_size: int = 0,
+                 max_batch: int = 1, keep_volume: bool = False, fuse_vertical: bool | None = None, median_size: int = 0,
                  median_maxbad: int = 100, median_iters: int = 1):
         self.params = capi.PipelineParams(w, h, max_disp, window, popc_mode, P1, P2, np.float32(img_scale),
                                           int(dohoriz), int(dovert), int(doreverse), int(dodiag), int(subpix),
                                           int(lrcheck), lr_maxdiff, max_batch, int(keep_volume),
-                                          0 if fuse_vertical else -1, median_size, median_maxbad, median_iters)
+                                          _fuse_flag(fuse_vertical), median_size, median_maxbad, median_iters)
         self.w, self.h, self.max_disp = w, h, max_disp
         self._h = C.c_void_p()
         check(lib().roo_engine_create(C.byref(self._h), C.byref(self.params)), "roo_engine_create")
@@ -370,7 +375,7 @@ class MultiGpuStereoEngine:
         proto = StereoEngine.__new__(StereoEngine)
         defaults = dict(window=WIN_9x7, popc_mode=POPC32_COMPAT, P1=0.01, P2=0.02, img_scale=1.0 / 255.0, dohoriz=True,
                         dovert=True, doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff=1.0,
-                        max_batch=1, keep_volume=False, fuse_vertical=True, median_size=0, median_maxbad=100,
+                        max_batch=1, keep_volume=False, fuse_vertical=None, median_size=0, median_maxbad=100,
                         median_iters=1)
         defaults.update(kw)
         d = defaults
@@ -378,7 +383,7 @@ class MultiGpuStereoEngine:
                                           np.float32(d["img_scale"]), int(d["dohoriz"]), int(d["dovert"]),
                                           int(d["doreverse"]), int(d["dodiag"]), int(d["subpix"]), int(d["lrcheck"]),
                                           d["lr_maxdiff"], d["max_batch"], int(d["keep_volume"]),
-                                          0 if d["fuse_vertical"] else -1, d["median_size"], d["median_maxbad"],
+                                          _fuse_flag(d["fuse_vertical"]), d["median_size"], d["median_maxbad"],
                                           d["median_iters"])
         del proto
         self.w, self.h = w, h

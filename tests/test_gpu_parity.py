@@ -285,6 +285,7 @@ def test_left_right_check(golden):
 
 def run_engine(L, R, D, batch=1, **kw):
     h, w = L.shape
+    kw.setdefault("fuse_vertical", True)   # the engine's own choice (None) would not fuse at these small sizes
     eng = roo.StereoEngine(w, h, D, max_batch=batch, keep_volume=True, **kw)
     l = torch.from_numpy(np.stack([L] * batch)).cuda()
     r = torch.from_numpy(np.stack([R] * batch)).cuda()
@@ -420,7 +421,7 @@ def test_engine_batch_slots_are_independent_and_groups_wrap():
     L = np.stack([p[0] for p in pairs])
     R = np.stack([p[1] for p in pairs])
     roo.set_ieee_division(True)
-    eng = roo.StereoEngine(w, h, D, dodiag=True, subpix=True, lrcheck=True, max_batch=3)
+    eng = roo.StereoEngine(w, h, D, dodiag=True, subpix=True, lrcheck=True, max_batch=3, fuse_vertical=True)
     disp = eng.run_device(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy()
     eng.close()
     for i in range(7):
@@ -546,6 +547,20 @@ def test_engine_median_stage_equals_operator_sequence(size, iters):
     assert np.array_equal(np.isnan(fused[0]), np.isnan(want))
     assert np.array_equal(fused[0][~np.isnan(want)], want[~np.isnan(want)])
     assert np.isnan(want).mean() < 0.5   # the check leaves most of the image valid
+
+
+def test_engine_auto_plan_matches_both_forced_plans():
+    """fuse_vertical = auto picks one pass per path for a small group and the fused passes for a large one; the
+    result is the same bit for bit either way."""
+    w, h, D = 300, 120, 64
+    L, R, _ = stereo_pair(w, h, D, config=44)
+    outs = {}
+    for name, fv, batch in (("auto1", None, 1), ("auto40", None, 40), ("fused", True, 2), ("separate", False, 2)):
+        d, _, _ = run_engine(L, R, D, batch=batch, dodiag=True, subpix=True, fuse_vertical=fv)
+        outs[name] = d
+    for name in ("auto1", "auto40", "separate"):
+        for b in range(outs[name].shape[0]):
+            assert np.array_equal(outs[name][b], outs["fused"][0], equal_nan=True), (name, b)
 
 
 def test_engine_submit_host_pipeline_equals_run_device():

@@ -165,7 +165,7 @@ typedef struct roo_pipeline_params_t {
     float lr_maxdiff;
     int max_batch;        /* stereo pairs in flight per call (scratch is sized for this many) */
     int keep_volume;      /* 1: the last sweep also writes the aggregate so roo_engine_export_volume() works */
-    int fuse_vertical;    /* a vertical path and its two diagonals aggregated in ONE pass: 1 always, -1 never, 0 (default) when the group is large enough to fill the GPU (one or two pairs at 1280x720 run faster with one pass per path) */
+    int fuse_vertical;    /* a vertical path and its two diagonals aggregated in ONE pass: 1 always, -1 never, 0 (default) unless the group is a large frame in too few pairs to fill the GPU (one or two pairs at 1280x720x128 run faster with one pass per path) */
     int median_size;      /* 0 (none), 5, 7 or 9: MedianFilterRejectNegativeNxN on the disparities between WTA and the */
     int median_maxbad;    /*   left-right check, median_iters times, on both disparity images when lrcheck is set      */
     int median_iters;     /*   (main.cpp:438-444; out of place into engine scratch, so without the reference's race)   */

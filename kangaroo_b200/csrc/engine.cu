@@ -54,6 +54,8 @@ struct roo_engine {
 
 // fuse_vertical == 0 (auto): minimum number of (band, pair) CTAs per launch for the fused passes to be chosen
 constexpr long long FUSE_MIN_CTAS = 100;
+// ... unless the group is so small that single-path sweeps are not bandwidth-bound either (pixel*disparity units)
+constexpr long long FUSE_MIN_UNITS = 100000000;
 
 static void prof_mark(roo_engine* e, int kind, cudaStream_t st) {
     if (!e->profiling) return;
@@ -87,8 +89,12 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
     }
     // Plan per group.  A fused pass walks the rows of a band serially (~1.1 ms per pass at 720 rows whatever the
     // batch) and pays off once there are enough (band, pair) CTAs to fill the GPU; a single pair is faster with one
-    // pass per path (1280x720x128, 8 paths: 1 pair 1.8 ms vs 3.0 ms, 2 pairs equal, 4 pairs 6.0 ms vs 4.1 ms).
-    const bool use_fused = p.fuse_vertical > 0 || (p.fuse_vertical == 0 && (long long)batch * e->n_bands >= FUSE_MIN_CTAS);
+    // pass per path (1280x720x128, 8 paths: 1 pair 1.8 ms vs 3.0 ms).
+    // Measured on B200, 8 paths, fused / separate: 640x480x64 x1 1.8 / 1.9 ms (sweeps of so few columns are
+    // latency-bound too), 1280x720x128 x2 3.3 / 3.2, x3 3.7 / 4.6, 1920x1080x256 x1 6.4 / 7.4, 3840x2160x256 x1 17.9 / 27.1.
+    const long long units = (long long)w * h * e->DP * batch;
+    const bool use_fused = p.fuse_vertical > 0 ||
+                           (p.fuse_vertical == 0 && ((long long)batch * e->n_bands >= FUSE_MIN_CTAS || units < FUSE_MIN_UNITS));
     const SgmPlan& plan = use_fused ? e->plan : e->plan_sep;
     const int ndir = plan.n;
     if (ndir == 0) {

@@ -555,12 +555,19 @@ def test_engine_auto_plan_matches_both_forced_plans():
     w, h, D = 300, 120, 64
     L, R, _ = stereo_pair(w, h, D, config=44)
     outs = {}
-    for name, fv, batch in (("auto1", None, 1), ("auto40", None, 40), ("fused", True, 2), ("separate", False, 2)):
+    # 300x120x64: 9 bands; 1 pair = 2.3 M units (small: fused), 60 pairs = 138 M units in 540 CTAs (fused),
+    # 50 pairs = 115 M units in 450 CTAs (fused); the unfused branch of the rule needs a big frame: see below
+    for name, fv, batch in (("auto1", None, 1), ("auto60", None, 60), ("fused", True, 2), ("separate", False, 2)):
         d, _, _ = run_engine(L, R, D, batch=batch, dodiag=True, subpix=True, fuse_vertical=fv)
         outs[name] = d
-    for name in ("auto1", "auto40", "separate"):
+    for name in ("auto1", "auto60", "separate"):
         for b in range(outs[name].shape[0]):
             assert np.array_equal(outs[name][b], outs["fused"][0], equal_nan=True), (name, b)
+    # one 1280x720x128 pair: 118 M units in 42 CTAs -> the engine picks one pass per path; same result as forced fusion
+    L, R, _ = stereo_pair(1280, 720, 128, config=2)
+    a, _, _ = run_engine(L, R, 128, dodiag=True, fuse_vertical=None)
+    f, _, _ = run_engine(L, R, 128, dodiag=True, fuse_vertical=True)
+    assert np.array_equal(a, f)
 
 
 def test_engine_submit_host_pipeline_equals_run_device():

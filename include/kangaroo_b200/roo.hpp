@@ -201,6 +201,10 @@ inline void BoxHalf(Image<To> out, const Image<Ti> in) {
     auto co = b200::c(out), ci = b200::c(in);
     b200::done(roo_box_half(&co, &ci, b200::pix_type<Ti>::value, b200::stream_slot()), "BoxHalf");
 }
+inline void CreateMatlabLookupTable(Image<float2> lookup, float fu, float fv, float u0, float v0, float k1, float k2) {
+    auto cl = b200::c(lookup);
+    b200::done(roo_create_matlab_lookup_table(&cl, fu, fv, u0, v0, k1, k2, b200::stream_slot()), "CreateMatlabLookupTable");
+}
 inline void Warp(Image<unsigned char> out, const Image<unsigned char> in, const Image<float2> lookup) {
     auto co = b200::c(out), ci = b200::c(in), cl = b200::c(lookup);
     b200::done(roo_warp(&co, &ci, &cl, b200::stream_slot()), "Warp");

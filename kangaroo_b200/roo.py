@@ -231,6 +231,13 @@ def BoxReduce(pyramid, stream=None) -> None:
 FLOAT2 = np.dtype((np.float32, (2,)))   # float2
 
 
+def CreateMatlabLookupTable(lookup: Image, fu: float, fv: float, u0: float, v0: float, k1: float, k2: float,
+                            stream=None) -> None:
+    """roo::CreateMatlabLookupTable (cu_lookup_warp.cu:32-38); lookup is an Image of FLOAT2."""
+    check(lib().roo_create_matlab_lookup_table(C.byref(lookup.c()), fu, fv, u0, v0, k1, k2, _stream(stream)),
+          "CreateMatlabLookupTable")
+
+
 def Warp(out: Image, in_: Image, lookup: Image, stream=None) -> None:
     """roo::Warp (cu_lookup_warp.cu:96-106): rectify `in_` through a FLOAT2 lookup table (bilinear)."""
     check(lib().roo_warp(C.byref(out.c()), C.byref(in_.c()), C.byref(lookup.c()), _stream(stream)), "Warp")

@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         L.ko_disparity_image_to_vbo.argtypes = [P(KoImage), P(KoImage)] + [C.c_float] * 5
         L.ko_median_filter_reject_negative.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
         L.ko_warp.argtypes = [P(KoImage), P(KoImage), P(KoImage)]
+        L.ko_create_matlab_lookup_table.argtypes = [P(KoImage)] + [C.c_float] * 6
         L.ko_costvol_abs_and_grad.argtypes = [P(KoVolume), P(KoImage), P(KoImage), C.c_float, C.c_float, C.c_float, C.c_float]
         L.ko_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ko_hamming.restype = C.c_uint
@@ -248,6 +249,12 @@ def costvol_abs_and_grad(left: np.ndarray, right: np.ndarray, depth: int, sd: fl
     vol = np.zeros((depth, h, w), np.float32)
     lib().ko_costvol_abs_and_grad(C.byref(_vol(vol)), C.byref(_img(left)), C.byref(_img(right)), sd, alpha, r1, r2)
     return vol
+
+
+def create_matlab_lookup_table(w: int, h: int, fu, fv, u0, v0, k1, k2) -> np.ndarray:
+    lut = np.zeros((h, w, 2), np.float32)
+    lib().ko_create_matlab_lookup_table(C.byref(_img(lut)), fu, fv, u0, v0, k1, k2)
+    return lut
 
 
 def warp(img: np.ndarray, lookup: np.ndarray) -> np.ndarray:

@@ -524,6 +524,23 @@ static inline size_t f2size_floor(float v) {   /* cvt.rmi.u64.f32: floor, negati
     return (size_t)floorf(v);
 }
 
+/* cu_lookup_warp.cu:13-30 */
+void ko_create_matlab_lookup_table(const ko_image* lookup, float fu, float fv, float u0, float v0, float k1, float k2) {
+    const int w = (int)lookup->w, h = (int)lookup->h;
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < h; ++v)
+        for (int u = 0; u < w; ++u) {
+            const float pnu = ((float)u - u0) / fu;
+            const float pnv = ((float)v - v0) / fv;
+            const float r = sqrtf(pnu * pnu + pnv * pnv);
+            const float rr = r * r;
+            const float rf = 1 + k1 * rr + k2 * rr * rr;
+            float* o = (float*)img_at(lookup, (size_t)u, (size_t)v, 8);
+            o[0] = (pnu * rf) * fu + u0;
+            o[1] = (pnv * rf) * fv + v0;
+        }
+}
+
 /* cu_lookup_warp.cu:85-94, Image.h:317-334 */
 void ko_warp(const ko_image* out, const ko_image* in, const ko_image* lookup) {
     const int w = (int)out->w, h = (int)out->h;

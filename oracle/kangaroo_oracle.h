@@ -104,6 +104,11 @@ void ko_disparity_image_to_vbo(const ko_image* vbo_f32x4, const ko_image* disp_f
 void ko_costvol_abs_and_grad(const ko_volume* vol_f32, const ko_image* left_f32, const ko_image* right_f32, float sd,
                              float alpha, float r1, float r2);
 
+/* src/cu_lookup_warp.cu:13-38 (the variant without homography): radial distortion lookup for roo::Warp,
+ * lookup(u,v) = (pnu*rf*fu + u0, pnv*rf*fv + v0), pn = ((u-u0)/fu, (v-v0)/fv), r = sqrt(pn.pn), rf = 1 + k1 r^2 + k2 r^4.
+ * IEEE here; the reference build uses reciprocal / square-root approximations and contractions. */
+void ko_create_matlab_lookup_table(const ko_image* lookup_f32x2, float fu, float fv, float u0, float v0, float k1, float k2);
+
 /* src/cu_lookup_warp.cu:85-106 + Image.h:317-334 (GetBilinear): out(x,y) = (unsigned char) bilinear sample of `in` at
  * lookup(x,y) = (u, v).  lerp(a,b,t) = a + t*(b-a), one fused multiply-add each as in the reference build; the float
  * result is truncated to unsigned 32 bit and its low byte stored.  Row / column indices come from float -> size_t

@@ -42,6 +42,7 @@ def lib() -> C.CDLL:
         L.kref_disparity_image_to_vbo.argtypes = [p, z, p, z, z, z, f, f, f, f, f]
         L.kref_median_reject_negative.argtypes = [p, p, z, z, z, i, i]
         L.kref_warp.argtypes = [p, z, p, z, z, z, p, z, z, z]
+        L.kref_create_matlab_lookup_table.argtypes = [p, z, z, z, f, f, f, f, f, f]
         L.kref_costvol_abs_and_grad.argtypes = [p, z, z, z, p, p, z, z, z, f, f, f, f]
         _lib = L
     return _lib
@@ -265,3 +266,10 @@ def costvol_abs_and_grad(left: np.ndarray, right: np.ndarray, depth: int, sd: fl
     _ck(lib().kref_costvol_abs_and_grad(vol.data_ptr(), w * 4, w * h * 4, depth, dl.data_ptr() + off, dr.data_ptr() + off,
                                         pitch, w, h, sd, alpha, r1, r2), "CostVolumeFromStereoTruncatedAbsAndGrad")
     return _back(vol, np.float32, (depth, h, w))
+
+
+def create_matlab_lookup_table(w: int, h: int, fu, fv, u0, v0, k1, k2) -> np.ndarray:
+    import torch
+    out = torch.zeros(h * w * 8, dtype=torch.uint8, device="cuda")
+    _ck(lib().kref_create_matlab_lookup_table(out.data_ptr(), w * 8, w, h, fu, fv, u0, v0, k1, k2), "CreateMatlabLookupTable")
+    return _back(out, np.float32, (h, w, 2))

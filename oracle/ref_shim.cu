@@ -226,4 +226,10 @@ int kref_costvol_abs_and_grad(void* v, size_t v_pitch, size_t v_img_pitch, size_
     return finish();
 }
 
+int kref_create_matlab_lookup_table(void* lookup, size_t pitch, size_t w, size_t h, float fu, float fv, float u0, float v0,
+                                    float k1, float k2) {
+    roo::CreateMatlabLookupTable(img<float2>(lookup, pitch, w, h), fu, fv, u0, v0, k1, k2);
+    return finish();
+}
+
 }  // extern "C"

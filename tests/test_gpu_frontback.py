@@ -241,3 +241,27 @@ def test_costvol_abs_and_grad_bitexact_and_feeds_sgm(golden):
     volH = roo.Volume(101, 37, 21, np.float32)
     roo.SemiGlobalMatching(volH, vol, roo.Image.from_numpy(l), 21, 0.01, 0.02, True, True, True)
     assert same_bits(volH.numpy(), ko.sgm(ko.costvol_abs_and_grad(l, r, 21, -1.0), l, 21, 0.01, 0.02))
+
+
+def test_create_matlab_lookup_table_bitexact_both_modes_and_feeds_warp(golden):
+    g = golden("lookup")
+    for nm in ("a", "b"):
+        p = g["params_" + nm]
+        w, h, par = int(p[0]), int(p[1]), [float(x) for x in p[2:]]
+        lut = roo.Image(w, h, roo.FLOAT2)
+        roo.CreateMatlabLookupTable(lut, *par)
+        assert same_bits(lut.numpy().reshape(h, w * 2), g["lut_" + nm].reshape(h, w * 2))   # the reference's fast-math SASS
+        roo.set_ieee_division(True)
+        roo.CreateMatlabLookupTable(lut, *par)
+        assert same_bits(lut.numpy().reshape(h, w * 2), ko.create_matlab_lookup_table(w, h, *par).reshape(h, w * 2))
+        roo.set_ieee_division(False)
+    # table -> Warp, as applications/stereo2/main.cpp:362-365 (positions clamped into the image like cu_lookup_warp.cu:69-73)
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (48, 64), dtype=np.uint8)
+    p = g["params_a"]
+    lut = roo.Image(64, 48, roo.FLOAT2)
+    roo.CreateMatlabLookupTable(lut, *[float(x) for x in p[2:]])
+    t = lut.numpy()
+    t[..., 0] = np.clip(t[..., 0], 1, 62)
+    t[..., 1] = np.clip(t[..., 1], 1, 46)
+    assert np.array_equal(warp(img, t), ko.warp(img, t))

@@ -366,3 +366,16 @@ def test_costvol_abs_and_grad_matches_reference(golden):
     d, x = 5, 20
     assert a[d, 3, x] == np.abs(g["right"][3, x - d] - g["left"][3, x])
     assert (a[d, :, :d] == np.float32(1e37)).all()
+
+
+def test_create_matlab_lookup_table_matches_reference_within_fast_math(golden):
+    """The reference build uses MUFU.RCP / MUFU.SQRT and contractions here: positions agree to 1e-4 px."""
+    g = golden("lookup")
+    for nm in ("a", "b"):
+        p = g["params_" + nm]
+        lut = ko.create_matlab_lookup_table(int(p[0]), int(p[1]), *[float(x) for x in p[2:]])
+        assert np.abs(lut - g["lut_" + nm]).max() <= 1e-4
+    p = g["params_a"]   # KAT: no distortion -> identity
+    ident = ko.create_matlab_lookup_table(8, 4, float(p[2]), float(p[3]), 3.0, 1.0, 0.0, 0.0)
+    yy, xx = np.mgrid[0:4, 0:8].astype(np.float32)
+    assert np.abs(ident[..., 0] - xx).max() <= 1e-5 and np.abs(ident[..., 1] - yy).max() <= 1e-5

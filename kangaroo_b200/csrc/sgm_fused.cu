@@ -224,9 +224,17 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     // upstream band (higher u) and the rows of it this band consumes: row y-1 for every own row y >= 1
     const int pulo = ulo + NC;
     const int pymin = max(0, -(pulo + NC - 1));
+#ifdef VG_NO_HANDOFF   // timing experiment only (wrong results): bands do not wait for each other
+    const int pymax = -1;
+#else
     const int pymax = band > 0 ? min(h - 1, w - 1 - pulo) : -1;
+#endif
     const int hbeg = max(pymin, ymin - 1), hend = min(pymax, ymax - 1) + 1;   // [hbeg, hend) upstream rows to stage
+#ifdef VG_NO_HANDOFF
+    const bool downstream = false;
+#else
     const bool downstream = band + 1 < a.n_bands;
+#endif
 
     float* e_hp = a.edge_hp + ((size_t)pair * a.n_bands + band) * (size_t)h * 3 * DP;   // this band's outgoing rows
     float* e_sc = a.edge_sc + ((size_t)pair * a.n_bands + band) * (size_t)h * 8;

@@ -205,6 +205,13 @@ inline void CreateMatlabLookupTable(Image<float2> lookup, float fu, float fv, fl
     auto cl = b200::c(lookup);
     b200::done(roo_create_matlab_lookup_table(&cl, fu, fv, u0, v0, k1, k2, b200::stream_slot()), "CreateMatlabLookupTable");
 }
+// the overload with a homography (cu_lookup_warp.cu:77-83); H_on = 9 floats, row-major, e.g. Mat<float,9>::m
+inline void CreateMatlabLookupTable(Image<float2> lookup, float fu, float fv, float u0, float v0, float k1, float k2,
+                                    const float (&H_on)[9]) {
+    auto cl = b200::c(lookup);
+    b200::done(roo_create_matlab_lookup_table_homography(&cl, fu, fv, u0, v0, k1, k2, H_on, b200::stream_slot()),
+               "CreateMatlabLookupTable");
+}
 inline void Warp(Image<unsigned char> out, const Image<unsigned char> in, const Image<float2> lookup) {
     auto co = b200::c(out), ci = b200::c(in), cl = b200::c(lookup);
     b200::done(roo_warp(&co, &ci, &cl, b200::stream_slot()), "Warp");

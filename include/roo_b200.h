@@ -119,9 +119,12 @@ int roo_elementwise_scale_bias(const roo_image_t* b_f32, const roo_image_t* a, i
 int roo_box_half(const roo_image_t* out, const roo_image_t* in, int pix_type, void* stream);
 
 /* roo::CreateMatlabLookupTable(lookup, fu, fv, u0, v0, k1, k2) (cu_lookup_warp.cu:13-38): the radial-distortion table
- * roo::Warp consumes; one-time setup.  (The overload that also applies a homography, :44-83, is not provided.) */
+ * roo::Warp consumes; one-time setup.  The second form is the overload that first applies the homography H_on
+ * (Mat<float,9>, row-major 3x3, a HOST pointer here) and clamps the positions to [1, w-2] x [1, h-2] (:44-83). */
 int roo_create_matlab_lookup_table(const roo_image_t* lookup_f32x2, float fu, float fv, float u0, float v0, float k1,
                                    float k2, void* stream);
+int roo_create_matlab_lookup_table_homography(const roo_image_t* lookup_f32x2, float fu, float fv, float u0, float v0,
+                                              float k1, float k2, const float* H_on, void* stream);
 
 /* roo::Warp (cu_lookup_warp.h; cu_lookup_warp.cu:85-106): out(x,y) = bilinear sample of `in` at lookup(x,y) (float2
  * pixel coordinates), the rectification step of applications/stereo2/main.cpp:362-365.  Taps outside `in` are clamped

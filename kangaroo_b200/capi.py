@@ -62,6 +62,7 @@ SYMBOLS = {
     "roo_elementwise_scale_bias": (C.c_int, [_IMG, _IMG, C.c_int, C.c_float, C.c_float, _S]),
     "roo_box_half": (C.c_int, [_IMG, _IMG, C.c_int, _S]),
     "roo_create_matlab_lookup_table": (C.c_int, [_IMG] + [C.c_float] * 6 + [_S]),
+    "roo_create_matlab_lookup_table_homography": (C.c_int, [_IMG] + [C.c_float] * 6 + [_P(C.c_float), _S]),
     "roo_warp": (C.c_int, [_IMG, _IMG, _IMG, _S]),
     "roo_disp2depth": (C.c_int, [_IMG, _IMG, C.c_float, C.c_float, C.c_float, _S]),
     "roo_disparity_image_to_vbo": (C.c_int, [_IMG, _IMG, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _S]),

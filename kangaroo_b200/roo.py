@@ -231,11 +231,16 @@ def BoxReduce(pyramid, stream=None) -> None:
 FLOAT2 = np.dtype((np.float32, (2,)))   # float2
 
 
-def CreateMatlabLookupTable(lookup: Image, fu: float, fv: float, u0: float, v0: float, k1: float, k2: float,
+def CreateMatlabLookupTable(lookup: Image, fu: float, fv: float, u0: float, v0: float, k1: float, k2: float, H_on=None,
                             stream=None) -> None:
-    """roo::CreateMatlabLookupTable (cu_lookup_warp.cu:32-38); lookup is an Image of FLOAT2."""
-    check(lib().roo_create_matlab_lookup_table(C.byref(lookup.c()), fu, fv, u0, v0, k1, k2, _stream(stream)),
-          "CreateMatlabLookupTable")
+    """roo::CreateMatlabLookupTable (cu_lookup_warp.cu:32-38, and :77-83 with a 3x3 homography H_on); lookup is FLOAT2."""
+    if H_on is None:
+        check(lib().roo_create_matlab_lookup_table(C.byref(lookup.c()), fu, fv, u0, v0, k1, k2, _stream(stream)),
+              "CreateMatlabLookupTable")
+    else:
+        Hc = (C.c_float * 9)(*[float(x) for x in np.asarray(H_on).ravel()])
+        check(lib().roo_create_matlab_lookup_table_homography(C.byref(lookup.c()), fu, fv, u0, v0, k1, k2, Hc,
+                                                              _stream(stream)), "CreateMatlabLookupTable")
 
 
 def Warp(out: Image, in_: Image, lookup: Image, stream=None) -> None:

@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         L.ko_median_filter_reject_negative.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
         L.ko_warp.argtypes = [P(KoImage), P(KoImage), P(KoImage)]
         L.ko_create_matlab_lookup_table.argtypes = [P(KoImage)] + [C.c_float] * 6
+        L.ko_create_matlab_lookup_table_h.argtypes = [P(KoImage)] + [C.c_float] * 6 + [P(C.c_float)]
         L.ko_costvol_abs_and_grad.argtypes = [P(KoVolume), P(KoImage), P(KoImage), C.c_float, C.c_float, C.c_float, C.c_float]
         L.ko_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ko_hamming.restype = C.c_uint
@@ -254,6 +255,13 @@ def costvol_abs_and_grad(left: np.ndarray, right: np.ndarray, depth: int, sd: fl
 def create_matlab_lookup_table(w: int, h: int, fu, fv, u0, v0, k1, k2) -> np.ndarray:
     lut = np.zeros((h, w, 2), np.float32)
     lib().ko_create_matlab_lookup_table(C.byref(_img(lut)), fu, fv, u0, v0, k1, k2)
+    return lut
+
+
+def create_matlab_lookup_table_h(w: int, h: int, fu, fv, u0, v0, k1, k2, H_on) -> np.ndarray:
+    lut = np.zeros((h, w, 2), np.float32)
+    Hc = (C.c_float * 9)(*[float(x) for x in np.asarray(H_on).ravel()])
+    lib().ko_create_matlab_lookup_table_h(C.byref(_img(lut)), fu, fv, u0, v0, k1, k2, Hc)
     return lut
 
 

@@ -541,6 +541,30 @@ void ko_create_matlab_lookup_table(const ko_image* lookup, float fu, float fv, f
         }
 }
 
+/* cu_lookup_warp.cu:44-75 */
+void ko_create_matlab_lookup_table_h(const ko_image* lookup, float fu, float fv, float u0, float v0, float k1, float k2,
+                                     const float* H) {
+    const int w = (int)lookup->w, h = (int)lookup->h;
+#pragma omp parallel for schedule(static)
+    for (int yi = 0; yi < h; ++yi)
+        for (int xi = 0; xi < w; ++xi) {
+            const float x = (float)xi, y = (float)yi;
+            const float hdiv = H[6] * x + H[7] * y + H[8];
+            const float u = (H[0] * x + H[1] * y + H[2]) / hdiv;
+            const float v = (H[3] * x + H[4] * y + H[5]) / hdiv;
+            const float pnu = (u - u0) / fu;
+            const float pnv = (v - v0) / fv;
+            const float r = sqrtf(pnu * pnu + pnv * pnv);
+            const float rr = r * r;
+            const float rf = 1 + k1 * rr + k2 * rr * rr;
+            float px = (pnu * rf) * fu + u0, py = (pnv * rf) * fv + v0;
+            px = fmaxf(px, 1.0f); py = fmaxf(py, 1.0f);
+            px = fminf(px, (float)lookup->w - 2.0f); py = fminf(py, (float)lookup->h - 2.0f);
+            float* o = (float*)img_at(lookup, (size_t)xi, (size_t)yi, 8);
+            o[0] = px; o[1] = py;
+        }
+}
+
 /* cu_lookup_warp.cu:85-94, Image.h:317-334 */
 void ko_warp(const ko_image* out, const ko_image* in, const ko_image* lookup) {
     const int w = (int)out->w, h = (int)out->h;

@@ -109,6 +109,11 @@ void ko_costvol_abs_and_grad(const ko_volume* vol_f32, const ko_image* left_f32,
  * IEEE here; the reference build uses reciprocal / square-root approximations and contractions. */
 void ko_create_matlab_lookup_table(const ko_image* lookup_f32x2, float fu, float fv, float u0, float v0, float k1, float k2);
 
+/* src/cu_lookup_warp.cu:44-83: the same table after the homography H_on (row-major 3x3, new image -> original), clamped
+ * to [1, w-2] x [1, h-2] (:69-73). */
+void ko_create_matlab_lookup_table_h(const ko_image* lookup_f32x2, float fu, float fv, float u0, float v0, float k1, float k2,
+                                     const float* H_on);
+
 /* src/cu_lookup_warp.cu:85-106 + Image.h:317-334 (GetBilinear): out(x,y) = (unsigned char) bilinear sample of `in` at
  * lookup(x,y) = (u, v).  lerp(a,b,t) = a + t*(b-a), one fused multiply-add each as in the reference build; the float
  * result is truncated to unsigned 32 bit and its low byte stored.  Row / column indices come from float -> size_t

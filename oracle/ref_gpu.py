@@ -43,6 +43,7 @@ def lib() -> C.CDLL:
         L.kref_median_reject_negative.argtypes = [p, p, z, z, z, i, i]
         L.kref_warp.argtypes = [p, z, p, z, z, z, p, z, z, z]
         L.kref_create_matlab_lookup_table.argtypes = [p, z, z, z, f, f, f, f, f, f]
+        L.kref_create_matlab_lookup_table_h.argtypes = [p, z, z, z, f, f, f, f, f, f, C.POINTER(C.c_float)]
         L.kref_costvol_abs_and_grad.argtypes = [p, z, z, z, p, p, z, z, z, f, f, f, f]
         _lib = L
     return _lib
@@ -272,4 +273,13 @@ def create_matlab_lookup_table(w: int, h: int, fu, fv, u0, v0, k1, k2) -> np.nda
     import torch
     out = torch.zeros(h * w * 8, dtype=torch.uint8, device="cuda")
     _ck(lib().kref_create_matlab_lookup_table(out.data_ptr(), w * 8, w, h, fu, fv, u0, v0, k1, k2), "CreateMatlabLookupTable")
+    return _back(out, np.float32, (h, w, 2))
+
+
+def create_matlab_lookup_table_h(w: int, h: int, fu, fv, u0, v0, k1, k2, H_on) -> np.ndarray:
+    import torch
+    out = torch.zeros(h * w * 8, dtype=torch.uint8, device="cuda")
+    Hc = (C.c_float * 9)(*[float(x) for x in np.asarray(H_on).ravel()])
+    _ck(lib().kref_create_matlab_lookup_table_h(out.data_ptr(), w * 8, w, h, fu, fv, u0, v0, k1, k2, Hc),
+        "CreateMatlabLookupTable(H)")
     return _back(out, np.float32, (h, w, 2))

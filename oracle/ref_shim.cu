@@ -232,4 +232,12 @@ int kref_create_matlab_lookup_table(void* lookup, size_t pitch, size_t w, size_t
     return finish();
 }
 
+int kref_create_matlab_lookup_table_h(void* lookup, size_t pitch, size_t w, size_t h, float fu, float fv, float u0, float v0,
+                                      float k1, float k2, const float* H_on) {
+    roo::Mat<float, 9> H;
+    for (int i = 0; i < 9; ++i) H[i] = H_on[i];
+    roo::CreateMatlabLookupTable(img<float2>(lookup, pitch, w, h), fu, fv, u0, v0, k1, k2, H);
+    return finish();
+}
+
 }  // extern "C"

@@ -22,6 +22,11 @@ def main(out_dir: str) -> None:
     for nm in ("a", "b"):
         p = g["params_" + nm]
         g["lut_" + nm] = ref.create_matlab_lookup_table(int(p[0]), int(p[1]), *[float(x) for x in p[2:]])
+    # the overload with a homography (a small rotation + shear + perspective term), clamped to [1, w-2] x [1, h-2]
+    g["H"] = np.array([0.998, -0.021, 1.7, 0.019, 1.003, -0.9, 1.2e-5, -0.8e-5, 1.0], np.float32)
+    for nm in ("a", "b"):
+        p = g["params_" + nm]
+        g["lut_h_" + nm] = ref.create_matlab_lookup_table_h(int(p[0]), int(p[1]), *[float(x) for x in p[2:]], g["H"])
     np.savez_compressed(os.path.join(out_dir, "lookup.npz"), **g)
     print("wrote", os.path.join(out_dir, "lookup.npz"))
 

@@ -254,7 +254,11 @@ def test_create_matlab_lookup_table_bitexact_both_modes_and_feeds_warp(golden):
         roo.set_ieee_division(True)
         roo.CreateMatlabLookupTable(lut, *par)
         assert same_bits(lut.numpy().reshape(h, w * 2), ko.create_matlab_lookup_table(w, h, *par).reshape(h, w * 2))
+        roo.CreateMatlabLookupTable(lut, *par, H_on=g["H"])
+        assert same_bits(lut.numpy().reshape(h, w * 2), ko.create_matlab_lookup_table_h(w, h, *par, g["H"]).reshape(h, w * 2))
         roo.set_ieee_division(False)
+        roo.CreateMatlabLookupTable(lut, *par, H_on=g["H"])
+        assert same_bits(lut.numpy().reshape(h, w * 2), g["lut_h_" + nm].reshape(h, w * 2))
     # table -> Warp, as applications/stereo2/main.cpp:362-365 (positions clamped into the image like cu_lookup_warp.cu:69-73)
     rng = np.random.default_rng(12)
     img = rng.integers(0, 256, (48, 64), dtype=np.uint8)

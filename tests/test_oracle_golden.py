@@ -375,6 +375,9 @@ def test_create_matlab_lookup_table_matches_reference_within_fast_math(golden):
         p = g["params_" + nm]
         lut = ko.create_matlab_lookup_table(int(p[0]), int(p[1]), *[float(x) for x in p[2:]])
         assert np.abs(lut - g["lut_" + nm]).max() <= 1e-4
+        luth = ko.create_matlab_lookup_table_h(int(p[0]), int(p[1]), *[float(x) for x in p[2:]], g["H"])
+        assert np.abs(luth - g["lut_h_" + nm]).max() <= 1e-4
+        assert luth.min() >= 1.0 and luth[..., 0].max() <= p[0] - 2 and luth[..., 1].max() <= p[1] - 2   # :69-73 clamp
     p = g["params_a"]   # KAT: no distortion -> identity
     ident = ko.create_matlab_lookup_table(8, 4, float(p[2]), float(p[3]), 3.0, 1.0, 0.0, 0.0)
     yy, xx = np.mgrid[0:4, 0:8].astype(np.float32)

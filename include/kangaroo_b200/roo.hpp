@@ -284,6 +284,13 @@ public:
     void RunHost(const uint8_t* left, const uint8_t* right, float* disp, int n) {
         b200::done(roo_engine_run_host(e_, left, right, disp, n), "roo_engine_run_host");
     }
+    // raw frames in: rectify through the lookup tables (or none) and BoxReduce `level` times before the path
+    void SetFrontEnd(int level, const Image<float2>* lookupLeft = nullptr, const Image<float2>* lookupRight = nullptr) {
+        roo_image_t l{}, r{};
+        if (lookupLeft && lookupRight) { l = b200::c(*lookupLeft); r = b200::c(*lookupRight); }
+        b200::done(roo_engine_set_front_end(e_, level, lookupLeft ? &l : nullptr, lookupRight ? &r : nullptr),
+                   "roo_engine_set_front_end");
+    }
     // streaming form: enqueue one group (n <= max_batch) and return a ticket; Wait(ticket) blocks until its
     // disparities are in `disp`.  Two groups may be in flight (copies overlap the other group's kernels).
     long long SubmitHost(const uint8_t* left, const uint8_t* right, float* disp, int n) {

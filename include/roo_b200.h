@@ -186,6 +186,15 @@ int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t* params);
 int roo_engine_destroy(roo_engine_t* e);
 size_t roo_engine_scratch_bytes(const roo_engine_t* e);
 
+/* Optional front end, the steps before Census in applications/stereo2/main.cpp:360-375: the engine then takes RAW
+ * frames of (w << level) x (h << level) pixels, rectifies them through the two float2 lookup tables (roo::Warp; both
+ * NULL = already rectified) and reduces them `level` times with BoxHalf<uchar,uint,uchar> (BoxReduce) to its working
+ * size w x h.  The tables stay caller-owned device memory and must outlive the engine.  Call once, before the first
+ * run; every later run_device / run_host / submit_host call passes frames of the raw size.  (Not available through
+ * roo_multi_engine_*.) */
+int roo_engine_set_front_end(roo_engine_t* e, int level, const roo_image_t* lookup_left_f32x2,
+                             const roo_image_t* lookup_right_f32x2);
+
 /* n_pairs tightly packed (h x w) uint8 images each side, device memory; disp: n_pairs x h x w float.
  * Processes the pairs in groups of max_batch on `stream`. */
 int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const uint8_t* right, float* disp, int n_pairs,

@@ -72,6 +72,7 @@ SYMBOLS = {
     "roo_engine_create": (C.c_int, [_P(C.c_void_p), _P(PipelineParams)]),
     "roo_engine_destroy": (C.c_int, [C.c_void_p]),
     "roo_engine_scratch_bytes": (C.c_size_t, [C.c_void_p]),
+    "roo_engine_set_front_end": (C.c_int, [C.c_void_p, C.c_int, _IMG, _IMG]),
     "roo_engine_run_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _S]),
     "roo_engine_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "roo_engine_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _P(C.c_longlong)]),

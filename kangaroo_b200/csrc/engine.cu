@@ -32,6 +32,13 @@ struct roo_engine {
     float* imgf = nullptr;                            // [batch][h][w] adaptive-P2 intensity (u8 * img_scale)
     float* edge = nullptr;                            // fused vertical groups: band-to-band state rows
     int* flags = nullptr;                             //                        and their progress flags
+    // optional front end (roo_engine_set_front_end): raw frames of (w << level) x (h << level) -> [Warp] -> BoxHalf x level
+    int fe_level = 0;
+    bool fe_rectify = false;
+    roo_image_t fe_lut[2] = {};                       // float2 lookup tables (caller-owned device memory)
+    unsigned char* fe_rect[2] = {nullptr, nullptr};   // [batch][raw h][raw w] rectified frames
+    unsigned char* fe_pyr[2] = {nullptr, nullptr};    // pyramid levels 1..level, one after the other, each [batch][h_l][w_l]
+    size_t in_npx = 0;                                // pixels of one INPUT frame (= npx without a front end)
     SgmPlan plan{};                                   // fused vertical groups where possible
     SgmPlan plan_sep{};                               // one pass per path
     int n_bands = 0;
@@ -76,6 +83,28 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
     const size_t npx = e->npx;
     int rc;
     prof_mark(e, -1, st);
+    // front end (stereo2/main.cpp:360-375): Warp(rectify) -> BoxReduce down to the working level
+    if (e->fe_rectify || e->fe_level > 0) {
+        const unsigned char* src[2] = {left, right};
+        for (int side = 0; side < 2; ++side) {
+            int cw = w << e->fe_level, ch = h << e->fe_level;
+            if (e->fe_rectify) {
+                rc = launch_warp_u8(e->fe_rect[side], src[side], cw, ch, batch, e->fe_lut[side], st);
+                if (rc) return rc;
+                src[side] = e->fe_rect[side];
+            }
+            unsigned char* dst = e->fe_pyr[side];
+            for (int l = 1; l <= e->fe_level; ++l) {
+                rc = launch_box_half_u8(dst, src[side], cw >> 1, ch >> 1, cw, ch, batch, st);
+                if (rc) return rc;
+                cw >>= 1; ch >>= 1;
+                src[side] = dst;
+                dst += (size_t)e->p.max_batch * cw * ch;
+            }
+        }
+        left = src[0]; right = src[1];
+        prof_mark(e, ROO_PROF_CENSUS, st);
+    }
     for (int side = 0; side < 2; ++side) {
         rc = launch_census((char*)e->cen[side], (size_t)w * e->words * 8, npx * e->words * 8,
                            (const char*)(side == 0 ? left : right), (size_t)w, npx, w, h, batch, p.window, ROO_IMG_U8, st);
@@ -147,7 +176,8 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
 }
 
 static void engine_free(roo_engine* e) {
-    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->med); cudaFree(e->imgf); cudaFree(e->edge); cudaFree(e->flags);
+    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->med); cudaFree(e->imgf);
+    for (int sd = 0; sd < 2; ++sd) { cudaFree(e->fe_rect[sd]); cudaFree(e->fe_pyr[sd]); } cudaFree(e->edge); cudaFree(e->flags);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
         if (e->ev_in[b]) cudaEventDestroy(e->ev_in[b]);
@@ -177,6 +207,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     e->DP = disp_padded(p.max_disp);
     e->words = p.window == ROO_WIN_9x7 ? 1 : (p.window == ROO_WIN_11x11 ? 2 : 4);
     e->npx = (size_t)p.w * p.h;
+    e->in_npx = e->npx;
     const size_t B = (size_t)p.max_batch, npx = e->npx;
     auto alloc = [&](void** ptr, size_t bytes) -> bool {
         if (cudaMalloc(ptr, bytes) != cudaSuccess) return false;
@@ -222,6 +253,33 @@ static bool on_engine_device(const roo_engine* e) {
     return cudaGetDevice(&dev) == cudaSuccess && dev == e->device;
 }
 
+extern "C" int roo_engine_set_front_end(roo_engine_t* e, int level, const roo_image_t* lookup_left,
+                                        const roo_image_t* lookup_right) {
+    if (!e || level < 0 || level > 8 || (lookup_left == nullptr) != (lookup_right == nullptr) || !on_engine_device(e))
+        return ROO_ERR_INVALID_ARGUMENT;
+    if (e->s_compute || e->fe_rectify || e->fe_level > 0) return ROO_ERR_INVALID_ARGUMENT;   // once, before the first host run
+    const size_t rw = (size_t)e->p.w << level, rh = (size_t)e->p.h << level, B = (size_t)e->p.max_batch;
+    if (lookup_left) {
+        const roo_image_t* lut[2] = {lookup_left, lookup_right};
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!valid_image(lut[sd], 8) || lut[sd]->w < rw || lut[sd]->h < rh || (((uintptr_t)lut[sd]->ptr | lut[sd]->pitch) & 7))
+                return ROO_ERR_INVALID_ARGUMENT;
+            e->fe_lut[sd] = *lut[sd];
+        }
+    }
+    size_t pyr = 0;
+    for (int l = 1; l <= level; ++l) pyr += B * (rw >> l) * (rh >> l);
+    for (int sd = 0; sd < 2; ++sd) {
+        if (lookup_left && cudaMalloc((void**)&e->fe_rect[sd], B * rw * rh) != cudaSuccess) return ROO_ERR_OUT_OF_MEMORY;
+        if (pyr && cudaMalloc((void**)&e->fe_pyr[sd], pyr) != cudaSuccess) return ROO_ERR_OUT_OF_MEMORY;
+        e->scratch_bytes += (lookup_left ? B * rw * rh : 0) + pyr;
+    }
+    e->fe_level = level;
+    e->fe_rectify = lookup_left != nullptr;
+    e->in_npx = rw * rh;
+    return ROO_OK;
+}
+
 extern "C" size_t roo_engine_scratch_bytes(const roo_engine_t* e) { return e ? e->scratch_bytes : 0; }
 
 extern "C" int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const uint8_t* right, float* disp, int n_pairs,
@@ -230,7 +288,7 @@ extern "C" int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const
     cudaStream_t st = as_stream(stream);
     for (int g = 0; g < n_pairs; g += e->p.max_batch) {
         const int batch = n_pairs - g < e->p.max_batch ? n_pairs - g : e->p.max_batch;
-        const int rc = engine_group(e, left + (size_t)g * e->npx, right + (size_t)g * e->npx, disp + (size_t)g * e->npx, batch, st);
+        const int rc = engine_group(e, left + (size_t)g * e->in_npx, right + (size_t)g * e->in_npx, disp + (size_t)g * e->npx, batch, st);
         if (rc) return rc;
     }
     return ROO_OK;
@@ -245,10 +303,10 @@ static int host_streams_init(roo_engine_t* e) {
     ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
-        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][0], B * npx));
-        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][1], B * npx));
+        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][0], B * e->in_npx));
+        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][1], B * e->in_npx));
         ROO_CUDA_TRY(cudaMalloc((void**)&e->out_dev[b], B * npx * 4));
-        e->scratch_bytes += 2 * B * npx + B * npx * 4;
+        e->scratch_bytes += 2 * B * e->in_npx + B * npx * 4;
         ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[b], cudaEventDisableTiming));
         ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
         ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[b], cudaEventDisableTiming));
@@ -263,8 +321,8 @@ static int submit_group(roo_engine_t* e, const uint8_t* left_host, const uint8_t
     const size_t npx = e->npx;
     const int b = (int)(e->ticket & 1);
     if (e->ticket >= 2) ROO_CUDA_TRY(cudaEventSynchronize(e->ev_out[b]));
-    ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][0], left_host, (size_t)batch * npx, cudaMemcpyHostToDevice, e->s_in));
-    ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][1], right_host, (size_t)batch * npx, cudaMemcpyHostToDevice, e->s_in));
+    ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][0], left_host, (size_t)batch * e->in_npx, cudaMemcpyHostToDevice, e->s_in));
+    ROO_CUDA_TRY(cudaMemcpyAsync(e->in_dev[b][1], right_host, (size_t)batch * e->in_npx, cudaMemcpyHostToDevice, e->s_in));
     ROO_CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
     ROO_CUDA_TRY(cudaStreamWaitEvent(e->s_compute, e->ev_in[b], 0));
     const int rc = engine_group(e, e->in_dev[b][0], e->in_dev[b][1], e->out_dev[b], batch, e->s_compute);
@@ -306,7 +364,7 @@ extern "C" int roo_engine_run_host(roo_engine_t* e, const uint8_t* left_host, co
     const int B = e->p.max_batch;
     for (int g = 0; g < n_pairs; g += B) {
         const int batch = n_pairs - g < B ? n_pairs - g : B;
-        const int rc = submit_group(e, left_host + (size_t)g * npx, right_host + (size_t)g * npx, disp_host + (size_t)g * npx, batch);
+        const int rc = submit_group(e, left_host + (size_t)g * e->in_npx, right_host + (size_t)g * e->in_npx, disp_host + (size_t)g * npx, batch);
         if (rc) return rc;
     }
     ROO_CUDA_TRY(cudaStreamSynchronize(e->s_out));

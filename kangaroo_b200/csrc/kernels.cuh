@@ -72,6 +72,11 @@ int launch_internal_to_vol(const roo_volume_t* dst, const float* src, int DP, in
 int sgm_directions(int dohoriz, int dovert, int doreverse, int dodiag, int dxs[8], int dys[8]);
 
 // ---- wta.cu ----
+// ---- frontback.cu: batched front-end stages of the engine (tightly packed u8 images)
+int launch_warp_u8(unsigned char* out, const unsigned char* in, int w, int h, int batch, const roo_image_t& lookup,
+                   cudaStream_t st);
+int launch_box_half_u8(unsigned char* out, const unsigned char* in, int w_out, int h_out, int w_in, int h_in, int batch,
+                       cudaStream_t st);
 // MedianFilterRejectNegative{5,7,9} over a batch of images (out must not overlap in)
 int launch_median(float* out, size_t out_pitch, size_t out_batch, const float* in, size_t in_pitch, size_t in_batch, int w,
                   int h, int batch, int size, int maxbad, cudaStream_t st);

@@ -326,6 +326,14 @@ class StereoEngine:
     def scratch_bytes(self) -> int:
         return int(lib().roo_engine_scratch_bytes(self._h))
 
+    def set_front_end(self, level: int = 0, lookup_left: Image | None = None, lookup_right: Image | None = None) -> None:
+        """Raw frames of (w << level, h << level) in: [Warp through the FLOAT2 tables] -> BoxHalf x level -> the path."""
+        self._luts = (lookup_left, lookup_right)   # keep the tables alive
+        check(lib().roo_engine_set_front_end(self._h, level,
+                                             C.byref(lookup_left.c()) if lookup_left is not None else None,
+                                             C.byref(lookup_right.c()) if lookup_right is not None else None),
+              "roo_engine_set_front_end")
+
     def run_device(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor | None = None, stream=None):
         """left/right: (n, h, w) uint8 CUDA tensors (contiguous); returns (n, h, w) float32."""
         assert left.is_cuda and left.dtype == torch.uint8 and left.is_contiguous() and right.is_contiguous()

@@ -570,6 +570,47 @@ def test_engine_auto_plan_matches_both_forced_plans():
     assert np.array_equal(a, f)
 
 
+@pytest.mark.parametrize("level,rectify", [(1, True), (2, False), (0, True)])
+def test_engine_front_end_equals_operator_sequence(level, rectify):
+    """stereo2/main.cpp:360-375 inside the engine: raw frames -> Warp -> BoxReduce -> path == the same done with the
+    operators and an engine without a front end, bit for bit; also through the host-buffer path."""
+    w, h, D, B = 96, 40, 32, 3
+    rw, rh = w << level, h << level
+    rng = np.random.default_rng(70 + level)
+    rawL = rng.integers(0, 256, (B, rh, rw), dtype=np.uint8)
+    rawR = np.roll(rawL, -3 << level, axis=2)
+    yy, xx = np.mgrid[0:rh, 0:rw].astype(np.float32)
+    lutL = np.stack([np.clip(xx * 0.99 + 1.3, 1, rw - 2), np.clip(yy * 1.01 - 0.4, 1, rh - 2)], -1).astype(np.float32)
+    lutR = np.stack([np.clip(xx * 1.01 - 0.7, 1, rw - 2), np.clip(yy * 0.99 + 0.6, 1, rh - 2)], -1).astype(np.float32)
+    kw = dict(dodiag=True, subpix=True, lrcheck=True, max_batch=B, fuse_vertical=True)
+    eng = roo.StereoEngine(w, h, D, **kw)
+    tabs = (roo.Image.from_numpy(lutL), roo.Image.from_numpy(lutR)) if rectify else (None, None)
+    eng.set_front_end(level, *tabs)
+    got = eng.run_device(torch.from_numpy(rawL).cuda(), torch.from_numpy(rawR).cuda()).cpu().numpy()
+    host = torch.empty((B, h, w), dtype=torch.float32).pin_memory()
+    eng.run_host(torch.from_numpy(rawL).pin_memory(), torch.from_numpy(rawR).pin_memory(), host)
+    eng.close()
+
+    def front(raw, lut):
+        out = []
+        for b in range(B):
+            cur = roo.Image.from_numpy(raw[b])
+            if rectify:
+                rect = roo.Image(rw, rh, np.uint8)
+                roo.Warp(rect, cur, roo.Image.from_numpy(lut))
+                cur = rect
+            pyr = [cur] + [roo.Image(rw >> l, rh >> l, np.uint8) for l in range(1, level + 1)]
+            roo.BoxReduce(pyr)
+            out.append(pyr[-1].numpy())
+        return np.stack(out)
+    ref_eng = roo.StereoEngine(w, h, D, **kw)
+    want = ref_eng.run_device(torch.from_numpy(front(rawL, lutL)).cuda(), torch.from_numpy(front(rawR, lutR)).cuda()).cpu().numpy()
+    ref_eng.close()
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.array_equal(host.numpy(), want, equal_nan=True)
+    assert np.isfinite(want).mean() > 0.3
+
+
 def test_engine_submit_host_pipeline_equals_run_device():
     """roo_engine_submit_host / roo_engine_wait: five groups streamed with two in flight, different inputs each."""
     w, h, D, B = 160, 64, 32, 2

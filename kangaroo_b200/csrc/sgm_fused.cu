@@ -121,6 +121,9 @@ __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
 #ifndef VG_SPIN_NS
 #define VG_SPIN_NS 30
 #endif
+#ifndef VG_COMM_NS
+#define VG_COMM_NS 200   // idle back-off of the communication warp
+#endif
 // poll a monotonically growing shared-memory flag until it reaches `need`
 __device__ __forceinline__ void spin_until(unsigned flag_addr, int need) {
     int v;
@@ -321,7 +324,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
                     progress = true;
                 }
             }
-            if (!progress) __nanosleep(200);
+            if (!progress) __nanosleep(VG_COMM_NS);
         }
         return;
     }

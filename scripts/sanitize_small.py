@@ -32,5 +32,24 @@ roo.BoxHalf(half, img)
 vbo = roo.Image(53, 37, roo.FLOAT4)
 roo.DisparityImageToVbo(vbo, img, 0.1, 500.0, 500.0, 26.0, 18.0)
 roo.Disp2Depth(img, out, 500.0, 0.1)
+lut = roo.Image(53, 37, roo.FLOAT2)
+roo.CreateMatlabLookupTable(lut, 60.0, 58.0, 26.0, 18.0, -0.2, 0.05)
+roo.CreateMatlabLookupTable(lut, 60.0, 58.0, 26.0, 18.0, -0.2, 0.05, H_on=[1, 0.01, 0.5, -0.01, 1, 0.2, 1e-5, 0, 1])
+raw = roo.Image.from_numpy(np.random.default_rng(1).integers(0, 256, (37, 53), dtype=np.uint8))
+rect = roo.Image(53, 37, np.uint8)
+roo.Warp(rect, raw, lut)
+vol = roo.Volume(53, 37, 19, np.float32)
+roo.CostVolumeFromStereoTruncatedAbsAndGrad(vol, img, img, -1.0, 0.9, 0.03, 0.008)
+# engine with front end (rectify + one pyramid level) and the median stage
+w, h, D, B = 80, 36, 32, 2
+yy, xx = np.mgrid[0:2 * h, 0:2 * w].astype(np.float32)
+tab = roo.Image.from_numpy(np.ascontiguousarray(np.stack([np.clip(xx + 0.3, 1, 2 * w - 2), np.clip(yy - 0.2, 1, 2 * h - 2)], -1)))
+eng = roo.StereoEngine(w, h, D, dodiag=True, subpix=True, lrcheck=True, max_batch=B, fuse_vertical=True, median_size=7,
+                       median_maxbad=20, median_iters=2)
+eng.set_front_end(1, tab, tab)
+rawb = torch.from_numpy(np.random.default_rng(2).integers(0, 256, (B, 2 * h, 2 * w), dtype=np.uint8)).cuda()
+d = eng.run_device(rawb, rawb)
+torch.cuda.synchronize()
+eng.close()
 torch.cuda.synchronize()
 print("done")

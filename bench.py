@@ -38,6 +38,7 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "c2_1280x720x128_8path_wta"
 P1, P2 = 0.01, 0.02  # applications/stereo2/main.cpp:246-247
 L2_BYTES = 126e6
+_WINDOW = 0  # census window of this run (0 = 9x7, 1 = 11x11, 2 = 16x16), set from --window
 
 
 def measured_peak_hbm():
@@ -116,7 +117,7 @@ def cpu_port_throughput(w, h, D, paths, subpix, lrcheck, cfg, rows=None, reps=1)
     L, R = np.ascontiguousarray(L[:rows]), np.ascontiguousarray(R[:rows])
     t0 = time.perf_counter()
     for _ in range(reps):
-        ko.pipeline_u8(L, R, D, dodiag=(paths == 8), subpix=bool(subpix), lrcheck=bool(lrcheck), p1=P1, p2=P2)
+        ko.pipeline_u8(L, R, D, window=_WINDOW, dodiag=(paths == 8), subpix=bool(subpix), lrcheck=bool(lrcheck), p1=P1, p2=P2)
     dt = (time.perf_counter() - t0) / reps
     frac = rows / h
     return frac / dt, dt, ko.num_threads(), rows
@@ -145,7 +146,7 @@ def run_reference(args, wl):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "mpix_disp_per_s": value * w * h * D / 1e6,
-           "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": "9x7",
+           "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": args.window,
                       "note": "reference kernels are CUDA-only; CPU arm = OpenMP scalar port of the kernel bodies"},
            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -161,9 +162,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="stereo pairs per step per GPU (0 = workload default)")
+    ap.add_argument("--window", default="9x7", choices=["9x7", "11x11", "16x16"],
+                    help="census descriptor: 9x7 -> u64 (north_star headline), 16x16 = 8w x 16h -> ulong4 (what the apps run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    global _WINDOW
+    _WINDOW = {"9x7": 0, "11x11": 1, "16x16": 2}[args.window]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = args.workload
     if args.impl == "reference":
@@ -190,7 +195,8 @@ def main():
     left = torch.from_numpy(Lh).cuda()
     right = torch.from_numpy(Rh).cuda()
     disp = torch.empty((B, h, w), dtype=torch.float32, device="cuda")
-    eng = roo.StereoEngine(w, h, D, window=roo.WIN_9x7, P1=P1, P2=P2, dohoriz=True, dovert=True, doreverse=True,
+    win = {"9x7": roo.WIN_9x7, "11x11": roo.WIN_11x11, "16x16": roo.WIN_16x16}[args.window]
+    eng = roo.StereoEngine(w, h, D, window=win, P1=P1, P2=P2, dohoriz=True, dovert=True, doreverse=True,
                            dodiag=(paths == 8), subpix=bool(subpix), lrcheck=bool(lrcheck), max_batch=B)
 
     def barrier():
@@ -234,7 +240,7 @@ def main():
         # one submit = one batch: upload (H2D), the whole path, download (D2H); two batches in flight, so the copies of
         # step k+1 / k-1 overlap the kernels of step k.  Every step's result is read on the host after its wait.
         g = B
-        eng_h = roo.StereoEngine(w, h, D, window=roo.WIN_9x7, P1=P1, P2=P2, dodiag=(paths == 8), subpix=bool(subpix),
+        eng_h = roo.StereoEngine(w, h, D, window=win, P1=P1, P2=P2, dodiag=(paths == 8), subpix=bool(subpix),
                                  lrcheck=bool(lrcheck), max_batch=g)
 
         def run_steps(n):
@@ -296,7 +302,7 @@ def main():
             "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mpix_disp_per_s": value * w * h * D / 1e6,
-            "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": "9x7",
+            "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": args.window,
                        "popcount": "popc32-compat", "subpix": subpix, "lrcheck": lrcheck, "pairs_per_step_per_gpu": B,
                        "sharding": f"pair-batch x{world}, no collective",
                        "l2": f"per-step working set {B * w * h * D * 5 / 1e9:.2f} GB (fp32 aggregate + u8 cost) vs "

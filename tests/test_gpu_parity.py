@@ -6,6 +6,8 @@ costs within 1e-5 relative (bit-exact against the oracle under IEEE division, bi
 reference kernels under the default div.approx mode); integer WTA identical on >= 99.9 % of pixels;
 subpixel disparity within 0.01 px.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -447,7 +449,7 @@ def test_engine_degenerate_shapes(shape, dodiag):
         assert np.array_equal(disp[0], od) and np.array_equal(disp[1], od)
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ROO_STRESS_SEEDS", "6"))))   # raise for a one-off stress run
 def test_engine_random_shapes_and_flags_bitexact_vs_oracle(seed):
     """Seeded sweep over shapes around the kernels' internal sizes (32 lanes, 4 columns per warp, 48/24-column bands,
     128-pixel cost segments, 32-row intensity blocks) with random flag combinations; IEEE mode, bit-exact."""

@@ -117,7 +117,10 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
         const float p2 = r == 0 ? 0.0f : P2;
         const float denom = 1.0f + fabsf(last_c - pix);
         const int lim = MASKED ? min(M, x + 1) - d0 : 0;
-        sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, rc, cscale, hin, lim, lane, hnew, hp, best);
+        float craw[DPL];
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) craw[j] = rc.raw(j);
+        sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, craw, cscale, hin, lim, lane, hnew, hp, best);
         lastBest = r == 0 ? 0.0f : best;
         last_c = pix;
         if (EPI != EPI_WTA_ONLY) store_f<DPL>(hst, hnew);

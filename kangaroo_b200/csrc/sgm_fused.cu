@@ -162,7 +162,7 @@ __device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, 
     RawCost<DPL, COST> rc;
     rc.lds(stg + DP * 4 + lane * DPL * CE);
 #pragma unroll
-    for (int j = 0; j < DPL; ++j) cost[j] = rc.get(j, cscale);
+    for (int j = 0; j < DPL; ++j) cost[j] = rc.raw(j);
     float p2V = P2, p2D = P2, p2A = P2;
     bool sV = false, sD = false, sA = false;
     if (EDGE) {
@@ -181,7 +181,7 @@ __device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, 
     sgm_step3<DPL, MASKED, FIRST, IEEE>(hpV, lbV, 1.0f + fabsf(ppV - pix), p2V,
                                         hpD, lbD, 1.0f + fabsf(pixD - pix), p2D,
                                         hpA, lbA, 1.0f + fabsf(ppA - pix), p2A,
-                                        cost, hin, P1, lim, lane, H3, bV, bD, bA);
+                                        cost, cscale, hin, P1, lim, lane, H3, bV, bD, bA);
     if (EDGE) { if (sV) bV = 0.0f; if (sD) bD = 0.0f; if (sA) bA = 0.0f; }
     lbV = bV; lbD = bD; lbA = bA;
     pixD = pix;

@@ -114,6 +114,7 @@ template <int DPL> struct RawCost<DPL, COST_F32> {
         else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(saddr));
     }
     __device__ __forceinline__ float get(int j, float) const { return v[j]; }
+    __device__ __forceinline__ float raw(int j) const { return v[j]; }   // cost = raw * 1
     static constexpr int ELEM = 4;
 };
 template <int DPL> struct RawCost<DPL, COST_U8> {
@@ -134,8 +135,31 @@ template <int DPL> struct RawCost<DPL, COST_U8> {
     __device__ __forceinline__ float get(int j, float scale) const {
         return (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * scale;
     }
+    __device__ __forceinline__ float raw(int j) const { return (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu); }
     static constexpr int ELEM = 1;
 };
+
+// ---- packed fp32 pairs (sm_100a add/fma.rn.f32x2 -> SASS FADD2 / FFMA2) -----------------------------------------
+// One instruction, two IEEE-rounded fp32 results (each half is rounded exactly like the scalar instruction, so
+// results stay bit-identical); the aggregation kernels are bound by instruction issue, and the recurrence's
+// additions on adjacent disparities are independent, so pairing them halves their issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 // The recurrence for one pixel of one path.
 //   hp[]      previous pixel's aggregate row on this path, +inf where d >= that pixel's disparity range
@@ -143,37 +167,59 @@ template <int DPL> struct RawCost<DPL, COST_U8> {
 //   denom     1 + |I(prev) - I(cur)|
 //   P2        0 at a path start: together with hp = +inf and lastBest = 0 this makes Cr == cost, i.e. the
 //             start pixel's `volH += volC` (cu_semi_global_matching.cu:31-35) is the same code path
+//   craw/cs   raw matching cost and its scale: cost = craw * cs, exact (cs is a power of two, or 1 for fp32 costs),
+//             so fma(craw, cs, CM) is the reference's CM + cost with its single rounding
 //   lim       (MASKED only) number of in-range disparities of this lane: min(maxDisp, x+1) - lane*DPL
 // Outputs hnew = hin + Cr (hin where out of range), hp_out = hnew masked with +inf, best = min_d Cr.
-template <int DPL, bool MASKED, bool FIRST, bool IEEE, typename CostT>
+template <int DPL, bool MASKED, bool FIRST, bool IEEE>
 __device__ __forceinline__ void sgm_step(const float (&hp)[DPL], float lastBest, float denom, float P1, float P2,
-                                         const CostT& cost, float cost_scale, const float (&hin)[DPL], int lim,
+                                         const float (&craw)[DPL], float cs, const float (&hin)[DPL], int lim,
                                          int lane, float (&hnew)[DPL], float (&hp_out)[DPL], float& best_out) {
-    float hpP[DPL];
+    float hpP[DPL], Cr[DPL], h[DPL];
+    if constexpr (DPL >= 2) {
+        const f32x2 P1P1 = pk2(P1, P1);
 #pragma unroll
-    for (int j = 0; j < DPL; ++j) hpP[j] = hp[j] + P1;
+        for (int q = 0; q < DPL / 2; ++q) upk2(add2(pk2(hp[2 * q], hp[2 * q + 1]), P1P1), hpP[2 * q], hpP[2 * q + 1]);
+    } else {
+        hpP[0] = hp[0] + P1;
+    }
     float up = __shfl_up_sync(0xffffffffu, hpP[DPL - 1], 1);   // H(prev, d-1) + P1 for j == 0
     float dn = __shfl_down_sync(0xffffffffu, hpP[0], 1);       // H(prev, d+1) + P1 for j == DPL-1
     if (lane == 0) up = ROO_INF;
     if (lane == 31) dn = ROO_INF;
     const float base = sgm_p2_base<IEEE>(lastBest, P2, denom);
-    float best = SGM_MAX_ERROR;
+    float CM[DPL];
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
         const float hm = j > 0 ? hpP[j - 1] : up;
         const float hq = j < DPL - 1 ? hpP[j + 1] : dn;
-        const float CM = fminf(fminf(base, hp[j]), fminf(hm, hq));
-        const float Cr = (CM + cost.get(j, cost_scale)) - lastBest;
-        const float h = FIRST ? Cr : hin[j] + Cr;
+        CM[j] = fminf(fminf(base, hp[j]), fminf(hm, hq));
+    }
+    if constexpr (DPL >= 2) {
+        const f32x2 cs2 = pk2(cs, cs), nlb = pk2(-lastBest, -lastBest);
+#pragma unroll
+        for (int q = 0; q < DPL / 2; ++q) {
+            const f32x2 cr = add2(fma2(pk2(craw[2 * q], craw[2 * q + 1]), cs2, pk2(CM[2 * q], CM[2 * q + 1])), nlb);
+            upk2(cr, Cr[2 * q], Cr[2 * q + 1]);
+            if (FIRST) { h[2 * q] = Cr[2 * q]; h[2 * q + 1] = Cr[2 * q + 1]; }
+            else upk2(add2(pk2(hin[2 * q], hin[2 * q + 1]), cr), h[2 * q], h[2 * q + 1]);
+        }
+    } else {
+        Cr[0] = __fmaf_rn(craw[0], cs, CM[0]) - lastBest;
+        h[0] = FIRST ? Cr[0] : hin[0] + Cr[0];
+    }
+    float best = SGM_MAX_ERROR;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
         if (MASKED) {
             const bool in = j < lim;
-            best = in ? fminf(best, Cr) : best;
-            hnew[j] = in ? h : (FIRST ? 0.0f : hin[j]);
-            hp_out[j] = in ? h : ROO_INF;
+            best = in ? fminf(best, Cr[j]) : best;
+            hnew[j] = in ? h[j] : (FIRST ? 0.0f : hin[j]);
+            hp_out[j] = in ? h[j] : ROO_INF;
         } else {
-            best = fminf(best, Cr);
-            hnew[j] = h;
-            hp_out[j] = h;
+            best = fminf(best, Cr[j]);
+            hnew[j] = h[j];
+            hp_out[j] = h[j];
         }
     }
     best_out = warp_min_f32(best);
@@ -185,15 +231,26 @@ __device__ __forceinline__ void sgm_step(const float (&hp)[DPL], float lastBest,
 // that the three recurrences -- which only meet in the final additions -- are scheduled interleaved and a
 // pixel costs one chain latency (shuffle -> min -> redux) instead of three.  The matching cost is decoded
 // once.  hpX are in/out: previous pixel's row on entry, this pixel's masked row on exit.
+// All additions run on pairs of adjacent disparities (FADD2 / FFMA2): 12 + 12 + 12 scalar adds and 12 scalar
+// fmas per four disparities become 18 packed instructions.
 template <int DPL, bool MASKED, bool FIRST, bool IEEE>
 __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float denV, float p2V,
                                           float (&hpD)[DPL], float lbD, float denD, float p2D,
                                           float (&hpA)[DPL], float lbA, float denA, float p2A,
-                                          const float (&cost)[DPL], const float (&hin)[DPL], float P1, int lim,
+                                          const float (&craw)[DPL], float cs, const float (&hin)[DPL], float P1, int lim,
                                           int lane, float (&H3)[DPL], float& bV, float& bD, float& bA) {
     float pV[DPL], pD[DPL], pA[DPL];
+    if constexpr (DPL >= 2) {
+        const f32x2 P1P1 = pk2(P1, P1);
 #pragma unroll
-    for (int j = 0; j < DPL; ++j) { pV[j] = hpV[j] + P1; pD[j] = hpD[j] + P1; pA[j] = hpA[j] + P1; }
+        for (int q = 0; q < DPL / 2; ++q) {
+            upk2(add2(pk2(hpV[2 * q], hpV[2 * q + 1]), P1P1), pV[2 * q], pV[2 * q + 1]);
+            upk2(add2(pk2(hpD[2 * q], hpD[2 * q + 1]), P1P1), pD[2 * q], pD[2 * q + 1]);
+            upk2(add2(pk2(hpA[2 * q], hpA[2 * q + 1]), P1P1), pA[2 * q], pA[2 * q + 1]);
+        }
+    } else {
+        pV[0] = hpV[0] + P1; pD[0] = hpD[0] + P1; pA[0] = hpA[0] + P1;
+    }
     float upV = __shfl_up_sync(0xffffffffu, pV[DPL - 1], 1), dnV = __shfl_down_sync(0xffffffffu, pV[0], 1);
     float upD = __shfl_up_sync(0xffffffffu, pD[DPL - 1], 1), dnD = __shfl_down_sync(0xffffffffu, pD[0], 1);
     float upA = __shfl_up_sync(0xffffffffu, pA[DPL - 1], 1), dnA = __shfl_down_sync(0xffffffffu, pA[0], 1);
@@ -202,39 +259,61 @@ __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float de
     const float baseV = sgm_p2_base<IEEE>(lbV, p2V, denV);
     const float baseD = sgm_p2_base<IEEE>(lbD, p2D, denD);
     const float baseA = sgm_p2_base<IEEE>(lbA, p2A, denA);
+    float cmV[DPL], cmD[DPL], cmA[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+        cmV[j] = fminf(fminf(baseV, hpV[j]), fminf(j > 0 ? pV[j - 1] : upV, j < DPL - 1 ? pV[j + 1] : dnV));
+        cmD[j] = fminf(fminf(baseD, hpD[j]), fminf(j > 0 ? pD[j - 1] : upD, j < DPL - 1 ? pD[j + 1] : dnD));
+        cmA[j] = fminf(fminf(baseA, hpA[j]), fminf(j > 0 ? pA[j - 1] : upA, j < DPL - 1 ? pA[j + 1] : dnA));
+    }
+    float crV[DPL], crD[DPL], crA[DPL], h1[DPL], h2[DPL], h3[DPL];
+    if constexpr (DPL >= 2) {
+        const f32x2 cs2 = pk2(cs, cs), nV = pk2(-lbV, -lbV), nD = pk2(-lbD, -lbD), nA = pk2(-lbA, -lbA);
+#pragma unroll
+        for (int q = 0; q < DPL / 2; ++q) {
+            const int a = 2 * q, b = 2 * q + 1;
+            const f32x2 c2 = pk2(craw[a], craw[b]);
+            const f32x2 rV = add2(fma2(c2, cs2, pk2(cmV[a], cmV[b])), nV);
+            const f32x2 rD = add2(fma2(c2, cs2, pk2(cmD[a], cmD[b])), nD);
+            const f32x2 rA = add2(fma2(c2, cs2, pk2(cmA[a], cmA[b])), nA);
+            const f32x2 s1 = FIRST ? rV : add2(pk2(hin[a], hin[b]), rV);
+            const f32x2 s2 = add2(s1, rD);
+            const f32x2 s3 = add2(s2, rA);
+            upk2(rV, crV[a], crV[b]); upk2(rD, crD[a], crD[b]); upk2(rA, crA[a], crA[b]);
+            upk2(s1, h1[a], h1[b]); upk2(s2, h2[a], h2[b]); upk2(s3, h3[a], h3[b]);
+        }
+    } else {
+        crV[0] = __fmaf_rn(craw[0], cs, cmV[0]) - lbV;
+        crD[0] = __fmaf_rn(craw[0], cs, cmD[0]) - lbD;
+        crA[0] = __fmaf_rn(craw[0], cs, cmA[0]) - lbA;
+        h1[0] = FIRST ? crV[0] : hin[0] + crV[0];
+        h2[0] = h1[0] + crD[0];
+        h3[0] = h2[0] + crA[0];
+    }
     float mV = SGM_MAX_ERROR, mD = SGM_MAX_ERROR, mA = SGM_MAX_ERROR;
     float tV = 0.0f, tD = 0.0f, tA = 0.0f;
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
-        const float cmV = fminf(fminf(baseV, hpV[j]), fminf(j > 0 ? pV[j - 1] : upV, j < DPL - 1 ? pV[j + 1] : dnV));
-        const float cmD = fminf(fminf(baseD, hpD[j]), fminf(j > 0 ? pD[j - 1] : upD, j < DPL - 1 ? pD[j + 1] : dnD));
-        const float cmA = fminf(fminf(baseA, hpA[j]), fminf(j > 0 ? pA[j - 1] : upA, j < DPL - 1 ? pA[j + 1] : dnA));
-        const float crV = (cmV + cost[j]) - lbV;
-        const float crD = (cmD + cost[j]) - lbD;
-        const float crA = (cmA + cost[j]) - lbA;
-        const float h1 = FIRST ? crV : hin[j] + crV;
-        const float h2 = h1 + crD;
-        const float h3 = h2 + crA;
         if (MASKED) {
             const bool in = j < lim;
-            mV = in ? fminf(mV, crV) : mV;
-            mD = in ? fminf(mD, crD) : mD;
-            mA = in ? fminf(mA, crA) : mA;
-            hpV[j] = in ? h1 : ROO_INF;
-            hpD[j] = in ? h2 : ROO_INF;
-            hpA[j] = in ? h3 : ROO_INF;
-            H3[j] = in ? h3 : (FIRST ? 0.0f : hin[j]);
+            mV = in ? fminf(mV, crV[j]) : mV;
+            mD = in ? fminf(mD, crD[j]) : mD;
+            mA = in ? fminf(mA, crA[j]) : mA;
+            hpV[j] = in ? h1[j] : ROO_INF;
+            hpD[j] = in ? h2[j] : ROO_INF;
+            hpA[j] = in ? h3[j] : ROO_INF;
+            H3[j] = in ? h3[j] : (FIRST ? 0.0f : hin[j]);
         } else {
             // pairs first, so that every second min is a three-input FMNMX3 (min is exact: any grouping agrees)
             if (j & 1) {
-                mV = fminf(mV, fminf(tV, crV)); mD = fminf(mD, fminf(tD, crD)); mA = fminf(mA, fminf(tA, crA));
+                mV = fminf(mV, fminf(tV, crV[j])); mD = fminf(mD, fminf(tD, crD[j])); mA = fminf(mA, fminf(tA, crA[j]));
             } else if (j == DPL - 1) {
-                mV = fminf(mV, crV); mD = fminf(mD, crD); mA = fminf(mA, crA);
+                mV = fminf(mV, crV[j]); mD = fminf(mD, crD[j]); mA = fminf(mA, crA[j]);
             } else {
-                tV = crV; tD = crD; tA = crA;
+                tV = crV[j]; tD = crD[j]; tA = crA[j];
             }
-            hpV[j] = h1; hpD[j] = h2; hpA[j] = h3;
-            H3[j] = h3;
+            hpV[j] = h1[j]; hpD[j] = h2[j]; hpA[j] = h3[j];
+            H3[j] = h3[j];
         }
     }
     bV = warp_min_f32(mV);

@@ -166,6 +166,8 @@ def main():
                     help="census descriptor: 9x7 -> u64 (north_star headline), 16x16 = 8w x 16h -> ulong4 (what the apps run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--generic-hsweep", action="store_true",
+                    help="A/B: run the horizontal paths through the generic sweep kernel instead of sgm_hsweep.cu")
     args = ap.parse_args()
     global _WINDOW
     _WINDOW = {"9x7": 0, "11x11": 1, "16x16": 2}[args.window]
@@ -184,6 +186,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: kangaroo_b200 has no CPU path")
+    if args.generic_hsweep:
+        roo.set_tuning(capi.TUNE_HSWEEP, 0)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -278,7 +282,7 @@ def main():
         # algorithmic bytes: fp32 aggregate passed over S times, first pass write-only:
         # 4 B * (2S - 1) per pixel*disparity over the S pass launches of one batch
         unit = float(w) * h * D * B
-        step_kernel_ms = sum(v[0] for v in prof.values())
+        step_kernel_ms = sum(v[0] for k, v in prof.items() if not k.startswith("pass"))
         if vg_n and vg_ms >= sw_ms:   # dominant kernel: the fused vertical group (first launch writes, second reads+writes)
             kname, k_ms, k_n = "sgm_vgroup_kernel", vg_ms, vg_n
             bytes_per_launch = 4.0 * (1 + 2) / 2 * unit if vg_n // K == 2 else 4.0 * unit

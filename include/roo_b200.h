@@ -58,8 +58,14 @@ const char* roo_status_string(int status);
 /* Number of kernels this library has launched in this process (all threads), for bench.py. */
 unsigned long long roo_launch_count(void);
 /* 0 (default): divisions as the reference's -use_fast_math build (div.approx.ftz) -> results bit-identical to
- * the reference kernels; 1: IEEE division -> bit-identical to the CPU oracle.  Process-wide. */
+ * the reference kernels; 1: IEEE division -> bit-identical to the CPU oracle.  Process-wide DEFAULT: the granular
+ * operators (whose signatures are the reference's and carry no mode) read it at call time; an engine takes its own
+ * mode from roo_pipeline_params_t.fp_mode when it is created, so engines in different modes can run side by side. */
 void roo_set_ieee_division(int on);
+/* Development knobs for A/B measurements (never needed for correct results).  ROO_TUNE_HSWEEP: 1 (default) runs the
+ * horizontal aggregation paths through the bulk-copy kernel (sgm_hsweep.cu), 0 through the generic sweep kernel. */
+enum roo_tuning_knob { ROO_TUNE_HSWEEP = 0 };
+int roo_set_tuning(int knob, int value);
 
 /* ---- granular operators: one per reference launcher -------------------------------------- */
 
@@ -160,6 +166,11 @@ int roo_median_filter_reject_negative(const roo_image_t* out_f32, const roo_imag
 
 typedef struct roo_engine roo_engine_t;
 
+/* Divisions of the path (adaptive P2, subpixel parabola): ROO_FP_REFERENCE reproduces the SASS of the reference's
+ * -use_fast_math build (results bit-identical to its kernels), ROO_FP_IEEE uses IEEE division (bit-identical to the
+ * CPU oracle).  ROO_FP_DEFAULT = whatever roo_set_ieee_division() says when the engine is created. */
+enum roo_fp_mode { ROO_FP_DEFAULT = 0, ROO_FP_REFERENCE = 1, ROO_FP_IEEE = 2 };
+
 typedef struct roo_pipeline_params_t {
     int w, h;             /* image size (any; not limited to 1024 like the reference, Q4) */
     int max_disp;         /* 1..256 */
@@ -177,6 +188,7 @@ typedef struct roo_pipeline_params_t {
     int median_size;      /* 0 (none), 5, 7 or 9: MedianFilterRejectNegativeNxN on the disparities between WTA and the */
     int median_maxbad;    /*   left-right check, median_iters times, on both disparity images when lrcheck is set      */
     int median_iters;     /*   (main.cpp:438-444; out of place into engine scratch, so without the reference's race)   */
+    int fp_mode;          /* enum roo_fp_mode: floating-point mode of THIS engine (two engines may differ) */
 } roo_pipeline_params_t;
 
 /* The engine allocates its scratch on the CURRENT device; later calls must come with that device current (else
@@ -229,7 +241,10 @@ int roo_multi_engine_run_host(roo_multi_engine_t* m, const uint8_t* left_host, c
  * every launch on the launching stream; roo_engine_get_profile (call after synchronising) returns the
  * accumulated milliseconds and launch counts per kernel kind since profiling was switched on. */
 enum roo_prof_kind { ROO_PROF_CENSUS = 0, ROO_PROF_COST = 1, ROO_PROF_SWEEP = 2, ROO_PROF_WTA = 3, ROO_PROF_LRCHECK = 4,
-                     ROO_PROF_VGROUP = 5, ROO_PROF_KINDS = 6 };
+                     ROO_PROF_VGROUP = 5,
+                     ROO_PROF_PASS0 = 6,   /* ROO_PROF_PASS0 + i: the i-th aggregation pass of the plan (also counted
+                                              under SWEEP / VGROUP), i < 8 */
+                     ROO_PROF_KINDS = 14 };
 int roo_engine_set_profiling(roo_engine_t* e, int on);
 int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long long* launches_by_kind);
 /* development aid: in-kernel cycle counters of a -DVG_TIMING build (zeros in a normal build) */

@@ -15,9 +15,11 @@ WIN_9x7, WIN_11x11, WIN_16x16 = 0, 1, 2
 WORDS = {WIN_9x7: 1, WIN_11x11: 2, WIN_16x16: 4}
 IMG_U8, IMG_F32 = 0, 1
 POPC32_COMPAT, POPC64 = 0, 1
+FP_DEFAULT, FP_REFERENCE, FP_IEEE = 0, 1, 2
+TUNE_HSWEEP = 0
 VOL_U16, VOL_F32, VOL_I32, VOL_U32, VOL_U8, VOL_ELEM = 0, 1, 2, 3, 4, 5
 DISP_I8, DISP_F32 = 0, 1
-PROF_KINDS = ("census", "cost", "sweep", "wta", "lrcheck", "vgroup")
+PROF_KINDS = ("census", "cost", "sweep", "wta", "lrcheck", "vgroup") + tuple(f"pass{i}" for i in range(8))
 
 
 class RooImage(C.Structure):
@@ -37,7 +39,8 @@ class PipelineParams(C.Structure):
                 ("dohoriz", C.c_int), ("dovert", C.c_int), ("doreverse", C.c_int), ("dodiag", C.c_int),
                 ("subpix", C.c_int), ("lrcheck", C.c_int), ("lr_maxdiff", C.c_float),
                 ("max_batch", C.c_int), ("keep_volume", C.c_int), ("fuse_vertical", C.c_int),
-                ("median_size", C.c_int), ("median_maxbad", C.c_int), ("median_iters", C.c_int)]
+                ("median_size", C.c_int), ("median_maxbad", C.c_int), ("median_iters", C.c_int),
+                ("fp_mode", C.c_int)]
 
 
 # every symbol include/roo_b200.h declares: name -> (restype, argtypes)
@@ -48,6 +51,7 @@ SYMBOLS = {
     "roo_status_string": (C.c_char_p, [C.c_int]),
     "roo_launch_count": (C.c_ulonglong, []),
     "roo_set_ieee_division": (None, [C.c_int]),
+    "roo_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "roo_census": (C.c_int, [_IMG, _IMG, C.c_int, C.c_int, _S]),
     "roo_census_stereo": (C.c_int, [_IMG, _IMG, _IMG, C.c_int, _S]),
     "roo_census_stereo_volume": (C.c_int, [_VOL, _IMG, _IMG, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _S]),

@@ -381,11 +381,11 @@ census_wta_kernel(float* __restrict__ disp, const unsigned long long* __restrict
 }
 
 int launch_census_wta(float* disp, const void* cself, const void* cother, int w, int h, int batch, int maxDisp,
-                      int words, int popc_mode, int subpix, int sdi, cudaStream_t st) {
+                      int words, int popc_mode, int subpix, int sdi, int ieee_mode, cudaStream_t st) {
     dim3 grid(cdiv(w, 128), h, batch), block(128);
     const auto* a = (const unsigned long long*)cself;
     const auto* b = (const unsigned long long*)cother;
-    const bool p64 = popc_mode == ROO_POPC64, ieee = g_ieee_div.load() != 0;
+    const bool p64 = popc_mode == ROO_POPC64, ieee = ieee_mode != 0;
     const size_t smem = (size_t)(128 + maxDisp - 1) * words * 8;
 #define ROO_RW(W, P, I) census_wta_kernel<W, P, I><<<grid, block, smem, st>>>(disp, a, b, w, h, maxDisp, subpix, sdi)
 #define ROO_RW2(W)                                                                 \

@@ -22,6 +22,7 @@ struct roo_engine {
     roo_pipeline_params_t p;
     int device = 0;
     int DP = 0, words = 0;
+    int ieee = 0;          // fp mode of THIS engine (roo_pipeline_params_t.fp_mode; resolved at creation)
     size_t npx = 0;
     // scratch (device)
     unsigned long long* cen[2] = {nullptr, nullptr};  // [batch][h][w][words]
@@ -54,6 +55,7 @@ struct roo_engine {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_kinds;   // kind of the launch that ENDS at event i (-1 = group start marker)
+    std::vector<int> prof_pass;    // aggregation pass index of that launch (-1: not an aggregation pass)
     size_t prof_used = 0;
     double prof_ms[ROO_PROF_KINDS] = {0};
     long long prof_n[ROO_PROF_KINDS] = {0};
@@ -64,15 +66,17 @@ constexpr long long FUSE_MIN_CTAS = 100;
 // ... unless the group is so small that single-path sweeps are not bandwidth-bound either (pixel*disparity units)
 constexpr long long FUSE_MIN_UNITS = 100000000;
 
-static void prof_mark(roo_engine* e, int kind, cudaStream_t st) {
+static void prof_mark(roo_engine* e, int kind, cudaStream_t st, int pass = -1) {
     if (!e->profiling) return;
     if (e->prof_used == e->prof_events.size()) {
         cudaEvent_t ev;
         if (cudaEventCreate(&ev) != cudaSuccess) return;
         e->prof_events.push_back(ev);
         e->prof_kinds.push_back(kind);
+        e->prof_pass.push_back(pass);
     }
     e->prof_kinds[e->prof_used] = kind;
+    e->prof_pass[e->prof_used] = pass;
     cudaEventRecord(e->prof_events[e->prof_used++], st);
 }
 
@@ -112,7 +116,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         prof_mark(e, ROO_PROF_CENSUS, st);
     }
     if (p.lrcheck) {
-        rc = launch_census_wta(e->dispR, e->cen[1], e->cen[0], w, h, batch, p.max_disp, e->words, p.popc_mode, p.subpix, +1, st);
+        rc = launch_census_wta(e->dispR, e->cen[1], e->cen[0], w, h, batch, p.max_disp, e->words, p.popc_mode, p.subpix, +1, e->ieee, st);
         if (rc) return rc;
         prof_mark(e, ROO_PROF_WTA, st);
     }
@@ -127,7 +131,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
     const SgmPlan& plan = use_fused ? e->plan : e->plan_sep;
     const int ndir = plan.n;
     if (ndir == 0) {
-        rc = launch_census_wta(disp, e->cen[0], e->cen[1], w, h, batch, p.max_disp, e->words, p.popc_mode, p.subpix, -1, st);
+        rc = launch_census_wta(disp, e->cen[0], e->cen[1], w, h, batch, p.max_disp, e->words, p.popc_mode, p.subpix, -1, e->ieee, st);
         if (rc) return rc;
         prof_mark(e, ROO_PROF_WTA, st);
     } else {
@@ -140,13 +144,13 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         a.H = e->H; a.h_pair = npx * e->DP; a.C = e->c8; a.c_pair = npx * e->DP;
         a.img = e->imgf; a.img_pair = npx; a.cost_scale = 1.0f / (float)(e->words * 64);
         a.w = w; a.h = h; a.DP = e->DP; a.maxDisp = p.max_disp; a.batch = batch;
-        a.P1 = p.P1; a.P2 = p.P2; a.cost_kind = COST_U8; a.subpix = p.subpix; a.disp = disp; a.disp_pair = npx;
+        a.P1 = p.P1; a.P2 = p.P2; a.cost_kind = COST_U8; a.ieee = e->ieee; a.subpix = p.subpix; a.disp = disp; a.disp_pair = npx;
         for (int i = 0; i < ndir; ++i) {
             a.first = i == 0;
             a.epi = i + 1 < ndir ? EPI_NONE : (p.keep_volume ? EPI_WTA_WRITE : EPI_WTA_ONLY);
             rc = launch_pass(a, plan.pass[i], e->edge, e->flags, st);
             if (rc) return rc;
-            prof_mark(e, plan.pass[i].fused ? ROO_PROF_VGROUP : ROO_PROF_SWEEP, st);
+            prof_mark(e, plan.pass[i].fused ? ROO_PROF_VGROUP : ROO_PROF_SWEEP, st, i);
         }
     }
     // MedianFilterRejectNegativeNxN(disp[di], disp[di], maxbad) x iters on every disparity image (main.cpp:438-444),
@@ -196,6 +200,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     if (p.w <= 0 || p.h <= 0 || p.max_disp <= 0 || p.max_batch <= 0 || p.window < 0 || p.window > 2)
         return ROO_ERR_INVALID_ARGUMENT;
     if (p.max_disp > 256) return ROO_ERR_UNSUPPORTED;
+    if (p.fp_mode < ROO_FP_DEFAULT || p.fp_mode > ROO_FP_IEEE) return ROO_ERR_INVALID_ARGUMENT;
     if (p.median_size != 0 && p.median_size != 5 && p.median_size != 7 && p.median_size != 9) return ROO_ERR_UNSUPPORTED;
     if (p.median_size != 0 && p.median_iters < 0) return ROO_ERR_INVALID_ARGUMENT;
     int ndev = 0;
@@ -204,6 +209,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     if (!e) return ROO_ERR_OUT_OF_MEMORY;
     e->p = p;
     cudaGetDevice(&e->device);
+    e->ieee = p.fp_mode == ROO_FP_DEFAULT ? (g_ieee_div.load() != 0) : (p.fp_mode == ROO_FP_IEEE);
     e->DP = disp_padded(p.max_disp);
     e->words = p.window == ROO_WIN_9x7 ? 1 : (p.window == ROO_WIN_11x11 ? 2 : 4);
     e->npx = (size_t)p.w * p.h;
@@ -407,6 +413,8 @@ extern "C" int roo_engine_get_profile(roo_engine_t* e, double* ms_by_kind, long 
         if (cudaEventElapsedTime(&ms, e->prof_events[i - 1], e->prof_events[i]) == cudaSuccess) {
             e->prof_ms[kind] += ms;
             e->prof_n[kind] += 1;
+            const int pass = e->prof_pass[i];
+            if (pass >= 0 && pass < 8) { e->prof_ms[ROO_PROF_PASS0 + pass] += ms; e->prof_n[ROO_PROF_PASS0 + pass] += 1; }
         }
     }
     e->prof_used = 0;
@@ -512,6 +520,13 @@ extern "C" const char* roo_b200_version(void) { return "kangaroo_b200 0.1 (sm_10
 extern "C" unsigned long long roo_launch_count(void) { return g_launches.load(); }
 
 extern "C" void roo_set_ieee_division(int on) { g_ieee_div.store(on ? 1 : 0); }
+
+extern "C" int roo_set_tuning(int knob, int value) {
+    switch (knob) {
+        case ROO_TUNE_HSWEEP: g_use_hsweep.store(value ? 1 : 0); return ROO_OK;
+        default: return ROO_ERR_INVALID_ARGUMENT;
+    }
+}
 
 extern "C" const char* roo_status_string(int status) {
     switch (status) {

@@ -10,7 +10,7 @@ int launch_census(char* out, size_t out_pitch, size_t out_batch, const char* in,
 int launch_cost_u8(unsigned char* c8, const void* cl, const void* cr, int w, int h, int batch, int DP, int maxDisp,
                    int words, int popc_mode, cudaStream_t st);
 int launch_census_wta(float* disp, const void* cself, const void* cother, int w, int h, int batch, int maxDisp,
-                      int words, int popc_mode, int subpix, int sdi, cudaStream_t st);
+                      int words, int popc_mode, int subpix, int sdi, int ieee, cudaStream_t st);
 
 // ---- sgm.cu ----
 enum EpiKind { EPI_NONE = 0, EPI_WTA_WRITE = 1, EPI_WTA_ONLY = 2 };
@@ -34,8 +34,13 @@ struct SweepArgs {
     int subpix;          // epilogue: 0 CostVolMinimum<float,float>, 1 CostVolMinimumSubpix(sd=-1)
     float* disp;         // epilogue output [pair][y][x]
     size_t disp_pair;    // elements
+    int ieee;            // 0: the reference's fast-math divisions (bit-identical to its kernels), 1: IEEE (== CPU oracle)
 };
 int launch_sweep(const SweepArgs& a, cudaStream_t st);
+// sgm_hsweep.cu: the horizontal paths (a.dy == 0), bulk-copy prefetch
+int launch_hsweep(const SweepArgs& a, cudaStream_t st);
+// development knob (roo_set_tuning): 0 = horizontal paths through the generic sweep kernel
+extern std::atomic<int> g_use_hsweep;
 int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pair, int img_type, int w, int h,
                         int batch, float scale, cudaStream_t st);
 inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : 256)); }
@@ -49,6 +54,7 @@ struct VGroupArgs {
     int w, h, maxDisp, batch;
     float P1, P2;
     int fwd;            // 1: (0,+1),(+1,+1),(-1,+1) ; 0: (0,-1),(-1,-1),(+1,-1)
+    int ieee;           // fp mode, as SweepArgs::ieee
     float* edge_hp;     // [pair][band][h][3][DP]  states handed from band b to band b+1
     float* edge_sc;     // [pair][band][h][8]
     int* progress;      // [pair][band] rows published

@@ -145,7 +145,7 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
 
 template <int DPL, int COST, int EPI>
 static void sweep_launch3(const SweepArgs& a, int n_scan, dim3 grid, cudaStream_t st) {
-    const bool ieee = g_ieee_div.load() != 0;
+    const bool ieee = a.ieee != 0;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
     const size_t smem = (size_t)SWEEP_WARPS * sweep_pfs(DPL, CE) * sweep_stage_bytes<DPL, COST>();
 #define ROO_SWEEP(F, I)                                                                                  \
@@ -172,7 +172,10 @@ static void sweep_launch_cost(const SweepArgs& a, int n_scan, dim3 grid, cudaStr
     else sweep_launch_epi<DPL, COST_U8>(a, n_scan, grid, st);
 }
 
+std::atomic<int> g_use_hsweep{1};
+
 int launch_sweep(const SweepArgs& a, cudaStream_t st) {
+    if (a.dy == 0 && g_use_hsweep.load(std::memory_order_relaxed)) return launch_hsweep(a, st);
     const int n_scan = a.dx == 0 ? a.w : (a.dy == 0 ? a.h : a.w + a.h - 1);
     dim3 grid(cdiv(n_scan, SWEEP_WARPS), a.batch);
     switch (a.DP) {
@@ -369,6 +372,7 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
     a.H = Hi; a.h_pair = n; a.C = Ci; a.c_pair = n;
     a.img = imgf; a.img_pair = 0; a.cost_scale = 1.0f;
     a.w = w; a.h = h; a.DP = DP; a.maxDisp = maxDisp; a.batch = 1;
+    a.ieee = ieee;
     a.P1 = P1; a.P2 = P2; a.cost_kind = COST_F32; a.epi = EPI_NONE; a.subpix = 0; a.disp = nullptr; a.disp_pair = 0;
     for (int i = 0; i < plan.n && rc == 0; ++i) {
         a.first = i == 0;

@@ -145,7 +145,11 @@ __host__ __device__ constexpr int vg_r(int DPL) { return VG_R; }   // max rows p
 #ifndef VG_S_DEPTH
 #define VG_S_DEPTH 4
 #endif
-constexpr int VG_S = VG_S_DEPTH;   // depth (rows) of the in-band state ring in shared memory
+#ifndef VG_S_DEPTH8
+#define VG_S_DEPTH8 VG_S_DEPTH
+#endif
+// depth (rows) of the in-band state ring in shared memory
+__host__ __device__ constexpr int vg_s(int DPL) { return DPL >= 8 ? VG_S_DEPTH8 : VG_S_DEPTH; }
 
 // One pixel of the three paths.  V/D/A = vertical / diagonal / anti-diagonal.  hpV, hpD, hpA: previous pixel's
 // state rows on entry, this pixel's on exit.  Handles path starts when EDGE.
@@ -195,7 +199,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int CE = RawCost<DPL, COST>::ELEM;
     constexpr int NC = NCW * NWW;                     // skewed columns per band
     constexpr int PFS = vg_pfs(DPL, CE);
-    constexpr int R = vg_r(DPL), RING = 2 * R, S = VG_S;
+    constexpr int R = vg_r(DPL), RING = 2 * R, S = vg_s(DPL);
     constexpr int STAGE_B = DP * 4 + DP * CE;        // one prefetched pixel: aggregate row, cost row
     extern __shared__ __align__(16) float smem[];
     // state rows of one warp and one image row, for its two lowest columns c0 and c1 (all that the warp below
@@ -584,11 +588,11 @@ static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     constexpr int DP = 32 * DPL;
     constexpr int NWW = vg_nww(DPL), NCW = vg_ncw(DPL);
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    constexpr size_t smem = (size_t)(VG_S * NWW * 3 * DP + VG_S * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
+    constexpr size_t smem = (size_t)(vg_s(DPL) * NWW * 3 * DP + vg_s(DPL) * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
                             sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * NCW * vg_pfs(DPL, CE) * (DP * 4 + DP * CE);
     static_assert(smem <= 227 * 1024, "vertical-group kernel: shared memory budget of one sm_100 CTA exceeded");
     dim3 grid(a.n_bands * a.batch), block((NWW + 1) * 32);
-    const bool ieee = g_ieee_div.load() != 0;
+    const bool ieee = a.ieee != 0;
 #define ROO_VG(F, I)                                                                                          \
     do {                                                                                                      \
         auto kern = a.fwd ? sgm_vgroup_kernel<DPL, COST, F, I, NWW, NCW, true>                                \
@@ -611,7 +615,7 @@ int launch_vgroup(const SweepArgs& s, int fwd, float* edge, int* progress, cudaS
     VGroupArgs a{};
     a.H = s.H; a.h_pair = s.h_pair; a.C = s.C; a.c_pair = s.c_pair; a.img = s.img; a.img_pair = s.img_pair;
     a.cost_scale = s.cost_scale; a.w = s.w; a.h = s.h; a.maxDisp = s.maxDisp; a.batch = s.batch; a.P1 = s.P1; a.P2 = s.P2;
-    a.fwd = fwd;
+    a.fwd = fwd; a.ieee = s.ieee;
     a.n_bands = vgroup_bands(s.w, s.h, s.DP);
     const size_t hp_floats = (size_t)a.n_bands * s.h * 3 * s.DP;
     a.edge_hp = edge;

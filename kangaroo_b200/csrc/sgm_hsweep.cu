@@ -1,0 +1,223 @@
+// Horizontal aggregation sweeps (paths (+1,0) and (-1,0); src/cu_semi_global_matching.cu:79-84 of the
+// reference launches them as ONE block of h threads with stride-`pitch` accesses).
+//
+// On the internal layout H[pair][y][x][DP] a horizontal scanline is ONE contiguous run of memory
+// (w * DP * 4 bytes), so this kernel does not move its rows with per-lane loads at all:
+//  * one warp per scanline; lane l owns disparities [l*DPL, (l+1)*DPL), previous pixel's row in registers,
+//    d-1 / d+1 neighbours by two shuffles, min over d by one redux.sync (as in sgm.cu);
+//  * the aggregate and cost rows of CH consecutive pixels (2.5 KB) are ONE chunk, copied global -> shared by the
+//    bulk-copy engine (cp.async.bulk, SASS UBLKCP) that ONE elected lane issues, completion counted in bytes on an
+//    mbarrier (expect_tx / try_wait.parity).  NST chunks per warp are in flight; no lane spends an issue slot on a
+//    load, an address or a cp.async group -- the sweep was bound by instruction issue, not by HBM, once the
+//    winner-takes-all epilogue rides on it;
+//  * intensities for the adaptive P2: lane k keeps the pixel 32*blk + k of the scanline (one coalesced load per 32
+//    pixels, the next block already in flight); a step takes its value with one shuffle;
+//  * direction is a template parameter: every address inside a chunk is an immediate offset.
+// Numerics: sgm_step() -- identical to the generic sweep, the reference and the oracle.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "sgm_step.cuh"
+
+#include <type_traits>
+
+namespace roo_b200 {
+
+constexpr int HS_WARPS = 4;   // scanlines per CTA
+constexpr int HS_NST = 4;     // chunks in flight per warp
+
+// pixels per chunk: ~2.5 KB of aggregate + cost per bulk copy pair
+template <int DPL, int COST> __host__ __device__ constexpr int hs_chunk() {
+    constexpr int px_bytes = 32 * DPL * (4 + RawCost<DPL, COST>::ELEM);
+    return px_bytes >= 2560 ? 1 : (px_bytes >= 1280 ? 2 : (px_bytes >= 640 ? 4 : (px_bytes >= 320 ? 8 : 16)));
+}
+
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned sdst, const void* gsrc, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "HS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra HS_DONE;\n\t"
+        "bra HS_WAIT;\n"
+        "HS_DONE:\n\t}"
+        ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// DX = +1: path (+1,0), travel index t == x;  DX = -1: path (-1,0), t == w-1-x.
+template <int DPL, int COST, int EPI, bool FIRST, bool IEEE, int DX>
+__global__ void __launch_bounds__(HS_WARPS * 32)
+sgm_hsweep_kernel(const SweepArgs a) {
+    constexpr int DP = 32 * DPL;
+    constexpr int CE = RawCost<DPL, COST>::ELEM;
+    constexpr int CH = hs_chunk<DPL, COST>();
+    constexpr int NST = HS_NST;
+    constexpr unsigned HROW = DP * 4, CROW = DP * CE;            // bytes of one pixel's aggregate / cost row
+    constexpr unsigned STAGE_B = CH * (HROW + CROW);             // [CH aggregate rows][CH cost rows], ascending x
+    extern __shared__ __align__(128) unsigned char hs_smem[];    // [HS_WARPS][NST][STAGE_B], then the mbarriers
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+    const int y = blockIdx.x * HS_WARPS + warp;
+    const int pair = blockIdx.y;
+    const int w = a.w, M = a.maxDisp, subpix = a.subpix;
+    const float P1 = a.P1, P2 = a.P2, cscale = a.cost_scale;
+
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(hs_smem) + warp * NST * STAGE_B;
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(hs_smem) + HS_WARPS * NST * STAGE_B + warp * NST * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(mbar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy
+    }
+    __syncwarp();
+    if (y >= a.h) return;
+
+    // scanline bases (element (0, y, lane's first disparity))
+    const size_t row0 = (size_t)y * w;
+    float* const Hrow = a.H + (size_t)pair * a.h_pair + row0 * DP;
+    const char* const Crow = (const char*)a.C + ((size_t)pair * a.c_pair + row0 * DP) * CE;
+    const float* const Irow = a.img + (size_t)pair * a.img_pair + row0;
+    float* const Drow = (EPI != EPI_NONE) ? a.disp + (size_t)pair * a.disp_pair + row0 : nullptr;
+
+    const int nchunks = (w + CH - 1) / CH;
+    // chunk k covers travel indices [k*CH, k*CH + n): x ascending from xlo = (DX > 0 ? k*CH : w - k*CH - n);
+    // its rows go to the stage slots [s0, s0 + n) with s0 = (DX > 0 ? 0 : CH - n), so that travel index i always
+    // sits in slot (DX > 0 ? i : CH-1-i)
+    auto issue = [&](int k) {   // lane 0 only
+        const int t0 = k * CH, n = min(CH, w - t0);
+        const int xlo = DX > 0 ? t0 : w - t0 - n, s0 = DX > 0 ? 0 : CH - n;
+        const unsigned st = sbase + (unsigned)(k % NST) * STAGE_B, mb = mbar0 + 8 * (unsigned)(k % NST);
+        mbar_expect_tx(mb, (unsigned)n * ((FIRST ? 0u : HROW) + CROW));
+        if (!FIRST) bulk_g2s(st + s0 * HROW, Hrow + (size_t)xlo * DP, (unsigned)n * HROW, mb);
+        bulk_g2s(st + CH * HROW + s0 * CROW, Crow + (size_t)xlo * DP * CE, (unsigned)n * CROW, mb);
+    };
+    if (lane == 0)
+        for (int k = 0; k < NST && k < nchunks; ++k) issue(k);
+
+    // intensities in travel order: lane k holds pixel t = 32*blk + k
+    auto gather = [&](int blk) {
+        const int t = 32 * blk + lane;
+        return t < w ? __ldg(Irow + (DX > 0 ? t : w - 1 - t)) : 0.0f;
+    };
+    float icur = gather(0), inxt = gather(1);
+
+    float hp[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) hp[j] = ROO_INF;   // path start: no previous pixel
+    float lastBest = 0.0f, last_c = 0.0f;
+    const int d0 = lane * DPL;
+    const int xf = (M == DP) ? DP - 1 : 0x3fffffff;   // every lane in range iff x >= xf
+
+    auto chunk = [&](auto masked_tag, auto full_tag, int k, unsigned st) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int t0 = k * CH, n = FULL ? CH : min(CH, w - t0);
+        const int x0 = DX > 0 ? t0 : w - 1 - t0;    // x of travel index t0
+        float* const hst = Hrow + (size_t)x0 * DP + d0;
+        const bool first = k == 0;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (FULL || i < n) {
+                const unsigned slot = DX > 0 ? i : CH - 1 - i;
+                float hin[DPL], hnew[DPL], craw[DPL], best;
+                if (!FIRST) lds_vec<DPL>(hin, st + slot * HROW + lane * DPL * 4);
+                RawCost<DPL, COST> rc;
+                rc.lds(st + CH * HROW + slot * CROW + lane * DPL * CE);
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) craw[j] = rc.raw(j);
+                const float pix = __shfl_sync(0xffffffffu, icur, (t0 + i) & 31);
+                // start pixel: `volH += volC`, lastBestCr = 0 (cu_semi_global_matching.cu:31-35) == a step with P2 = 0
+                const float p2 = (i == 0 && first) ? 0.0f : P2;
+                const float denom = 1.0f + fabsf(last_c - pix);
+                const int x = x0 + DX * i;
+                const int lim = MASKED ? min(M, x + 1) - d0 : 0;
+                sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, craw, cscale, hin, lim, lane, hnew, hp, best);
+                lastBest = (i == 0 && first) ? 0.0f : best;
+                last_c = pix;
+                if (EPI != EPI_WTA_ONLY) store_f<DPL>(hst + DX * i * DP, hnew);
+                if (EPI != EPI_NONE) {
+                    const float out = wta_epilogue<DPL, IEEE>(hp, lane, x, w, M, subpix);
+                    if (lane == 0) Drow[x] = out;
+                }
+            }
+        }
+    };
+
+    const int tmask_lo = DX > 0 ? xf : 0x3fffffff;              // DX > 0: unmasked from t >= xf on
+    const int tmask_hi = DX > 0 ? 0x3fffffff : w - 1 - xf;      // DX < 0: unmasked while t <= w-1-xf (x >= xf)
+#pragma unroll 1
+    for (int k = 0; k < nchunks; ++k) {
+        const unsigned s = (unsigned)(k % NST);
+        const unsigned st = sbase + s * STAGE_B;
+        if (((k * CH) & 31) == 0 && k != 0) { icur = inxt; inxt = gather((k * CH >> 5) + 1); }
+        mbar_wait(mbar0 + 8 * s, (unsigned)(k / NST) & 1u);
+        const int t0 = k * CH;
+        const bool unmasked = t0 >= tmask_lo && t0 + CH - 1 <= tmask_hi;
+        const bool full = t0 + CH <= w;
+        if (full) {
+            if (unmasked) chunk(std::false_type{}, std::true_type{}, k, st);
+            else chunk(std::true_type{}, std::true_type{}, k, st);
+        } else {
+            chunk(std::true_type{}, std::false_type{}, k, st);
+        }
+        __syncwarp();   // every lane has read the stage: it may be refilled
+        if (lane == 0 && k + NST < nchunks) issue(k + NST);
+    }
+}
+
+template <int DPL, int COST, int EPI, int DX>
+static int hsweep_launch4(const SweepArgs& a, cudaStream_t st) {
+    constexpr int CH = hs_chunk<DPL, COST>();
+    constexpr size_t smem = (size_t)HS_WARPS * HS_NST * (CH * 32 * DPL * (4 + RawCost<DPL, COST>::ELEM)) + HS_WARPS * HS_NST * 8;
+    static_assert(32 % CH == 0 || CH % 32 == 0, "chunks must not straddle a 32-pixel intensity block");
+    dim3 grid(cdiv(a.h, HS_WARPS), a.batch);
+    const bool ieee = a.ieee != 0;
+#define ROO_HS(F, I)                                                                                          \
+    do {                                                                                                      \
+        auto kern = sgm_hsweep_kernel<DPL, COST, EPI, F, I, DX>;                                              \
+        if (smem > 48 * 1024) {                                                                               \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                              \
+        }                                                                                                     \
+        kern<<<grid, HS_WARPS * 32, smem, st>>>(a);                                                           \
+    } while (0)
+    if (a.first) { if (ieee) ROO_HS(true, true); else ROO_HS(true, false); }
+    else { if (ieee) ROO_HS(false, true); else ROO_HS(false, false); }
+#undef ROO_HS
+    count_launch();
+    return launch_status();
+}
+
+template <int DPL, int COST>
+static int hsweep_launch2(const SweepArgs& a, cudaStream_t st) {
+    const bool fwd = a.dx > 0;
+    switch (a.epi) {
+        case EPI_NONE: return fwd ? hsweep_launch4<DPL, COST, EPI_NONE, 1>(a, st) : hsweep_launch4<DPL, COST, EPI_NONE, -1>(a, st);
+        case EPI_WTA_WRITE: return fwd ? hsweep_launch4<DPL, COST, EPI_WTA_WRITE, 1>(a, st) : hsweep_launch4<DPL, COST, EPI_WTA_WRITE, -1>(a, st);
+        default: return fwd ? hsweep_launch4<DPL, COST, EPI_WTA_ONLY, 1>(a, st) : hsweep_launch4<DPL, COST, EPI_WTA_ONLY, -1>(a, st);
+    }
+}
+
+// a.dy == 0, a.dx == +-1
+int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
+    const bool f32 = a.cost_kind == COST_F32;
+    switch (a.DP) {
+        case 32: return f32 ? hsweep_launch2<1, COST_F32>(a, st) : hsweep_launch2<1, COST_U8>(a, st);
+        case 64: return f32 ? hsweep_launch2<2, COST_F32>(a, st) : hsweep_launch2<2, COST_U8>(a, st);
+        case 128: return f32 ? hsweep_launch2<4, COST_F32>(a, st) : hsweep_launch2<4, COST_U8>(a, st);
+        case 256: return f32 ? hsweep_launch2<8, COST_F32>(a, st) : hsweep_launch2<8, COST_U8>(a, st);
+        default: return ROO_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace roo_b200

@@ -286,6 +286,11 @@ def set_ieee_division(on: bool) -> None:
     lib().roo_set_ieee_division(int(on))
 
 
+def set_tuning(knob: int, value: int) -> None:
+    """Development knobs for A/B measurements (roo_set_tuning); results never depend on them."""
+    check(lib().roo_set_tuning(int(knob), int(value)), "roo_set_tuning")
+
+
 # ---------------------------------------------------------------------------------------------------
 # fused engine
 # ---------------------------------------------------------------------------------------------------
@@ -302,11 +307,11 @@ class StereoEngine:
                  P1: float = 0.01, P2: float = 0.02, img_scale: float = 1.0 / 255.0, dohoriz=True, dovert=True,
                  doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff: float = 1.0,
                  max_batch: int = 1, keep_volume: bool = False, fuse_vertical: bool | None = None, median_size: int = 0,
-                 median_maxbad: int = 100, median_iters: int = 1):
+                 median_maxbad: int = 100, median_iters: int = 1, fp_mode: int = capi.FP_DEFAULT):
         self.params = capi.PipelineParams(w, h, max_disp, window, popc_mode, P1, P2, np.float32(img_scale),
                                           int(dohoriz), int(dovert), int(doreverse), int(dodiag), int(subpix),
                                           int(lrcheck), lr_maxdiff, max_batch, int(keep_volume),
-                                          _fuse_flag(fuse_vertical), median_size, median_maxbad, median_iters)
+                                          _fuse_flag(fuse_vertical), median_size, median_maxbad, median_iters, fp_mode)
         self.w, self.h, self.max_disp = w, h, max_disp
         self._h = C.c_void_p()
         check(lib().roo_engine_create(C.byref(self._h), C.byref(self.params)), "roo_engine_create")
@@ -396,7 +401,7 @@ class MultiGpuStereoEngine:
         defaults = dict(window=WIN_9x7, popc_mode=POPC32_COMPAT, P1=0.01, P2=0.02, img_scale=1.0 / 255.0, dohoriz=True,
                         dovert=True, doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff=1.0,
                         max_batch=1, keep_volume=False, fuse_vertical=None, median_size=0, median_maxbad=100,
-                        median_iters=1)
+                        median_iters=1, fp_mode=capi.FP_DEFAULT)
         defaults.update(kw)
         d = defaults
         self.params = capi.PipelineParams(w, h, max_disp, d["window"], d["popc_mode"], d["P1"], d["P2"],
@@ -404,7 +409,7 @@ class MultiGpuStereoEngine:
                                           int(d["doreverse"]), int(d["dodiag"]), int(d["subpix"]), int(d["lrcheck"]),
                                           d["lr_maxdiff"], d["max_batch"], int(d["keep_volume"]),
                                           _fuse_flag(d["fuse_vertical"]), d["median_size"], d["median_maxbad"],
-                                          d["median_iters"])
+                                          d["median_iters"], d["fp_mode"])
         del proto
         self.w, self.h = w, h
         self._h = C.c_void_p()

@@ -1,9 +1,22 @@
 #!/bin/bash
-# usage: scripts/build_variant.sh NAME "-DVG_S_DEPTH=8 ..."  -> scripts/variants/NAME.so (tuning experiments only)
+# usage: scripts/build_variant.sh NAME "-DVG_S_DEPTH=8 ..." [source.cu ...]  -> scripts/variants/NAME.so
+# Tuning experiments only: recompiles the listed sources (default sgm_fused.cu) with the extra flags and links them
+# with the objects of the regular build.
 set -e
 cd "$(dirname "$0")/.."
-make -C kangaroo_b200/csrc >/dev/null
+make -C kangaroo_b200/csrc -j8 >/dev/null
 O=kangaroo_b200/lib/obj
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O2 $2 -c kangaroo_b200/csrc/sgm_fused.cu -o scripts/variants/$1.o
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o scripts/variants/$1.so $O/census.o $O/sgm.o scripts/variants/$1.o $O/wta.o $O/frontback.o $O/median.o $O/engine.o -lcudart
-rm scripts/variants/$1.o
+NAME=$1; FLAGS=$2; shift 2 || true
+SRCS=${@:-sgm_fused.cu}
+mkdir -p scripts/variants/obj_$NAME
+OBJS=""
+for s in census sgm sgm_hsweep sgm_fused wta frontback median engine; do
+  if [[ " $SRCS " == *" $s.cu "* ]]; then
+    nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O2 $FLAGS -c kangaroo_b200/csrc/$s.cu -o scripts/variants/obj_$NAME/$s.o
+    OBJS="$OBJS scripts/variants/obj_$NAME/$s.o"
+  else
+    OBJS="$OBJS $O/$s.o"
+  fi
+done
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o scripts/variants/$NAME.so $OBJS -lcudart
+rm -rf scripts/variants/obj_$NAME

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, call 3: bulk-copy horizontal sweep -- parity, then A/B against the generic sweep on c2 and c4
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "bulk_copy or sgm or engine or fused" > gpurun_out/r2_call3_tests.log 2>&1
+tail -15 gpurun_out/r2_call3_tests.log
+for wl in c2_1280x720x128_8path_wta c4_1920x1080x256_8path_subpix_lr c3_kitti_1242x375x128_4path; do
+for flag in "" "--generic-hsweep"; do
+  echo -n "$wl $flag: "
+  timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --no-e2e $flag 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['ms_per_step'],2), {k:round(v,2) for k,v in d['kernel_ms_per_step'].items() if v>0})"
+done; done 2>&1 | tee gpurun_out/r2_call3_ab.txt

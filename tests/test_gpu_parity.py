@@ -420,6 +420,26 @@ def test_fused_vertical_group_equals_separate_sweeps_and_oracle(shape):
     assert np.array_equal(Hf2, Hs2) and np.array_equal(df2, ds2)
 
 
+@pytest.mark.parametrize("shape", [(64, 9, 32), (257, 33, 64), (131, 20, 128), (1000, 12, 128), (300, 7, 256), (3, 5, 16), (37, 4, 200)])
+@pytest.mark.parametrize("opts", [dict(), dict(dovert=False), dict(dodiag=True, subpix=True)])
+def test_bulk_copy_horizontal_sweep_equals_generic_sweep(shape, opts):
+    """sgm_hsweep.cu (cp.async.bulk + mbarrier prefetch, direction as a template parameter) against the generic
+    sweep kernel on the same inputs: aggregate and disparities bit-identical, in both fp modes, for widths that are
+    not multiples of the chunk or of the 32-pixel intensity block, and with the horizontal pass first (dovert=False)."""
+    w, h, D = shape
+    L, R, _ = stereo_pair(w, h, D, config=71)
+    for ieee in (False, True):
+        roo.set_ieee_division(ieee)
+        try:
+            roo.set_tuning(roo.capi.TUNE_HSWEEP, 0)
+            d0, H0, _ = run_engine(L, R, D, batch=2, **opts)
+        finally:
+            roo.set_tuning(roo.capi.TUNE_HSWEEP, 1)
+        d1, H1, _ = run_engine(L, R, D, batch=2, **opts)
+        assert np.array_equal(H0, H1)
+        assert np.array_equal(np.isnan(d0), np.isnan(d1)) and np.array_equal(d0[~np.isnan(d0)], d1[~np.isnan(d1)])
+
+
 def test_engine_batch_slots_are_independent_and_groups_wrap():
     """Different stereo pairs in every batch slot, more pairs than max_batch (several groups per call)."""
     w, h, D = 161, 57, 64

@@ -166,6 +166,8 @@ def main():
                     help="census descriptor: 9x7 -> u64 (north_star headline), 16x16 = 8w x 16h -> ulong4 (what the apps run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--materialised-cost", action="store_true",
+                    help="A/B: every pass reads the u8 cost volume (no in-sweep cost from census words)")
     ap.add_argument("--generic-hsweep", action="store_true",
                     help="A/B: run the horizontal paths through the generic sweep kernel instead of sgm_hsweep.cu")
     args = ap.parse_args()
@@ -188,6 +190,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: kangaroo_b200 has no CPU path")
     if args.generic_hsweep:
         roo.set_tuning(capi.TUNE_HSWEEP, 0)
+    if args.materialised_cost:
+        roo.set_tuning(capi.TUNE_INSWEEP_COST, 0)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -64,7 +64,10 @@ unsigned long long roo_launch_count(void);
 void roo_set_ieee_division(int on);
 /* Development knobs for A/B measurements (never needed for correct results).  ROO_TUNE_HSWEEP: 1 (default) runs the
  * horizontal aggregation paths through the bulk-copy kernel (sgm_hsweep.cu), 0 through the generic sweep kernel. */
-enum roo_tuning_knob { ROO_TUNE_HSWEEP = 0 };
+enum roo_tuning_knob { ROO_TUNE_HSWEEP = 0,
+                       /* 1 (default): passes that can recompute the matching cost from the census words do so and do
+                        * not read the u8 cost volume; 0: always through the materialised volume */
+                       ROO_TUNE_INSWEEP_COST = 1 };
 int roo_set_tuning(int knob, int value);
 
 /* ---- granular operators: one per reference launcher -------------------------------------- */

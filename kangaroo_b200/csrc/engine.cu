@@ -14,6 +14,7 @@
 namespace roo_b200 {
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_ieee_div{0};
+std::atomic<int> g_insweep_cost{1};
 }  // namespace roo_b200
 
 using namespace roo_b200;
@@ -135,8 +136,19 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         if (rc) return rc;
         prof_mark(e, ROO_PROF_WTA, st);
     } else {
-        rc = launch_cost_u8(e->c8, e->cen[0], e->cen[1], w, h, batch, e->DP, p.max_disp, e->words, p.popc_mode, st);
-        if (rc) return rc;
+        // In-sweep matching cost (COST_CEN32): a pass that can recompute popc(L ^ R) from the census words does not
+        // read the u8 cost volume; when every pass of the plan can, the volume is never built (north_star (3)).
+        // Eligible: one-word descriptors under the reference's 32-bit popcount (9x7 window, hamming_distance.h:40-44).
+        const bool cen_ok = e->words == 1 && p.popc_mode == ROO_POPC32_COMPAT && g_insweep_cost.load(std::memory_order_relaxed);
+        auto pass_in_sweep = [&](const SgmPass& ps) {
+            return cen_ok && !ps.fused && ps.dy == 0 && g_use_hsweep.load(std::memory_order_relaxed);
+        };
+        bool need_c8 = false;
+        for (int i = 0; i < ndir; ++i) need_c8 |= !pass_in_sweep(plan.pass[i]);
+        if (need_c8) {
+            rc = launch_cost_u8(e->c8, e->cen[0], e->cen[1], w, h, batch, e->DP, p.max_disp, e->words, p.popc_mode, st);
+            if (rc) return rc;
+        }
         rc = launch_image_to_f32(e->imgf, left, (size_t)w, npx, ROO_IMG_U8, w, h, batch, p.img_scale, st);
         if (rc) return rc;
         prof_mark(e, ROO_PROF_COST, st);
@@ -144,9 +156,11 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         a.H = e->H; a.h_pair = npx * e->DP; a.C = e->c8; a.c_pair = npx * e->DP;
         a.img = e->imgf; a.img_pair = npx; a.cost_scale = 1.0f / (float)(e->words * 64);
         a.w = w; a.h = h; a.DP = e->DP; a.maxDisp = p.max_disp; a.batch = batch;
-        a.P1 = p.P1; a.P2 = p.P2; a.cost_kind = COST_U8; a.ieee = e->ieee; a.subpix = p.subpix; a.disp = disp; a.disp_pair = npx;
+        a.P1 = p.P1; a.P2 = p.P2; a.ieee = e->ieee; a.subpix = p.subpix;
+        a.cenL = e->cen[0]; a.cenR = e->cen[1]; a.cen_pair = npx; a.disp = disp; a.disp_pair = npx;
         for (int i = 0; i < ndir; ++i) {
             a.first = i == 0;
+            a.cost_kind = pass_in_sweep(plan.pass[i]) ? COST_CEN32 : COST_U8;
             a.epi = i + 1 < ndir ? EPI_NONE : (p.keep_volume ? EPI_WTA_WRITE : EPI_WTA_ONLY);
             rc = launch_pass(a, plan.pass[i], e->edge, e->flags, st);
             if (rc) return rc;
@@ -524,6 +538,7 @@ extern "C" void roo_set_ieee_division(int on) { g_ieee_div.store(on ? 1 : 0); }
 extern "C" int roo_set_tuning(int knob, int value) {
     switch (knob) {
         case ROO_TUNE_HSWEEP: g_use_hsweep.store(value ? 1 : 0); return ROO_OK;
+        case ROO_TUNE_INSWEEP_COST: g_insweep_cost.store(value ? 1 : 0); return ROO_OK;
         default: return ROO_ERR_INVALID_ARGUMENT;
     }
 }

@@ -35,12 +35,18 @@ struct SweepArgs {
     float* disp;         // epilogue output [pair][y][x]
     size_t disp_pair;    // elements
     int ieee;            // 0: the reference's fast-math divisions (bit-identical to its kernels), 1: IEEE (== CPU oracle)
+    // cost_kind == COST_CEN32: one-word census descriptors [pair][y][x] (u64, low half used) instead of C
+    const unsigned long long* cenL;
+    const unsigned long long* cenR;
+    size_t cen_pair;     // elements between pairs
 };
 int launch_sweep(const SweepArgs& a, cudaStream_t st);
 // sgm_hsweep.cu: the horizontal paths (a.dy == 0), bulk-copy prefetch
 int launch_hsweep(const SweepArgs& a, cudaStream_t st);
 // development knob (roo_set_tuning): 0 = horizontal paths through the generic sweep kernel
 extern std::atomic<int> g_use_hsweep;
+// development knob: 0 = always materialise the u8 cost volume (no in-sweep cost from census words)
+extern std::atomic<int> g_insweep_cost;
 int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pair, int img_type, int w, int h,
                         int batch, float scale, cudaStream_t st);
 inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : 256)); }

@@ -5,7 +5,7 @@
 // (w * DP * 4 bytes), so this kernel does not move its rows with per-lane loads at all:
 //  * one warp per scanline; lane l owns disparities [l*DPL, (l+1)*DPL), previous pixel's row in registers,
 //    d-1 / d+1 neighbours by two shuffles, min over d by one redux.sync (as in sgm.cu);
-//  * the aggregate and cost rows of CH consecutive pixels (2.5 KB) are ONE chunk, copied global -> shared by the
+//  * the aggregate and cost rows of CH consecutive pixels (5 KB) are ONE chunk, copied global -> shared by the
 //    bulk-copy engine (cp.async.bulk, SASS UBLKCP) that ONE elected lane issues, completion counted in bytes on an
 //    mbarrier (expect_tx / try_wait.parity).  NST chunks per warp are in flight; no lane spends an issue slot on a
 //    load, an address or a cp.async group -- the sweep was bound by instruction issue, not by HBM, once the
@@ -22,13 +22,25 @@
 
 namespace roo_b200 {
 
-constexpr int HS_WARPS = 4;   // scanlines per CTA
-constexpr int HS_NST = 4;     // chunks in flight per warp
+#ifndef HS_WARPS_N
+#define HS_WARPS_N 4
+#endif
+// measured on B200, 1280x720x128 x16 (right + left pass, ms): 2.5 KB x 4 chunks 4.49, 2.5 KB x 3 4.41, 1.25 KB x 4 4.83,
+// 1.25 KB x 8 4.94, 5 KB x 3 4.36, 5 KB x 2 4.28 -- the bulk-copy engine likes few large copies
+#ifndef HS_NST_N
+#define HS_NST_N 2
+#endif
+#ifndef HS_CHUNK_BYTES
+#define HS_CHUNK_BYTES 5120
+#endif
+constexpr int HS_WARPS = HS_WARPS_N;   // scanlines per CTA
+constexpr int HS_NST = HS_NST_N;       // chunks in flight per warp
 
-// pixels per chunk: ~2.5 KB of aggregate + cost per bulk copy pair
+// pixels per chunk: ~5 KB of aggregate + cost per bulk copy pair
 template <int DPL, int COST> __host__ __device__ constexpr int hs_chunk() {
     constexpr int px_bytes = 32 * DPL * (4 + RawCost<DPL, COST>::ELEM);
-    return px_bytes >= 2560 ? 1 : (px_bytes >= 1280 ? 2 : (px_bytes >= 640 ? 4 : (px_bytes >= 320 ? 8 : 16)));
+    constexpr int n = HS_CHUNK_BYTES / px_bytes;
+    return n >= 16 ? 16 : (n >= 8 ? 8 : (n >= 4 ? 4 : (n >= 2 ? 2 : 1)));
 }
 
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
@@ -63,6 +75,8 @@ sgm_hsweep_kernel(const SweepArgs a) {
     constexpr int NST = HS_NST;
     constexpr unsigned HROW = DP * 4, CROW = DP * CE;            // bytes of one pixel's aggregate / cost row
     constexpr unsigned STAGE_B = CH * (HROW + CROW);             // [CH aggregate rows][CH cost rows], ascending x
+    constexpr bool CEN = COST == COST_CEN32;                     // cost recomputed from census words, nothing staged for it
+    constexpr bool STAGED = !FIRST || CROW > 0;                  // anything to prefetch at all?
     extern __shared__ __align__(128) unsigned char hs_smem[];    // [HS_WARPS][NST][STAGE_B], then the mbarriers
 
     const int lane = threadIdx.x & 31;
@@ -99,10 +113,37 @@ sgm_hsweep_kernel(const SweepArgs a) {
         const unsigned st = sbase + (unsigned)(k % NST) * STAGE_B, mb = mbar0 + 8 * (unsigned)(k % NST);
         mbar_expect_tx(mb, (unsigned)n * ((FIRST ? 0u : HROW) + CROW));
         if (!FIRST) bulk_g2s(st + s0 * HROW, Hrow + (size_t)xlo * DP, (unsigned)n * HROW, mb);
-        bulk_g2s(st + CH * HROW + s0 * CROW, Crow + (size_t)xlo * DP * CE, (unsigned)n * CROW, mb);
+        if (CROW > 0) bulk_g2s(st + CH * HROW + s0 * CROW, Crow + (size_t)xlo * DP * CE, (unsigned)n * CROW, mb);
     };
-    if (lane == 0)
+    if (STAGED && lane == 0)
         for (int k = 0; k < NST && k < nchunks; ++k) issue(k);
+
+    // ---- COST_CEN32: sliding window of right-image census words in registers -------------------------------
+    // rw[j] = low word of R(x - d0 - j, y) for this lane's disparities.  A step to the next pixel shifts the window by
+    // one disparity: one shuffle between neighbouring lanes plus ONE new word per warp (d = 0 entering at lane 0 going
+    // right, d = DP-1 entering at lane 31 going left).  New words and the left image's words come out of per-32-pixel
+    // register blocks like the intensities.  Words of pixels left of the image are 0: their disparities are masked.
+    const unsigned long long* const Lc = CEN ? a.cenL + (size_t)pair * a.cen_pair + row0 : nullptr;
+    const unsigned long long* const Rc = CEN ? a.cenR + (size_t)pair * a.cen_pair + row0 : nullptr;
+    auto cen_word = [&](const unsigned long long* row, int x) -> unsigned {
+        return (x >= 0 && x < w) ? __ldg(reinterpret_cast<const unsigned*>(row + x)) : 0u;   // little endian: low half first
+    };
+    // travel index tau <-> x: DX > 0: x = tau;  DX < 0: x = w-1-tau.  The word entering the window at step t is
+    // R(x) going right (tau = t) and R(x - (DP-1)) going left (tau = t + DP-1).
+    constexpr int RSHIFT = DX > 0 ? 0 : DP - 1;
+    auto gatherL = [&](int blk) { const int t = 32 * blk + lane; return cen_word(Lc, DX > 0 ? t : w - 1 - t); };
+    auto gatherR = [&](int blk) { const int t = 32 * blk + lane; return cen_word(Rc, DX > 0 ? t : w - 1 - t); };
+    unsigned lcur = 0, lnxt = 0, rcur = 0, rnxt = 0, rw[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) rw[j] = 0;
+    if (CEN) {
+        lcur = gatherL(0); lnxt = gatherL(1);
+        rcur = gatherR(RSHIFT >> 5); rnxt = gatherR((RSHIFT >> 5) + 1);
+        if (DX < 0) {   // window of the position one step before the start (x = w): R(w - d), d >= 1
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) rw[j] = cen_word(Rc, w - lane * DPL - j);
+        }
+    }
 
     // intensities in travel order: lane k holds pixel t = 32*blk + k
     auto gather = [&](int blk) {
@@ -132,9 +173,32 @@ sgm_hsweep_kernel(const SweepArgs a) {
                 float hin[DPL], hnew[DPL], craw[DPL], best;
                 if (!FIRST) lds_vec<DPL>(hin, st + slot * HROW + lane * DPL * 4);
                 RawCost<DPL, COST> rc;
-                rc.lds(st + CH * HROW + slot * CROW + lane * DPL * CE);
+                if (!CEN) {
+                    rc.lds(st + CH * HROW + slot * CROW + lane * DPL * CE);
 #pragma unroll
-                for (int j = 0; j < DPL; ++j) craw[j] = rc.raw(j);
+                    for (int j = 0; j < DPL; ++j) craw[j] = rc.raw(j);
+                } else {
+                    // the R block advances where (t + RSHIFT) & 31 == 0: going left that is t & 31 == 1, i.e. i == 1
+                    // of a chunk that starts a 32-pixel block (chunks never straddle blocks)
+                    if (DX < 0 && i == (1 % CH) && ((t0 + i + RSHIFT) & 31) == 0) {
+                        rcur = rnxt; rnxt = gatherR(((t0 + i + RSHIFT) >> 5) + 1);
+                    }
+                    const unsigned nw = __shfl_sync(0xffffffffu, rcur, (t0 + i + RSHIFT) & 31);
+                    const unsigned lw = __shfl_sync(0xffffffffu, lcur, (t0 + i) & 31);
+                    if (DX > 0) {
+                        const unsigned up = __shfl_up_sync(0xffffffffu, rw[DPL - 1], 1);
+#pragma unroll
+                        for (int j = DPL - 1; j > 0; --j) rw[j] = rw[j - 1];
+                        rw[0] = lane == 0 ? nw : up;
+                    } else {
+                        const unsigned dn = __shfl_down_sync(0xffffffffu, rw[0], 1);
+#pragma unroll
+                        for (int j = 0; j < DPL - 1; ++j) rw[j] = rw[j + 1];
+                        rw[DPL - 1] = lane == 31 ? nw : dn;
+                    }
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) craw[j] = (float)__popc(lw ^ rw[j]);
+                }
                 const float pix = __shfl_sync(0xffffffffu, icur, (t0 + i) & 31);
                 // start pixel: `volH += volC`, lastBestCr = 0 (cu_semi_global_matching.cu:31-35) == a step with P2 = 0
                 const float p2 = (i == 0 && first) ? 0.0f : P2;
@@ -159,8 +223,14 @@ sgm_hsweep_kernel(const SweepArgs a) {
     for (int k = 0; k < nchunks; ++k) {
         const unsigned s = (unsigned)(k % NST);
         const unsigned st = sbase + s * STAGE_B;
-        if (((k * CH) & 31) == 0 && k != 0) { icur = inxt; inxt = gather((k * CH >> 5) + 1); }
-        mbar_wait(mbar0 + 8 * s, (unsigned)(k / NST) & 1u);
+        if (((k * CH) & 31) == 0 && k != 0) {
+            icur = inxt; inxt = gather((k * CH >> 5) + 1);
+            if (CEN) {
+                lcur = lnxt; lnxt = gatherL((k * CH >> 5) + 1);
+                if (DX > 0) { rcur = rnxt; rnxt = gatherR((k * CH >> 5) + 1); }
+            }
+        }
+        if (STAGED) mbar_wait(mbar0 + 8 * s, (unsigned)(k / NST) & 1u);
         const int t0 = k * CH;
         const bool unmasked = t0 >= tmask_lo && t0 + CH - 1 <= tmask_hi;
         const bool full = t0 + CH <= w;
@@ -170,8 +240,10 @@ sgm_hsweep_kernel(const SweepArgs a) {
         } else {
             chunk(std::true_type{}, std::false_type{}, k, st);
         }
-        __syncwarp();   // every lane has read the stage: it may be refilled
-        if (lane == 0 && k + NST < nchunks) issue(k + NST);
+        if (STAGED) {
+            __syncwarp();   // every lane has read the stage: it may be refilled
+            if (lane == 0 && k + NST < nchunks) issue(k + NST);
+        }
     }
 }
 
@@ -210,14 +282,21 @@ static int hsweep_launch2(const SweepArgs& a, cudaStream_t st) {
 
 // a.dy == 0, a.dx == +-1
 int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
-    const bool f32 = a.cost_kind == COST_F32;
+#define ROO_HS_DP(DPL)                                                          \
+    switch (a.cost_kind) {                                                      \
+        case COST_F32: return hsweep_launch2<DPL, COST_F32>(a, st);             \
+        case COST_U8: return hsweep_launch2<DPL, COST_U8>(a, st);               \
+        case COST_CEN32: return hsweep_launch2<DPL, COST_CEN32>(a, st);         \
+        default: return ROO_ERR_INVALID_ARGUMENT;                               \
+    }
     switch (a.DP) {
-        case 32: return f32 ? hsweep_launch2<1, COST_F32>(a, st) : hsweep_launch2<1, COST_U8>(a, st);
-        case 64: return f32 ? hsweep_launch2<2, COST_F32>(a, st) : hsweep_launch2<2, COST_U8>(a, st);
-        case 128: return f32 ? hsweep_launch2<4, COST_F32>(a, st) : hsweep_launch2<4, COST_U8>(a, st);
-        case 256: return f32 ? hsweep_launch2<8, COST_F32>(a, st) : hsweep_launch2<8, COST_U8>(a, st);
+        case 32: ROO_HS_DP(1)
+        case 64: ROO_HS_DP(2)
+        case 128: ROO_HS_DP(4)
+        case 256: ROO_HS_DP(8)
         default: return ROO_ERR_UNSUPPORTED;
     }
+#undef ROO_HS_DP
 }
 
 }  // namespace roo_b200

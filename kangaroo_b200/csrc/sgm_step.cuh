@@ -100,7 +100,9 @@ __device__ __forceinline__ void cp_async_4_if(int pred, unsigned sdst, const voi
 }
 
 // raw matching cost of one pixel as loaded; converted to float at use
-enum CostKind { COST_F32 = 0, COST_U8 = 1 };
+// COST_CEN32: no cost volume at all -- the sweep recomputes popc(L ^ R) from the 32-bit halves of the census
+// descriptors the reference's HammingDistance looks at (hamming_distance.h:40-44; 9x7 window, compat popcount)
+enum CostKind { COST_F32 = 0, COST_U8 = 1, COST_CEN32 = 2 };
 template <int DPL, int COST> struct RawCost;
 template <int DPL> struct RawCost<DPL, COST_F32> {
     float v[DPL];
@@ -116,6 +118,11 @@ template <int DPL> struct RawCost<DPL, COST_F32> {
     __device__ __forceinline__ float get(int j, float) const { return v[j]; }
     __device__ __forceinline__ float raw(int j) const { return v[j]; }   // cost = raw * 1
     static constexpr int ELEM = 4;
+};
+template <int DPL> struct RawCost<DPL, COST_CEN32> {
+    static constexpr int ELEM = 0;   // nothing staged: the cost comes out of registers
+    __device__ __forceinline__ void lds(unsigned) {}
+    __device__ __forceinline__ float raw(int) const { return 0.0f; }
 };
 template <int DPL> struct RawCost<DPL, COST_U8> {
     unsigned w[(DPL + 3) / 4];
@@ -326,15 +333,17 @@ __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float de
 template <int DPL, bool IEEE>
 __device__ __forceinline__ float wta_epilogue(const float (&hp)[DPL], int lane, int x, int w, int maxDispVal, int subpix) {
     const int d0 = lane * DPL;
-    float lc = ROO_INF;
-    int ld = 0;
+    // lane minimum by a min tree (no index tracking), warp minimum by one redux.sync.min.f32; then the LOWEST
+    // disparity that holds it: first j inside the lane, lowest lane through one integer redux.sync.min.s32
+    // (all rows masked out are +inf; if every entry is +inf the answer is 0, as with the reference's strict `<`)
+    float lc = hp[0];
 #pragma unroll
-    for (int j = 0; j < DPL; ++j)
-        if (hp[j] < lc) { lc = hp[j]; ld = d0 + j; }
+    for (int j = 1; j < DPL; ++j) lc = fminf(lc, hp[j]);
     const float m = warp_min_f32(lc);
-    const unsigned ball = __ballot_sync(0xffffffffu, lc == m);
-    const int win = __ffs(ball) - 1;           // lowest lane = lowest disparity among equal minima
-    int bestd = __shfl_sync(0xffffffffu, ld, win);
+    int cand = 0x7fffffff;
+#pragma unroll
+    for (int j = DPL - 1; j >= 0; --j) cand = (hp[j] == m) ? d0 + j : cand;
+    int bestd = __reduce_min_sync(0xffffffffu, cand);
     if (!subpix) return (float)bestd;
     float bestc = m;
     if (!(bestc < 1E10f)) { bestc = 1E10f; bestd = 0; }  // the reference starts from bestc = 1e10

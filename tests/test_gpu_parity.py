@@ -440,6 +440,26 @@ def test_bulk_copy_horizontal_sweep_equals_generic_sweep(shape, opts):
         assert np.array_equal(np.isnan(d0), np.isnan(d1)) and np.array_equal(d0[~np.isnan(d0)], d1[~np.isnan(d1)])
 
 
+@pytest.mark.parametrize("shape", [(64, 9, 32), (257, 33, 64), (131, 20, 128), (1000, 12, 128), (300, 7, 256), (3, 5, 16), (37, 4, 200), (129, 3, 128)])
+@pytest.mark.parametrize("opts", [dict(), dict(dovert=False), dict(dodiag=True, subpix=True, lrcheck=True)])
+def test_in_sweep_census_cost_equals_materialised_cost_volume(shape, opts):
+    """COST_CEN32 (the sweep recomputes popc(L ^ R) from a sliding window of census words in registers, the u8 cost
+    volume is not read -- and not even built when no pass needs it) against the same passes reading the volume."""
+    w, h, D = shape
+    L, R, _ = stereo_pair(w, h, D, config=72)
+    roo.set_ieee_division(True)
+    try:
+        roo.set_tuning(roo.capi.TUNE_INSWEEP_COST, 0)
+        d0, H0, _ = run_engine(L, R, D, batch=2, **opts)
+    finally:
+        roo.set_tuning(roo.capi.TUNE_INSWEEP_COST, 1)
+    d1, H1, _ = run_engine(L, R, D, batch=2, **opts)
+    assert np.array_equal(H0, H1)
+    assert np.array_equal(np.isnan(d0), np.isnan(d1)) and np.array_equal(d0[~np.isnan(d0)], d1[~np.isnan(d1)])
+    od, oH = ko.pipeline_u8(L, R, D, want_volume=True, **opts)
+    assert np.array_equal(H1, oH)
+
+
 def test_engine_batch_slots_are_independent_and_groups_wrap():
     """Different stereo pairs in every batch slot, more pairs than max_batch (several groups per call)."""
     w, h, D = 161, 57, 64

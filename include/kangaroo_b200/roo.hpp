@@ -29,6 +29,13 @@
 
 #include "../roo_b200.h"
 
+#ifdef ROO_B200_USE_KANGAROO_TYPES
+// the reference's own data model: roo::Image / roo::Volume (and their Target / Management policies) and CostVolElem
+#include <kangaroo/Image.h>
+#include <kangaroo/Volume.h>
+#include <kangaroo/CostVolElem.h>
+#endif
+
 namespace roo {
 
 #ifndef ROO_B200_USE_KANGAROO_TYPES
@@ -162,6 +169,19 @@ inline void CostVolMinimumSubpix(Image<float> disp, Volume<float> vol, unsigned 
     auto d = b200::c(disp); auto v = b200::c(vol);
     b200::done(roo_costvol_minimum_subpix(&d, &v, maxDisp, sd, b200::stream_slot()), "CostVolMinimumSubpix");
 }
+// ---- cu_dense_stereo.h:87-89
+inline void CostVolMinimumSquarePenaltySubpix(Image<float> imga, Volume<float> vol, Image<float> imgd, unsigned maxDisp, float sd,
+                                              float lambda, float theta) {
+    auto a = b200::c(imga), d = b200::c(imgd);
+    auto v = b200::c(vol);
+    b200::done(roo_costvol_minimum_square_penalty_subpix(&a, &v, &d, maxDisp, sd, lambda, theta, b200::stream_slot()),
+               "CostVolMinimumSquarePenaltySubpix");
+}
+// ---- cu_dense_stereo.h:101-103 (dOut may be dIn, as in stereo2/main.cpp:457)
+inline void FilterDispGrad(Image<float> dOut, Image<float> dIn, float threshold) {
+    auto o = b200::c(dOut), i2 = b200::c(dIn);
+    b200::done(roo_filter_disp_grad(&o, &i2, threshold, b200::stream_slot()), "FilterDispGrad");
+}
 // ---- cu_dense_stereo.h:45-47
 inline void DenseStereoSubpixelRefine(Image<float> dDispOut, const Image<unsigned char> dDisp,
                                       const Image<unsigned char> dCamLeft, const Image<unsigned char> dCamRight) {
@@ -234,7 +254,7 @@ inline void CostVolumeFromStereoTruncatedAbsAndGrad(Volume<float> dvol, Image<fl
     b200::done(roo_costvol_from_stereo_truncated_abs_and_grad(&v, &l, &r, sd, alpha, r1, r2, b200::stream_slot()),
                "CostVolumeFromStereoTruncatedAbsAndGrad");
 }
-// ---- cu_median.h:19-32 (out of place only: the reference races when dOut aliases dIn)
+// ---- cu_median.h:19-32 (dOut may alias dIn as in the applications: the library then filters through a temporary)
 inline void MedianFilterRejectNegative5x5(Image<float> dOut, Image<float> dIn, int maxbad = 100) {
     auto o = b200::c(dOut), i = b200::c(dIn);
     b200::done(roo_median_filter_reject_negative(&o, &i, 5, maxbad, b200::stream_slot()), "MedianFilterRejectNegative5x5");

@@ -161,9 +161,24 @@ int roo_costvol_from_stereo_truncated_abs_and_grad(const roo_volume_t* vol_f32, 
  * fewer than maxbad (and not all) samples of the clamp-to-edge window are non-finite, else the median of the valid
  * samples.  Bit-identical to the reference for windows without invalid samples; with invalid samples the reference
  * returns a comparator-order-dependent near-median, this returns the true median of the valid
- * ones.  `out` must not overlap `in` (the reference races when called in place, as its applications do). */
+ * ones.  `out` may alias `in` (both reference applications call it in place, where the reference itself races):
+ * an overlapping call filters into a stream-ordered temporary and copies back, i.e. gives the out-of-place result. */
 int roo_median_filter_reject_negative(const roo_image_t* out_f32, const roo_image_t* in_f32, int size, int maxbad,
                                       void* stream);
+
+/* roo::FilterDispGrad (cu_dense_stereo.h:101-103; cu_dense_stereo.cu:793-812; stereo2/main.cpp:457):
+ * out(x,y) = dx^2 + dy^2 < threshold ? in(x,y) : -1 with dx, dy the central differences of what `out` holds when the call
+ * is made.  The reference reads the image it is writing (meaningful only in place, where it races with itself); here
+ * the gradient source is a snapshot of `out`, so in-place calls (out == in, as in the applications) are deterministic.
+ * On the border pixels the reference reads outside the image (undefined); here those neighbours clamp to the edge. */
+int roo_filter_disp_grad(const roo_image_t* out_f32, const roo_image_t* in_f32, float threshold, void* stream);
+
+/* roo::CostVolMinimumSquarePenaltySubpix (cu_dense_stereo.h:87-89; cu_dense_stereo.cu:122-174): argmin over d of
+ * (imgd(x,y) - d)^2 / (2 theta) + lambda * vol(x,y,d) with the parabola refinement of CostVolMinimumSubpix on the
+ * penalised costs; same guards as roo_costvol_minimum_subpix (Q7), sd must be +-1 (Q12). */
+int roo_costvol_minimum_square_penalty_subpix(const roo_image_t* imga_f32, const roo_volume_t* vol_f32,
+                                              const roo_image_t* imgd_f32, unsigned maxDisp, float sd, float lambda,
+                                              float theta, void* stream);
 
 /* ---- fused engine: the whole per-frame path of applications/stereo2/main.cpp:375-454 ------- */
 

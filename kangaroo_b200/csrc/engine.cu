@@ -27,6 +27,8 @@ struct roo_engine {
     size_t npx = 0;
     // scratch (device)
     unsigned long long* cen[2] = {nullptr, nullptr};  // [batch][h][w][words]
+    unsigned long long* cen_base[2] = {nullptr, nullptr};   // the allocations: cen[] sits CEN_PAD elements inside (in-sweep
+                                                            // cost reads strips that stick out of a row by < 2 * 256 + 32 pixels)
     unsigned char* c8 = nullptr;                      // [batch][h][w][DP]
     float* H = nullptr;                               // [batch][h][w][DP]
     float* dispR = nullptr;                           // [batch][h][w]
@@ -66,6 +68,7 @@ struct roo_engine {
 constexpr long long FUSE_MIN_CTAS = 100;
 // ... unless the group is so small that single-path sweeps are not bandwidth-bound either (pixel*disparity units)
 constexpr long long FUSE_MIN_UNITS = 100000000;
+constexpr size_t CEN_PAD = 1024;   // elements of padding before and after the census arrays
 
 static void prof_mark(roo_engine* e, int kind, cudaStream_t st, int pass = -1) {
     if (!e->profiling) return;
@@ -141,7 +144,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         // Eligible: one-word descriptors under the reference's 32-bit popcount (9x7 window, hamming_distance.h:40-44).
         const bool cen_ok = e->words == 1 && p.popc_mode == ROO_POPC32_COMPAT && g_insweep_cost.load(std::memory_order_relaxed);
         auto pass_in_sweep = [&](const SgmPass& ps) {
-            return cen_ok && !ps.fused && ps.dy == 0 && g_use_hsweep.load(std::memory_order_relaxed);
+            return cen_ok && (ps.fused || (ps.dy == 0 && g_use_hsweep.load(std::memory_order_relaxed)));
         };
         bool need_c8 = false;
         for (int i = 0; i < ndir; ++i) need_c8 |= !pass_in_sweep(plan.pass[i]);
@@ -194,7 +197,7 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
 }
 
 static void engine_free(roo_engine* e) {
-    cudaFree(e->cen[0]); cudaFree(e->cen[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->med); cudaFree(e->imgf);
+    cudaFree(e->cen_base[0]); cudaFree(e->cen_base[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->med); cudaFree(e->imgf);
     for (int sd = 0; sd < 2; ++sd) { cudaFree(e->fe_rect[sd]); cudaFree(e->fe_pyr[sd]); } cudaFree(e->edge); cudaFree(e->flags);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
@@ -240,7 +243,15 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     const int ndir = e->plan.n;
     bool fused = false;
     for (int i = 0; i < ndir; ++i) fused |= e->plan.pass[i].fused != 0;
-    bool ok = alloc((void**)&e->cen[0], B * npx * e->words * 8) && alloc((void**)&e->cen[1], B * npx * e->words * 8);
+    bool ok = alloc((void**)&e->cen_base[0], (B * npx * e->words + 2 * CEN_PAD) * 8) &&
+              alloc((void**)&e->cen_base[1], (B * npx * e->words + 2 * CEN_PAD) * 8);
+    if (ok) {
+        for (int sd = 0; sd < 2; ++sd) {
+            e->cen[sd] = e->cen_base[sd] + CEN_PAD;
+            cudaMemset(e->cen_base[sd], 0, CEN_PAD * 8);
+            cudaMemset(e->cen[sd] + B * npx * e->words, 0, CEN_PAD * 8);
+        }
+    }
     if (ok && ndir > 0)
         ok = alloc((void**)&e->c8, B * npx * e->DP) && alloc((void**)&e->H, B * npx * e->DP * 4) &&
              alloc((void**)&e->imgf, B * npx * 4);

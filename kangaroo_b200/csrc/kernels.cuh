@@ -61,6 +61,9 @@ struct VGroupArgs {
     float P1, P2;
     int fwd;            // 1: (0,+1),(+1,+1),(-1,+1) ; 0: (0,-1),(-1,-1),(+1,-1)
     int ieee;           // fp mode, as SweepArgs::ieee
+    const unsigned long long* cenL;   // COST_CEN32: census descriptors (padded arrays), as SweepArgs
+    const unsigned long long* cenR;
+    size_t cen_pair;
     float* edge_hp;     // [pair][band][h][3][DP]  states handed from band b to band b+1
     float* edge_sc;     // [pair][band][h][8]
     int* progress;      // [pair][band] rows published
@@ -92,6 +95,7 @@ int launch_box_half_u8(unsigned char* out, const unsigned char* in, int w_out, i
 // MedianFilterRejectNegative{5,7,9} over a batch of images (out must not overlap in)
 int launch_median(float* out, size_t out_pitch, size_t out_batch, const float* in, size_t in_pitch, size_t in_batch, int w,
                   int h, int batch, int size, int maxbad, cudaStream_t st);
+int launch_filter_disp_grad(const roo_image_t& out, const roo_image_t& grad, const roo_image_t& in, float threshold, cudaStream_t st);
 int launch_lr_check_f32(float* dispL, size_t pitchL, const float* dispR, size_t pitchR, int w, int h, int batch,
                         size_t batchL, size_t batchR, float sd, float maxDiff, cudaStream_t st);
 

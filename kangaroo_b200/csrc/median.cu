@@ -119,9 +119,20 @@ extern "C" int roo_median_filter_reject_negative(const roo_image_t* out, const r
                                                  void* stream) {
     if (size != 5 && size != 7 && size != 9) return ROO_ERR_UNSUPPORTED;
     if (!valid_image(out, 4) || !valid_image(in, 4) || in->w != out->w || in->h != out->h) return ROO_ERR_INVALID_ARGUMENT;
-    // in place = a data race in the reference (neighbours are read while other blocks overwrite them): refuse overlap
+    cudaStream_t st = as_stream(stream);
+    // Both reference applications call the filter IN PLACE (stereo2/main.cpp:440-442), which races in the reference
+    // (a block reads neighbours another block has already overwritten).  Here an overlapping call filters into a
+    // stream-ordered temporary and copies back: the result is what the out-of-place call gives, never a silent no-op.
     const char *ob = (const char*)out->ptr, *ib = (const char*)in->ptr;
-    if (ob < ib + in->pitch * in->h && ib < ob + out->pitch * out->h) return ROO_ERR_INVALID_ARGUMENT;
+    if (ob < ib + in->pitch * in->h && ib < ob + out->pitch * out->h) {
+        const size_t tp = out->w * sizeof(float);
+        float* tmp = nullptr;
+        ROO_CUDA_TRY(cudaMallocAsync((void**)&tmp, tp * out->h, st));
+        int rc = launch_median(tmp, tp, 0, (const float*)in->ptr, in->pitch, 0, (int)out->w, (int)out->h, 1, size, maxbad, st);
+        if (rc == 0) rc = (int)cudaMemcpy2DAsync(out->ptr, out->pitch, tmp, tp, tp, out->h, cudaMemcpyDeviceToDevice, st);
+        const cudaError_t fe = cudaFreeAsync(tmp, st);
+        return rc != 0 ? rc : (int)fe;
+    }
     return launch_median((float*)out->ptr, out->pitch, 0, (const float*)in->ptr, in->pitch, 0, (int)out->w, (int)out->h, 1,
-                         size, maxbad, as_stream(stream));
+                         size, maxbad, st);
 }

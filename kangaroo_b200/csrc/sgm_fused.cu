@@ -57,8 +57,17 @@ __host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? VG_NCW8 : 
 #ifndef VG_NWW
 #define VG_NWW 12
 #endif
-__host__ __device__ constexpr int vg_nww(int DPL) { return DPL >= 8 ? VG_NWW8 : VG_NWW; }
-inline int vg_cols_of_dp(int DP) { return vg_ncw(DP / 32) * vg_nww(DP / 32); }
+// a write-only first pass with in-sweep cost prefetches nothing but census strips: shared memory leaves room for more warps
+#ifndef VG_NWW_FC
+#define VG_NWW_FC VG_NWW
+#endif
+#ifndef VG_NWW8_FC
+#define VG_NWW8_FC VG_NWW8
+#endif
+__host__ __device__ constexpr int vg_nww(int DPL, bool first_cen = false) {
+    return DPL >= 8 ? (first_cen ? VG_NWW8_FC : VG_NWW8) : (first_cen ? VG_NWW_FC : VG_NWW);
+}
+inline int vg_cols_of_dp(int DP, bool first_cen = false) { return vg_ncw(DP / 32) * vg_nww(DP / 32, first_cen); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -153,20 +162,14 @@ __host__ __device__ constexpr int vg_s(int DPL) { return DPL >= 8 ? VG_S_DEPTH8 
 
 // One pixel of the three paths.  V/D/A = vertical / diagonal / anti-diagonal.  hpV, hpD, hpA: previous pixel's
 // state rows on entry, this pixel's on exit.  Handles path starts when EDGE.
-template <int DPL, int COST, bool MASKED, bool EDGE, bool FIRST, bool IEEE>
-__device__ __forceinline__ void vg_pixel(unsigned stg, int lane, int y, int xp, int x, int w, int M, float P1, float P2,
-                                         float cscale, float pix, float (&hpV)[DPL], float& lbV, float ppV,
+template <int DPL, bool MASKED, bool EDGE, bool FIRST, bool IEEE>
+__device__ __forceinline__ void vg_pixel(unsigned stg, const float (&cost)[DPL], int lane, int y, int xp, int x, int w, int M,
+                                         float P1, float P2, float cscale, float pix, float (&hpV)[DPL], float& lbV, float ppV,
                                          float (&hpD)[DPL], float& lbD, float& pixD,
                                          float (&hpA)[DPL], float& lbA, float ppA, float* hst) {
-    constexpr int DP = 32 * DPL;
-    constexpr int CE = RawCost<DPL, COST>::ELEM;
     const int lim = MASKED ? min(M, x + 1) - lane * DPL : 0;
-    float hin[DPL], H3[DPL], cost[DPL];
+    float hin[DPL], H3[DPL];
     if (!FIRST) lds_vec<DPL>(hin, stg + lane * DPL * 4);
-    RawCost<DPL, COST> rc;
-    rc.lds(stg + DP * 4 + lane * DPL * CE);
-#pragma unroll
-    for (int j = 0; j < DPL; ++j) cost[j] = rc.raw(j);
     float p2V = P2, p2D = P2, p2A = P2;
     bool sV = false, sD = false, sA = false;
     if (EDGE) {
@@ -200,7 +203,16 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int NC = NCW * NWW;                     // skewed columns per band
     constexpr int PFS = vg_pfs(DPL, CE);
     constexpr int R = vg_r(DPL), RING = 2 * R, S = vg_s(DPL);
-    constexpr int STAGE_B = DP * 4 + DP * CE;        // one prefetched pixel: aggregate row, cost row
+    constexpr int HOFF_B = FIRST ? 0 : DP * 4;       // a write-only first pass prefetches no aggregate rows
+    constexpr int STAGE_B = HOFF_B + DP * CE;        // one prefetched pixel: aggregate row, cost row
+    // COST_CEN32: no cost rows; instead ONE strip of census words per warp and image row, from which every lane
+    // recomputes popc(L ^ R) for its NCW x DPL (pixel, disparity) pairs:
+    //   seg[0 .. DP+NCW-2]   low words of the right descriptors R(S0 + i), S0 = x(lowest-address column) - (DP-1)
+    //   seg[DP+8 .. DP+8+NCW-1]  low words of the NCW left descriptors, ascending x
+    // (lane l reads the DPL+NCW-1 words from seg[DPL*(31-l)] on -- 16-byte aligned, conflict-free LDS.128)
+    constexpr bool CEN = COST == COST_CEN32;
+    constexpr int CEN_W = DP + 16, CEN_B = CEN_W * 4;
+    constexpr int WIN = (DPL + NCW - 1 + 3) / 4 * 4;   // words of the lane's window, rounded up to whole LDS.128
     extern __shared__ __align__(16) float smem[];
     // state rows of one warp and one image row, for its two lowest columns c0 and c1 (all that the warp below
     // needs): rec0 = c0.vertical, rec1 = c0.anti-diagonal, rec2 = c1.anti-diagonal;
@@ -215,6 +227,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     VCtl* ctl = reinterpret_cast<VCtl*>(s_esc + RING * 8);
     volatile int* prog = reinterpret_cast<volatile int*>(ctl + 1);   // [NWW] rows < prog[v] of warp v are done
     char* s_pf = reinterpret_cast<char*>(ctl + 1) + ((NWW * 4 + 15) / 16) * 16;   // [NWW][NCW cols][PFS][STAGE_B]
+    char* s_cen = s_pf + (size_t)NWW * NCW * PFS * STAGE_B;                        // [NWW][PFS][CEN_B] (COST_CEN32 only)
 
     // warp index through a shuffle: ptxas then knows it is warp-uniform, and every branch on it is a uniform branch
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -352,6 +365,17 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     float* hst = Hp + e_in;                          // row being computed
     const float* hld = hst;                          // row being prefetched
     const char* cld = Cp + e_in * CE;
+    // COST_CEN32 cursors (one u64 descriptor per pixel; the arrays are padded, so strips may stick out of the row):
+    // cenR: word i = 32k + lane of the strip;  cenX: lanes 0-7 the strip's words DP + lane, lanes 8-15 the left words
+    const int xlow_in = fwd ? u0 + y_in : w - 1 - (u0 + NCW - 1) - y_in;           // x of the lowest-address column in row y_in
+    const ptrdiff_t c_in = ((ptrdiff_t)(fwd ? y_in : h - 1 - y_in) * w + xlow_in);
+    const unsigned long long* cenR = CEN ? a.cenR + (size_t)pair * a.cen_pair + c_in - (DP - 1) + lane : nullptr;
+    const unsigned long long* cenX = CEN ? ((lane & 15) < 8 ? a.cenR + (size_t)pair * a.cen_pair + c_in - (DP - 1) + DP + (lane & 7)
+                                                            : a.cenL + (size_t)pair * a.cen_pair + c_in + (lane & 7))
+                                         : nullptr;
+    const ptrdiff_t cstep = fwd ? (ptrdiff_t)(w + 1) : -(ptrdiff_t)(w + 1);
+    // (through a shuffle: kept in a register instead of being rematerialised from the CTA's window base every row)
+    const unsigned cen0 = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared(s_cen) + warp * PFS * CEN_B, 0);
 
     // Prefetch: row y+PFS-1 of every column is copied global -> shared (asynchronously, no registers) while row y
     // is computed.  Every lane copies and later reads its own bytes, so no barrier is needed.
@@ -359,7 +383,7 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     auto issue_px = [&](int c, int yl) {
         const unsigned dst = pf0 + c * PFS * STAGE_B + ((unsigned)yl & (PFS - 1)) * STAGE_B;
         if (!FIRST) cp_async_bytes<DPL * 4>(dst + lane * DPL * 4, hld + coff(c));
-        cp_async_bytes<DPL * CE>(dst + DP * 4 + lane * DPL * CE, cld + coff(c) * CE);
+        if (CE > 0) cp_async_bytes<DPL * (CE > 0 ? CE : 1)>(dst + HOFF_B + lane * DPL * CE, cld + coff(c) * CE);
     };
     int aLo = max(0, -u0), aHi = min(h - 1, w - 1 - (u0 + NCW - 1));   // rows in which every column is active
     auto issue_row = [&](int yl) {
@@ -371,7 +395,13 @@ sgm_vgroup_kernel(const VGroupArgs a) {
             for (int c = 0; c < NCW; ++c)
                 if (col_active(c, yl)) issue_px(c, yl);
         }
-        hld += estep; cld += estep * CE;
+        if (CEN && yl <= y_out) {   // (rows after the last one would leave the image: nothing to fetch)
+            const unsigned dst = cen0 + ((unsigned)yl & (PFS - 1)) * CEN_B + lane * 4;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) cp_async_bytes<4>(dst + k * 128, reinterpret_cast<const unsigned*>(cenR + 32 * k));
+            cp_async_bytes<4>(cen0 + ((unsigned)yl & (PFS - 1)) * CEN_B + (DP + (lane & 15)) * 4, reinterpret_cast<const unsigned*>(cenX));
+        }
+        hld += estep; cld += estep * CE; cenR += cstep; cenX += cstep;
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     for (int k = 0; k < PFS - 1; ++k) issue_row(y_in + k);
@@ -446,6 +476,24 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         const float4 scUp0 = lds_f4(upsc);        // upper warp's c0: {lastBest(V), lastBest(A), pix, -}
         const float4 scUp1 = lds_f4(upsc + 16);   // upper warp's c1: {-, lastBest(A), pix, -}
         float4 sc0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sc1 = sc0;
+        unsigned rwin[WIN], lwin[4 * ((NCW + 3) / 4)];
+        if (CEN) {
+            const unsigned cs = cen0 + ((unsigned)y & (PFS - 1)) * CEN_B;
+            if constexpr (DPL >= 4) {
+#pragma unroll
+                for (int q = 0; q < WIN / 4; ++q)
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rwin[4 * q]), "=r"(rwin[4 * q + 1]), "=r"(rwin[4 * q + 2]), "=r"(rwin[4 * q + 3])
+                                 : "r"(cs + (DPL * (31 - lane)) * 4 + 16 * q));
+            } else {   // 32 / 64 disparities: the lane's window is not 16-byte aligned
+#pragma unroll
+                for (int q = 0; q < DPL + NCW - 1; ++q)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rwin[q]) : "r"(cs + (DPL * (31 - lane) + q) * 4));
+            }
+#pragma unroll
+            for (int q = 0; q < (NCW + 3) / 4; ++q)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lwin[4 * q]), "=r"(lwin[4 * q + 1]), "=r"(lwin[4 * q + 2]), "=r"(lwin[4 * q + 3])
+                             : "r"(cs + (DP + 8) * 4 + 16 * q));
+        }
         // ascending c: column c reads the previous-row registers of c+1 and c+2 before those columns overwrite them
 #pragma unroll
         for (int c = 0; c < NCW; ++c) {
@@ -473,7 +521,19 @@ sgm_vgroup_kernel(const VGroupArgs a) {
                     lds_vec<DPL>(ha, up + 2 * REC_B);
                     lbA = scUp1.y; ppA = scUp1.z;
                 }
-                vg_pixel<DPL, COST, MASKED, EDGE, FIRST, IEEE>(stg0 + c * PFS * STAGE_B, lane, y, xp, x, w, M, P1, P2, cscale, pix,
+                float cost[DPL];
+                if (CEN) {
+                    // column c is the (fwd ? c : NCW-1-c)-th pixel of the strip; R(x_c - d) for d = DPL*lane + j
+                    const int cc = fwd ? c : NCW - 1 - c;
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) cost[j] = (float)__popc(lwin[cc] ^ rwin[DPL - 1 + cc - j]);
+                } else {
+                    RawCost<DPL, COST> rc;
+                    rc.lds(stg0 + c * PFS * STAGE_B + HOFF_B + lane * DPL * CE);
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) cost[j] = rc.raw(j);
+                }
+                vg_pixel<DPL, MASKED, EDGE, FIRST, IEEE>(stg0 + c * PFS * STAGE_B, cost, lane, y, xp, x, w, M, P1, P2, cscale, pix,
                                                                hv, lbV, ppV, Dr[c], lbD[c], pixD[c], ha, lbA, ppA, hst + coff(c));
                 if (c == 0) {
                     sts_vec<DPL>(mine, hv);
@@ -580,34 +640,50 @@ sgm_vgroup_kernel(const VGroupArgs a) {
 #endif
 }
 
-int vgroup_bands(int w, int h, int DP) { return cdiv(w + h - 1, vg_cols_of_dp(DP)); }
+// scratch sizing: the geometry with the narrower bands (more bands)
+int vgroup_bands(int w, int h, int DP) {
+    const int nc = vg_cols_of_dp(DP, false) < vg_cols_of_dp(DP, true) ? vg_cols_of_dp(DP, false) : vg_cols_of_dp(DP, true);
+    return cdiv(w + h - 1, nc);
+}
 size_t vgroup_edge_floats(int w, int h, int DP) { return (size_t)vgroup_bands(w, h, DP) * h * (3 * (size_t)DP + 8); }
 
-template <int DPL, int COST>
-static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
-    constexpr int DP = 32 * DPL;
-    constexpr int NWW = vg_nww(DPL), NCW = vg_ncw(DPL);
-    constexpr int CE = RawCost<DPL, COST>::ELEM;
-    constexpr size_t smem = (size_t)(vg_s(DPL) * NWW * 3 * DP + vg_s(DPL) * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
-                            sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * NCW * vg_pfs(DPL, CE) * (DP * 4 + DP * CE);
+// dynamic shared memory of one band (CTA)
+template <int DPL, int COST, bool FIRST, int NWW, int NCW>
+constexpr size_t vg_smem_bytes() {
+    constexpr int DP = 32 * DPL, CE = RawCost<DPL, COST>::ELEM;
+    return (size_t)(vg_s(DPL) * NWW * 3 * DP + vg_s(DPL) * NWW * 8 + 2 * (2 * vg_r(DPL) * (3 * DP + 8))) * sizeof(float) +
+           sizeof(VCtl) + ((NWW * 4 + 15) / 16) * 16 + (size_t)NWW * NCW * vg_pfs(DPL, CE) * ((FIRST ? 0 : DP * 4) + DP * CE) +
+           (COST == COST_CEN32 ? (size_t)NWW * vg_pfs(DPL, CE) * (DP + 16) * 4 : 0);
+}
+
+template <int DPL, int COST, bool FIRST, bool FC>
+static int vgroup_launch3(VGroupArgs a, cudaStream_t st) {
+    constexpr int NWW = vg_nww(DPL, FC), NCW = vg_ncw(DPL);
+    a.n_bands = cdiv(a.w + a.h - 1, NWW * NCW);
+    constexpr size_t smem = vg_smem_bytes<DPL, COST, FIRST, NWW, NCW>();
     static_assert(smem <= 227 * 1024, "vertical-group kernel: shared memory budget of one sm_100 CTA exceeded");
     dim3 grid(a.n_bands * a.batch), block((NWW + 1) * 32);
-    const bool ieee = a.ieee != 0;
-#define ROO_VG(F, I)                                                                                          \
+#define ROO_VG(I)                                                                                             \
     do {                                                                                                      \
-        auto kern = a.fwd ? sgm_vgroup_kernel<DPL, COST, F, I, NWW, NCW, true>                                \
-                          : sgm_vgroup_kernel<DPL, COST, F, I, NWW, NCW, false>;                              \
+        auto kern = a.fwd ? sgm_vgroup_kernel<DPL, COST, FIRST, I, NWW, NCW, true>                            \
+                          : sgm_vgroup_kernel<DPL, COST, FIRST, I, NWW, NCW, false>;                          \
         if (smem > 48 * 1024) {                                                                               \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                              \
         }                                                                                                     \
         kern<<<grid, block, smem, st>>>(a);                                                                   \
     } while (0)
-    if (first) { if (ieee) ROO_VG(true, true); else ROO_VG(true, false); }
-    else { if (ieee) ROO_VG(false, true); else ROO_VG(false, false); }
+    if (a.ieee) ROO_VG(true); else ROO_VG(false);
 #undef ROO_VG
     count_launch();
     return launch_status();
+}
+
+template <int DPL, int COST>
+static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
+    if (!first) return vgroup_launch3<DPL, COST, false, false>(a, st);
+    if constexpr (COST == COST_CEN32 && vg_nww(DPL, true) != vg_nww(DPL, false)) return vgroup_launch3<DPL, COST, true, true>(a, st);
+    else return vgroup_launch3<DPL, COST, true, false>(a, st);
 }
 
 // scratch: edge buffer of vgroup_edge_floats(w,h,DP) * batch floats and n_bands * batch ints of progress flags
@@ -616,6 +692,7 @@ int launch_vgroup(const SweepArgs& s, int fwd, float* edge, int* progress, cudaS
     a.H = s.H; a.h_pair = s.h_pair; a.C = s.C; a.c_pair = s.c_pair; a.img = s.img; a.img_pair = s.img_pair;
     a.cost_scale = s.cost_scale; a.w = s.w; a.h = s.h; a.maxDisp = s.maxDisp; a.batch = s.batch; a.P1 = s.P1; a.P2 = s.P2;
     a.fwd = fwd; a.ieee = s.ieee;
+    a.cenL = s.cenL; a.cenR = s.cenR; a.cen_pair = s.cen_pair;
     a.n_bands = vgroup_bands(s.w, s.h, s.DP);
     const size_t hp_floats = (size_t)a.n_bands * s.h * 3 * s.DP;
     a.edge_hp = edge;
@@ -623,14 +700,21 @@ int launch_vgroup(const SweepArgs& s, int fwd, float* edge, int* progress, cudaS
     a.progress = progress;
     ROO_CUDA_TRY(cudaMemsetAsync(progress, 0, sizeof(int) * (size_t)a.n_bands * s.batch, st));
     const bool first = s.first != 0;
-    const bool f32 = s.cost_kind == COST_F32;
+#define ROO_VG_DP(DPL)                                                              \
+    switch (s.cost_kind) {                                                          \
+        case COST_F32: return vgroup_launch2<DPL, COST_F32>(a, first, st);          \
+        case COST_U8: return vgroup_launch2<DPL, COST_U8>(a, first, st);            \
+        case COST_CEN32: return vgroup_launch2<DPL, COST_CEN32>(a, first, st);      \
+        default: return ROO_ERR_INVALID_ARGUMENT;                                   \
+    }
     switch (s.DP) {
-        case 32: return f32 ? vgroup_launch2<1, COST_F32>(a, first, st) : vgroup_launch2<1, COST_U8>(a, first, st);
-        case 64: return f32 ? vgroup_launch2<2, COST_F32>(a, first, st) : vgroup_launch2<2, COST_U8>(a, first, st);
-        case 128: return f32 ? vgroup_launch2<4, COST_F32>(a, first, st) : vgroup_launch2<4, COST_U8>(a, first, st);
-        case 256: return f32 ? vgroup_launch2<8, COST_F32>(a, first, st) : vgroup_launch2<8, COST_U8>(a, first, st);
+        case 32: ROO_VG_DP(1)
+        case 64: ROO_VG_DP(2)
+        case 128: ROO_VG_DP(4)
+        case 256: ROO_VG_DP(8)
         default: return ROO_ERR_UNSUPPORTED;
     }
+#undef ROO_VG_DP
 }
 
 }  // namespace roo_b200

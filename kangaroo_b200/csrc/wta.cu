@@ -81,6 +81,61 @@ costvol_min_subpix_kernel(Img<float> disp, Vol<float> vol, unsigned maxDispVal, 
     disp(x, y) = out;
 }
 
+// ---- CostVolMinimumSquarePenaltySubpix (cu_dense_stereo.cu:122-174) --------------------------------------
+// argmin_d of  (lastd - d)^2 / (2 theta) + lambda * vol(x,y,d)  (the coupling step of the applications' variational
+// refinement, stereo/main.cpp:376), then the same parabola as CostVolMinimumSubpix on the penalised costs.
+// Reference SASS (fast-math): inv2theta = MUFU.RCP(theta + theta); c = FFMA(ddif, inv2theta * ddif, lambda * vol).
+template <bool IEEE>
+__device__ __forceinline__ float sqpen_cost(float lastd, float d, float inv2theta, float lambda, float v) {
+    const float ddif = __fadd_rn(lastd, -d);
+    if (IEEE) return __fadd_rn(__fmul_rn(__fmul_rn(inv2theta, ddif), ddif), __fmul_rn(lambda, v));
+    return __fmaf_rn(ddif, __fmul_rn(inv2theta, ddif), __fmul_rn(v, lambda));
+}
+template <bool IEEE>
+__global__ void __launch_bounds__(WTA_TX)
+costvol_min_sqpen_subpix_kernel(Img<float> imga, Vol<float> vol, Img<float> imgd, unsigned maxDispVal, int sdi, float lambda,
+                                float theta) {
+    const int x = blockIdx.x * WTA_TX + threadIdx.x, y = blockIdx.y;
+    if (x >= imga.w) return;
+    const float lastd = imgd(x, y);
+    const float inv2theta = IEEE ? __fdiv_rn(1.0f, __fmul_rn(2.0f, theta)) : rcp_approx_ftz(__fadd_rn(theta, theta));
+    int bestd = 0;
+    float bestc = sqpen_cost<IEEE>(lastd, 0.0f, inv2theta, lambda, vol(x, y, 0));
+    for (int d = 1; d < (int)maxDispVal; ++d) {
+        const int xr = x + sdi * d;
+        if (0 <= xr && xr < vol.w) {
+            const float c = sqpen_cost<IEEE>(lastd, (float)d, inv2theta, lambda, vol(x, y, d));
+            if (c < bestc) { bestc = c; bestd = d; }
+        }
+    }
+    float out = (float)bestd;
+    const int bestxr = x + sdi * bestd;
+    if (0 < bestxr && bestxr < vol.w - 1 && bestd + 1 < vol.d) {   // bestd+1 == vol.d: the reference reads out of bounds (Q7)
+        const float dl = (float)(bestd - 1), dr = (float)(bestd + 1);
+        const float sl = sqpen_cost<IEEE>(lastd, dl, inv2theta, lambda, vol(x, y, max(bestd - 1, 0)));   // index saturates at 0 (Q7)
+        const float sr = sqpen_cost<IEEE>(lastd, dr, inv2theta, lambda, vol(x, y, bestd + 1));
+        const float sub = parabola_vertex<IEEE>((float)bestd, bestc, sl, sr);
+        if (dl < sub && sub < dr) out = sub;
+    }
+    imga(x, y) = out;
+}
+
+// ---- FilterDispGrad (cu_dense_stereo.cu:793-812) ----------------------------------------------------------
+// out(x,y) = |central-difference gradient of G|^2 < threshold ? in(x,y) : -1, G = the contents of `out` BEFORE the call
+// (the applications call it in place, main.cpp:457, where the reference races with itself; here G is a snapshot).
+// Reference SASS: dx = (G(x+1,y) - G(x-1,y)) * 0.5, dy likewise, m = FFMA(dx, dx, dy * dy), valid = !(m >= threshold).
+// The reference reads outside the image on the border pixels (undefined); here out-of-image neighbours clamp to the edge.
+__global__ void __launch_bounds__(WTA_TX)
+filter_disp_grad_kernel(Img<float> out, Img<float> grad, Img<float> in, float threshold) {
+    const int x = blockIdx.x * WTA_TX + threadIdx.x, y = blockIdx.y;
+    if (x >= out.w) return;
+    const float* row = grad.row(y);
+    const float dx = __fmul_rn(__fadd_rn(row[min(x + 1, grad.w - 1)], -row[max(x - 1, 0)]), 0.5f);
+    const float dy = __fmul_rn(__fadd_rn(grad(x, min(y + 1, grad.h - 1)), -grad(x, max(y - 1, 0))), 0.5f);
+    const float m = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+    out(x, y) = m < threshold ? in(x, y) : -1.0f;
+}
+
 // ---- LeftRightCheck -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WTA_TX)
 lr_check_f32_kernel(char* dispL, size_t pitchL, size_t batchL, const char* dispR, size_t pitchR, size_t batchR, int w,
@@ -225,6 +280,50 @@ extern "C" int roo_costvol_minimum_subpix(const roo_image_t* disp, const roo_vol
         costvol_min_subpix_kernel<false><<<grid, WTA_TX, 0, as_stream(stream)>>>(Img<float>(*disp), Vol<float>(*vol), maxDisp, sdi);
     count_launch();
     return launch_status();
+}
+
+extern "C" int roo_costvol_minimum_square_penalty_subpix(const roo_image_t* imga, const roo_volume_t* vol, const roo_image_t* imgd,
+                                                         unsigned maxDisp, float sd, float lambda, float theta, void* stream) {
+    if (!valid_image(imga, 4) || !valid_image(imgd, 4) || !valid_volume(vol, 4) || imga->w != vol->w || imga->h != vol->h ||
+        imgd->w != vol->w || imgd->h != vol->h || maxDisp > vol->d)
+        return ROO_ERR_INVALID_ARGUMENT;
+    if (sd != -1.0f && sd != 1.0f) return ROO_ERR_UNSUPPORTED;
+    dim3 grid(cdiv((int)imga->w, WTA_TX), (unsigned)imga->h);
+    const int sdi = sd < 0 ? -1 : 1;
+    if (g_ieee_div.load())
+        costvol_min_sqpen_subpix_kernel<true><<<grid, WTA_TX, 0, as_stream(stream)>>>(Img<float>(*imga), Vol<float>(*vol), Img<float>(*imgd), maxDisp, sdi, lambda, theta);
+    else
+        costvol_min_sqpen_subpix_kernel<false><<<grid, WTA_TX, 0, as_stream(stream)>>>(Img<float>(*imga), Vol<float>(*vol), Img<float>(*imgd), maxDisp, sdi, lambda, theta);
+    count_launch();
+    return launch_status();
+}
+
+namespace roo_b200 {
+// out(x,y) from the gradient of `grad` (must not overlap out) and the values of `in` (may be `grad`)
+int launch_filter_disp_grad(const roo_image_t& out, const roo_image_t& grad, const roo_image_t& in, float threshold, cudaStream_t st) {
+    dim3 grid(cdiv((int)out.w, WTA_TX), (unsigned)out.h);
+    filter_disp_grad_kernel<<<grid, WTA_TX, 0, st>>>(Img<float>(out), Img<float>(grad), Img<float>(in), threshold);
+    count_launch();
+    return launch_status();
+}
+}  // namespace roo_b200
+
+extern "C" int roo_filter_disp_grad(const roo_image_t* out, const roo_image_t* in, float threshold, void* stream) {
+    if (!valid_image(out, 4) || !valid_image(in, 4) || out->w != in->w || out->h != in->h) return ROO_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+    // the gradient is taken of what `out` holds when the call is made: snapshot it (stream-ordered temporary), then write
+    const size_t tp = out->w * sizeof(float);
+    float* snap = nullptr;
+    ROO_CUDA_TRY(cudaMallocAsync((void**)&snap, tp * out->h, st));
+    int rc = (int)cudaMemcpy2DAsync(snap, tp, out->ptr, out->pitch, tp, out->h, cudaMemcpyDeviceToDevice, st);
+    const roo_image_t g{tp, snap, out->w, out->h};
+    // `in` aliasing `out` (the applications' call): its values are the snapshot's
+    const char *ob = (const char*)out->ptr, *ib = (const char*)in->ptr;
+    const bool alias = ob < ib + in->pitch * in->h && ib < ob + out->pitch * out->h;
+    if (alias && (in->ptr != out->ptr || in->pitch != out->pitch)) rc = rc ? rc : ROO_ERR_INVALID_ARGUMENT;   // partial overlap
+    if (rc == 0) rc = launch_filter_disp_grad(*out, g, alias ? g : *in, threshold, st);
+    const cudaError_t fe = cudaFreeAsync(snap, st);
+    return rc != 0 ? rc : (int)fe;
 }
 
 extern "C" int roo_dense_stereo_subpixel_refine(const roo_image_t* out, const roo_image_t* disp, const roo_image_t* left,

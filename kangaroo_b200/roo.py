@@ -186,6 +186,18 @@ def CostVolMinimumSubpix(disp: Image, vol: Volume, maxDisp: int, sd: float, stre
           "CostVolMinimumSubpix")
 
 
+def CostVolMinimumSquarePenaltySubpix(imga: Image, vol: Volume, imgd: Image, maxDisp: int, sd: float, lam: float, theta: float,
+                                      stream=None) -> None:
+    """roo::CostVolMinimumSquarePenaltySubpix (cu_dense_stereo.h:87-89)."""
+    check(lib().roo_costvol_minimum_square_penalty_subpix(C.byref(imga.c()), C.byref(vol.c()), C.byref(imgd.c()), maxDisp, sd,
+                                                          lam, theta, _stream(stream)), "CostVolMinimumSquarePenaltySubpix")
+
+
+def FilterDispGrad(dOut: Image, dIn: Image, threshold: float, stream=None) -> None:
+    """roo::FilterDispGrad (cu_dense_stereo.h:101-103); dOut may be dIn, as in the applications."""
+    check(lib().roo_filter_disp_grad(C.byref(dOut.c()), C.byref(dIn.c()), threshold, _stream(stream)), "FilterDispGrad")
+
+
 def DenseStereoSubpixelRefine(dDispOut: Image, dDisp: Image, dCamLeft: Image, dCamRight: Image, stream=None) -> None:
     check(lib().roo_dense_stereo_subpixel_refine(C.byref(dDispOut.c()), C.byref(dDisp.c()), C.byref(dCamLeft.c()),
                                                  C.byref(dCamRight.c()), _stream(stream)), "DenseStereoSubpixelRefine")

@@ -71,6 +71,9 @@ def lib() -> C.CDLL:
         L.ko_costvol_minimum_subpix.argtypes = [P(KoImage), P(KoVolume), C.c_uint, C.c_float, P(KoImage)]
         L.ko_dense_stereo_subpixel_refine.argtypes = [P(KoImage)] * 5
         L.ko_left_right_check_f32.argtypes = [P(KoImage), P(KoImage), C.c_float, C.c_float]
+        L.ko_costvol_minimum_square_penalty_subpix.argtypes = [P(KoImage), P(KoVolume), P(KoImage), C.c_uint, C.c_float, C.c_float,
+                                                               C.c_float, P(KoImage)]
+        L.ko_filter_disp_grad.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_float]
         L.ko_left_right_check_i8.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
         L.ko_elementwise_scale_bias.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_float, C.c_float]
         L.ko_box_half.argtypes = [P(KoImage), P(KoImage), C.c_int]
@@ -191,6 +194,25 @@ def costvol_minimum_subpix(vol: np.ndarray, max_disp: int, sd: float):
     mask = np.zeros((h, w), np.uint8)
     lib().ko_costvol_minimum_subpix(C.byref(_img(disp)), C.byref(_vol(vol)), max_disp, sd, C.byref(_img(mask)))
     return disp, mask
+
+
+def costvol_minimum_square_penalty_subpix(vol: np.ndarray, lastd: np.ndarray, max_disp: int, sd: float, lam: float, theta: float):
+    d, h, w = vol.shape
+    out = np.zeros((h, w), np.float32)
+    mask = np.zeros((h, w), np.uint8)
+    lastd = np.ascontiguousarray(lastd, np.float32)
+    lib().ko_costvol_minimum_square_penalty_subpix(C.byref(_img(out)), C.byref(_vol(vol)), C.byref(_img(lastd)), max_disp, sd,
+                                                   lam, theta, C.byref(_img(mask)))
+    return out, mask
+
+
+def filter_disp_grad(grad_src: np.ndarray, img_in: np.ndarray, threshold: float) -> np.ndarray:
+    """FilterDispGrad with the gradient taken of grad_src (what the output image held before the call)."""
+    grad_src = np.ascontiguousarray(grad_src, np.float32)
+    img_in = np.ascontiguousarray(img_in, np.float32)
+    out = np.zeros_like(grad_src)
+    lib().ko_filter_disp_grad(C.byref(_img(out)), C.byref(_img(grad_src)), C.byref(_img(img_in)), threshold)
+    return out
 
 
 def dense_stereo_subpixel_refine(disp: np.ndarray, left: np.ndarray, right: np.ndarray):

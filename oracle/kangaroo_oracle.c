@@ -372,6 +372,64 @@ void ko_costvol_minimum_subpix(const ko_image* disp, const ko_volume* vol, unsig
         }
 }
 
+/* cu_dense_stereo.cu:122-174 (KernCostVolMinimumSquarePenaltySubpix<float,float>), IEEE evaluation in source order */
+void ko_costvol_minimum_square_penalty_subpix(const ko_image* imga, const ko_volume* vol, const ko_image* imgd,
+                                              unsigned maxDispVal, float sd, float lambda, float theta, const ko_image* mask) {
+    const int w = (int)imga->w, h = (int)imga->h;
+    const int have_mask = mask && mask->ptr;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float lastd = *(const float*)img_at(imgd, (size_t)x, (size_t)y, 4);
+            const float inv2theta = 1.0f / (2.0f * theta);
+            float bestd = 0.0f;
+            float bestc = inv2theta * lastd * lastd + lambda * *(const float*)vol_at(vol, (size_t)x, (size_t)y, 0, 4);
+            for (int d = 1; d < (int)maxDispVal; ++d) {
+                const int xr = (int)((float)x + sd * (float)d);
+                if (0 <= xr && xr < (int)vol->w) {
+                    const float ddif = lastd - (float)d;
+                    const float c = inv2theta * ddif * ddif + lambda * *(const float*)vol_at(vol, (size_t)x, (size_t)y, (size_t)d, 4);
+                    if (c < bestc) { bestc = c; bestd = (float)d; }
+                }
+            }
+            float out = bestd;
+            unsigned char m = 0;
+            const int bestxr = (int)((float)x + sd * bestd);
+            if (0 < bestxr && bestxr < (int)vol->w - 1) {
+                const float dl = bestd - 1.0f, dr = bestd + 1.0f;
+                const size_t il = dl < 0.0f ? 0 : (size_t)dl;   /* cvt.rzi.u64.f32 saturates -1 to 0 (Q7) */
+                const size_t ir = (size_t)dr;
+                if (ir >= vol->d) {
+                    m = 1; /* the reference reads one slice past the volume */
+                } else {
+                    const float sl = inv2theta * (lastd - dl) * (lastd - dl) + lambda * *(const float*)vol_at(vol, (size_t)x, (size_t)y, il, 4);
+                    const float sr = inv2theta * (lastd - dr) * (lastd - dr) + lambda * *(const float*)vol_at(vol, (size_t)x, (size_t)y, ir, 4);
+                    const float subpixdisp = bestd - (sr - sl) / (2.0f * (sr - 2.0f * bestc + sl));
+                    if (dl < subpixdisp && subpixdisp < dr) out = subpixdisp;
+                }
+            }
+            *(float*)img_at(imga, (size_t)x, (size_t)y, 4) = out;
+            if (have_mask) *(uint8_t*)img_at(mask, (size_t)x, (size_t)y, 1) = m;
+        }
+}
+
+/* cu_dense_stereo.cu:793-812 (KernFilterDispGrad<float,float>): out = |grad G|^2 < threshold ? in : -1, where G is what the
+ * output image held before the call (Image.h:367-379 central differences, (a - b) / 2).  The sum of squares is ONE fused
+ * multiply-add in the reference's SASS -- FFMA(dx, dx, dy*dy) -- restated with fmaf().  `grad` must not alias `out`.
+ * Border pixels: the reference reads outside the image (undefined); out-of-image neighbours clamp to the edge here. */
+void ko_filter_disp_grad(const ko_image* out, const ko_image* grad, const ko_image* in, float threshold) {
+    const int w = (int)out->w, h = (int)out->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const int xm = x > 0 ? x - 1 : 0, xp = x + 1 < w ? x + 1 : w - 1, ym = y > 0 ? y - 1 : 0, yp = y + 1 < h ? y + 1 : h - 1;
+            const float dx = (*(const float*)img_at(grad, (size_t)xp, (size_t)y, 4) - *(const float*)img_at(grad, (size_t)xm, (size_t)y, 4)) / 2.0f;
+            const float dy = (*(const float*)img_at(grad, (size_t)x, (size_t)yp, 4) - *(const float*)img_at(grad, (size_t)x, (size_t)ym, 4)) / 2.0f;
+            const float m = fmaf(dx, dx, dy * dy);
+            *(float*)img_at(out, (size_t)x, (size_t)y, 4) = m < threshold ? *(const float*)img_at(in, (size_t)x, (size_t)y, 4) : -1.0f;
+        }
+}
+
 /* ---------------------------------------------------------------- subpixel refine ---- */
 
 /* patch_score.h:257-298, SANDPatchScore<float,2,ImgAccessRaw> on unsigned char images */

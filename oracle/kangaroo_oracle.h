@@ -131,6 +131,12 @@ void ko_warp(const ko_image* out_u8, const ko_image* in_u8, const ko_image* look
 void ko_median_filter_reject_negative(const ko_image* out_f32, const ko_image* in_f32, int size, int maxbad);
 
 /* src/cu_dense_stereo.cu:512-546 */
+/* src/cu_dense_stereo.cu:122-174; mask (optional, u8): 1 where the reference reads slice vol.d (Q7) */
+void ko_costvol_minimum_square_penalty_subpix(const ko_image* imga_f32, const ko_volume* vol_f32, const ko_image* imgd_f32,
+                                              unsigned maxDisp, float sd, float lambda, float theta, const ko_image* mask);
+/* src/cu_dense_stereo.cu:793-812; grad = the image whose gradient gates the output (the reference uses the output image's
+ * own previous contents), must not alias out */
+void ko_filter_disp_grad(const ko_image* out_f32, const ko_image* grad_f32, const ko_image* in_f32, float threshold);
 void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff);
 void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd, int maxDiff);
 

@@ -237,6 +237,41 @@ def median_filter_reject_negative(img: np.ndarray, size: int, maxbad: int) -> np
     return _back(out, np.float32, (h, w))
 
 
+def costvol_minimum_square_penalty_subpix(vol: np.ndarray, lastd: np.ndarray, max_disp: int, sd: float, lam: float,
+                                          theta: float) -> np.ndarray:
+    import torch
+    d, h, w = vol.shape
+    dv, dd = _dev(vol), _dev(np.ascontiguousarray(lastd, np.float32))
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    lib().kref_costvol_minimum_square_penalty_subpix.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                                 C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint,
+                                                                 C.c_float, C.c_float, C.c_float]
+    _ck(lib().kref_costvol_minimum_square_penalty_subpix(out.data_ptr(), dv.data_ptr(), w * 4, w * h * 4, d, dd.data_ptr(), w * 4,
+                                                         w, h, max_disp, sd, lam, theta), "CostVolMinimumSquarePenaltySubpix")
+    return _back(out, np.float32, (h, w))
+
+
+def filter_disp_grad(grad_src: np.ndarray, img_in: np.ndarray, threshold: float, margin: int = 16) -> np.ndarray:
+    """FilterDispGrad OUT OF PLACE: the output image is pre-filled with grad_src (whose central differences the kernel
+    reads), the values come from img_in.  Both live inside a larger zero-filled allocation because the kernel reads one
+    pixel beyond every border unguarded; returns the (h, w) interior."""
+    import torch
+    h, w = grad_src.shape
+    assert h % 16 == 0 and w % 16 == 0
+
+    def emb(a):
+        big = np.zeros((h + 2 * margin, w + 2 * margin), np.float32)
+        big[margin:-margin, margin:-margin] = a
+        return big
+    W = w + 2 * margin
+    do, di = _dev(emb(grad_src)), _dev(emb(img_in))
+    off = (margin * W + margin) * 4
+    lib().kref_filter_disp_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float]
+    _ck(lib().kref_filter_disp_grad(do.data_ptr() + off, di.data_ptr() + off, W * 4, w, h, threshold), "FilterDispGrad")
+    big = _back(do, np.float32, (h + 2 * margin, W))
+    return np.ascontiguousarray(big[margin:-margin, margin:-margin])
+
+
 def warp(img: np.ndarray, lookup: np.ndarray) -> np.ndarray:
     """roo::Warp: lookup is (h, w, 2) float32 = (x, y) sample positions inside [0, W-2] x [0, H-2] of img."""
     import torch

@@ -226,6 +226,23 @@ int kref_costvol_abs_and_grad(void* v, size_t v_pitch, size_t v_img_pitch, size_
     return finish();
 }
 
+// cu_dense_stereo.cu:122-174
+int kref_costvol_minimum_square_penalty_subpix(void* imga, void* v, size_t v_pitch, size_t v_img_pitch, size_t d, void* imgd,
+                                               size_t i_pitch, size_t w, size_t h, unsigned maxDisp, float sd, float lambda, float theta) {
+    roo::CostVolMinimumSquarePenaltySubpix(img<float>(imga, i_pitch, w, h), vol<float>(v, v_pitch, v_img_pitch, w, h, d),
+                                           img<float>(imgd, i_pitch, w, h), maxDisp, sd, lambda, theta);
+    return finish();
+}
+
+// cu_dense_stereo.cu:793-812: reads the central differences of OUT (its previous contents) and the values of IN; called
+// out of place here (out != in), on images that are the interior of a larger allocation (the kernel reads x-1, x+1, y-1, y+1
+// unguarded).  w and h must be multiples of 16 (gcd grid, launch_utils.h:61-65).
+int kref_filter_disp_grad(void* out, void* in, size_t pitch, size_t w, size_t h, float threshold) {
+    if (out == in) return -3;
+    roo::FilterDispGrad(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), threshold);
+    return finish();
+}
+
 int kref_create_matlab_lookup_table(void* lookup, size_t pitch, size_t w, size_t h, float fu, float fv, float u0, float v0,
                                     float k1, float k2) {
     roo::CreateMatlabLookupTable(img<float2>(lookup, pitch, w, h), fu, fv, u0, v0, k1, k2);

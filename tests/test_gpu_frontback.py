@@ -189,13 +189,69 @@ def test_median_reject_negative_vs_reference_and_oracle(golden, size):
     assert same_float(median(big, size, 10), ko.median_filter_reject_negative(big, size, 10))
 
 
-def test_median_refuses_in_place():
-    from kangaroo_b200.capi import RooError
-    img = roo.Image(32, 32, np.float32)
-    with pytest.raises(RooError):
-        roo.MedianFilterRejectNegative5x5(img, img, 100)
-    with pytest.raises(RooError):
-        roo.MedianFilterRejectNegative5x5(img.sub_image(0, 0, 16, 16), img.sub_image(8, 8, 16, 16), 100)
+def test_median_in_place_equals_out_of_place():
+    """Both reference applications call the filter in place (stereo2/main.cpp:440-442), where the reference races with
+    itself; here an aliasing call goes through a temporary and gives exactly the out-of-place result."""
+    rng = np.random.default_rng(3)
+    a = np.round(rng.normal(30, 10, (70, 90)), 1).astype(np.float32)
+    a[rng.random(a.shape) < 0.04] = np.nan
+    for size, fn in ((5, roo.MedianFilterRejectNegative5x5), (7, roo.MedianFilterRejectNegative7x7), (9, roo.MedianFilterRejectNegative9x9)):
+        img = roo.Image.from_numpy(a, pitch=90 * 4 + 8)
+        fn(img, img, 20)
+        assert same_float(img.numpy(), ko.median_filter_reject_negative(a, size, 20))
+    # partially overlapping views
+    img = roo.Image.from_numpy(a)
+    roo.MedianFilterRejectNegative5x5(img.sub_image(8, 8, 40, 40), img.sub_image(0, 0, 40, 40), 20)
+    assert same_float(img.numpy()[8:48, 8:48], ko.median_filter_reject_negative(np.ascontiguousarray(a[0:40, 0:40]), 5, 20))
+
+
+# ---------------------------------------------------------------- FilterDispGrad (SURVEY 8f N1), CostVolMinimumSquarePenaltySubpix (N4)
+
+def test_filter_disp_grad_vs_reference_and_oracle(golden):
+    g = golden("filtgrad")
+    gs, vin = g["grad_src"], g["img_in"]
+    inner = (slice(1, -1), slice(1, -1))   # the reference reads outside the image on the border ring (undefined)
+    for thr in (0.05, 0.5, 4.0):
+        out = roo.Image.from_numpy(gs, pitch=64 * 4 + 32)
+        roo.FilterDispGrad(out, roo.Image.from_numpy(vin), thr)
+        assert same_bits(out.numpy()[inner], g[f"out_{thr}"][inner])
+        assert same_bits(out.numpy(), ko.filter_disp_grad(gs, vin, thr))
+    # in place, as applications/stereo2/main.cpp:457 calls it
+    img = roo.Image.from_numpy(gs)
+    roo.FilterDispGrad(img, img, 0.5)
+    assert same_bits(img.numpy()[inner], g["inplace_0.5"][inner])
+    assert same_bits(img.numpy(), ko.filter_disp_grad(gs, gs, 0.5))
+    # camera-sized frame, odd size
+    rng = np.random.default_rng(11)
+    big = (rng.normal(0, 1, (375, 1242)).cumsum(axis=1) * 0.3).astype(np.float32)
+    big[rng.random(big.shape) < 0.02] = np.nan
+    o = roo.Image.from_numpy(big)
+    roo.FilterDispGrad(o, o, 0.3)
+    assert same_bits(o.numpy(), ko.filter_disp_grad(big, big, 0.3))
+
+
+def test_costvol_minimum_square_penalty_subpix_vs_reference_and_oracle(golden):
+    g = golden("sqpen")
+    vol, lastd = g["vol"], g["lastd"]
+    D = vol.shape[0]
+    for nm in ("a", "b", "c"):
+        sd, lam, theta = (float(v) for v in g[f"par_{nm}"])
+        out = roo.Image(vol.shape[2], vol.shape[1], np.float32)
+        roo.CostVolMinimumSquarePenaltySubpix(out, roo.Volume.from_numpy(vol), roo.Image.from_numpy(lastd), D, sd, lam, theta)
+        ref = g[f"out_{nm}"]
+        o_or, mask = ko.costvol_minimum_square_penalty_subpix(vol, lastd, D, sd, lam, theta)
+        ok = mask == 0                        # Q7: the reference reads slice vol.d there
+        # default mode = the reference's fast-math SASS: bit-identical
+        assert same_bits(out.numpy()[ok], ref[ok])
+        # IEEE mode = the oracle, bit-identical; and the oracle within the parity bars of the reference
+        roo.set_ieee_division(True)
+        try:
+            roo.CostVolMinimumSquarePenaltySubpix(out, roo.Volume.from_numpy(vol), roo.Image.from_numpy(lastd), D, sd, lam, theta)
+        finally:
+            roo.set_ieee_division(False)
+        assert same_bits(out.numpy(), o_or)
+        assert (np.rint(o_or[ok]) == np.rint(ref[ok])).mean() >= 0.999
+        assert (np.abs(o_or - ref)[ok] <= 0.01).mean() >= 0.999
 
 
 # ---------------------------------------------------------------- rectification warp (SURVEY 8f N3)

@@ -382,3 +382,47 @@ def test_create_matlab_lookup_table_matches_reference_within_fast_math(golden):
     ident = ko.create_matlab_lookup_table(8, 4, float(p[2]), float(p[3]), 3.0, 1.0, 0.0, 0.0)
     yy, xx = np.mgrid[0:4, 0:8].astype(np.float32)
     assert np.abs(ident[..., 0] - xx).max() <= 1e-5 and np.abs(ident[..., 1] - yy).max() <= 1e-5
+
+
+# ---------------------------------------------------------------- FilterDispGrad (N1), CostVolMinimumSquarePenaltySubpix (N4)
+
+def test_filter_disp_grad_matches_reference(golden):
+    """Interior pixels bit-identical to the reference kernel run out of place on a B200 (tests/golden/make_golden_n4b.py);
+    the border ring is where the reference reads outside the image."""
+    g = golden("filtgrad")
+    inner = (slice(1, -1), slice(1, -1))
+    for thr in (0.05, 0.5, 4.0):
+        out = ko.filter_disp_grad(g["grad_src"], g["img_in"], thr)
+        assert np.array_equal(out[inner].view(np.uint32), g[f"out_{thr}"][inner].view(np.uint32))
+    out = ko.filter_disp_grad(g["grad_src"], g["grad_src"], 0.5)
+    assert np.array_equal(out[inner].view(np.uint32), g["inplace_0.5"][inner].view(np.uint32))
+
+
+def test_kat_filter_disp_grad():
+    img = np.zeros((5, 5), np.float32)
+    img[2, 3] = 2.0                                   # at (2,2): dx = (2 - 0) / 2 = 1, dy = 0 -> |grad|^2 = 1
+    assert ko.filter_disp_grad(img, img + 7, 1.5)[2, 2] == 7.0
+    assert ko.filter_disp_grad(img, img + 7, 1.0)[2, 2] == -1.0      # strict <
+    nan = img.copy(); nan[2, 1] = np.nan
+    assert ko.filter_disp_grad(nan, img + 7, 1e9)[2, 2] == -1.0      # NaN neighbour: not valid
+
+
+def test_costvol_minimum_square_penalty_subpix_matches_reference(golden):
+    g = golden("sqpen")
+    D = g["vol"].shape[0]
+    for nm in ("a", "b", "c"):
+        sd, lam, theta = (float(v) for v in g[f"par_{nm}"])
+        out, mask = ko.costvol_minimum_square_penalty_subpix(g["vol"], g["lastd"], D, sd, lam, theta)
+        ok = mask == 0
+        ref = g[f"out_{nm}"]
+        assert (np.rint(out[ok]) == np.rint(ref[ok])).mean() >= 0.999
+        assert (np.abs(out - ref)[ok] <= 0.01).mean() >= 0.999
+
+
+def test_kat_square_penalty_pulls_towards_previous_disparity():
+    vol = np.ones((8, 1, 12), np.float32)
+    vol[2, 0, :] = 0.0                                 # data term prefers d = 2 everywhere
+    lastd = np.full((1, 12), 6.0, np.float32)
+    weak, _ = ko.costvol_minimum_square_penalty_subpix(vol, lastd, 8, -1.0, 1.0, 1e6)    # no coupling: data wins
+    strong, _ = ko.costvol_minimum_square_penalty_subpix(vol, lastd, 8, -1.0, 1.0, 1e-3)  # stiff coupling: lastd wins
+    assert np.rint(weak[0, 9]) == 2 and np.rint(strong[0, 9]) == 6

@@ -207,6 +207,7 @@ typedef struct roo_pipeline_params_t {
     int median_maxbad;    /*   left-right check, median_iters times, on both disparity images when lrcheck is set      */
     int median_iters;     /*   (main.cpp:438-444; out of place into engine scratch, so without the reference's race)   */
     int fp_mode;          /* enum roo_fp_mode: floating-point mode of THIS engine (two engines may differ) */
+    float filtgrad_threshold; /* > 0: FilterDispGrad(disp, disp, threshold) as the last stage (main.cpp:456-458); 0: off */
 } roo_pipeline_params_t;
 
 /* The engine allocates its scratch on the CURRENT device; later calls must come with that device current (else
@@ -254,6 +255,21 @@ int roo_multi_engine_destroy(roo_multi_engine_t* m);
 int roo_multi_engine_device_count(const roo_multi_engine_t* m);
 int roo_multi_engine_run_host(roo_multi_engine_t* m, const uint8_t* left_host, const uint8_t* right_host, float* disp_host,
                               int n_pairs);
+
+/* ---- multi-GPU, ONE pair: row-strip split with halo hand-off over NVLink (BASELINE config 5).
+ * GPU k owns a strip of image rows (its part of the aggregate never moves); the six paths that travel in y hand their
+ * state from strip to strip through peer memory (st.release.sys / ld.acquire.sys on the exported record), horizontal paths,
+ * winner-takes-all and the left-right check are strip-local.  No collective.  Results are bit-identical to roo_engine_*.
+ * devices == NULL / n_devices <= 0: all visible devices, one strip each.  A device may be listed more than once (strips that
+ * share a device are ordered by CUDA events instead of in-kernel polling).  median_size and filtgrad_threshold must be 0. */
+typedef struct roo_split_engine roo_split_engine_t;
+int roo_split_engine_create(roo_split_engine_t** out, const roo_pipeline_params_t* params, const int* devices, int n_devices);
+int roo_split_engine_destroy(roo_split_engine_t* e);
+int roo_split_engine_strip_count(const roo_split_engine_t* e);
+/* one pair: whole (h x w) uint8 frames in host memory (pinned recommended) -> (h x w) float disparities in host memory */
+int roo_split_engine_run_host(roo_split_engine_t* e, const uint8_t* left_host, const uint8_t* right_host, float* disp_host);
+/* device time of the last frame (census .. left-right check, max over strips, CUDA events) and bytes handed between strips */
+int roo_split_engine_last_stats(const roo_split_engine_t* e, float* device_ms, unsigned long long* exchanged_bytes);
 
 /* Per-kernel device timing for bench.py: with profiling on, the engine records a CUDA event after
  * every launch on the launching stream; roo_engine_get_profile (call after synchronising) returns the

@@ -22,6 +22,11 @@ DISP_I8, DISP_F32 = 0, 1
 PROF_KINDS = ("census", "cost", "sweep", "wta", "lrcheck", "vgroup") + tuple(f"pass{i}" for i in range(8))
 
 
+def disp_padded(max_disp: int) -> int:
+    """internal disparity count: maxDisp rounded up to 32 / 64 / 128 / 256"""
+    return 32 if max_disp <= 32 else (64 if max_disp <= 64 else (128 if max_disp <= 128 else 256))
+
+
 class RooImage(C.Structure):
     """roo_image_t == roo::Image<T> (Image.h:617-620)."""
     _fields_ = [("pitch", C.c_size_t), ("ptr", C.c_void_p), ("w", C.c_size_t), ("h", C.c_size_t)]
@@ -40,7 +45,7 @@ class PipelineParams(C.Structure):
                 ("subpix", C.c_int), ("lrcheck", C.c_int), ("lr_maxdiff", C.c_float),
                 ("max_batch", C.c_int), ("keep_volume", C.c_int), ("fuse_vertical", C.c_int),
                 ("median_size", C.c_int), ("median_maxbad", C.c_int), ("median_iters", C.c_int),
-                ("fp_mode", C.c_int)]
+                ("fp_mode", C.c_int), ("filtgrad_threshold", C.c_float)]
 
 
 # every symbol include/roo_b200.h declares: name -> (restype, argtypes)
@@ -85,6 +90,11 @@ SYMBOLS = {
     "roo_engine_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
     "roo_engine_export_volume": (C.c_int, [C.c_void_p, C.c_int, _VOL, _S]),
     "roo_engine_export_census": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _IMG, _S]),
+    "roo_split_engine_create": (C.c_int, [_P(C.c_void_p), _P(PipelineParams), _P(C.c_int), C.c_int]),
+    "roo_split_engine_destroy": (C.c_int, [C.c_void_p]),
+    "roo_split_engine_strip_count": (C.c_int, [C.c_void_p]),
+    "roo_split_engine_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "roo_split_engine_last_stats": (C.c_int, [C.c_void_p, _P(C.c_float), _P(C.c_ulonglong)]),
     "roo_multi_engine_create": (C.c_int, [_P(C.c_void_p), _P(PipelineParams), _P(C.c_int), C.c_int]),
     "roo_multi_engine_destroy": (C.c_int, [C.c_void_p]),
     "roo_multi_engine_device_count": (C.c_int, [C.c_void_p]),

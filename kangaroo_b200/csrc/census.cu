@@ -159,14 +159,14 @@ constexpr int CSV_TX = 128;
 template <int WORDS, typename Tvol, bool POPC64>
 __global__ void __launch_bounds__(CSV_TX)
 census_stereo_volume_kernel(Vol<Tvol> vol, const char* __restrict__ left, const char* __restrict__ right,
-                            size_t c_pitch, int rw, int maxDisp, int sdi) {
+                            size_t l_pitch, size_t r_pitch, int rw, int maxDisp, int sdi) {
     extern __shared__ unsigned long long cache_r[];  // [(CSV_TX + maxDisp - 1) * WORDS], word-major
     const int x0 = blockIdx.x * CSV_TX, y = blockIdx.y;
     const int x = x0 + threadIdx.x;
     const int span = CSV_TX + maxDisp - 1;
     // right-image x range touched by this segment: sd=-1: [x0-(maxDisp-1), x0+TX) ; sd=+1: [x0, x0+TX+maxDisp-1)
     const int rx0 = sdi < 0 ? x0 - (maxDisp - 1) : x0;
-    const unsigned long long* rrow = reinterpret_cast<const unsigned long long*>(right + (size_t)y * c_pitch);
+    const unsigned long long* rrow = reinterpret_cast<const unsigned long long*>(right + (size_t)y * r_pitch);
     for (int i = threadIdx.x; i < span; i += CSV_TX) {
         const int gx = rx0 + i;
         const bool ok = gx >= 0 && gx < rw;
@@ -176,7 +176,7 @@ census_stereo_volume_kernel(Vol<Tvol> vol, const char* __restrict__ left, const 
     __syncthreads();
     if (x >= vol.w) return;
     unsigned long long p[WORDS];
-    const unsigned long long* lrow = reinterpret_cast<const unsigned long long*>(left + (size_t)y * c_pitch);
+    const unsigned long long* lrow = reinterpret_cast<const unsigned long long*>(left + (size_t)y * l_pitch);
 #pragma unroll
     for (int k = 0; k < WORDS; ++k) p[k] = lrow[(size_t)x * WORDS + k];
     const float inv_bits = 1.0f / (float)(WORDS * 64);  // power of two: exact, equals the reference's divide
@@ -203,7 +203,7 @@ static int csv_launch(const roo_volume_t* vol, const roo_image_t* l, const roo_i
     auto kern = popc_mode == ROO_POPC64 ? census_stereo_volume_kernel<WORDS, Tvol, true>
                                         : census_stereo_volume_kernel<WORDS, Tvol, false>;
     if (smem > 48 * 1024) ROO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, block, smem, st>>>(Vol<Tvol>(*vol), (const char*)l->ptr, (const char*)r->ptr, l->pitch, (int)r->w,
+    kern<<<grid, block, smem, st>>>(Vol<Tvol>(*vol), (const char*)l->ptr, (const char*)r->ptr, l->pitch, r->pitch, (int)r->w,
                                     maxDisp, sdi);
     count_launch();
     return launch_status();
@@ -434,7 +434,7 @@ extern "C" int roo_census_stereo_volume(const roo_volume_t* vol, const roo_image
     if (!valid_volume(vol, vol_type == ROO_VOL_F32 ? 4 : 2) || !valid_image(left, (size_t)words * 8) ||
         !valid_image(right, (size_t)words * 8))
         return ROO_ERR_INVALID_ARGUMENT;
-    if (vol->w != left->w || vol->h != left->h || right->h != left->h || left->pitch != right->pitch)
+    if (vol->w != left->w || vol->h != left->h || right->h != left->h)
         return ROO_ERR_INVALID_ARGUMENT;
     if (maxDisp <= 0) return ROO_OK;  // reference: empty loop
     if ((size_t)maxDisp > vol->d) return ROO_ERR_INVALID_ARGUMENT;

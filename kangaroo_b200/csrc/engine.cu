@@ -32,7 +32,7 @@ struct roo_engine {
     unsigned char* c8 = nullptr;                      // [batch][h][w][DP]
     float* H = nullptr;                               // [batch][h][w][DP]
     float* dispR = nullptr;                           // [batch][h][w]
-    float* med = nullptr;                             // [batch][h][w] output of the median stage
+    float* med = nullptr;                             // [batch][h][w] output of the median stage / FilterDispGrad snapshot
     float* imgf = nullptr;                            // [batch][h][w] adaptive-P2 intensity (u8 * img_scale)
     float* edge = nullptr;                            // fused vertical groups: band-to-band state rows
     int* flags = nullptr;                             //                        and their progress flags
@@ -50,6 +50,7 @@ struct roo_engine {
     unsigned char* in_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][side]
     float* out_dev[2] = {nullptr, nullptr};
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    bool host_ready = false;   // streams, events and staging buffers below all exist
     long long ticket = 0;   // groups submitted through the host-buffer path so far
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     size_t scratch_bytes = 0;
@@ -192,23 +193,25 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         if (rc) return rc;
         prof_mark(e, ROO_PROF_LRCHECK, st);
     }
+    // FilterDispGrad(disp[0], disp[0], filtgradthresh) (main.cpp:456-458): gradient of a snapshot of the disparities
+    if (p.filtgrad_threshold > 0.0f) {
+        ROO_CUDA_TRY(cudaMemcpyAsync(e->med, disp, (size_t)batch * npx * 4, cudaMemcpyDeviceToDevice, st));
+        const roo_image_t o{(size_t)w * 4, disp, (size_t)w, (size_t)h}, g{(size_t)w * 4, e->med, (size_t)w, (size_t)h};
+        rc = launch_filter_disp_grad(o, g, g, p.filtgrad_threshold, st, batch, npx * 4, npx * 4, npx * 4);
+        if (rc) return rc;
+        prof_mark(e, ROO_PROF_LRCHECK, st);
+    }
     e->last_batch = batch;
     return ROO_OK;
 }
 
+static void host_streams_free(roo_engine* e);
+
 static void engine_free(roo_engine* e) {
     cudaFree(e->cen_base[0]); cudaFree(e->cen_base[1]); cudaFree(e->c8); cudaFree(e->H); cudaFree(e->dispR); cudaFree(e->med); cudaFree(e->imgf);
     for (int sd = 0; sd < 2; ++sd) { cudaFree(e->fe_rect[sd]); cudaFree(e->fe_pyr[sd]); } cudaFree(e->edge); cudaFree(e->flags);
-    for (int b = 0; b < 2; ++b) {
-        cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
-        if (e->ev_in[b]) cudaEventDestroy(e->ev_in[b]);
-        if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
-        if (e->ev_out[b]) cudaEventDestroy(e->ev_out[b]);
-    }
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
-    if (e->s_compute) cudaStreamDestroy(e->s_compute);
-    if (e->s_in) cudaStreamDestroy(e->s_in);
-    if (e->s_out) cudaStreamDestroy(e->s_out);
+    host_streams_free(e);
 }
 
 extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t* params) {
@@ -256,7 +259,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
         ok = alloc((void**)&e->c8, B * npx * e->DP) && alloc((void**)&e->H, B * npx * e->DP * 4) &&
              alloc((void**)&e->imgf, B * npx * 4);
     if (ok && p.lrcheck) ok = alloc((void**)&e->dispR, B * npx * 4);
-    if (ok && p.median_size > 0) ok = alloc((void**)&e->med, B * npx * 4);
+    if (ok && (p.median_size > 0 || p.filtgrad_threshold > 0.0f)) ok = alloc((void**)&e->med, B * npx * 4);
     if (ok && fused)
         ok = alloc((void**)&e->edge, B * vgroup_edge_floats(p.w, p.h, e->DP) * 4) &&
              alloc((void**)&e->flags, B * (size_t)vgroup_bands(p.w, p.h, e->DP) * 4 + 256);   // + debug counters (VG_TIMING builds)
@@ -288,7 +291,7 @@ extern "C" int roo_engine_set_front_end(roo_engine_t* e, int level, const roo_im
                                         const roo_image_t* lookup_right) {
     if (!e || level < 0 || level > 8 || (lookup_left == nullptr) != (lookup_right == nullptr) || !on_engine_device(e))
         return ROO_ERR_INVALID_ARGUMENT;
-    if (e->s_compute || e->fe_rectify || e->fe_level > 0) return ROO_ERR_INVALID_ARGUMENT;   // once, before the first host run
+    if (e->host_ready || e->fe_rectify || e->fe_level > 0) return ROO_ERR_INVALID_ARGUMENT;   // once, before the first host run
     const size_t rw = (size_t)e->p.w << level, rh = (size_t)e->p.h << level, B = (size_t)e->p.max_batch;
     if (lookup_left) {
         const roo_image_t* lut[2] = {lookup_left, lookup_right};
@@ -327,21 +330,49 @@ extern "C" int roo_engine_run_device(roo_engine_t* e, const uint8_t* left, const
 
 // Host buffers: upload group g+1 and download group g-1 while group g computes (three streams, two
 // staging buffers).  Pinned host memory makes the copies truly asynchronous.
-static int host_streams_init(roo_engine_t* e) {
-    if (e->s_compute) return ROO_OK;
-    const size_t npx = e->npx, B = (size_t)e->p.max_batch;
-    ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
-    ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
-    ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+static void host_streams_free(roo_engine_t* e) {
     for (int b = 0; b < 2; ++b) {
-        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][0], B * e->in_npx));
-        ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][1], B * e->in_npx));
-        ROO_CUDA_TRY(cudaMalloc((void**)&e->out_dev[b], B * npx * 4));
-        e->scratch_bytes += 2 * B * e->in_npx + B * npx * 4;
-        ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[b], cudaEventDisableTiming));
-        ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
-        ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[b], cudaEventDisableTiming));
+        cudaFree(e->in_dev[b][0]); cudaFree(e->in_dev[b][1]); cudaFree(e->out_dev[b]);
+        e->in_dev[b][0] = e->in_dev[b][1] = nullptr; e->out_dev[b] = nullptr;
+        if (e->ev_in[b]) cudaEventDestroy(e->ev_in[b]);
+        if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
+        if (e->ev_out[b]) cudaEventDestroy(e->ev_out[b]);
+        e->ev_in[b] = e->ev_done[b] = e->ev_out[b] = nullptr;
     }
+    if (e->s_compute) cudaStreamDestroy(e->s_compute);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
+    e->s_compute = e->s_in = e->s_out = nullptr;
+}
+
+// Streams, events and staging buffers of the host-buffer path, created on first use.  `host_ready` is set only after
+// EVERY allocation succeeded; a failure (e.g. out of memory for the 2 x max_batch staging frames) rolls everything back,
+// so a later call starts from scratch instead of running on half-initialised state.
+static int host_streams_init(roo_engine_t* e) {
+    if (e->host_ready) return ROO_OK;
+    const size_t npx = e->npx, B = (size_t)e->p.max_batch;
+    auto attempt = [&]() -> int {
+        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+        ROO_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][0], B * e->in_npx));
+            ROO_CUDA_TRY(cudaMalloc((void**)&e->in_dev[b][1], B * e->in_npx));
+            ROO_CUDA_TRY(cudaMalloc((void**)&e->out_dev[b], B * npx * 4));
+            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[b], cudaEventDisableTiming));
+            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
+            ROO_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[b], cudaEventDisableTiming));
+        }
+        return ROO_OK;
+    };
+    const int rc = attempt();
+    if (rc != ROO_OK) {
+        cudaGetLastError();
+        host_streams_free(e);
+        return rc;
+    }
+    e->scratch_bytes += 2 * (2 * B * e->in_npx + B * npx * 4);
+    e->host_ready = true;
     return ROO_OK;
 }
 
@@ -515,7 +546,9 @@ extern "C" int roo_multi_engine_run_host(roo_multi_engine_t* m, const uint8_t* l
     const int n = (int)m->engines.size();
     std::vector<int> status(n, ROO_OK);
     std::vector<std::thread> workers;
-    for (int i = 0; i < n; ++i) {
+    bool spawn_failed = false;
+    for (int i = 0; i < n && !spawn_failed; ++i) {
+        try {   // std::thread may throw (resource exhaustion): nothing may propagate through the extern "C" boundary
         workers.emplace_back([&, i]() {
             int begin = 0, count = 0;
             shard_of(n_pairs, n, i, &begin, &count);
@@ -524,8 +557,10 @@ extern "C" int roo_multi_engine_run_host(roo_multi_engine_t* m, const uint8_t* l
             const size_t off = (size_t)begin * m->npx;
             status[i] = roo_engine_run_host(m->engines[i], left_host + off, right_host + off, disp_host + off, count);
         });
+        } catch (...) { spawn_failed = true; }
     }
     for (auto& t : workers) t.join();
+    if (spawn_failed) return ROO_ERR_OUT_OF_MEMORY;
     for (int i = 0; i < n; ++i)
         if (status[i] != ROO_OK) return status[i];
     return ROO_OK;
@@ -534,7 +569,7 @@ extern "C" int roo_multi_engine_run_host(roo_multi_engine_t* m, const uint8_t* l
 // Development aid: cycle counters written by a -DVG_TIMING build of sgm_fused.cu (zeros otherwise).
 extern "C" int roo_engine_debug_counters(roo_engine_t* e, unsigned long long* out, int n, int reset) {
     if (!e || !e->flags || !out || n <= 0 || n > 32) return ROO_ERR_INVALID_ARGUMENT;
-    char* base = reinterpret_cast<char*>(e->flags) + (size_t)e->p.max_batch * vgroup_bands(e->p.w, e->p.h, e->DP) * 4;
+    char* base = reinterpret_cast<char*>(e->flags) + ((size_t)e->p.max_batch * vgroup_bands(e->p.w, e->p.h, e->DP) + 2) * 4;
     ROO_CUDA_TRY(cudaMemcpy(out, base, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (reset) ROO_CUDA_TRY(cudaMemset(base, 0, 256));
     return ROO_OK;

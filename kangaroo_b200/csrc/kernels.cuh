@@ -39,7 +39,17 @@ struct SweepArgs {
     const unsigned long long* cenL;
     const unsigned long long* cenR;
     size_t cen_pair;     // elements between pairs
+    // Row-strip split of ONE pair across GPUs (roo_split_engine): this launch covers a strip of image rows;
+    // a path that enters the strip through its first row (in travel direction) continues from the state the upstream
+    // strip exported for the pixel it comes from, and a path that leaves through the last row exports its state for the
+    // downstream strip.  Records of strip_rec_floats(DP) floats, indexed by the x of the boundary-row pixel; the last
+    // word is a sequence number published with st.release.sys (the record lives in the CONSUMER's memory, written
+    // over NVLink) and polled with ld.acquire.sys.  nullptr: the strip edge is the image edge.
+    const float* strip_import;   // local memory, written by the upstream GPU
+    float* strip_export;         // peer memory of the downstream GPU
+    int strip_seq;               // value that marks the records of THIS sweep
 };
+inline size_t strip_rec_floats(int DP) { return (size_t)DP + 4; }   // [DP aggregate row | lastBest | pixel | - | seq]
 int launch_sweep(const SweepArgs& a, cudaStream_t st);
 // sgm_hsweep.cu: the horizontal paths (a.dy == 0), bulk-copy prefetch
 int launch_hsweep(const SweepArgs& a, cudaStream_t st);
@@ -67,6 +77,7 @@ struct VGroupArgs {
     float* edge_hp;     // [pair][band][h][3][DP]  states handed from band b to band b+1
     float* edge_sc;     // [pair][band][h][8]
     int* progress;      // [pair][band] rows published
+    int* ticket;        // CTA start counter of this launch (zeroed with the flags)
     int n_bands;
 };
 size_t vgroup_edge_floats(int w, int h, int DP);   // per pair
@@ -95,7 +106,9 @@ int launch_box_half_u8(unsigned char* out, const unsigned char* in, int w_out, i
 // MedianFilterRejectNegative{5,7,9} over a batch of images (out must not overlap in)
 int launch_median(float* out, size_t out_pitch, size_t out_batch, const float* in, size_t in_pitch, size_t in_batch, int w,
                   int h, int batch, int size, int maxbad, cudaStream_t st);
-int launch_filter_disp_grad(const roo_image_t& out, const roo_image_t& grad, const roo_image_t& in, float threshold, cudaStream_t st);
+// FilterDispGrad over `batch` images (byte strides between them); grad must not overlap out
+int launch_filter_disp_grad(const roo_image_t& out, const roo_image_t& grad, const roo_image_t& in, float threshold, cudaStream_t st,
+                            int batch = 1, size_t out_pair = 0, size_t grad_pair = 0, size_t in_pair = 0);
 int launch_lr_check_f32(float* dispL, size_t pitchL, const float* dispR, size_t pitchR, int w, int h, int batch,
                         size_t batchL, size_t batchR, float sd, float maxDiff, cudaStream_t st);
 

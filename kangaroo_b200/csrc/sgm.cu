@@ -102,6 +102,26 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
     for (int j = 0; j < DPL; ++j) hp[j] = ROO_INF;   // path start: no previous pixel
     float lastBest = 0.0f, last_c = 0.0f;
     int x = sl.x0;
+    // ---- row-strip split: continue a path that comes in through the strip's entry row
+    constexpr int REC = DP + 4;
+    const int y_entry = a.dy > 0 ? 0 : a.h - 1, y_exit = a.dy > 0 ? a.h - 1 : 0;
+    bool continued = false;
+    if (a.strip_import != nullptr && a.dy != 0 && sl.y0 == y_entry) {
+        const int xin = sl.x0 - dx;                  // the pixel of the upstream strip's exit row this path comes from
+        if (xin >= 0 && xin < w) {
+            const float* rec = a.strip_import + ((size_t)pair * w + xin) * REC;
+            if (lane == 0) {
+                int seq;
+                do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seq) : "l"(rec + DP + 3) : "memory"); } while (seq != a.strip_seq);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) hp[j] = __ldcg(rec + d0 + j);
+            lastBest = __ldcg(rec + DP);
+            last_c = __ldcg(rec + DP + 1);
+            continued = true;
+        }
+    }
     // all lanes in range iff x >= xf (possible only when maxDisp fills the padded range)
     const int xf = (M == DP) ? DP - 1 : 0x3fffffff;
 
@@ -114,14 +134,14 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
         rc.lds(stg + DP * 4 + lane * DPL * CE);
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + DP * CE));
         // start pixel: `volH += volC`, lastBestCr = 0 (cu_semi_global_matching.cu:31-35) == a step with P2 = 0
-        const float p2 = r == 0 ? 0.0f : P2;
+        const float p2 = (r == 0 && !continued) ? 0.0f : P2;
         const float denom = 1.0f + fabsf(last_c - pix);
         const int lim = MASKED ? min(M, x + 1) - d0 : 0;
         float craw[DPL];
 #pragma unroll
         for (int j = 0; j < DPL; ++j) craw[j] = rc.raw(j);
         sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, craw, cscale, hin, lim, lane, hnew, hp, best);
-        lastBest = r == 0 ? 0.0f : best;
+        lastBest = (r == 0 && !continued) ? 0.0f : best;
         last_c = pix;
         if (EPI != EPI_WTA_ONLY) store_f<DPL>(hst, hnew);
         hst += estep;
@@ -140,6 +160,19 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
         __syncwarp();
         if (x >= xf) step(std::false_type{}, r);
         else step(std::true_type{}, r);
+    }
+    // ---- row-strip split: hand the state of a path that leaves through the strip's exit row to the downstream strip
+    if (a.strip_export != nullptr && a.dy != 0 && sl.y0 + a.dy * (len - 1) == y_exit) {
+        const int xout = x - dx;                     // x of the last pixel
+        float* rec = a.strip_export + ((size_t)pair * w + xout) * REC;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) rec[d0 + j] = hp[j];
+        if (lane == 0) { rec[DP] = lastBest; rec[DP + 1] = last_c; }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(rec + DP + 3), "r"(a.strip_seq) : "memory");
+        }
     }
 }
 
@@ -347,7 +380,7 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
     bool fused = false;
     for (int i = 0; i < plan.n; ++i) fused |= plan.pass[i].fused != 0;
     const size_t edge_n = fused ? vgroup_edge_floats(w, h, DP) : 0;
-    const size_t flag_n = fused ? (size_t)vgroup_bands(w, h, DP) : 0;
+    const size_t flag_n = fused ? (size_t)vgroup_bands(w, h, DP) + 2 : 0;   // + the CTA ticket counter
     // [Ci | Hi | fp32 image | edge rows | flags], stream-ordered pool memory; every segment 256-byte aligned
     auto al = [](size_t nfloats) { return (nfloats + 63) / 64 * 64; };
     const size_t img_n = al((size_t)w * h);

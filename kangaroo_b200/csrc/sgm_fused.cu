@@ -126,6 +126,20 @@ __device__ __forceinline__ void cp_async_row(float* smem_dst, const float* gsrc)
 // for the compiler by the volatile flag accesses and this barrier) is enough; a MEMBAR here would also wait
 // for the warp's outstanding GLOBAL prefetch loads and serialise every row on DRAM latency.
 __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
+// VG_RELACQ=1 (default): the in-band progress words are published with st.release.cta and polled with ld.acquire.cta --
+// race-free under the PTX memory model.  Measured on B200 (1280x720x128 x16, both fused passes): 5.98 ms against 5.92 ms
+// for -DVG_RELACQ=0, the round-1 variant that relied on program order through the SM's in-order shared-memory pipeline
+// (volatile accesses + a compiler barrier); a full __threadfence_block() per row had cost 27 %.
+#ifndef VG_RELACQ
+#define VG_RELACQ 1
+#endif
+__device__ __forceinline__ void publish_flag(volatile int* flag, int v) {
+#if VG_RELACQ
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(const_cast<int*>(flag))), "r"(v) : "memory");
+#else
+    *flag = v;
+#endif
+}
 
 #ifndef VG_SPIN_NS
 #define VG_SPIN_NS 30
@@ -136,11 +150,17 @@ __device__ __forceinline__ void smem_order() { asm volatile("" ::: "memory"); }
 // poll a monotonically growing shared-memory flag until it reaches `need`
 __device__ __forceinline__ void spin_until(unsigned flag_addr, int need) {
     int v;
-    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(flag_addr) : "memory");
+#if VG_RELACQ
+#define VG_FLAG_LD "ld.acquire.cta.shared.s32 %0, [%1];"
+#else
+#define VG_FLAG_LD "ld.volatile.shared.s32 %0, [%1];"
+#endif
+    asm volatile(VG_FLAG_LD : "=r"(v) : "r"(flag_addr) : "memory");
     while (v < need) {
         __nanosleep(VG_SPIN_NS);
-        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(flag_addr) : "memory");
+        asm volatile(VG_FLAG_LD : "=r"(v) : "r"(flag_addr) : "memory");
     }
+#undef VG_FLAG_LD
 }
 
 // smem control words
@@ -233,7 +253,14 @@ sgm_vgroup_kernel(const VGroupArgs a) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // pair fastest: the resident window of CTAs then holds the same few bands of EVERY pair, so the
     // band-to-band pipeline of each pair has only a short ramp
-    const int pair = blockIdx.x % a.batch, band = blockIdx.x / a.batch;
+    // The logical CTA index is a ticket drawn when the CTA starts, not blockIdx: band b spins on flags of band b-1 of the
+    // same pair, which holds a LOWER ticket and has therefore already been dispatched -- forward progress no longer
+    // depends on the hardware handing out CTAs in blockIdx order (which CUDA does not promise).
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int cta = s_ticket;
+    const int pair = cta % a.batch, band = cta / a.batch;
     const int w = a.w, h = a.h, M = a.maxDisp;
     constexpr bool fwd = FWD;   // travel direction in y: compile-time, so that the columns' address offsets are immediates
     const float P1 = a.P1, P2 = a.P2, cscale = a.cost_scale;
@@ -622,14 +649,14 @@ sgm_vgroup_kernel(const VGroupArgs a) {
         hst += estep;
         __syncwarp();
         smem_order();
-        if (lane == 0) prog[warp] = (y == y_out) ? 0x7fffffff : y + 1;
+        if (lane == 0) publish_flag(prog + warp, (y == y_out) ? 0x7fffffff : y + 1);
 #ifdef VG_TIMING
         tbody += clock64() - t3;
 #endif
     }
 #ifdef VG_TIMING
     if (lane == 0) {
-        unsigned long long* dbg = reinterpret_cast<unsigned long long*>(a.progress + (size_t)a.n_bands * a.batch);
+        unsigned long long* dbg = reinterpret_cast<unsigned long long*>(a.ticket + 2);
         const int role = warp == NWW - 1 ? 2 : (warp == 0 ? 0 : 1);   // lowest / interior / highest warp
         atomicAdd(dbg + role * 5 + 0, (unsigned long long)tcp);
         atomicAdd(dbg + role * 5 + 1, (unsigned long long)tup);
@@ -698,7 +725,8 @@ int launch_vgroup(const SweepArgs& s, int fwd, float* edge, int* progress, cudaS
     a.edge_hp = edge;
     a.edge_sc = edge + hp_floats * s.batch;
     a.progress = progress;
-    ROO_CUDA_TRY(cudaMemsetAsync(progress, 0, sizeof(int) * (size_t)a.n_bands * s.batch, st));
+    a.ticket = progress + (size_t)a.n_bands * s.batch;   // one more int after the flags (scratch is sized for it)
+    ROO_CUDA_TRY(cudaMemsetAsync(progress, 0, sizeof(int) * ((size_t)a.n_bands * s.batch + 1), st));
     const bool first = s.first != 0;
 #define ROO_VG_DP(DPL)                                                              \
     switch (s.cost_kind) {                                                          \

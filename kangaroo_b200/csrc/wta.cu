@@ -126,9 +126,11 @@ costvol_min_sqpen_subpix_kernel(Img<float> imga, Vol<float> vol, Img<float> imgd
 // Reference SASS: dx = (G(x+1,y) - G(x-1,y)) * 0.5, dy likewise, m = FFMA(dx, dx, dy * dy), valid = !(m >= threshold).
 // The reference reads outside the image on the border pixels (undefined); here out-of-image neighbours clamp to the edge.
 __global__ void __launch_bounds__(WTA_TX)
-filter_disp_grad_kernel(Img<float> out, Img<float> grad, Img<float> in, float threshold) {
+filter_disp_grad_kernel(Img<float> out, Img<float> grad, Img<float> in, float threshold, size_t out_pair, size_t grad_pair,
+                        size_t in_pair) {
     const int x = blockIdx.x * WTA_TX + threadIdx.x, y = blockIdx.y;
     if (x >= out.w) return;
+    out.ptr += blockIdx.z * out_pair; grad.ptr += blockIdx.z * grad_pair; in.ptr += blockIdx.z * in_pair;   // bytes between pairs
     const float* row = grad.row(y);
     const float dx = __fmul_rn(__fadd_rn(row[min(x + 1, grad.w - 1)], -row[max(x - 1, 0)]), 0.5f);
     const float dy = __fmul_rn(__fadd_rn(grad(x, min(y + 1, grad.h - 1)), -grad(x, max(y - 1, 0))), 0.5f);
@@ -300,9 +302,11 @@ extern "C" int roo_costvol_minimum_square_penalty_subpix(const roo_image_t* imga
 
 namespace roo_b200 {
 // out(x,y) from the gradient of `grad` (must not overlap out) and the values of `in` (may be `grad`)
-int launch_filter_disp_grad(const roo_image_t& out, const roo_image_t& grad, const roo_image_t& in, float threshold, cudaStream_t st) {
-    dim3 grid(cdiv((int)out.w, WTA_TX), (unsigned)out.h);
-    filter_disp_grad_kernel<<<grid, WTA_TX, 0, st>>>(Img<float>(out), Img<float>(grad), Img<float>(in), threshold);
+int launch_filter_disp_grad(const roo_image_t& out, const roo_image_t& grad, const roo_image_t& in, float threshold, cudaStream_t st,
+                            int batch, size_t out_pair, size_t grad_pair, size_t in_pair) {
+    dim3 grid(cdiv((int)out.w, WTA_TX), (unsigned)out.h, (unsigned)batch);
+    filter_disp_grad_kernel<<<grid, WTA_TX, 0, st>>>(Img<float>(out), Img<float>(grad), Img<float>(in), threshold, out_pair,
+                                                     grad_pair, in_pair);
     count_launch();
     return launch_status();
 }

@@ -319,11 +319,13 @@ class StereoEngine:
                  P1: float = 0.01, P2: float = 0.02, img_scale: float = 1.0 / 255.0, dohoriz=True, dovert=True,
                  doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff: float = 1.0,
                  max_batch: int = 1, keep_volume: bool = False, fuse_vertical: bool | None = None, median_size: int = 0,
-                 median_maxbad: int = 100, median_iters: int = 1, fp_mode: int = capi.FP_DEFAULT):
+                 median_maxbad: int = 100, median_iters: int = 1, fp_mode: int = capi.FP_DEFAULT,
+                 filtgrad_threshold: float = 0.0):
         self.params = capi.PipelineParams(w, h, max_disp, window, popc_mode, P1, P2, np.float32(img_scale),
                                           int(dohoriz), int(dovert), int(doreverse), int(dodiag), int(subpix),
                                           int(lrcheck), lr_maxdiff, max_batch, int(keep_volume),
-                                          _fuse_flag(fuse_vertical), median_size, median_maxbad, median_iters, fp_mode)
+                                          _fuse_flag(fuse_vertical), median_size, median_maxbad, median_iters, fp_mode,
+                                          filtgrad_threshold)
         self.w, self.h, self.max_disp = w, h, max_disp
         self._h = C.c_void_p()
         check(lib().roo_engine_create(C.byref(self._h), C.byref(self.params)), "roo_engine_create")
@@ -350,11 +352,31 @@ class StereoEngine:
                                              C.byref(lookup_left.c()) if lookup_left is not None else None,
                                              C.byref(lookup_right.c()) if lookup_right is not None else None),
               "roo_engine_set_front_end")
+        self._fe_level = level
+
+    def _in_shape(self):
+        """(h, w) of the frames a run takes: the working size, or the raw size when a front end is set."""
+        lvl = getattr(self, "_fe_level", 0)
+        return (self.h << lvl, self.w << lvl)
+
+    def _check_io(self, left, right, disp, cuda: bool) -> int:
+        """The C library takes raw pointers: shapes, dtypes, devices and contiguity are checked here."""
+        n = int(left.shape[0]) if left.dim() == 3 else -1
+        ih, iw = self._in_shape()
+        for name, t, dt, shape in (("left", left, torch.uint8, (n, ih, iw)), ("right", right, torch.uint8, (n, ih, iw)),
+                                   ("disp", disp, torch.float32, (n, self.h, self.w))):
+            if t is None:
+                continue
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.is_cuda != cuda:
+                raise ValueError(f"{name}: expected a contiguous {'CUDA' if cuda else 'host'} {dt} tensor of shape {shape}, "
+                                 f"got {tuple(t.shape)} {t.dtype} {'cuda' if t.is_cuda else 'cpu'}")
+        if cuda and (right.device != left.device or (disp is not None and disp.device != left.device)):
+            raise ValueError("left, right and disp must live on the same device")
+        return n
 
     def run_device(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor | None = None, stream=None):
         """left/right: (n, h, w) uint8 CUDA tensors (contiguous); returns (n, h, w) float32."""
-        assert left.is_cuda and left.dtype == torch.uint8 and left.is_contiguous() and right.is_contiguous()
-        n = left.shape[0]
+        n = self._check_io(left, right, disp, cuda=True)
         if disp is None:
             disp = torch.empty((n, self.h, self.w), dtype=torch.float32, device=left.device)
         check(lib().roo_engine_run_device(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(), n,
@@ -363,7 +385,7 @@ class StereoEngine:
 
     def run_host(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
         """Host (ideally pinned) tensors in, host tensor out; H2D + compute + D2H, synchronous."""
-        assert not left.is_cuda and left.dtype == torch.uint8 and disp.dtype == torch.float32
+        self._check_io(left, right, disp, cuda=False)
         check(lib().roo_engine_run_host(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(), left.shape[0]),
               "roo_engine_run_host")
         return disp
@@ -371,7 +393,7 @@ class StereoEngine:
     def submit_host(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor) -> int:
         """Asynchronous run_host for one group (<= max_batch pairs): returns a ticket for wait().  The tensors must
         stay alive (and should be pinned) until wait(ticket) returns."""
-        assert not left.is_cuda and left.dtype == torch.uint8 and disp.dtype == torch.float32
+        self._check_io(left, right, disp, cuda=False)
         t = C.c_longlong(-1)
         check(lib().roo_engine_submit_host(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(), left.shape[0],
                                            C.byref(t)), "roo_engine_submit_host")
@@ -413,7 +435,7 @@ class MultiGpuStereoEngine:
         defaults = dict(window=WIN_9x7, popc_mode=POPC32_COMPAT, P1=0.01, P2=0.02, img_scale=1.0 / 255.0, dohoriz=True,
                         dovert=True, doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff=1.0,
                         max_batch=1, keep_volume=False, fuse_vertical=None, median_size=0, median_maxbad=100,
-                        median_iters=1, fp_mode=capi.FP_DEFAULT)
+                        median_iters=1, fp_mode=capi.FP_DEFAULT, filtgrad_threshold=0.0)
         defaults.update(kw)
         d = defaults
         self.params = capi.PipelineParams(w, h, max_disp, d["window"], d["popc_mode"], d["P1"], d["P2"],
@@ -421,7 +443,7 @@ class MultiGpuStereoEngine:
                                           int(d["doreverse"]), int(d["dodiag"]), int(d["subpix"]), int(d["lrcheck"]),
                                           d["lr_maxdiff"], d["max_batch"], int(d["keep_volume"]),
                                           _fuse_flag(d["fuse_vertical"]), d["median_size"], d["median_maxbad"],
-                                          d["median_iters"], d["fp_mode"])
+                                          d["median_iters"], d["fp_mode"], d["filtgrad_threshold"])
         del proto
         self.w, self.h = w, h
         self._h = C.c_void_p()
@@ -436,7 +458,11 @@ class MultiGpuStereoEngine:
         return int(lib().roo_multi_engine_device_count(self._h))
 
     def run_host(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
-        assert not left.is_cuda and left.dtype == torch.uint8 and disp.dtype == torch.float32
+        n = int(left.shape[0]) if left.dim() == 3 else -1
+        for name, t, dt, shape in (("left", left, torch.uint8, (n, self.h, self.w)), ("right", right, torch.uint8, (n, self.h, self.w)),
+                                   ("disp", disp, torch.float32, (n, self.h, self.w))):
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.is_cuda:
+                raise ValueError(f"{name}: expected a contiguous host {dt} tensor of shape {shape}, got {tuple(t.shape)} {t.dtype}")
         check(lib().roo_multi_engine_run_host(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr(),
                                               left.shape[0]), "roo_multi_engine_run_host")
         return disp
@@ -444,6 +470,58 @@ class MultiGpuStereoEngine:
     def close(self) -> None:
         if self._h:
             lib().roo_multi_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SplitStereoEngine:
+    """ONE pair split into row strips across GPUs (roo_split_engine_*): the paths that travel in y hand their state from
+    strip to strip through peer memory over NVLink; everything else is strip-local.  Host tensors in, host tensor out."""
+
+    def __init__(self, w: int, h: int, max_disp: int, devices=None, **kw):
+        defaults = dict(window=WIN_9x7, popc_mode=POPC32_COMPAT, P1=0.01, P2=0.02, img_scale=1.0 / 255.0, dohoriz=True,
+                        dovert=True, doreverse=True, dodiag=False, subpix=False, lrcheck=False, lr_maxdiff=1.0,
+                        keep_volume=False, fp_mode=capi.FP_DEFAULT)
+        defaults.update(kw)
+        d = defaults
+        self.params = capi.PipelineParams(w, h, max_disp, d["window"], d["popc_mode"], d["P1"], d["P2"],
+                                          np.float32(d["img_scale"]), int(d["dohoriz"]), int(d["dovert"]),
+                                          int(d["doreverse"]), int(d["dodiag"]), int(d["subpix"]), int(d["lrcheck"]),
+                                          d["lr_maxdiff"], 1, int(d["keep_volume"]), -1, 0, 100, 1, d["fp_mode"], 0.0)
+        self.w, self.h = w, h
+        self._h = C.c_void_p()
+        if devices is None:
+            arr, n = None, 0
+        else:
+            arr, n = (C.c_int * len(devices))(*devices), len(devices)
+        check(lib().roo_split_engine_create(C.byref(self._h), C.byref(self.params), arr, n), "roo_split_engine_create")
+
+    @property
+    def strip_count(self) -> int:
+        return int(lib().roo_split_engine_strip_count(self._h))
+
+    def run_host(self, left: torch.Tensor, right: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+        for name, t, dt in (("left", left, torch.uint8), ("right", right, torch.uint8), ("disp", disp, torch.float32)):
+            if tuple(t.shape) != (self.h, self.w) or t.dtype != dt or not t.is_contiguous() or t.is_cuda:
+                raise ValueError(f"{name}: expected a contiguous host {dt} tensor of shape {(self.h, self.w)}")
+        check(lib().roo_split_engine_run_host(self._h, left.data_ptr(), right.data_ptr(), disp.data_ptr()),
+              "roo_split_engine_run_host")
+        return disp
+
+    def last_stats(self):
+        """(device milliseconds of the last frame, bytes handed between strips through peer memory)"""
+        ms, nb = C.c_float(0), C.c_ulonglong(0)
+        check(lib().roo_split_engine_last_stats(self._h, C.byref(ms), C.byref(nb)), "roo_split_engine_last_stats")
+        return float(ms.value), int(nb.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib().roo_split_engine_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

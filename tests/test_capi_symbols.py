@@ -65,3 +65,19 @@ def test_cpp_shim_program_compiles_and_links(tmp_path):
     subprocess.check_call(["nvcc", "-std=c++17", "-O0", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "test_roo_shim.cpp"), "-o", str(tmp_path / "shim"),
                            "-L", lib_dir, "-lroo_b200"])
+
+
+def test_cpp_shim_compiles_against_the_reference_types(tmp_path):
+    """include/kangaroo_b200/roo.hpp with ROO_B200_USE_KANGAROO_TYPES against the reference's real Image.h / Volume.h /
+    CostVolElem.h, Manage-owning images and volumes, every overload and explicit instantiation plus the call sequence of
+    applications/stereo2/main.cpp:375-458 (compile + link; tests/test_gpu_cpp_shim.py runs it where a GPU is present)."""
+    import shutil
+    import subprocess
+    ref_inc = "/root/reference/include"
+    if not os.path.isdir(ref_inc) or shutil.which("nvcc") is None:
+        pytest.skip("reference headers or nvcc not present")
+    lib_dir = os.path.join(ROOT, "kangaroo_b200", "lib")
+    subprocess.check_call(["nvcc", "-std=c++17", "-O0", "-w", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "ref_config"), "-I", ref_inc,
+                           os.path.join(ROOT, "tests", "cpp", "test_roo_shim_kangaroo_types.cu"), "-o",
+                           str(tmp_path / "shimk"), "-L", lib_dir, "-lroo_b200"])

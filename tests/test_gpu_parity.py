@@ -640,6 +640,30 @@ def test_engine_median_stage_equals_operator_sequence(size, iters):
     assert np.isnan(want).mean() < 0.5   # the check leaves most of the image valid
 
 
+def test_engine_filtgrad_stage_and_per_engine_fp_mode():
+    """The engine's last stage = FilterDispGrad(disp, disp, thr) of the operator API (stereo2/main.cpp:456-458), and two
+    engines in different fp modes side by side (fp_mode is per engine, not process state)."""
+    w, h, D = 200, 64, 48
+    L, R, _ = stereo_pair(w, h, D, config=33)
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    kw = dict(dodiag=True, subpix=True, lrcheck=True, fuse_vertical=True)
+    e_ref = roo.StereoEngine(w, h, D, fp_mode=roo.capi.FP_REFERENCE, **kw)
+    e_ieee = roo.StereoEngine(w, h, D, fp_mode=roo.capi.FP_IEEE, **kw)
+    e_fg = roo.StereoEngine(w, h, D, fp_mode=roo.capi.FP_IEEE, filtgrad_threshold=0.4, **kw)
+    d_ref, d_ieee, d_fg = (e.run_device(l, r)[0].cpu().numpy() for e in (e_ref, e_ieee, e_fg))
+    for e in (e_ref, e_ieee, e_fg):
+        e.close()
+    od = ko.pipeline_u8(L, R, D, dodiag=True, subpix=True, lrcheck=True)
+    assert np.array_equal(np.isnan(d_ieee), np.isnan(od)) and np.array_equal(d_ieee[~np.isnan(od)], od[~np.isnan(od)])
+    both = np.isfinite(d_ref) & np.isfinite(d_ieee)
+    assert (np.abs(d_ref - d_ieee)[both] <= 0.01).mean() >= 0.999
+    img = roo.Image.from_numpy(d_ieee)
+    roo.FilterDispGrad(img, img, 0.4)
+    exp = img.numpy()
+    assert np.array_equal(np.isnan(d_fg), np.isnan(exp)) and np.array_equal(d_fg[~np.isnan(exp)], exp[~np.isnan(exp)])
+    assert (d_fg == -1).any()
+
+
 def test_engine_auto_plan_matches_both_forced_plans():
     """fuse_vertical = auto picks one pass per path for a small group and the fused passes for a large one; the
     result is the same bit for bit either way."""
@@ -751,6 +775,79 @@ def test_multi_gpu_engine_shards_pairs_across_all_devices():
     m1.run_host(L, R, out1)
     m1.close()
     assert torch.equal(out, out1)
+
+
+def test_fused_passes_soak_two_engines_concurrently():
+    """Robustness of the band pipeline (flags polled across CTAs of one launch): two engines on two streams of the same
+    GPU, thousands of fused launches with CTAs of both interleaving on the SMs; every result must equal the first one,
+    and the fused result must equal the one-pass-per-path result."""
+    w, h, D = 300, 200, 64
+    L, R, _ = stereo_pair(w, h, D, config=81)
+    l, r = torch.from_numpy(np.stack([L] * 3)).cuda(), torch.from_numpy(np.stack([R] * 3)).cuda()
+    sep = roo.StereoEngine(w, h, D, dodiag=True, max_batch=3, fuse_vertical=False)
+    expect = sep.run_device(l, r).clone()
+    sep.close()
+    engines = [roo.StereoEngine(w, h, D, dodiag=True, max_batch=3, fuse_vertical=True) for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = [torch.empty_like(expect) for _ in range(2)]
+    bad = 0
+    for it in range(600):          # x 2 engines x 2 fused passes = 2400 fused launches
+        for e, s, o in zip(engines, streams, outs):
+            e.run_device(l, r, o, stream=s)
+        if it % 50 == 49:
+            torch.cuda.synchronize()
+            bad += sum(int(not torch.equal(o, expect)) for o in outs)
+    torch.cuda.synchronize()
+    bad += sum(int(not torch.equal(o, expect)) for o in outs)
+    for e in engines:
+        e.close()
+    assert bad == 0
+
+
+def test_census_stereo_volume_accepts_different_pitches():
+    rng = np.random.default_rng(12)
+    l = rng.integers(0, 2**63, (20, 50), dtype=np.uint64)
+    r = rng.integers(0, 2**63, (20, 50), dtype=np.uint64)
+    vol = roo.Volume(50, 20, 16, np.float32)
+    roo.CensusStereoVolume(vol, roo.Image.from_numpy(l, pitch=50 * 8 + 16), roo.Image.from_numpy(r, pitch=50 * 8 + 64), 16, -1.0)
+    assert np.array_equal(vol.numpy(), ko.census_stereo_volume(np.ascontiguousarray(l[:, :, None]), np.ascontiguousarray(r[:, :, None]), 16, -1.0))
+
+
+def test_engine_python_wrappers_validate_tensors():
+    eng = roo.StereoEngine(64, 32, 16, max_batch=2)
+    good = torch.zeros((2, 32, 64), dtype=torch.uint8, device="cuda")
+    for bad in (torch.zeros((2, 32, 60), dtype=torch.uint8, device="cuda"), good.float(), good.cpu(), good.transpose(1, 2)):
+        with pytest.raises(ValueError):
+            eng.run_device(good, bad)
+    with pytest.raises(ValueError):
+        eng.run_host(good.cpu(), good.cpu(), torch.zeros((2, 32, 60)))
+    eng.close()
+
+
+@pytest.mark.parametrize("shape,strips", [((150, 61, 48), 2), ((150, 61, 48), 3), ((320, 100, 128), 4), ((97, 40, 256), 2), ((64, 9, 32), 8)])
+@pytest.mark.parametrize("opts", [dict(), dict(dodiag=True, subpix=True, lrcheck=True), dict(dohoriz=False, dodiag=True)])
+def test_single_pair_row_strip_split_bitexact(shape, strips, opts):
+    """BASELINE config 5's mechanism: one pair split into row strips, the paths that travel in y handing their state from
+    strip to strip (roo_split_engine_*).  On a one-GPU box every strip sits on device 0 (hand-offs ordered by events); with
+    several GPUs the strips spread over them and the hand-off is a peer store + release/acquire flag.  Bit-identical to the
+    single-GPU engine and to the CPU oracle (IEEE mode)."""
+    w, h, D = shape
+    L, R, _ = stereo_pair(w, h, D, config=91)
+    ndev = torch.cuda.device_count()
+    devices = [i % ndev for i in range(strips)]
+    roo.set_ieee_division(True)
+    se = roo.SplitStereoEngine(w, h, D, devices=devices, **opts)
+    assert se.strip_count == strips
+    out = torch.empty((h, w), dtype=torch.float32).pin_memory()
+    for _ in range(2):   # twice: the exchange records are reused from frame to frame
+        se.run_host(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory(), out)
+    ms, nbytes = se.last_stats()
+    se.close()
+    od = ko.pipeline_u8(L, R, D, **opts)
+    got = out.numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(od)) and np.array_equal(got[~np.isnan(od)], od[~np.isnan(od)])
+    crossing = (2 if opts.get("dovert", True) else 0) + (4 if opts.get("dodiag") else 0)
+    assert nbytes == crossing * (strips - 1) * w * (roo.capi.disp_padded(D) + 4) * 4 and ms > 0
 
 
 def test_invalid_arguments_are_reported_not_ignored():

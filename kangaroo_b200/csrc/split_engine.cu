@@ -68,12 +68,14 @@ static void split_free(roo_split_engine* e) {
         cudaFree(s.frame[0]); cudaFree(s.frame[1]); cudaFree(s.cen_base[0]); cudaFree(s.cen_base[1]);
         cudaFree(s.imgf); cudaFree(s.c8); cudaFree(s.H); cudaFree(s.disp); cudaFree(s.dispR);
         for (float* b : s.import) cudaFree(b);
-        for (cudaEvent_t ev : s.ev_sweep) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : s.ev_sweep)
+            if (ev) cudaEventDestroy(ev);
         if (s.ev_begin) cudaEventDestroy(s.ev_begin);
         if (s.ev_end) cudaEventDestroy(s.ev_end);
         if (s.st) cudaStreamDestroy(s.st);
     }
     cudaSetDevice(prev);
+    cudaGetLastError();
 }
 
 extern "C" int roo_split_engine_create(roo_split_engine_t** out, const roo_pipeline_params_t* params, const int* devices,

@@ -810,7 +810,9 @@ def test_census_stereo_volume_accepts_different_pitches():
     r = rng.integers(0, 2**63, (20, 50), dtype=np.uint64)
     vol = roo.Volume(50, 20, 16, np.float32)
     roo.CensusStereoVolume(vol, roo.Image.from_numpy(l, pitch=50 * 8 + 16), roo.Image.from_numpy(r, pitch=50 * 8 + 64), 16, -1.0)
-    assert np.array_equal(vol.numpy(), ko.census_stereo_volume(np.ascontiguousarray(l[:, :, None]), np.ascontiguousarray(r[:, :, None]), 16, -1.0))
+    l3, r3 = np.empty((20, 50, 1), np.uint64), np.empty((20, 50, 1), np.uint64)
+    l3[:, :, 0], r3[:, :, 0] = l, r
+    assert np.array_equal(vol.numpy(), ko.census_stereo_volume(l3, r3, 16, -1.0))
 
 
 def test_engine_python_wrappers_validate_tensors():

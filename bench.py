@@ -41,6 +41,18 @@ L2_BYTES = 126e6
 _WINDOW = 0  # census window of this run (0 = 9x7, 1 = 11x11, 2 = 16x16), set from --window
 
 
+def csrc_hash() -> str:
+    """sha256 over the kernel sources: ties a committed ncu traffic figure to the code it was measured on"""
+    import hashlib
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "kangaroo_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            hsh.update(f.encode())
+            hsh.update(open(os.path.join(d, f), "rb").read())
+    return hsh.hexdigest()
+
+
 def measured_peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -49,6 +61,16 @@ def measured_peak_hbm():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(wl, window, B, world, materialised=False, generic_hsweep=False):
+    """The `config` object of the JSON line -- the same for this repo's arm and the CPU reference arm."""
+    w, h, D, paths, subpix, lrcheck, _, _ = WORKLOADS[wl]
+    return {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": window,
+            "popcount": "popc32-compat", "subpix": subpix, "lrcheck": lrcheck, "pairs_per_step_per_gpu": B,
+            "sharding": f"pair-batch x{world}, no collective",
+            "l2": f"per-step working set {B * w * h * D * 4 / 1e9:.2f} GB (fp32 aggregate) vs "
+                  f"{L2_BYTES / 1e6:.0f} MB L2: inputs larger than L2, no flush"}
 
 
 class ClockSampler:
@@ -146,8 +168,8 @@ def run_reference(args, wl):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "mpix_disp_per_s": value * w * h * D / 1e6,
-           "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": args.window,
-                      "note": "reference kernels are CUDA-only; CPU arm = OpenMP scalar port of the kernel bodies"},
+           "config": workload_config(wl, args.window, args.batch or WORKLOADS[wl][6], max(1, int(os.environ.get("WORLD_SIZE", "1")))),
+           "note": "reference kernels are CUDA-only; CPU arm = OpenMP scalar port of the kernel bodies (oracle/), one pair at a time",
            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -279,52 +301,73 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        # aggregation passes over the fp32 volume: a vertical path and its two diagonals are ONE pass (sgm_fused.cu)
-        vg_ms, vg_n = prof["vgroup"]
-        sw_ms, sw_n = prof["sweep"]
-        S = (vg_n + sw_n) // K if K else 0
-        # algorithmic bytes: fp32 aggregate passed over S times, first pass write-only:
-        # 4 B * (2S - 1) per pixel*disparity over the S pass launches of one batch
-        unit = float(w) * h * D * B
+        unit = float(w) * h * D * B                       # pixel*disparity units one launch processes
         step_kernel_ms = sum(v[0] for k, v in prof.items() if not k.startswith("pass"))
-        if vg_n and vg_ms >= sw_ms:   # dominant kernel: the fused vertical group (first launch writes, second reads+writes)
-            kname, k_ms, k_n = "sgm_vgroup_kernel", vg_ms, vg_n
-            bytes_per_launch = 4.0 * (1 + 2) / 2 * unit if vg_n // K == 2 else 4.0 * unit
+        # ---- the aggregation passes of one step, in plan order (mirrors engine.cu: fused vertical groups when the batch
+        # fills the GPU, bulk-copy kernel for the horizontal paths, in-sweep cost where the descriptor allows it)
+        S = sum(1 for i in range(8) if prof[f"pass{i}"][1] > 0)
+        fused = prof["vgroup"][1] > 0
+        if paths == 8:
+            names = (["sgm_vgroup_kernel (down + 2 diagonals)", "sgm_vgroup_kernel (up + 2 diagonals)"] if fused else
+                     ["sgm_sweep_kernel"] * 6) + ["sgm_hsweep_kernel (right)", "sgm_hsweep_kernel (left, WTA epilogue)"]
         else:
-            kname, k_ms, k_n = "sgm_sweep_kernel", sw_ms, sw_n
-            bytes_per_launch = 4.0 * (2 * S - 1) / max(S, 1) * unit
-        achieved = bytes_per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
-        # measured DRAM traffic per launch of that kernel from the committed ncu capture (scaled to this batch)
-        traffic = None
+            names = ["sgm_sweep_kernel (down)", "sgm_sweep_kernel (up)", "sgm_hsweep_kernel (right)",
+                     "sgm_hsweep_kernel (left, WTA epilogue)"]
+        cen_ok = args.window == "9x7" and not args.materialised_cost
+        passes = []
+        for i in range(S):
+            ms_i = prof[f"pass{i}"][0] / max(prof[f"pass{i}"][1], 1)
+            nm = names[i] if i < len(names) else "sgm_sweep_kernel"
+            in_sweep = cen_ok and ("vgroup" in nm or ("hsweep" in nm and not args.generic_hsweep))
+            alg = (4.0 if i == 0 else 8.0) * unit                      # first pass writes, later passes read + write
+            moved = ((0.0 if i == 0 else 4.0) + (0.0 if i == S - 1 else 4.0) + (0.0 if in_sweep else 1.0)) * unit
+            passes.append({"pass": i, "kernel": nm, "ms": ms_i, "algorithmic_bytes": alg, "achieved_gbs": alg / ms_i / 1e6,
+                           "frac": alg / ms_i / 1e6 / peak, "bytes_this_design_moves": moved,
+                           "moved_gbs": moved / ms_i / 1e6, "moved_frac": moved / ms_i / 1e6 / peak,
+                           "cost": "in-sweep from census words" if in_sweep else "u8 volume read",
+                           "share_of_step": ms_i * K / step_kernel_ms if step_kernel_ms else None})
+        dom = max(passes, key=lambda q: q["ms"]) if passes else None
+        # measured DRAM traffic of the dominant launch from the committed ncu capture -- only while the kernels are the
+        # ones that were profiled (hash of kangaroo_b200/csrc at capture time), else null
+        traffic, traffic_note = None, "no ncu capture for this workload"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            inst = tr["kernels"].get(kname, [])
-            if inst and wl == DEFAULT_WORKLOAD:
-                traffic = sum(i["dram_bytes"] for i in inst) / len(inst) * B / tr["pairs_per_launch"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if tr.get("csrc_sha256") != csrc_hash():
+                traffic_note = "kernel sources changed since the ncu capture (profiles/r2_traffic.json): traffic not reported"
+            elif dom and wl in tr.get("workloads", {}):
+                ent = tr["workloads"][wl]["passes"]
+                if dom["pass"] < len(ent):
+                    traffic = ent[dom["pass"]]["dram_bytes"] * B / tr["workloads"][wl]["pairs_per_launch"]
+                    traffic_note = f"ncu dram__bytes_read+write, {tr['workloads'][wl]['source']}"
         except Exception:
-            traffic = None
-        agg_bytes = 4.0 * (2 * S - 1) * unit
-        agg_ms = (vg_ms + sw_ms) / K
+            pass
+        agg_ms = sum(q["ms"] for q in passes)
+        agg_alg = sum(q["algorithmic_bytes"] for q in passes)
+        agg_moved = sum(q["bytes_this_design_moves"] for q in passes)
         out = {
             "metric": "stereo_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mpix_disp_per_s": value * w * h * D / 1e6,
-            "config": {"workload": wl, "w": w, "h": h, "disparities": D, "paths": paths, "window": args.window,
-                       "popcount": "popc32-compat", "subpix": subpix, "lrcheck": lrcheck, "pairs_per_step_per_gpu": B,
-                       "sharding": f"pair-batch x{world}, no collective",
-                       "l2": f"per-step working set {B * w * h * D * 5 / 1e9:.2f} GB (fp32 aggregate + u8 cost) vs "
-                             f"{L2_BYTES / 1e6:.0f} MB L2: inputs larger than L2, no flush"},
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "avg_launch_ms": k_ms / max(k_n, 1), "launches_timed": k_n,
-                         "share_of_step": k_ms / step_kernel_ms if step_kernel_ms else None},
-            "aggregation": {"passes": S, "algorithmic_bytes_per_step": agg_bytes, "ms_per_step": agg_ms,
-                            "achieved_gbs": agg_bytes / (agg_ms * 1e-3) / 1e9 if agg_ms else None,
-                            "frac_of_peak": agg_bytes / (agg_ms * 1e-3) / 1e9 / peak if agg_ms else None},
-            "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()},
+            "config": workload_config(wl, args.window, B, world),
+            "matching_cost": "in-sweep from census words (no cost volume)" if cen_ok and fused and not args.generic_hsweep
+                             else "u8 cost volume",
+            "roofline": ({"bound": "hbm", "kernel": dom["kernel"], "pass": dom["pass"], "achieved": dom["achieved_gbs"],
+                          "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "traffic_note": traffic_note,
+                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+                          "avg_launch_ms": dom["ms"], "launches_timed": K, "share_of_step": dom["share_of_step"],
+                          "note": "the slowest aggregation launch of the step; every launch is listed in roofline_passes"}
+                         if dom else None),
+            "roofline_passes": passes,
+            "aggregation": {"passes": S, "ms_per_step": agg_ms,
+                            "algorithmic_bytes_per_step": agg_alg, "achieved_gbs": agg_alg / agg_ms / 1e6 if agg_ms else None,
+                            "frac_of_peak": agg_alg / agg_ms / 1e6 / peak if agg_ms else None,
+                            "bytes_this_design_moves_per_step": agg_moved,
+                            "moved_gbs": agg_moved / agg_ms / 1e6 if agg_ms else None,
+                            "moved_frac_of_peak": agg_moved / agg_ms / 1e6 / peak if agg_ms else None,
+                            "note": "algorithmic = SURVEY 8d, 4 B*(2S-1) per pixel*disparity; moved = what these launches "
+                                    "read and write (the last sweep writes no aggregate; + 1 B per pass that reads the u8 cost)"},
+            "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items() if not k.startswith("pass")},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

@@ -45,11 +45,14 @@ __host__ __device__ constexpr int vg_pfs(int DPL, int CE) {
 #ifndef VG_NCW
 #define VG_NCW 4
 #endif
+// 256 disparities (229+ registers per thread with four columns): measured on B200, fused pair of passes,
+// 1920x1080x256 x4 / 3840x2160x256 x1 (ms): 6 warps x 4 columns 8.45 / 11.97, 8 x 4 8.74 / 11.50, 12 x 2 9.09 / 9.88,
+// 8 x 3 (state ring 2 rows deep) 7.98 / 10.47
 #ifndef VG_NCW8
-#define VG_NCW8 4
+#define VG_NCW8 3
 #endif
 #ifndef VG_NWW8
-#define VG_NWW8 6
+#define VG_NWW8 8
 #endif
 __host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? VG_NCW8 : VG_NCW; }
 // 12 warps x 4 columns: 13 warps of <= 152 registers fill the register file, and ring + prefetch stages fill
@@ -64,6 +67,13 @@ __host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? VG_NCW8 : 
 #ifndef VG_NWW8_FC
 #define VG_NWW8_FC VG_NWW8
 #endif
+// narrow bands of a first pass with in-sweep cost need little shared memory: several of them share an SM
+#ifndef VG_MINB_FC
+#define VG_MINB_FC 2
+#endif
+__host__ __device__ constexpr int vg_min_ctas(int DPL, int cost, bool first, int nww) {
+    return (first && cost == COST_CEN32 && nww <= (DPL >= 8 ? 3 : 6)) ? VG_MINB_FC : 1;
+}
 __host__ __device__ constexpr int vg_nww(int DPL, bool first_cen = false) {
     return DPL >= 8 ? (first_cen ? VG_NWW8_FC : VG_NWW8) : (first_cen ? VG_NWW_FC : VG_NWW);
 }
@@ -175,7 +185,7 @@ __host__ __device__ constexpr int vg_r(int DPL) { return VG_R; }   // max rows p
 #define VG_S_DEPTH 4
 #endif
 #ifndef VG_S_DEPTH8
-#define VG_S_DEPTH8 VG_S_DEPTH
+#define VG_S_DEPTH8 2
 #endif
 // depth (rows) of the in-band state ring in shared memory
 __host__ __device__ constexpr int vg_s(int DPL) { return DPL >= 8 ? VG_S_DEPTH8 : VG_S_DEPTH; }
@@ -216,7 +226,7 @@ __device__ __forceinline__ void vg_pixel(unsigned stg, const float (&cost)[DPL],
 }
 
 template <int DPL, int COST, bool FIRST, bool IEEE, int NWW, int NCW, bool FWD>
-__global__ void __launch_bounds__((NWW + 1) * 32, 1)
+__global__ void __launch_bounds__((NWW + 1) * 32, vg_min_ctas(DPL, COST, FIRST, NWW))
 sgm_vgroup_kernel(const VGroupArgs a) {
     constexpr int DP = 32 * DPL;
     constexpr int CE = RawCost<DPL, COST>::ELEM;

@@ -52,4 +52,26 @@ d = eng.run_device(rawb, rawb)
 torch.cuda.synchronize()
 eng.close()
 torch.cuda.synchronize()
+# round 2: in-place median / FilterDispGrad, CostVolMinimumSquarePenaltySubpix, materialised-cost and generic-sweep code
+# paths, the row-strip split engine (two and three strips on this device), the engine's FilterDispGrad stage
+img2 = roo.Image.from_numpy(np.random.default_rng(4).random((40, 56), dtype=np.float32) * 20)
+roo.MedianFilterRejectNegative5x5(img2, img2, 10)
+roo.FilterDispGrad(img2, img2, 3.0)
+vol = roo.Volume.from_numpy(np.random.default_rng(5).random((16, 40, 56), dtype=np.float32))
+roo.CostVolMinimumSquarePenaltySubpix(roo.Image(56, 40, np.float32), vol, img2, 16, -1.0, 1.0, 2.0)
+L, R, _ = stereo_pair(150, 60, 64, config=8)
+l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+for knob in (roo.capi.TUNE_INSWEEP_COST, roo.capi.TUNE_HSWEEP):
+    roo.set_tuning(knob, 0)
+    e = roo.StereoEngine(150, 60, 64, dodiag=True, subpix=True, lrcheck=True, fuse_vertical=True, filtgrad_threshold=0.5)
+    e.run_device(l, r)
+    torch.cuda.synchronize()
+    e.close()
+    roo.set_tuning(knob, 1)
+for strips in (2, 3):
+    se = roo.SplitStereoEngine(150, 60, 64, devices=[0] * strips, dodiag=True, subpix=True, lrcheck=True)
+    out = torch.empty((60, 150), dtype=torch.float32).pin_memory()
+    se.run_host(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory(), out)
+    se.close()
+torch.cuda.synchronize()
 print("done")

@@ -42,14 +42,13 @@ _WINDOW = 0  # census window of this run (0 = 9x7, 1 = 11x11, 2 = 16x16), set fr
 
 
 def csrc_hash() -> str:
-    """sha256 over the kernel sources: ties a committed ncu traffic figure to the code it was measured on"""
+    """sha256 over the sources of the aggregation kernels: ties a committed ncu traffic figure to the code it was measured on"""
     import hashlib
     hsh = hashlib.sha256()
     d = os.path.join(ROOT, "kangaroo_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            hsh.update(f.encode())
-            hsh.update(open(os.path.join(d, f), "rb").read())
+    for f in ("common.cuh", "sgm_step.cuh", "sgm.cu", "sgm_hsweep.cu", "sgm_fused.cu", "census.cu"):
+        hsh.update(f.encode())
+        hsh.update(open(os.path.join(d, f), "rb").read())
     return hsh.hexdigest()
 
 
@@ -204,6 +203,7 @@ def main():
     import torch
     import torch.distributed as dist
     from kangaroo_b200 import capi, roo
+    from kangaroo_b200.sharding import aggregate_throughput, reduce_max   # the code tests/test_sharding_gloo.py covers
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,11 +254,8 @@ def main():
     clk = clocks.stop()
     prof = eng.get_profile()
     eng.set_profiling(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * B * K / (ms_max * 1e-3)
+    ms_max = reduce_max(ms, device="cuda")                               # slowest rank
+    value = aggregate_throughput(B * K, ms * 1e-3, device="cuda")         # all pairs of all ranks / slowest rank's time
 
     # ---- end to end through the public API with HOST buffers (H2D + compute + D2H every step) ----
     e2e = None
@@ -290,10 +287,7 @@ def main():
         t0 = time.perf_counter()
         run_steps(K)
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * K / float(tt.item()), "unit": "pairs/s", "h2d_bytes_per_step": int(2 * B * w * h),
+        e2e = {"value": aggregate_throughput(B * K, dt, device="cuda"), "unit": "pairs/s", "h2d_bytes_per_step": int(2 * B * w * h),
                "d2h_bytes_per_step": int(B * w * h * 4),
                "api": "roo_engine_submit_host / roo_engine_wait (pinned host buffers, two steps in flight)",
                "pairs_in_flight": 2 * g}

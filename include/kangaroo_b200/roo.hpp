@@ -177,6 +177,21 @@ inline void CostVolMinimumSquarePenaltySubpix(Image<float> imga, Volume<float> v
     b200::done(roo_costvol_minimum_square_penalty_subpix(&a, &v, &d, maxDisp, sd, lambda, theta, b200::stream_slot()),
                "CostVolMinimumSquarePenaltySubpix");
 }
+// ---- cu_bilateral.h:18-22 (the overload the applications run on cost-volume slices) and its whole-volume form
+template <typename To, typename Ti, typename Ti2>
+inline void BilateralFilter(Image<To> dOut, const Image<Ti> dIn, const Image<Ti2> dImg, float gs, float gr, float gc, unsigned size) {
+    static_assert(std::is_same<To, float>::value && std::is_same<Ti, float>::value, "float in, float out");
+    auto o = b200::c(dOut), i2 = b200::c(dIn), g = b200::c(dImg);
+    b200::done(roo_bilateral_filter_joint(&o, &i2, &g, b200::imgtype<Ti2>::v, gs, gr, gc, size, b200::stream_slot()), "BilateralFilter");
+}
+template <typename Ti2>
+inline void BilateralFilterVolume(Volume<float> vOut, Volume<float> vIn, const Image<Ti2> dImg, float gs, float gr, float gc,
+                                  unsigned size, int maxDisp) {
+    auto o = b200::c(vOut), i2 = b200::c(vIn);
+    auto g = b200::c(dImg);
+    b200::done(roo_bilateral_filter_volume(&o, &i2, &g, b200::imgtype<Ti2>::v, gs, gr, gc, size, maxDisp, b200::stream_slot()),
+               "BilateralFilterVolume");
+}
 // ---- cu_dense_stereo.h:101-103 (dOut may be dIn, as in stereo2/main.cpp:457)
 inline void FilterDispGrad(Image<float> dOut, Image<float> dIn, float threshold) {
     auto o = b200::c(dOut), i2 = b200::c(dIn);

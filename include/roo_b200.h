@@ -180,6 +180,16 @@ int roo_costvol_minimum_square_penalty_subpix(const roo_image_t* imga_f32, const
                                               const roo_image_t* imgd_f32, unsigned maxDisp, float sd, float lambda,
                                               float theta, void* stream);
 
+/* roo::BilateralFilter<float,float,Timg>(dOut, dIn, dImg, gs, gr, gc, size) -- joint bilateral filter with spatial, range and
+ * guide-image weights (cu_bilateral.h:18-22; cu_bilateral.cu:110-155), Timg = unsigned char or float.  Clamp-to-edge window
+ * of (2 size + 1)^2 taps; arithmetic = the reference's fast-math SASS (bit-identical results).  out must not overlap in. */
+int roo_bilateral_filter_joint(const roo_image_t* out_f32, const roo_image_t* in_f32, const roo_image_t* img, int img_type,
+                               float gs, float gr, float gc, unsigned size, void* stream);
+/* The applications filter a cost volume with it slice by slice (stereo2/main.cpp:407-421: per disparity a device copy of
+ * the slice and one launch).  This is the same result for the first maxDisp slices in ONE launch, out of place. */
+int roo_bilateral_filter_volume(const roo_volume_t* out_f32, const roo_volume_t* in_f32, const roo_image_t* img, int img_type,
+                                float gs, float gr, float gc, unsigned size, int maxDisp, void* stream);
+
 /* ---- fused engine: the whole per-frame path of applications/stereo2/main.cpp:375-454 ------- */
 
 typedef struct roo_engine roo_engine_t;

@@ -198,6 +198,22 @@ def FilterDispGrad(dOut: Image, dIn: Image, threshold: float, stream=None) -> No
     check(lib().roo_filter_disp_grad(C.byref(dOut.c()), C.byref(dIn.c()), threshold, _stream(stream)), "FilterDispGrad")
 
 
+def BilateralFilter(dOut: Image, dIn: Image, dImg: Image, gs: float, gr: float, gc: float, size: int, stream=None) -> None:
+    """roo::BilateralFilter<float,float,{uchar,float}>(dOut, dIn, dImg, gs, gr, gc, size) (cu_bilateral.h:18-22)."""
+    it = capi.IMG_U8 if dImg.dtype == np.uint8 else capi.IMG_F32
+    check(lib().roo_bilateral_filter_joint(C.byref(dOut.c()), C.byref(dIn.c()), C.byref(dImg.c()), it, gs, gr, gc, size,
+                                           _stream(stream)), "BilateralFilter")
+
+
+def BilateralFilterVolume(vOut: Volume, vIn: Volume, dImg: Image, gs: float, gr: float, gc: float, size: int, maxDisp: int,
+                          stream=None) -> None:
+    """Every slice d < maxDisp of a cost volume through the joint bilateral filter in ONE launch (the applications loop over
+    the slices on the host, stereo2/main.cpp:407-421)."""
+    it = capi.IMG_U8 if dImg.dtype == np.uint8 else capi.IMG_F32
+    check(lib().roo_bilateral_filter_volume(C.byref(vOut.c()), C.byref(vIn.c()), C.byref(dImg.c()), it, gs, gr, gc, size, maxDisp,
+                                            _stream(stream)), "BilateralFilterVolume")
+
+
 def DenseStereoSubpixelRefine(dDispOut: Image, dDisp: Image, dCamLeft: Image, dCamRight: Image, stream=None) -> None:
     check(lib().roo_dense_stereo_subpixel_refine(C.byref(dDispOut.c()), C.byref(dDisp.c()), C.byref(dCamLeft.c()),
                                                  C.byref(dCamRight.c()), _stream(stream)), "DenseStereoSubpixelRefine")

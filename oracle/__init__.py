@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         L.ko_costvol_minimum_square_penalty_subpix.argtypes = [P(KoImage), P(KoVolume), P(KoImage), C.c_uint, C.c_float, C.c_float,
                                                                C.c_float, P(KoImage)]
         L.ko_filter_disp_grad.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_float]
+        L.ko_bilateral_filter_joint.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
         L.ko_left_right_check_i8.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
         L.ko_elementwise_scale_bias.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_float, C.c_float]
         L.ko_box_half.argtypes = [P(KoImage), P(KoImage), C.c_int]
@@ -212,6 +213,15 @@ def filter_disp_grad(grad_src: np.ndarray, img_in: np.ndarray, threshold: float)
     img_in = np.ascontiguousarray(img_in, np.float32)
     out = np.zeros_like(grad_src)
     lib().ko_filter_disp_grad(C.byref(_img(out)), C.byref(_img(grad_src)), C.byref(_img(img_in)), threshold)
+    return out
+
+
+def bilateral_filter_joint(img_in: np.ndarray, guide: np.ndarray, gs: float, gr: float, gc: float, size: int) -> np.ndarray:
+    img_in = np.ascontiguousarray(img_in, np.float32)
+    guide = np.ascontiguousarray(guide)
+    out = np.zeros_like(img_in)
+    lib().ko_bilateral_filter_joint(C.byref(_img(out)), C.byref(_img(img_in)), C.byref(_img(guide)),
+                                    IMG_U8 if guide.dtype == np.uint8 else IMG_F32, gs, gr, gc, size)
     return out
 
 

@@ -430,6 +430,34 @@ void ko_filter_disp_grad(const ko_image* out, const ko_image* grad, const ko_ima
         }
 }
 
+/* src/cu_bilateral.cu:110-143 (KernBilateralFilter<float,float,Ti2>), IEEE evaluation in source order with expf():
+ * the reference's build uses the approximate ex2/rcp units, so this restatement agrees to ~1e-6 relative, not bit for bit. */
+void ko_bilateral_filter_joint(const ko_image* out, const ko_image* in, const ko_image* img, int img_type, float gs, float gr,
+                               float gc, int size) {
+    const int w = (int)out->w, h = (int)out->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float p = *(const float*)img_at(in, (size_t)x, (size_t)y, 4);
+            const float pc = img_type == KO_IMG_U8 ? (float)*(const uint8_t*)img_at(img, (size_t)x, (size_t)y, 1)
+                                                   : *(const float*)img_at(img, (size_t)x, (size_t)y, 4);
+            float sum = 0.0f, sumw = 0.0f;
+            for (int r = -size; r <= size; ++r)
+                for (int c = -size; c <= size; ++c) {
+                    const int xx = x + c < 0 ? 0 : (x + c > w - 1 ? w - 1 : x + c), yy = y + r < 0 ? 0 : (y + r > h - 1 ? h - 1 : y + r);
+                    const float q = *(const float*)img_at(in, (size_t)xx, (size_t)yy, 4);
+                    const float qc = img_type == KO_IMG_U8 ? (float)*(const uint8_t*)img_at(img, (size_t)xx, (size_t)yy, 1)
+                                                           : *(const float*)img_at(img, (size_t)xx, (size_t)yy, 4);
+                    const float rd = p - q, cd = pc - qc, sd2 = (float)(r * r + c * c);
+                    const float sw = expf(-(sd2) / (2 * gs * gs)), rw = expf(-(rd * rd) / (2 * gr * gr)), cw = expf(-(cd * cd) / (2 * gc * gc));
+                    const float wgt = sw * rw * cw;
+                    sumw += wgt;
+                    sum += wgt * q;
+                }
+            *(float*)img_at(out, (size_t)x, (size_t)y, 4) = sumw == 0 ? p : sum / sumw;
+        }
+}
+
 /* ---------------------------------------------------------------- subpixel refine ---- */
 
 /* patch_score.h:257-298, SANDPatchScore<float,2,ImgAccessRaw> on unsigned char images */

@@ -137,6 +137,9 @@ void ko_costvol_minimum_square_penalty_subpix(const ko_image* imga_f32, const ko
 /* src/cu_dense_stereo.cu:793-812; grad = the image whose gradient gates the output (the reference uses the output image's
  * own previous contents), must not alias out */
 void ko_filter_disp_grad(const ko_image* out_f32, const ko_image* grad_f32, const ko_image* in_f32, float threshold);
+/* src/cu_bilateral.cu:110-143, float in/out, guide image of KO_IMG_U8 or KO_IMG_F32; out must not alias in */
+void ko_bilateral_filter_joint(const ko_image* out_f32, const ko_image* in_f32, const ko_image* img, int img_type, float gs,
+                               float gr, float gc, int size);
 void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff);
 void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd, int maxDiff);
 

@@ -272,6 +272,18 @@ def filter_disp_grad(grad_src: np.ndarray, img_in: np.ndarray, threshold: float,
     return np.ascontiguousarray(big[margin:-margin, margin:-margin])
 
 
+def bilateral_filter_joint(img_in: np.ndarray, guide: np.ndarray, gs: float, gr: float, gc: float, size: int) -> np.ndarray:
+    import torch
+    h, w = img_in.shape
+    di, dg = _dev(np.ascontiguousarray(img_in, np.float32)), _dev(np.ascontiguousarray(guide))
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    lib().kref_bilateral_joint.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t,
+                                           C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_uint]
+    _ck(lib().kref_bilateral_joint(out.data_ptr(), di.data_ptr(), w * 4, dg.data_ptr(), w * guide.itemsize,
+                                   0 if guide.dtype == np.uint8 else 1, w, h, gs, gr, gc, size), "BilateralFilter")
+    return _back(out, np.float32, (h, w))
+
+
 def warp(img: np.ndarray, lookup: np.ndarray) -> np.ndarray:
     """roo::Warp: lookup is (h, w, 2) float32 = (x, y) sample positions inside [0, W-2] x [0, H-2] of img."""
     import torch

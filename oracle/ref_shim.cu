@@ -22,6 +22,7 @@
 #include <kangaroo/cu_depth_tools.h>
 #include <kangaroo/cu_median.h>
 #include <kangaroo/cu_lookup_warp.h>
+#include <kangaroo/cu_bilateral.h>
 
 namespace {
 template <typename T>
@@ -240,6 +241,14 @@ int kref_costvol_minimum_square_penalty_subpix(void* imga, void* v, size_t v_pit
 int kref_filter_disp_grad(void* out, void* in, size_t pitch, size_t w, size_t h, float threshold) {
     if (out == in) return -3;
     roo::FilterDispGrad(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), threshold);
+    return finish();
+}
+
+// cu_bilateral.cu:110-155; img_type: 0 = unsigned char, 1 = float guide image
+int kref_bilateral_joint(void* out, void* in, size_t pitch, void* gimg, size_t g_pitch, int img_type, size_t w, size_t h, float gs,
+                         float gr, float gc, unsigned size) {
+    if (img_type == 0) roo::BilateralFilter<float, float, unsigned char>(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), img<unsigned char>(gimg, g_pitch, w, h), gs, gr, gc, size);
+    else roo::BilateralFilter<float, float, float>(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), img<float>(gimg, g_pitch, w, h), gs, gr, gc, size);
     return finish();
 }
 

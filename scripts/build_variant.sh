@@ -10,7 +10,7 @@ NAME=$1; FLAGS=$2; shift 2 || true
 SRCS=${@:-sgm_fused.cu}
 mkdir -p scripts/variants/obj_$NAME
 OBJS=""
-for s in census sgm sgm_hsweep sgm_fused wta frontback median engine split_engine; do
+for s in census sgm sgm_hsweep sgm_fused wta frontback median volfilter engine split_engine; do
   if [[ " $SRCS " == *" $s.cu "* ]]; then
     nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O2 $FLAGS -c kangaroo_b200/csrc/$s.cu -o scripts/variants/obj_$NAME/$s.o
     OBJS="$OBJS scripts/variants/obj_$NAME/$s.o"

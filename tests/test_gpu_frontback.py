@@ -325,3 +325,39 @@ def test_create_matlab_lookup_table_bitexact_both_modes_and_feeds_warp(golden):
     t[..., 0] = np.clip(t[..., 0], 1, 62)
     t[..., 1] = np.clip(t[..., 1], 1, 46)
     assert np.array_equal(warp(img, t), ko.warp(img, t))
+
+
+# ---------------------------------------------------------------- joint bilateral filter on cost-volume slices
+
+def test_bilateral_filter_volume_vs_reference_and_oracle(golden):
+    """One launch over all slices == the reference kernel run slice by slice (bit-identical: the reference's fast-math SASS is
+    reproduced operation for operation), == the per-image entry point; the IEEE oracle agrees to 1e-5 relative."""
+    g = golden("bilateral")
+    vol = g["vol"]
+    D, h, w = vol.shape
+    for nm in ("u8_s2", "u8_s5", "f32_s3", "f32_s0"):
+        guide = g["guide_u8"] if nm.startswith("u8") else g["guide_f32"]
+        gs, gr, gc, size = (float(v) for v in g[f"par_{nm}"])
+        out = roo.Volume(w, h, D, np.float32)
+        roo.BilateralFilterVolume(out, roo.Volume.from_numpy(vol), roo.Image.from_numpy(guide, pitch=w * guide.itemsize + 8), gs, gr,
+                                  gc, int(size), D)
+        ref = g[f"out_{nm}"]
+        assert same_bits(out.numpy(), ref)
+        one = roo.Image(w, h, np.float32)
+        roo.BilateralFilter(one, roo.Image.from_numpy(vol[2]), roo.Image.from_numpy(guide), gs, gr, gc, int(size))
+        assert same_bits(one.numpy(), ref[2])
+        orc = np.stack([ko.bilateral_filter_joint(vol[d], guide, gs, gr, gc, int(size)) for d in range(D)])
+        assert (np.abs(orc - ref) <= 1e-5 * np.maximum(np.abs(ref), 1e-3)).all()
+    # a volume with more slices than one thread's chunk, maxDisp < depth: the slices beyond stay untouched
+    rng = np.random.default_rng(21)
+    big = rng.random((19, 33, 141), dtype=np.float32)
+    guide = rng.integers(0, 256, (33, 141), dtype=np.uint8)
+    out = roo.Volume.from_numpy(np.full_like(big, -3.0))
+    roo.BilateralFilterVolume(out, roo.Volume.from_numpy(big), roo.Image.from_numpy(guide), 2.0, 0.25, 12.0, 3, 17)
+    o = out.numpy()
+    assert (o[17:] == -3.0).all()
+    orc = np.stack([ko.bilateral_filter_joint(big[d], guide, 2.0, 0.25, 12.0, 3) for d in range(17)])
+    assert (np.abs(orc - o[:17]) <= 1e-5 * np.maximum(np.abs(orc), 1e-3)).all()
+    with pytest.raises(roo.capi.RooError):
+        v = roo.Volume.from_numpy(big)
+        roo.BilateralFilterVolume(v, v, roo.Image.from_numpy(guide), 2.0, 0.25, 12.0, 3, 17)   # in place: taps would read filtered values

@@ -426,3 +426,26 @@ def test_kat_square_penalty_pulls_towards_previous_disparity():
     weak, _ = ko.costvol_minimum_square_penalty_subpix(vol, lastd, 8, -1.0, 1.0, 1e6)    # no coupling: data wins
     strong, _ = ko.costvol_minimum_square_penalty_subpix(vol, lastd, 8, -1.0, 1.0, 1e-3)  # stiff coupling: lastd wins
     assert np.rint(weak[0, 9]) == 2 and np.rint(strong[0, 9]) == 6
+
+
+def test_bilateral_filter_joint_matches_reference(golden):
+    """The IEEE restatement against the reference kernel (approximate ex2 / rcp units under -use_fast_math): 1e-5 relative."""
+    g = golden("bilateral")
+    for nm in ("u8_s2", "u8_s5", "f32_s3", "f32_s0"):
+        guide = g["guide_u8"] if nm.startswith("u8") else g["guide_f32"]
+        gs, gr, gc, size = (float(v) for v in g[f"par_{nm}"])
+        for d in (0, 3):
+            out = ko.bilateral_filter_joint(g["vol"][d], guide, gs, gr, gc, int(size))
+            ref = g[f"out_{nm}"][d]
+            assert (np.abs(out - ref) <= 1e-5 * np.maximum(np.abs(ref), 1e-3)).all()
+
+
+def test_kat_bilateral_filter():
+    flat = np.full((9, 9), 0.25, np.float32)
+    guide = np.zeros((9, 9), np.uint8)
+    assert np.allclose(ko.bilateral_filter_joint(flat, guide, 2.0, 0.1, 5.0, 3), 0.25, rtol=1e-6)     # a constant image is a fixed point
+    step = flat.copy(); step[:, 5:] = 0.75
+    gstep = guide.copy(); gstep[:, 5:] = 200                                                           # an edge in the guide image
+    out = ko.bilateral_filter_joint(step, gstep, 2.0, 10.0, 5.0, 3)                                    # wide range kernel: only the guide protects the edge
+    assert abs(out[4, 4] - 0.25) < 1e-3 and abs(out[4, 5] - 0.75) < 1e-3
+    assert abs(ko.bilateral_filter_joint(step, guide, 2.0, 10.0, 5.0, 3)[4, 4] - 0.25) > 0.05          # without the guide edge it blurs

@@ -88,6 +88,9 @@ sgm_hsweep_kernel(const SweepArgs a) {
 
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(hs_smem) + warp * NST * STAGE_B;
     const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(hs_smem) + HS_WARPS * NST * STAGE_B + warp * NST * 8;
+    // per-warp row of DP floats for the epilogue's parabola taps (after the mbarriers; only when an epilogue runs)
+    const unsigned wta_scratch = EPI != EPI_NONE ? (unsigned)__cvta_generic_to_shared(hs_smem) + HS_WARPS * NST * STAGE_B +
+                                                       HS_WARPS * NST * 8 + warp * DP * 4 : 0u;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < NST; ++s) mbar_init(mbar0 + 8 * s, 1);
@@ -210,7 +213,7 @@ sgm_hsweep_kernel(const SweepArgs a) {
                 last_c = pix;
                 if (EPI != EPI_WTA_ONLY) store_f<DPL>(hst + DX * i * DP, hnew);
                 if (EPI != EPI_NONE) {
-                    const float out = wta_epilogue<DPL, IEEE>(hp, lane, x, w, M, subpix);
+                    const float out = wta_epilogue<DPL, IEEE>(hp, lane, x, w, M, subpix, wta_scratch);
                     if (lane == 0) Drow[x] = out;
                 }
             }
@@ -250,7 +253,8 @@ sgm_hsweep_kernel(const SweepArgs a) {
 template <int DPL, int COST, int EPI, int DX>
 static int hsweep_launch4(const SweepArgs& a, cudaStream_t st) {
     constexpr int CH = hs_chunk<DPL, COST>();
-    constexpr size_t smem = (size_t)HS_WARPS * HS_NST * (CH * 32 * DPL * (4 + RawCost<DPL, COST>::ELEM)) + HS_WARPS * HS_NST * 8;
+    constexpr size_t smem = (size_t)HS_WARPS * HS_NST * (CH * 32 * DPL * (4 + RawCost<DPL, COST>::ELEM)) + HS_WARPS * HS_NST * 8 +
+                            (EPI != EPI_NONE ? (size_t)HS_WARPS * 32 * DPL * 4 : 0);
     static_assert(32 % CH == 0 || CH % 32 == 0, "chunks must not straddle a 32-pixel intensity block");
     dim3 grid(cdiv(a.h, HS_WARPS), a.batch);
     const bool ieee = a.ieee != 0;

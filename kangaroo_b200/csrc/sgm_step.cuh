@@ -330,8 +330,12 @@ __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float de
 
 // Winner-takes-all (+ optional parabola) over the masked row hp[] of pixel x -- CostVolMinimum<float,float>
 // (cu_dense_stereo.cu:25-43) or CostVolMinimumSubpix with sd = -1 (cu_dense_stereo.cu:66-109).
+// scratch: 32-bit shared-window address of 32*DPL floats private to the warp (0: none).  With it the two parabola taps
+// H(bestd-1), H(bestd+1) -- warp-uniform positions -- are read back from the row each lane parks there (2 STS.128 + 2 broadcast
+// LDS at 256 disparities) instead of 2*DPL compare-select pairs per lane and two shuffles.
 template <int DPL, bool IEEE>
-__device__ __forceinline__ float wta_epilogue(const float (&hp)[DPL], int lane, int x, int w, int maxDispVal, int subpix) {
+__device__ __forceinline__ float wta_epilogue(const float (&hp)[DPL], int lane, int x, int w, int maxDispVal, int subpix,
+                                              unsigned scratch = 0) {
     const int d0 = lane * DPL;
     // lane minimum by a min tree (no index tracking), warp minimum by one redux.sync.min.f32; then the LOWEST
     // disparity that holds it: first j inside the lane, lowest lane through one integer redux.sync.min.s32
@@ -352,14 +356,23 @@ __device__ __forceinline__ float wta_epilogue(const float (&hp)[DPL], int lane, 
     if (0 < bestxr && bestxr < w - 1 && bestd + 1 < maxDispVal) {  // bestd+1 == vol.d: out of bounds in the reference
         const int dl = max(bestd - 1, 0);      // float -> unsigned saturation in the reference (Q7)
         const int dr = bestd + 1;
-        float slc = 0.0f, src = 0.0f;
+        float sl, sr;
+        if (scratch != 0) {
+            __syncwarp();                       // the previous pixel's taps have been read
+            sts_vec<DPL>(scratch + d0 * 4, hp);
+            __syncwarp();
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sl) : "r"(scratch + dl * 4));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sr) : "r"(scratch + dr * 4));
+        } else {
+            float slc = 0.0f, src = 0.0f;
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) {
-            if (d0 + j == dl) slc = hp[j];
-            if (d0 + j == dr) src = hp[j];
+            for (int j = 0; j < DPL; ++j) {
+                if (d0 + j == dl) slc = hp[j];
+                if (d0 + j == dr) src = hp[j];
+            }
+            sl = __shfl_sync(0xffffffffu, slc, dl / DPL);
+            sr = __shfl_sync(0xffffffffu, src, dr / DPL);
         }
-        const float sl = __shfl_sync(0xffffffffu, slc, dl / DPL);
-        const float sr = __shfl_sync(0xffffffffu, src, dr / DPL);
         const float sub = parabola_vertex<IEEE>((float)bestd, bestc, sl, sr);
         if ((float)(bestd - 1) < sub && sub < (float)(bestd + 1)) out = sub;
     }

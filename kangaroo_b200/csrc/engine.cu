@@ -145,7 +145,12 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
         // Eligible: one-word descriptors under the reference's 32-bit popcount (9x7 window, hamming_distance.h:40-44).
         const bool cen_ok = e->words == 1 && p.popc_mode == ROO_POPC32_COMPAT && g_insweep_cost.load(std::memory_order_relaxed);
         auto pass_in_sweep = [&](const SgmPass& ps) {
-            return cen_ok && (ps.fused || (ps.dy == 0 && g_use_hsweep.load(std::memory_order_relaxed)));
+            // The fused vertical groups and the bulk-copy horizontal kernel always can.  The generic single-path sweep stages
+            // the 32*DPL census words of every step with 4-byte cp.async: measured faster than the u8 volume only up to 64
+            // disparities (640x480x64 4-path: 5967 -> 6973 pairs/s; 1242x375x128: 2989 -> 2645, so it keeps the volume there).
+            if (!cen_ok) return false;
+            if (ps.fused || (ps.dy == 0 && g_use_hsweep.load(std::memory_order_relaxed))) return true;
+            return e->DP <= 64;
         };
         bool need_c8 = false;
         for (int i = 0; i < ndir; ++i) need_c8 |= !pass_in_sweep(plan.pass[i]);

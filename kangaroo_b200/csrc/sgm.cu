@@ -49,15 +49,22 @@ __device__ __forceinline__ Scanline scanline_of(int s, int w, int h, int dx, int
 // prefetch depth in path steps (stages of one pixel each, staged global -> shared by cp.async): under load a
 // DRAM access takes ~3000 SM cycles on B200, so each SM needs 60-80 KB in flight to stream at HBM speed
 __host__ __device__ constexpr int sweep_pfs(int DPL, int CE) { return DPL >= 8 ? 4 : (DPL == 4 && CE == 4 ? 4 : 8); }
-template <int DPL, int COST> __host__ __device__ constexpr int sweep_stage_bytes() { return 32 * DPL * 4 + 32 * DPL * RawCost<DPL, COST>::ELEM + 16; }
+// one prefetched path step: [aggregate row][cost row, or with in-sweep cost the 32*DPL right-image census words R(x-d)]
+// [intensity, left census word]
+template <int DPL, int COST> __host__ __device__ constexpr int sweep_cost_bytes() {
+    return COST == COST_CEN32 ? 32 * DPL * 4 : 32 * DPL * RawCost<DPL, COST>::ELEM;
+}
+template <int DPL, int COST> __host__ __device__ constexpr int sweep_stage_bytes() { return 32 * DPL * 4 + sweep_cost_bytes<DPL, COST>() + 16; }
 
 template <int DPL, int COST, int EPI, bool FIRST, bool IEEE>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
     constexpr int DP = 32 * DPL;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    constexpr int PFS = sweep_pfs(DPL, CE);
+    constexpr bool CEN = COST == COST_CEN32;                      // cost recomputed from census words (no cost volume)
+    constexpr int PFS = sweep_pfs(DPL, CEN ? 4 : CE);
     constexpr int STAGE_B = sweep_stage_bytes<DPL, COST>();
+    constexpr int CB = sweep_cost_bytes<DPL, COST>();
     extern __shared__ __align__(16) unsigned char sweep_smem[];   // [SWEEP_WARPS][PFS][STAGE_B]
 
     const int lane = threadIdx.x & 31;
@@ -80,6 +87,10 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
     const float* hld = hst;                                                           // prefetch cursors
     const char* cld = (const char*)a.C + ((size_t)pair * a.c_pair + e0) * CE;
     const float* ild = a.img + (size_t)pair * a.img_pair + (size_t)sl.y0 * w + sl.x0;
+    // in-sweep cost: this lane's right-image descriptors R(x - d0 - j) (u64 each, the low word is used; the arrays are
+    // padded, positions left of the image give masked garbage) and the left descriptor of the pixel
+    const unsigned long long* rld = CEN ? a.cenR + (size_t)pair * a.cen_pair + (size_t)sl.y0 * w + sl.x0 - d0 : nullptr;
+    const unsigned long long* lld = CEN ? a.cenL + (size_t)pair * a.cen_pair + (size_t)sl.y0 * w + sl.x0 : nullptr;
     float* dst = (EPI != EPI_NONE) ? a.disp + (size_t)pair * a.disp_pair + (size_t)sl.y0 * w + sl.x0 : nullptr;
 
     // Prefetch: step r+PFS-1 is copied global -> shared (asynchronously, no registers) while step r is computed.
@@ -89,8 +100,15 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
         if (rl < len) {
             const unsigned sd = pfBase + ((unsigned)rl & (PFS - 1)) * STAGE_B;
             if (!FIRST) cp_async_bytes<DPL * 4>(sd + lane * DPL * 4, hld);
-            cp_async_bytes<DPL * CE>(sd + DP * 4 + lane * DPL * CE, cld);
-            if (lane == 0) cp_async_bytes<4>(sd + DP * 4 + DP * CE, ild);
+            if (CEN) {
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) cp_async_bytes<4>(sd + DP * 4 + (lane * DPL + j) * 4, reinterpret_cast<const unsigned*>(rld - j));
+                if (lane == 1) cp_async_bytes<4>(sd + DP * 4 + CB + 4, reinterpret_cast<const unsigned*>(lld));
+                rld += pstep; lld += pstep;
+            } else {
+                cp_async_bytes<DPL * (CE > 0 ? CE : 1)>(sd + DP * 4 + lane * DPL * CE, cld);
+            }
+            if (lane == 0) cp_async_bytes<4>(sd + DP * 4 + CB, ild);
             hld += estep; cld += estep * CE; ild += pstep;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -130,16 +148,25 @@ sgm_sweep_kernel(const SweepArgs a, const int n_scan) {
         const unsigned stg = pfBase + ((unsigned)r & (PFS - 1)) * STAGE_B;
         float hin[DPL], hnew[DPL], best, pix;
         if (!FIRST) lds_vec<DPL>(hin, stg + lane * DPL * 4);
-        RawCost<DPL, COST> rc;
-        rc.lds(stg + DP * 4 + lane * DPL * CE);
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + DP * CE));
+        float craw[DPL];
+        if (CEN) {
+            unsigned rw[DPL], lw;
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rw[j]) : "r"(stg + DP * 4 + (lane * DPL + j) * 4));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lw) : "r"(stg + DP * 4 + CB + 4));
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) craw[j] = (float)__popc(lw ^ rw[j]);
+        } else {
+            RawCost<DPL, COST> rc;
+            rc.lds(stg + DP * 4 + lane * DPL * CE);
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) craw[j] = rc.raw(j);
+        }
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pix) : "r"(stg + DP * 4 + CB));
         // start pixel: `volH += volC`, lastBestCr = 0 (cu_semi_global_matching.cu:31-35) == a step with P2 = 0
         const float p2 = (r == 0 && !continued) ? 0.0f : P2;
         const float denom = 1.0f + fabsf(last_c - pix);
         const int lim = MASKED ? min(M, x + 1) - d0 : 0;
-        float craw[DPL];
-#pragma unroll
-        for (int j = 0; j < DPL; ++j) craw[j] = rc.raw(j);
         sgm_step<DPL, MASKED, FIRST, IEEE>(hp, lastBest, denom, P1, p2, craw, cscale, hin, lim, lane, hnew, hp, best);
         lastBest = (r == 0 && !continued) ? 0.0f : best;
         last_c = pix;
@@ -180,7 +207,7 @@ template <int DPL, int COST, int EPI>
 static void sweep_launch3(const SweepArgs& a, int n_scan, dim3 grid, cudaStream_t st) {
     const bool ieee = a.ieee != 0;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    const size_t smem = (size_t)SWEEP_WARPS * sweep_pfs(DPL, CE) * sweep_stage_bytes<DPL, COST>();
+    const size_t smem = (size_t)SWEEP_WARPS * sweep_pfs(DPL, COST == COST_CEN32 ? 4 : CE) * sweep_stage_bytes<DPL, COST>();
 #define ROO_SWEEP(F, I)                                                                                  \
     do {                                                                                                 \
         auto kern = sgm_sweep_kernel<DPL, COST, EPI, F, I>;                                              \
@@ -202,6 +229,7 @@ static void sweep_launch_epi(const SweepArgs& a, int n_scan, dim3 grid, cudaStre
 template <int DPL>
 static void sweep_launch_cost(const SweepArgs& a, int n_scan, dim3 grid, cudaStream_t st) {
     if (a.cost_kind == COST_F32) sweep_launch_epi<DPL, COST_F32>(a, n_scan, grid, st);
+    else if (a.cost_kind == COST_CEN32) sweep_launch_epi<DPL, COST_CEN32>(a, n_scan, grid, st);
     else sweep_launch_epi<DPL, COST_U8>(a, n_scan, grid, st);
 }
 

@@ -65,7 +65,7 @@ __host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? VG_NCW8 : 
 #define VG_NWW_FC VG_NWW
 #endif
 #ifndef VG_NWW8_FC
-#define VG_NWW8_FC VG_NWW8
+#define VG_NWW8_FC VG_NWW8_CEN
 #endif
 // narrow bands of a first pass with in-sweep cost need little shared memory: several of them share an SM
 #ifndef VG_MINB_FC
@@ -74,10 +74,15 @@ __host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? VG_NCW8 : 
 __host__ __device__ constexpr int vg_min_ctas(int DPL, int cost, bool first, int nww) {
     return (first && cost == COST_CEN32 && nww <= (DPL >= 8 ? 3 : 6)) ? VG_MINB_FC : 1;
 }
-__host__ __device__ constexpr int vg_nww(int DPL, bool first_cen = false) {
-    return DPL >= 8 ? (first_cen ? VG_NWW8_FC : VG_NWW8) : (first_cen ? VG_NWW_FC : VG_NWW);
+// with in-sweep cost the prefetch stages hold no cost rows: at 256 disparities that leaves room for more warps per band
+#ifndef VG_NWW8_CEN
+#define VG_NWW8_CEN VG_NWW8
+#endif
+// geometry class of a launch: 0 = cost read from a volume, 1 = in-sweep cost, 2 = in-sweep cost and write-only first pass
+__host__ __device__ constexpr int vg_nww(int DPL, int cls = 0) {
+    return DPL >= 8 ? (cls == 2 ? VG_NWW8_FC : (cls == 1 ? VG_NWW8_CEN : VG_NWW8)) : (cls == 2 ? VG_NWW_FC : VG_NWW);
 }
-inline int vg_cols_of_dp(int DP, bool first_cen = false) { return vg_ncw(DP / 32) * vg_nww(DP / 32, first_cen); }
+inline int vg_cols_of_dp(int DP, int cls = 0) { return vg_ncw(DP / 32) * vg_nww(DP / 32, cls); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -679,7 +684,8 @@ sgm_vgroup_kernel(const VGroupArgs a) {
 
 // scratch sizing: the geometry with the narrower bands (more bands)
 int vgroup_bands(int w, int h, int DP) {
-    const int nc = vg_cols_of_dp(DP, false) < vg_cols_of_dp(DP, true) ? vg_cols_of_dp(DP, false) : vg_cols_of_dp(DP, true);
+    int nc = vg_cols_of_dp(DP, 0);
+    for (int cls = 1; cls <= 2; ++cls) nc = vg_cols_of_dp(DP, cls) < nc ? vg_cols_of_dp(DP, cls) : nc;
     return cdiv(w + h - 1, nc);
 }
 size_t vgroup_edge_floats(int w, int h, int DP) { return (size_t)vgroup_bands(w, h, DP) * h * (3 * (size_t)DP + 8); }
@@ -693,9 +699,9 @@ constexpr size_t vg_smem_bytes() {
            (COST == COST_CEN32 ? (size_t)NWW * vg_pfs(DPL, CE) * (DP + 16) * 4 : 0);
 }
 
-template <int DPL, int COST, bool FIRST, bool FC>
+template <int DPL, int COST, bool FIRST, int CLS>
 static int vgroup_launch3(VGroupArgs a, cudaStream_t st) {
-    constexpr int NWW = vg_nww(DPL, FC), NCW = vg_ncw(DPL);
+    constexpr int NWW = vg_nww(DPL, CLS), NCW = vg_ncw(DPL);
     a.n_bands = cdiv(a.w + a.h - 1, NWW * NCW);
     constexpr size_t smem = vg_smem_bytes<DPL, COST, FIRST, NWW, NCW>();
     static_assert(smem <= 227 * 1024, "vertical-group kernel: shared memory budget of one sm_100 CTA exceeded");
@@ -718,9 +724,10 @@ static int vgroup_launch3(VGroupArgs a, cudaStream_t st) {
 
 template <int DPL, int COST>
 static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
-    if (!first) return vgroup_launch3<DPL, COST, false, false>(a, st);
-    if constexpr (COST == COST_CEN32 && vg_nww(DPL, true) != vg_nww(DPL, false)) return vgroup_launch3<DPL, COST, true, true>(a, st);
-    else return vgroup_launch3<DPL, COST, true, false>(a, st);
+    constexpr int CEN_CLS = COST == COST_CEN32 ? 1 : 0;
+    if (!first) return vgroup_launch3<DPL, COST, false, CEN_CLS>(a, st);
+    if constexpr (COST == COST_CEN32 && vg_nww(DPL, 2) != vg_nww(DPL, 1)) return vgroup_launch3<DPL, COST, true, 2>(a, st);
+    else return vgroup_launch3<DPL, COST, true, CEN_CLS>(a, st);
 }
 
 // scratch: edge buffer of vgroup_edge_floats(w,h,DP) * batch floats and n_bands * batch ints of progress flags

@@ -184,10 +184,13 @@ extern "C" int roo_split_engine_run_host(roo_split_engine_t* e, const uint8_t* l
     cudaGetDevice(&prev);
     ++e->frame;
     e->exchanged_bytes = 0;
-    const bool cen_ok = e->words == 1 && p.popc_mode == ROO_POPC32_COMPAT && g_insweep_cost.load(std::memory_order_relaxed) &&
-                        g_use_hsweep.load(std::memory_order_relaxed);
+    // in-sweep matching cost (no u8 cost volume at all) with the one-word descriptor under the reference's popcount
+    const bool cen_ok = e->words == 1 && p.popc_mode == ROO_POPC32_COMPAT && g_insweep_cost.load(std::memory_order_relaxed);
+    // (the generic single-path sweep recomputes the cost in the sweep only up to 64 disparities, see engine.cu)
+    const bool hs = g_use_hsweep.load(std::memory_order_relaxed) != 0;
+    auto in_sweep = [&](const SgmPass& ps) { return cen_ok && ((ps.dy == 0 && hs) || DP <= 64); };
     bool need_c8 = false;
-    for (int i = 0; i < ndir; ++i) need_c8 |= !(cen_ok && e->plan.pass[i].dy == 0);
+    for (int i = 0; i < ndir; ++i) need_c8 |= !in_sweep(e->plan.pass[i]);
     int rc = ROO_OK;
     // Stage 1 on every device: upload, census, cost, intensities, right-reference disparity.
     // Stage 2: the sweeps in plan order; the strips are visited in the travel direction of each crossing sweep so that a
@@ -228,7 +231,7 @@ extern "C" int roo_split_engine_run_host(roo_split_engine_t* e, const uint8_t* l
             a.cost_scale = 1.0f / (float)(e->words * 64);
             a.w = w; a.h = s.hl; a.DP = DP; a.maxDisp = p.max_disp; a.batch = 1; a.P1 = p.P1; a.P2 = p.P2;
             a.dx = ps.dx; a.dy = ps.dy; a.first = i == 0; a.ieee = e->ieee; a.subpix = p.subpix;
-            a.cost_kind = (cen_ok && !crossing) ? COST_CEN32 : COST_U8;
+            a.cost_kind = in_sweep(ps) ? COST_CEN32 : COST_U8;
             a.cenL = s.cen[0] + off; a.cenR = s.cen[1] + off; a.cen_pair = 0;
             a.epi = i + 1 < ndir ? EPI_NONE : (p.keep_volume ? EPI_WTA_WRITE : EPI_WTA_ONLY);
             a.disp = s.disp; a.disp_pair = 0;

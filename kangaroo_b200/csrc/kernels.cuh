@@ -57,6 +57,8 @@ int launch_hsweep(const SweepArgs& a, cudaStream_t st);
 extern std::atomic<int> g_use_hsweep;
 // development knob: 0 = always materialise the u8 cost volume (no in-sweep cost from census words)
 extern std::atomic<int> g_insweep_cost;
+// split engine: CTAs per SM of a strip-crossing sweep (0 = as many as fit); fewer = waves = earlier hand-offs
+extern std::atomic<int> g_strip_ctas_per_sm;
 int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pair, int img_type, int w, int h,
                         int batch, float scale, cudaStream_t st);
 inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : 256)); }

@@ -207,7 +207,16 @@ template <int DPL, int COST, int EPI>
 static void sweep_launch3(const SweepArgs& a, int n_scan, dim3 grid, cudaStream_t st) {
     const bool ieee = a.ieee != 0;
     constexpr int CE = RawCost<DPL, COST>::ELEM;
-    const size_t smem = (size_t)SWEEP_WARPS * sweep_pfs(DPL, COST == COST_CEN32 ? 4 : CE) * sweep_stage_bytes<DPL, COST>();
+    size_t smem = (size_t)SWEEP_WARPS * sweep_pfs(DPL, COST == COST_CEN32 ? 4 : CE) * sweep_stage_bytes<DPL, COST>();
+    // Row-strip split: all scanlines of a sweep advance in lock step when every CTA is resident, so a strip would export
+    // its states only at the very end and the strips of one sweep would run one after the other.  Asking for more shared
+    // memory than the kernel needs caps the CTAs per SM: the grid then runs in waves (lowest scanlines first on every
+    // strip), the first wave's states are exported early and the downstream strip starts while this one is still working.
+    const int cap = g_strip_ctas_per_sm.load(std::memory_order_relaxed);
+    if (cap > 0 && (a.strip_import != nullptr || a.strip_export != nullptr)) {
+        const size_t per_cta = (size_t)(227 * 1024) / cap - 1024;   // 1 KB per CTA is reserved by the runtime
+        if (per_cta > smem) smem = per_cta;
+    }
 #define ROO_SWEEP(F, I)                                                                                  \
     do {                                                                                                 \
         auto kern = sgm_sweep_kernel<DPL, COST, EPI, F, I>;                                              \
@@ -234,6 +243,7 @@ static void sweep_launch_cost(const SweepArgs& a, int n_scan, dim3 grid, cudaStr
 }
 
 std::atomic<int> g_use_hsweep{1};
+std::atomic<int> g_strip_ctas_per_sm{0};
 
 int launch_sweep(const SweepArgs& a, cudaStream_t st) {
     if (a.dy == 0 && g_use_hsweep.load(std::memory_order_relaxed)) return launch_hsweep(a, st);

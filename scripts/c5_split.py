@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default="")
     ap.add_argument("--small", action="store_true", help="1920x1080 instead of 3840x2160 (quick check)")
+    ap.add_argument("--strip-ctas", type=int, default=-1, help="roo_set_tuning(ROO_TUNE_STRIP_CTAS_PER_SM): CTAs per SM of a strip-crossing sweep")
     args = ap.parse_args()
     w, h, D = (1920, 1080, 256) if args.small else (3840, 2160, 256)
     opts = dict(dodiag=True, subpix=True, lrcheck=True, lr_maxdiff=1.0)
@@ -49,6 +50,9 @@ def main():
     eng.close()
     rec = {"workload": f"c5 {w}x{h}x{D} 8-path + subpix + LR check, one pair", "gpu_count_visible": ndev,
            "single_gpu_engine_ms_per_pair_device": single_ms, "splits": []}
+    if args.strip_ctas >= 0:
+        roo.set_tuning(roo.capi.TUNE_STRIP_CTAS_PER_SM, args.strip_ctas)
+        rec["strip_ctas_per_sm"] = args.strip_ctas
     counts = [args.gpus] if args.gpus else [n for n in (1, 2, 4, 8) if n <= ndev]
     for n in counts:
         se = roo.SplitStereoEngine(w, h, D, devices=list(range(n)), **opts)

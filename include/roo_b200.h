@@ -68,8 +68,8 @@ enum roo_tuning_knob { ROO_TUNE_HSWEEP = 0,
                        /* 1 (default): passes that can recompute the matching cost from the census words do so and do
                         * not read the u8 cost volume; 0: always through the materialised volume */
                        ROO_TUNE_INSWEEP_COST = 1,
-                       /* roo_split_engine: CTAs per SM of a sweep that crosses strips (0 = as many as fit).  A small
-                        * number makes the grid run in waves, so a strip hands its first scanlines on early */
+                       /* roo_split_engine: CTAs per SM of a sweep that crosses strips (0 = as many as fit; default 3).  A
+                        * small number makes the grid run in waves, so a strip hands its first scanlines on early */
                        ROO_TUNE_STRIP_CTAS_PER_SM = 2 };
 int roo_set_tuning(int knob, int value);
 

@@ -66,7 +66,9 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
 }
 
 // DX = +1: path (+1,0), travel index t == x;  DX = -1: path (-1,0), t == w-1-x.
-template <int DPL, int COST, int EPI, bool FIRST, bool IEEE, int DX>
+// SUBPIX (epilogue only): compile-time, so that the eight pixels of a chunk are ONE straight-line block in the plain
+// winner-takes-all case (no uniform branch per pixel: the census window rotates by register renaming, not by moves)
+template <int DPL, int COST, int EPI, bool FIRST, bool IEEE, int DX, bool SUBPIX>
 __global__ void __launch_bounds__(HS_WARPS * 32)
 sgm_hsweep_kernel(const SweepArgs a) {
     constexpr int DP = 32 * DPL;
@@ -83,7 +85,8 @@ sgm_hsweep_kernel(const SweepArgs a) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int y = blockIdx.x * HS_WARPS + warp;
     const int pair = blockIdx.y;
-    const int w = a.w, M = a.maxDisp, subpix = a.subpix;
+    const int w = a.w, M = a.maxDisp;
+    constexpr int subpix = SUBPIX ? 1 : 0;
     const float P1 = a.P1, P2 = a.P2, cscale = a.cost_scale;
 
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(hs_smem) + warp * NST * STAGE_B;
@@ -214,7 +217,8 @@ sgm_hsweep_kernel(const SweepArgs a) {
                 if (EPI != EPI_WTA_ONLY) store_f<DPL>(hst + DX * i * DP, hnew);
                 if (EPI != EPI_NONE) {
                     const float out = wta_epilogue<DPL, IEEE>(hp, lane, x, w, M, subpix, wta_scratch);
-                    if (lane == 0) Drow[x] = out;
+                    // lane 0 stores; a predicated store, not a branch: the pixels of a chunk stay one basic block
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 0;\n\t@p st.global.f32 [%1], %2;\n\t}" ::"r"(lane), "l"(Drow + x), "f"(out) : "memory");
                 }
             }
         }
@@ -260,7 +264,8 @@ static int hsweep_launch4(const SweepArgs& a, cudaStream_t st) {
     const bool ieee = a.ieee != 0;
 #define ROO_HS(F, I)                                                                                          \
     do {                                                                                                      \
-        auto kern = sgm_hsweep_kernel<DPL, COST, EPI, F, I, DX>;                                              \
+        auto kern = (EPI != EPI_NONE && a.subpix) ? sgm_hsweep_kernel<DPL, COST, EPI, F, I, DX, EPI != EPI_NONE>    \
+                                                  : sgm_hsweep_kernel<DPL, COST, EPI, F, I, DX, false>;       \
         if (smem > 48 * 1024) {                                                                               \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                              \

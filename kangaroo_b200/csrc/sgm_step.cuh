@@ -202,32 +202,30 @@ __device__ __forceinline__ void sgm_step(const float (&hp)[DPL], float lastBest,
         const float hq = j < DPL - 1 ? hpP[j + 1] : dn;
         CM[j] = fminf(fminf(base, hp[j]), fminf(hm, hq));
     }
+    // MASKED: an out-of-range disparity gets the cost +inf.  Cr and the new aggregate are then +inf by themselves -- which
+    // is exactly the masked state row (hp_out) -- and never win a minimum; only the value written to H needs a select.
+    float cm_[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) cm_[j] = (MASKED && !(j < lim)) ? ROO_INF : CM[j];
     if constexpr (DPL >= 2) {
         const f32x2 cs2 = pk2(cs, cs), nlb = pk2(-lastBest, -lastBest);
 #pragma unroll
         for (int q = 0; q < DPL / 2; ++q) {
-            const f32x2 cr = add2(fma2(pk2(craw[2 * q], craw[2 * q + 1]), cs2, pk2(CM[2 * q], CM[2 * q + 1])), nlb);
+            const f32x2 cr = add2(fma2(pk2(craw[2 * q], craw[2 * q + 1]), cs2, pk2(cm_[2 * q], cm_[2 * q + 1])), nlb);
             upk2(cr, Cr[2 * q], Cr[2 * q + 1]);
             if (FIRST) { h[2 * q] = Cr[2 * q]; h[2 * q + 1] = Cr[2 * q + 1]; }
             else upk2(add2(pk2(hin[2 * q], hin[2 * q + 1]), cr), h[2 * q], h[2 * q + 1]);
         }
     } else {
-        Cr[0] = __fmaf_rn(craw[0], cs, CM[0]) - lastBest;
+        Cr[0] = __fmaf_rn(craw[0], cs, cm_[0]) - lastBest;
         h[0] = FIRST ? Cr[0] : hin[0] + Cr[0];
     }
     float best = SGM_MAX_ERROR;
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
-        if (MASKED) {
-            const bool in = j < lim;
-            best = in ? fminf(best, Cr[j]) : best;
-            hnew[j] = in ? h[j] : (FIRST ? 0.0f : hin[j]);
-            hp_out[j] = in ? h[j] : ROO_INF;
-        } else {
-            best = fminf(best, Cr[j]);
-            hnew[j] = h[j];
-            hp_out[j] = h[j];
-        }
+        best = fminf(best, Cr[j]);                       // +inf where masked: never the minimum
+        hp_out[j] = h[j];                                // +inf where masked
+        hnew[j] = (MASKED && !(j < lim)) ? (FIRST ? 0.0f : hin[j]) : h[j];
     }
     best_out = warp_min_f32(best);
 }
@@ -273,6 +271,13 @@ __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float de
         cmD[j] = fminf(fminf(baseD, hpD[j]), fminf(j > 0 ? pD[j - 1] : upD, j < DPL - 1 ? pD[j + 1] : dnD));
         cmA[j] = fminf(fminf(baseA, hpA[j]), fminf(j > 0 ? pA[j - 1] : upA, j < DPL - 1 ? pA[j + 1] : dnA));
     }
+    // MASKED: out-of-range disparities get +inf in all three CM rows, so their Cr and aggregates are +inf (the masked
+    // state rows) and never win a minimum; only H3 needs a select (see sgm_step)
+    if (MASKED) {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+            if (!(j < lim)) { cmV[j] = ROO_INF; cmD[j] = ROO_INF; cmA[j] = ROO_INF; }
+    }
     float crV[DPL], crD[DPL], crA[DPL], h1[DPL], h2[DPL], h3[DPL];
     if constexpr (DPL >= 2) {
         const f32x2 cs2 = pk2(cs, cs), nV = pk2(-lbV, -lbV), nD = pk2(-lbD, -lbD), nA = pk2(-lbA, -lbA);
@@ -301,27 +306,16 @@ __device__ __forceinline__ void sgm_step3(float (&hpV)[DPL], float lbV, float de
     float tV = 0.0f, tD = 0.0f, tA = 0.0f;
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
-        if (MASKED) {
-            const bool in = j < lim;
-            mV = in ? fminf(mV, crV[j]) : mV;
-            mD = in ? fminf(mD, crD[j]) : mD;
-            mA = in ? fminf(mA, crA[j]) : mA;
-            hpV[j] = in ? h1[j] : ROO_INF;
-            hpD[j] = in ? h2[j] : ROO_INF;
-            hpA[j] = in ? h3[j] : ROO_INF;
-            H3[j] = in ? h3[j] : (FIRST ? 0.0f : hin[j]);
+        // pairs first, so that every second min is a three-input FMNMX3 (min is exact: any grouping agrees)
+        if (j & 1) {
+            mV = fminf(mV, fminf(tV, crV[j])); mD = fminf(mD, fminf(tD, crD[j])); mA = fminf(mA, fminf(tA, crA[j]));
+        } else if (j == DPL - 1) {
+            mV = fminf(mV, crV[j]); mD = fminf(mD, crD[j]); mA = fminf(mA, crA[j]);
         } else {
-            // pairs first, so that every second min is a three-input FMNMX3 (min is exact: any grouping agrees)
-            if (j & 1) {
-                mV = fminf(mV, fminf(tV, crV[j])); mD = fminf(mD, fminf(tD, crD[j])); mA = fminf(mA, fminf(tA, crA[j]));
-            } else if (j == DPL - 1) {
-                mV = fminf(mV, crV[j]); mD = fminf(mD, crD[j]); mA = fminf(mA, crA[j]);
-            } else {
-                tV = crV[j]; tD = crD[j]; tA = crA[j];
-            }
-            hpV[j] = h1[j]; hpD[j] = h2[j]; hpA[j] = h3[j];
-            H3[j] = h3[j];
+            tV = crV[j]; tD = crD[j]; tA = crA[j];
         }
+        hpV[j] = h1[j]; hpD[j] = h2[j]; hpA[j] = h3[j];
+        H3[j] = (MASKED && !(j < lim)) ? (FIRST ? 0.0f : hin[j]) : h3[j];
     }
     bV = warp_min_f32(mV);
     bD = warp_min_f32(mD);

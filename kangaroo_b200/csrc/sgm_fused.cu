@@ -186,8 +186,10 @@ struct VCtl { volatile int halo_ready; volatile int copied; int pad[2]; };
 #define VG_R 4
 #endif
 __host__ __device__ constexpr int vg_r(int DPL) { return VG_R; }   // max rows per hand-off batch between bands (ring = 2x)
+// depth of the in-band state ring: 2 rows measured 1 % faster than 4 (c2: 6.13 -> 6.06 ms for the two fused passes) and
+// frees 37 KB of shared memory
 #ifndef VG_S_DEPTH
-#define VG_S_DEPTH 4
+#define VG_S_DEPTH 2
 #endif
 #ifndef VG_S_DEPTH8
 #define VG_S_DEPTH8 2

@@ -5,6 +5,8 @@ mkdir -p gpurun_out/final
 O=gpurun_out/final
 timeout 1800 python -m pytest tests -q -m gpu > $O/gpu_tests.log 2>&1
 tail -3 $O/gpu_tests.log
+ROO_STRESS_SEEDS=60 timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "random_shapes" > $O/gpu_stress.log 2>&1
+tail -2 $O/gpu_stress.log
 python bench.py --steps 20 --warmup 5 > $O/bench_c2.json 2> $O/bench_c2.err
 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_reference.json 2>> $O/bench_c2.err
 for wl in c1_640x480x64_4path c3_kitti_1242x375x128_4path c4_1920x1080x256_8path_subpix_lr c5_3840x2160x256_8path_subpix_lr_single_gpu; do

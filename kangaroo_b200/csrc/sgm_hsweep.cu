@@ -290,7 +290,13 @@ static int hsweep_launch2(const SweepArgs& a, cudaStream_t st) {
 }
 
 // a.dy == 0, a.dx == +-1
+#ifdef HS_PART
+#define ROO_HS_CAT2(a, b) a##b
+#define ROO_HS_CAT(a, b) ROO_HS_CAT2(a, b)
+int ROO_HS_CAT(launch_hsweep_dpl, HS_PART)(const SweepArgs& a, cudaStream_t st) {
+#else
 int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
+#endif
 #define ROO_HS_DP(DPL)                                                          \
     switch (a.cost_kind) {                                                      \
         case COST_F32: return hsweep_launch2<DPL, COST_F32>(a, st);             \
@@ -298,6 +304,11 @@ int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
         case COST_CEN32: return hsweep_launch2<DPL, COST_CEN32>(a, st);         \
         default: return ROO_ERR_INVALID_ARGUMENT;                               \
     }
+    // The instantiations of one disparity count are one translation unit each (the Makefile compiles this file four
+    // times with -DHS_PART=<DPL>): build time, nothing else.
+#ifdef HS_PART
+    ROO_HS_DP(HS_PART)
+#else
     switch (a.DP) {
         case 32: ROO_HS_DP(1)
         case 64: ROO_HS_DP(2)
@@ -305,6 +316,7 @@ int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
         case 256: ROO_HS_DP(8)
         default: return ROO_ERR_UNSUPPORTED;
     }
+#endif
 #undef ROO_HS_DP
 }
 

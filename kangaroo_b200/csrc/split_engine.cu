@@ -3,9 +3,9 @@
 // (src/cu_semi_global_matching.cu:69-84 launches on the current device), so this is new design.
 //
 //   * GPU k owns the image rows [y0_k, y1_k): its strip of the aggregate H (fp32, disparity innermost), of the u8
-//     matching cost and of the disparity images never leaves it.  The input frames are small (8 MB at 4K) and go to
-//     every GPU whole; each GPU computes the census descriptors of the whole frame (0.2 ms) so that no halo rows of the
-//     census window have to be exchanged.
+//     matching cost and of the disparity images never leaves it.  Each GPU receives its rows of the input frames plus
+//     eight halo rows above and below (the reach of the largest census window) straight from the host and computes the
+//     census descriptors of those rows itself, so no census halo is exchanged between GPUs.
 //   * Horizontal paths (+1,0), (-1,0), the winner-takes-all epilogue, the right-reference disparity and the left-right
 //     check are local to a row: no exchange at all.
 //   * The six paths that travel in y (down, down-right, down-left, then up, up-left, up-right -- one sweep each, every
@@ -199,12 +199,17 @@ extern "C" int roo_split_engine_run_host(roo_split_engine_t* e, const uint8_t* l
         Strip& s = e->strips[k];
         cudaSetDevice(s.device);
         const size_t off = (size_t)s.y0 * w;
-        ROO_CUDA_TRY(cudaMemcpyAsync(s.frame[0], left_host, npx, cudaMemcpyHostToDevice, s.st));
-        ROO_CUDA_TRY(cudaMemcpyAsync(s.frame[1], right_host, npx, cudaMemcpyHostToDevice, s.st));
+        // Only the strip's rows plus the census window's reach above and below (8 rows covers all three windows) are
+        // uploaded and transformed: the clamp-to-edge of the census then acts at the true image border or inside the
+        // halo, never on a row this strip keeps.  Buffers stay whole-frame sized so that every row sits at its own offset.
+        const int ya = s.y0 - 8 > 0 ? s.y0 - 8 : 0, yb = s.y0 + s.hl + 8 < h ? s.y0 + s.hl + 8 : h;
+        const size_t hoff = (size_t)ya * w, hbytes = (size_t)(yb - ya) * w;
+        ROO_CUDA_TRY(cudaMemcpyAsync(s.frame[0] + hoff, left_host + hoff, hbytes, cudaMemcpyHostToDevice, s.st));
+        ROO_CUDA_TRY(cudaMemcpyAsync(s.frame[1] + hoff, right_host + hoff, hbytes, cudaMemcpyHostToDevice, s.st));
         ROO_CUDA_TRY(cudaEventRecord(s.ev_begin, s.st));
         for (int sd = 0; sd < 2 && rc == ROO_OK; ++sd)
-            rc = launch_census((char*)s.cen[sd], (size_t)w * e->words * 8, 0, (const char*)s.frame[sd], (size_t)w, 0, w, h, 1,
-                               p.window, ROO_IMG_U8, s.st);
+            rc = launch_census((char*)(s.cen[sd] + hoff * e->words), (size_t)w * e->words * 8, 0, (const char*)(s.frame[sd] + hoff),
+                               (size_t)w, 0, w, yb - ya, 1, p.window, ROO_IMG_U8, s.st);
         if (rc == ROO_OK && p.lrcheck)
             rc = launch_census_wta(s.dispR, s.cen[1] + off * e->words, s.cen[0] + off * e->words, w, s.hl, 1, p.max_disp, e->words,
                                    p.popc_mode, p.subpix, +1, e->ieee, s.st);

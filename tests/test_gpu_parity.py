@@ -827,7 +827,8 @@ def test_engine_python_wrappers_validate_tensors():
 
 
 @pytest.mark.parametrize("shape,strips", [((150, 61, 48), 2), ((150, 61, 48), 3), ((320, 100, 128), 4), ((97, 40, 256), 2), ((64, 9, 32), 8)])
-@pytest.mark.parametrize("opts", [dict(), dict(dodiag=True, subpix=True, lrcheck=True), dict(dohoriz=False, dodiag=True)])
+@pytest.mark.parametrize("opts", [dict(), dict(dodiag=True, subpix=True, lrcheck=True), dict(dohoriz=False, dodiag=True),
+                                  dict(window=2, dodiag=True, lrcheck=True)])   # 8w x 16h census: the tallest halo, u8 cost volume
 def test_single_pair_row_strip_split_bitexact(shape, strips, opts):
     """BASELINE config 5's mechanism: one pair split into row strips, the paths that travel in y handing their state from
     strip to strip (roo_split_engine_*).  On a one-GPU box every strip sits on device 0 (hand-offs ordered by events); with

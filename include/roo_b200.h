@@ -40,7 +40,7 @@ typedef struct roo_costvolelem_t { int32_t n; float sum; } roo_costvolelem_t;
 enum roo_status {
     ROO_OK = 0,
     ROO_ERR_INVALID_ARGUMENT = -1,
-    ROO_ERR_UNSUPPORTED = -2,     /* e.g. maxDisp > 256 or a non-integer disparity step sd */
+    ROO_ERR_UNSUPPORTED = -2,     /* e.g. maxDisp > 512 or a non-integer disparity step sd */
     ROO_ERR_OUT_OF_MEMORY = -3,
     ROO_ERR_NO_DEVICE = -4
 };
@@ -89,7 +89,7 @@ int roo_census_stereo_volume(const roo_volume_t* vol, const roo_image_t* left, c
 
 /* roo::SemiGlobalMatching<TH,TC,Timg> (cu_semi_global_matching.h:10-12; .cu:21-89).
  * volH float; volc_type in {ROO_VOL_F32, ROO_VOL_ELEM}; img_type in {ROO_IMG_U8, ROO_IMG_F32};
- * 1 <= maxDisp <= 256.  dodiag = 0 is the reference (paths down, up, right, left in that order);
+ * 1 <= maxDisp <= 512 (above 256 one pass per path: the fused vertical groups hold up to 256 disparities).  dodiag = 0 is the reference (paths down, up, right, left in that order);
  * dodiag = 1 adds the four diagonal paths (extension). */
 int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int volc_type, const roo_image_t* left, int img_type,
             int maxDisp, float P1, float P2, int dohoriz, int dovert, int doreverse, int dodiag, void* stream);
@@ -204,7 +204,7 @@ enum roo_fp_mode { ROO_FP_DEFAULT = 0, ROO_FP_REFERENCE = 1, ROO_FP_IEEE = 2 };
 
 typedef struct roo_pipeline_params_t {
     int w, h;             /* image size (any; not limited to 1024 like the reference, Q4) */
-    int max_disp;         /* 1..256 */
+    int max_disp;         /* 1..512 (257..512: one pass per path, no fused vertical groups) */
     int window;           /* enum roo_window */
     int popc_mode;        /* enum roo_popc_mode */
     float P1, P2;         /* stereo2/main.cpp:246-247 defaults: 0.01, 0.02 */

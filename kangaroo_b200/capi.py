@@ -23,8 +23,8 @@ PROF_KINDS = ("census", "cost", "sweep", "wta", "lrcheck", "vgroup") + tuple(f"p
 
 
 def disp_padded(max_disp: int) -> int:
-    """internal disparity count: maxDisp rounded up to 32 / 64 / 128 / 256"""
-    return 32 if max_disp <= 32 else (64 if max_disp <= 64 else (128 if max_disp <= 128 else 256))
+    """internal disparity count: maxDisp rounded up to 32 / 64 / 128 / 256 / 512"""
+    return 32 if max_disp <= 32 else (64 if max_disp <= 64 else (128 if max_disp <= 128 else (256 if max_disp <= 256 else 512)))
 
 
 class RooImage(C.Structure):

@@ -131,8 +131,8 @@ static int engine_group(roo_engine* e, const unsigned char* left, const unsigned
     // Measured on B200, 8 paths, fused / separate: 640x480x64 x1 1.8 / 1.9 ms (sweeps of so few columns are
     // latency-bound too), 1280x720x128 x2 3.3 / 3.2, x3 3.7 / 4.6, 1920x1080x256 x1 6.4 / 7.4, 3840x2160x256 x1 17.9 / 27.1.
     const long long units = (long long)w * h * e->DP * batch;
-    const bool use_fused = p.fuse_vertical > 0 ||
-                           (p.fuse_vertical == 0 && ((long long)batch * e->n_bands >= FUSE_MIN_CTAS || units < FUSE_MIN_UNITS));
+    const bool use_fused = e->DP <= ROO_MAX_DISP_FUSED && (p.fuse_vertical > 0 ||
+                           (p.fuse_vertical == 0 && ((long long)batch * e->n_bands >= FUSE_MIN_CTAS || units < FUSE_MIN_UNITS)));
     const SgmPlan& plan = use_fused ? e->plan : e->plan_sep;
     const int ndir = plan.n;
     if (ndir == 0) {
@@ -224,7 +224,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
     const roo_pipeline_params_t& p = *params;
     if (p.w <= 0 || p.h <= 0 || p.max_disp <= 0 || p.max_batch <= 0 || p.window < 0 || p.window > 2)
         return ROO_ERR_INVALID_ARGUMENT;
-    if (p.max_disp > 256) return ROO_ERR_UNSUPPORTED;
+    if (p.max_disp > ROO_MAX_DISP) return ROO_ERR_UNSUPPORTED;
     if (p.fp_mode < ROO_FP_DEFAULT || p.fp_mode > ROO_FP_IEEE) return ROO_ERR_INVALID_ARGUMENT;
     if (p.median_size != 0 && p.median_size != 5 && p.median_size != 7 && p.median_size != 9) return ROO_ERR_UNSUPPORTED;
     if (p.median_size != 0 && p.median_iters < 0) return ROO_ERR_INVALID_ARGUMENT;
@@ -245,7 +245,7 @@ extern "C" int roo_engine_create(roo_engine_t** out, const roo_pipeline_params_t
         e->scratch_bytes += bytes;
         return true;
     };
-    e->plan = sgm_plan(p.dohoriz, p.dovert, p.doreverse, p.dodiag, p.fuse_vertical >= 0 ? 1 : 0);
+    e->plan = sgm_plan(p.dohoriz, p.dovert, p.doreverse, p.dodiag, (p.fuse_vertical >= 0 && e->DP <= ROO_MAX_DISP_FUSED) ? 1 : 0);
     e->plan_sep = sgm_plan(p.dohoriz, p.dovert, p.doreverse, p.dodiag, 0);
     e->n_bands = vgroup_bands(p.w, p.h, e->DP);
     const int ndir = e->plan.n;

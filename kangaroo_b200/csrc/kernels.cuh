@@ -16,7 +16,7 @@ int launch_census_wta(float* disp, const void* cself, const void* cother, int w,
 enum EpiKind { EPI_NONE = 0, EPI_WTA_WRITE = 1, EPI_WTA_ONLY = 2 };
 
 // One aggregation sweep (one path direction) over `batch` pairs on the internal layout
-// H[pair][y][x][DP] (fp32, disparity innermost, DP = 32 * ceil(maxDisp/32) rounded to 32/64/128/256).
+// H[pair][y][x][DP] (fp32, disparity innermost, DP = 32 * ceil(maxDisp/32) rounded to 32/64/128/256/512).
 struct SweepArgs {
     float* H;            // in/out aggregate
     size_t h_pair;       // elements between pairs
@@ -61,7 +61,9 @@ extern std::atomic<int> g_insweep_cost;
 extern std::atomic<int> g_strip_ctas_per_sm;
 int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pair, int img_type, int w, int h,
                         int batch, float scale, cudaStream_t st);
-inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : 256)); }
+// 512: single-path sweeps only (the fused vertical groups hold three state rows per column in registers: up to 256)
+inline int disp_padded(int maxDisp) { return maxDisp <= 32 ? 32 : (maxDisp <= 64 ? 64 : (maxDisp <= 128 ? 128 : (maxDisp <= 256 ? 256 : 512))); }
+constexpr int ROO_MAX_DISP = 512, ROO_MAX_DISP_FUSED = 256;
 
 // ---- sgm_fused.cu: the three paths sharing a y travel direction in one pass ----
 struct VGroupArgs {

@@ -256,6 +256,7 @@ int launch_sweep(const SweepArgs& a, cudaStream_t st) {
         case 64: sweep_launch_cost<2>(a, n_scan, grid, st); break;
         case 128: sweep_launch_cost<4>(a, n_scan, grid, st); break;
         case 256: sweep_launch_cost<8>(a, n_scan, grid, st); break;
+        case 512: sweep_launch_cost<16>(a, n_scan, grid, st); break;
         default: return ROO_ERR_UNSUPPORTED;
     }
     count_launch();
@@ -403,7 +404,7 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
         return ROO_ERR_INVALID_ARGUMENT;
     if (volH->w != volC->w || volH->h != volC->h || left->w != volC->w || left->h != volC->h)
         return ROO_ERR_INVALID_ARGUMENT;
-    if (maxDisp > 256) return ROO_ERR_UNSUPPORTED;
+    if (maxDisp > ROO_MAX_DISP) return ROO_ERR_UNSUPPORTED;
     if ((size_t)maxDisp > volH->d || (size_t)maxDisp > volC->d) return ROO_ERR_INVALID_ARGUMENT;
     cudaStream_t st = as_stream(stream);
     // volH.Memset(0) (cu_semi_global_matching.cu:68; Volume.h:78-81 clears pitch*h*d bytes)
@@ -412,7 +413,7 @@ extern "C" int roo_sgm(const roo_volume_t* volH, const roo_volume_t* volC, int v
     } else {
         ROO_CUDA_TRY(cudaMemset2DAsync(volH->ptr, volH->img_pitch, 0, volH->pitch * volH->h, volH->d, st));
     }
-    const SgmPlan plan = sgm_plan(dohoriz, dovert, doreverse, dodiag, 1);
+    const SgmPlan plan = sgm_plan(dohoriz, dovert, doreverse, dodiag, maxDisp <= ROO_MAX_DISP_FUSED ? 1 : 0);
     if (plan.n == 0 || maxDisp <= 0) return ROO_OK;
 
     const int w = (int)volC->w, h = (int)volC->h, DP = disp_padded(maxDisp);

@@ -314,6 +314,7 @@ int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
         case 64: ROO_HS_DP(2)
         case 128: ROO_HS_DP(4)
         case 256: ROO_HS_DP(8)
+        case 512: ROO_HS_DP(16)
         default: return ROO_ERR_UNSUPPORTED;
     }
 #endif

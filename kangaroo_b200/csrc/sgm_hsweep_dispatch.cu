@@ -8,6 +8,7 @@ int launch_hsweep_dpl1(const SweepArgs& a, cudaStream_t st);
 int launch_hsweep_dpl2(const SweepArgs& a, cudaStream_t st);
 int launch_hsweep_dpl4(const SweepArgs& a, cudaStream_t st);
 int launch_hsweep_dpl8(const SweepArgs& a, cudaStream_t st);
+int launch_hsweep_dpl16(const SweepArgs& a, cudaStream_t st);
 
 int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
     switch (a.DP) {
@@ -15,6 +16,7 @@ int launch_hsweep(const SweepArgs& a, cudaStream_t st) {
         case 64: return launch_hsweep_dpl2(a, st);
         case 128: return launch_hsweep_dpl4(a, st);
         case 256: return launch_hsweep_dpl8(a, st);
+        case 512: return launch_hsweep_dpl16(a, st);
         default: return ROO_ERR_UNSUPPORTED;
     }
 }

@@ -11,9 +11,12 @@ constexpr float SGM_MAX_ERROR = 1E30f;  // cu_semi_global_matching.cu:24
 
 template <int DPL>
 __device__ __forceinline__ void load_f(float (&v)[DPL], const float* p) {
-    if constexpr (DPL == 8) {
-        const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if constexpr (DPL >= 8) {
+#pragma unroll
+        for (int q = 0; q < DPL / 4; ++q) {
+            const float4 a = reinterpret_cast<const float4*>(p)[q];
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
     } else if constexpr (DPL == 4) {
         const float4 a = *reinterpret_cast<const float4*>(p);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -26,9 +29,9 @@ __device__ __forceinline__ void load_f(float (&v)[DPL], const float* p) {
 }
 template <int DPL>
 __device__ __forceinline__ void store_f(float* p, const float (&v)[DPL]) {
-    if constexpr (DPL == 8) {
-        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    if constexpr (DPL >= 8) {
+#pragma unroll
+        for (int q = 0; q < DPL / 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else if constexpr (DPL == 4) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     } else if constexpr (DPL == 2) {
@@ -127,13 +130,15 @@ template <int DPL> struct RawCost<DPL, COST_CEN32> {
 template <int DPL> struct RawCost<DPL, COST_U8> {
     unsigned w[(DPL + 3) / 4];
     __device__ __forceinline__ void load(const void* p) {
-        if constexpr (DPL == 8) { const uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
+        if constexpr (DPL == 16) { const uint4 t = *reinterpret_cast<const uint4*>(p); w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w; }
+        else if constexpr (DPL == 8) { const uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
         else if constexpr (DPL == 4) w[0] = *reinterpret_cast<const unsigned*>(p);
         else if constexpr (DPL == 2) w[0] = *reinterpret_cast<const unsigned short*>(p);
         else w[0] = *reinterpret_cast<const unsigned char*>(p);
     }
     __device__ __forceinline__ void lds(unsigned saddr) {
-        if constexpr (DPL == 8) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
+        if constexpr (DPL == 16) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr));
+        else if constexpr (DPL == 8) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
         else if constexpr (DPL == 4) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(saddr));
         else if constexpr (DPL == 2) { unsigned short t; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(saddr)); w[0] = t; }
         else asm volatile("ld.shared.u8 %0, [%1];" : "=r"(w[0]) : "r"(saddr));

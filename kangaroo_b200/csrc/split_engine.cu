@@ -83,7 +83,7 @@ extern "C" int roo_split_engine_create(roo_split_engine_t** out, const roo_pipel
     if (!out || !params) return ROO_ERR_INVALID_ARGUMENT;
     const roo_pipeline_params_t& p = *params;
     if (p.w <= 0 || p.h <= 0 || p.max_disp <= 0 || p.window < 0 || p.window > 2) return ROO_ERR_INVALID_ARGUMENT;
-    if (p.max_disp > 256) return ROO_ERR_UNSUPPORTED;
+    if (p.max_disp > ROO_MAX_DISP) return ROO_ERR_UNSUPPORTED;
     if (p.median_size != 0 || p.filtgrad_threshold > 0.0f) return ROO_ERR_UNSUPPORTED;   // these stages need halo rows: single-GPU engine only
     if (p.fp_mode < ROO_FP_DEFAULT || p.fp_mode > ROO_FP_IEEE) return ROO_ERR_INVALID_ARGUMENT;
     int ndev = 0;

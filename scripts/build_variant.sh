@@ -18,7 +18,7 @@ for s in census sgm sgm_hsweep_dispatch sgm_fused wta frontback median volfilter
     OBJS="$OBJS $O/$s.o"
   fi
 done
-for p in 1 2 4 8; do
+for p in 1 2 4 8 16; do
   if [[ " $SRCS " == *" sgm_hsweep.cu "* ]]; then
     nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O2 $FLAGS -DHS_PART=$p -c kangaroo_b200/csrc/sgm_hsweep.cu -o scripts/variants/obj_$NAME/sgm_hsweep_dpl$p.o
     OBJS="$OBJS scripts/variants/obj_$NAME/sgm_hsweep_dpl$p.o"

@@ -815,6 +815,30 @@ def test_census_stereo_volume_accepts_different_pitches():
     assert np.array_equal(vol.numpy(), ko.census_stereo_volume(l3, r3, 16, -1.0))
 
 
+@pytest.mark.parametrize("D", [300, 512])
+def test_more_than_256_disparities_single_path_plan(D):
+    """The reference takes any maxDispVal (cu_semi_global_matching.cu:31).  257..512 disparities run one pass per path (lanes
+    own 16 disparities; the fused vertical groups stop at 256): engine, granular SemiGlobalMatching and the split engine, bit
+    for bit against the oracle (IEEE mode)."""
+    w, h = 640, 40
+    L, R, _ = stereo_pair(w, h, min(D, 256), config=95)
+    roo.set_ieee_division(True)
+    disp, H, cen = run_engine(L, R, D, fuse_vertical=None, dodiag=True, subpix=True, lrcheck=True)
+    od, oH = ko.pipeline_u8(L, R, D, dodiag=True, subpix=True, lrcheck=True, want_volume=True)
+    assert np.array_equal(H, oH)
+    _assert_disp_equal(disp[0], od)
+    cl, cr = np.empty((h, w, 1), np.uint64), np.empty((h, w, 1), np.uint64)
+    cl[:, :, 0], cr[:, :, 0] = ko.census(L, 0).reshape(h, w), ko.census(R, 0).reshape(h, w)
+    volc = ko.census_stereo_volume(cl, cr, D, -1.0)
+    lf = L.astype(np.float32)
+    assert np.array_equal(gpu_sgm(volc, lf, D, 0.5, 2.0, dg=True), ko.sgm(volc, lf, D, 0.5, 2.0, dodiag=True))
+    se = roo.SplitStereoEngine(w, h, D, devices=[0, 0], dodiag=True, subpix=True, lrcheck=True)
+    out = torch.empty((h, w), dtype=torch.float32).pin_memory()
+    se.run_host(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory(), out)
+    se.close()
+    _assert_disp_equal(out.numpy(), od)
+
+
 def test_engine_python_wrappers_validate_tensors():
     eng = roo.StereoEngine(64, 32, 16, max_batch=2)
     good = torch.zeros((2, 32, 64), dtype=torch.uint8, device="cuda")
@@ -859,4 +883,4 @@ def test_invalid_arguments_are_reported_not_ignored():
     with pytest.raises(roo.capi.RooError):
         roo.Census(cen, img)  # size mismatch
     with pytest.raises(roo.capi.RooError):
-        roo.StereoEngine(64, 64, 300)  # > 256 disparities
+        roo.StereoEngine(64, 64, 600)  # > 512 disparities

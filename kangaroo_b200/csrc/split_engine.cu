@@ -29,6 +29,12 @@
 using namespace roo_b200;
 
 namespace {
+// restores the caller's current device on every exit path
+struct DeviceGuard {
+    int prev = 0;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
 constexpr size_t CEN_PAD = 1024;   // elements of padding around the census arrays (in-sweep cost strips stick out of a row)
 
 struct Strip {
@@ -180,8 +186,7 @@ extern "C" int roo_split_engine_run_host(roo_split_engine_t* e, const uint8_t* l
     const roo_pipeline_params_t& p = e->p;
     const int G = (int)e->strips.size(), w = p.w, h = p.h, DP = e->DP, ndir = e->plan.n;
     const size_t npx = (size_t)w * h;
-    int prev = 0;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;
     ++e->frame;
     e->exchanged_bytes = 0;
     // in-sweep matching cost (no u8 cost volume at all) with the one-word descriptor under the reference's popcount
@@ -278,7 +283,6 @@ extern "C" int roo_split_engine_run_host(roo_split_engine_t* e, const uint8_t* l
         if (se == cudaSuccess && cudaEventElapsedTime(&ms, s.ev_begin, s.ev_end) == cudaSuccess && ms > ms_max) ms_max = ms;
     }
     e->last_ms = ms_max;
-    cudaSetDevice(prev);
     return rc;
 }
 

@@ -62,6 +62,10 @@ int main() {
     roo::CostVolMinimum<float, unsigned short>(disp[0], volu, maxdisp);
     roo::CostVolMinimum(disp[0], vole);
     roo::DenseStereoSubpixelRefine(dispf, disp_c, upload, upload);
+    roo::CostVolMinimumSquarePenaltySubpix(disp[0], vol[0], dispf, maxdisp, -1, 1.0f, 0.5f);      // stereo/main.cpp:376
+    roo::BilateralFilter<float, float, float>(dispf, depth, img[0], 2.0f, 0.2f, 0.1f, 3);         // stereo2/main.cpp:417 (one slice)
+    roo::BilateralFilter<float, float, unsigned char>(dispf, depth, upload, 2.0f, 0.2f, 10.0f, 3);
+    roo::BilateralFilterVolume<float>(vol[1], vol[0], img[0], 2.0f, 0.2f, 0.1f, 2, maxdisp);             // the loop at :407-421 in one launch
     roo::LeftRightCheck(dispi8, dispi8r, -1, 0);
     const cudaError_t err = cudaDeviceSynchronize();
     std::printf("%s\n", err == cudaSuccess ? "OK" : cudaGetErrorString(err));

@@ -877,6 +877,28 @@ def test_single_pair_row_strip_split_bitexact(shape, strips, opts):
     assert nbytes == crossing * (strips - 1) * w * (roo.capi.disp_padded(D) + 4) * 4 and ms > 0
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ROO_STRESS_SEEDS", "6"))))
+def test_split_engine_random_shapes_strips_and_flags(seed):
+    """Seeded random shapes, strip counts (strips of very different heights, down to one row) and flag combinations of the
+    row-strip split against the oracle, bit for bit (IEEE mode)."""
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(20, 300)), int(rng.integers(6, 120))
+    D = int(rng.choice([16, 48, 64, 100, 128, 200, 256, 300]))
+    strips = int(rng.integers(2, min(6, h) + 1))
+    opts = dict(dodiag=bool(rng.integers(2)), dovert=bool(rng.integers(2)), dohoriz=bool(rng.integers(2)),
+                doreverse=bool(rng.integers(2)), subpix=bool(rng.integers(2)), lrcheck=bool(rng.integers(2)),
+                window=int(rng.choice([0, 0, 1, 2])))
+    L, R, _ = stereo_pair(w, h, min(D, 256), config=96, index=seed)
+    ndev = torch.cuda.device_count()
+    roo.set_ieee_division(True)
+    se = roo.SplitStereoEngine(w, h, D, devices=[i % ndev for i in range(strips)], **opts)
+    out = torch.empty((h, w), dtype=torch.float32).pin_memory()
+    se.run_host(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory(), out)
+    se.close()
+    od = ko.pipeline_u8(L, R, D, **opts)
+    _assert_disp_equal(out.numpy(), od)
+
+
 def test_invalid_arguments_are_reported_not_ignored():
     img = roo.Image(16, 16, np.uint8)
     cen = roo.Image(8, 16, census_dtype(0))

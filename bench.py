@@ -368,6 +368,17 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
         }
+        # context next to the CPU arm: the reference's OWN CUDA kernels, recompiled unmodified for sm_100a, as measured by
+        # tests/test_gpu_reference_speed.py on a B200 (they only launch up to 1024 x 1024 pixels, so not on this workload)
+        try:
+            rg = json.load(open(os.path.join(ROOT, "profiles", "r2_reference_gpu_speed.json")))
+            out["reference_gpu_kernels"] = {
+                "source": "profiles/r2_reference_gpu_speed.json (committed record, not measured in this run)",
+                **{k: {"reference_ms_per_pair": v["reference_kernels"]["ms_per_pair"],
+                       "this_engine_ms_per_pair_batch8": 1e3 / v["engine_batch8"]["pairs_per_s"]}
+                   for k, v in rg.items() if isinstance(v, dict) and "reference_kernels" in v}}
+        except Exception:
+            pass
         if e2e:
             out["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:   # the CPU port is timed at N=1 only (rank 0)

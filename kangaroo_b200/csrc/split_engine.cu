@@ -185,7 +185,6 @@ extern "C" int roo_split_engine_run_host(roo_split_engine_t* e, const uint8_t* l
     if (!e || !left_host || !right_host || !disp_host) return ROO_ERR_INVALID_ARGUMENT;
     const roo_pipeline_params_t& p = e->p;
     const int G = (int)e->strips.size(), w = p.w, h = p.h, DP = e->DP, ndir = e->plan.n;
-    const size_t npx = (size_t)w * h;
     DeviceGuard guard;
     ++e->frame;
     e->exchanged_bytes = 0;

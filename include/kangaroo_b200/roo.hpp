@@ -192,6 +192,75 @@ inline void BilateralFilterVolume(Volume<float> vOut, Volume<float> vIn, const I
     b200::done(roo_bilateral_filter_volume(&o, &i2, &g, b200::imgtype<Ti2>::v, gs, gr, gc, size, maxDisp, b200::stream_slot()),
                "BilateralFilterVolume");
 }
+// ---- cu_operations.h:22-35, the float instantiations the guided filter is composed of
+template <typename Tout, typename Tin1, typename Tin2, typename Tup>
+inline void ElementwiseMultiply(Image<Tout> c, Image<Tin1> a, Image<Tin2> b, Tup scalar = 1, Tup offset = 0) {
+    static_assert(std::is_same<Tout, float>::value && std::is_same<Tin1, float>::value && std::is_same<Tin2, float>::value, "float images");
+    auto ci = b200::c(c), ai = b200::c(a), bi = b200::c(b);
+    b200::done(roo_elementwise_multiply(&ci, &ai, &bi, (float)scalar, (float)offset, b200::stream_slot()), "ElementwiseMultiply");
+}
+template <typename Tout, typename Tin1, typename Tin2, typename Tup>
+inline void ElementwiseDivision(Image<Tout> c, const Image<Tin1> a, const Image<Tin2> b, Tup sa = 0, Tup sb = 0, Tup scalar = 1, Tup offset = 0) {
+    static_assert(std::is_same<Tout, float>::value && std::is_same<Tin1, float>::value && std::is_same<Tin2, float>::value, "float images");
+    auto ci = b200::c(c), ai = b200::c(a), bi = b200::c(b);
+    b200::done(roo_elementwise_division(&ci, &ai, &bi, (float)sa, (float)sb, (float)scalar, (float)offset, b200::stream_slot()),
+               "ElementwiseDivision");
+}
+template <typename Tout, typename Tin, typename Tup>
+inline void ElementwiseSquare(Image<Tout> b, const Image<Tin> a, Tup scalar = 1, Tup offset = 0) {
+    static_assert(std::is_same<Tout, float>::value && std::is_same<Tin, float>::value, "float images");
+    auto bi = b200::c(b), ai = b200::c(a);
+    b200::done(roo_elementwise_square(&bi, &ai, (float)scalar, (float)offset, b200::stream_slot()), "ElementwiseSquare");
+}
+template <typename Tout, typename Tin1, typename Tin2, typename Tin3, typename Tup>
+inline void ElementwiseMultiplyAdd(Image<Tout> d, const Image<Tin1> a, const Image<Tin2> b, const Image<Tin3> c, Tup sab = 1, Tup sc = 1,
+                                   Tup offset = 0) {
+    static_assert(std::is_same<Tout, float>::value && std::is_same<Tin1, float>::value && std::is_same<Tin2, float>::value &&
+                  std::is_same<Tin3, float>::value, "float images");
+    auto di = b200::c(d), ai = b200::c(a), bi = b200::c(b), ci = b200::c(c);
+    b200::done(roo_elementwise_multiply_add(&di, &ai, &bi, &ci, (float)sab, (float)sc, (float)offset, b200::stream_slot()),
+               "ElementwiseMultiplyAdd");
+}
+// ---- cu_integral_image.h:26-38.  Scratch is part of the reference's signature; this library brings its own.
+template <typename Tout, typename Tin, typename TSum>
+inline void BoxFilter(Image<Tout> out, Image<Tin> in, Image<unsigned char> /*scratch*/, int rad) {
+    static_assert(std::is_same<Tout, float>::value && std::is_same<Tin, float>::value && std::is_same<TSum, float>::value, "float images");
+    auto o = b200::c(out), i2 = b200::c(in);
+    b200::done(roo_box_filter(&o, &i2, rad, b200::stream_slot()), "BoxFilter");
+}
+// ---- cu_integral_image.h:42-54
+template <typename Tout, typename Tin, typename TSum>
+inline void ComputeMeanVarience(Image<Tout> varI, Image<Tout> meanII, Image<Tout> meanI, const Image<Tin> I, Image<unsigned char> Scratch, int rad) {
+    BoxFilter<float, float, float>(meanI, I, Scratch, rad);
+    ElementwiseSquare<float, float, float>(varI, I);                       // I.*I, parked in the output image
+    BoxFilter<float, float, float>(meanII, varI, Scratch, rad);
+    ElementwiseMultiplyAdd<float, float, float, float, float>(varI, meanI, meanI, meanII, -1);
+}
+// ---- cu_integral_image.h:56-68
+inline void ComputeCovariance(Image<float> covIP, Image<float> meanIP, Image<float> meanP, const Image<float> P, const Image<float> meanI,
+                              const Image<float> I, Image<unsigned char> Scratch, int rad) {
+    BoxFilter<float, float, float>(meanP, P, Scratch, rad);
+    ElementwiseMultiply<float, float, float, float>(covIP, I, P);          // I.*p, parked in the output image
+    BoxFilter<float, float, float>(meanIP, covIP, Scratch, rad);
+    ElementwiseMultiplyAdd<float, float, float, float, float>(covIP, meanI, meanP, meanIP, -1);
+}
+// ---- cu_integral_image.h:72-93 (tmp1 holds a, then mean_b; tmp2 holds b; tmp3 holds mean_a)
+inline void GuidedFilter(Image<float> q, const Image<float> covIP, const Image<float> varI, const Image<float> meanP, const Image<float> meanI,
+                         const Image<float> I, Image<unsigned char> Scratch, Image<float> tmp1, Image<float> tmp2, Image<float> tmp3,
+                         int rad, float eps) {
+    ElementwiseDivision<float, float, float, float>(tmp1, covIP, varI, 0, eps);
+    BoxFilter<float, float, float>(tmp3, tmp1, Scratch, rad);
+    ElementwiseMultiplyAdd<float, float, float, float, float>(tmp2, tmp1, meanI, meanP, -1);
+    BoxFilter<float, float, float>(tmp1, tmp2, Scratch, rad);
+    ElementwiseMultiplyAdd<float, float, float, float, float>(q, tmp3, I, tmp1);
+}
+// The applications' loop (stereo2/main.cpp:392-405: ComputeMeanVarience once, then ComputeCovariance + GuidedFilter per
+// slice, in place) over the first maxDisp slices in a handful of launches.
+inline void GuidedFilterVolume(Volume<float> vol, const Image<float> I, int rad, float eps, int maxDisp) {
+    auto v = b200::c(vol);
+    auto g = b200::c(I);
+    b200::done(roo_guided_filter_volume(&v, &g, rad, eps, maxDisp, b200::stream_slot()), "GuidedFilterVolume");
+}
 // ---- cu_dense_stereo.h:101-103 (dOut may be dIn, as in stereo2/main.cpp:457)
 inline void FilterDispGrad(Image<float> dOut, Image<float> dIn, float threshold) {
     auto o = b200::c(dOut), i2 = b200::c(dIn);

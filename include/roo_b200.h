@@ -193,6 +193,34 @@ int roo_bilateral_filter_joint(const roo_image_t* out_f32, const roo_image_t* in
 int roo_bilateral_filter_volume(const roo_volume_t* out_f32, const roo_volume_t* in_f32, const roo_image_t* img, int img_type,
                                 float gs, float gr, float gc, unsigned size, int maxDisp, void* stream);
 
+/* ---- integral-image box filter and guided filter (gfilter.cu) ------------------------------ */
+
+/* roo::ElementwiseMultiply / Division / Square / MultiplyAdd for float images (cu_operations.h:22-35; cu_operations.cu:85-190):
+ *   c = scalar*(a*b) + offset;  c = scalar*(a+sa)/(b+sb) + offset;  b = scalar*a*a + offset;  d = sab*a*b + sc*c + offset.
+ * Default fp mode = the reference's fast-math SASS forms (bit-identical to its kernels), IEEE mode = source order. */
+int roo_elementwise_multiply(const roo_image_t* c_f32, const roo_image_t* a_f32, const roo_image_t* b_f32, float scalar, float offset,
+                             void* stream);
+int roo_elementwise_division(const roo_image_t* c_f32, const roo_image_t* a_f32, const roo_image_t* b_f32, float sa, float sb,
+                             float scalar, float offset, void* stream);
+int roo_elementwise_square(const roo_image_t* b_f32, const roo_image_t* a_f32, float scalar, float offset, void* stream);
+int roo_elementwise_multiply_add(const roo_image_t* d_f32, const roo_image_t* a_f32, const roo_image_t* b_f32, const roo_image_t* c_f32,
+                                 float sab, float sc, float offset, void* stream);
+
+/* roo::BoxFilter<float,float,float>(out, in, scratch, rad) (cu_integral_image.h:26-38): box mean through two exclusive prefix
+ * sums in the reference's tree order and its four-corner lookup (window [x-rad, x+rad) x [y-rad, y+rad), clamped; divisor =
+ * that window's area) -- bit-identical to the reference kernels.  No scratch image (stream-ordered internal scratch), any
+ * w <= 262144 and h <= 65536 (the reference: w, h <= 2048); out may be in. */
+int roo_box_filter(const roo_image_t* out_f32, const roo_image_t* in_f32, int rad, void* stream);
+
+/* The applications' guided filtering of a cost volume (stereo2/main.cpp:392-405): ComputeMeanVarience(I) once, then per slice
+ * ComputeCovariance + GuidedFilter (cu_integral_image.h:42-93), in place on the first maxDisp slices -- here 3 launches for
+ * the guide image + 6 per chunk of slices (one chunk unless 4 fp32 copies of the chunk exceed 2 GiB) instead of 37 per
+ * slice.  Same results as that sequence of reference calls, bit for bit. */
+int roo_guided_filter_volume(const roo_volume_t* vol_f32, const roo_image_t* guide_f32, int rad, float eps, int maxDisp, void* stream);
+/* Both take their scratch stream-ordered from a memory pool of this library that keeps it between calls (4 fp32 copies of
+ * the chunk of slices); this returns the current device's unused scratch to the driver. */
+int roo_release_scratch(void);
+
 /* ---- fused engine: the whole per-frame path of applications/stereo2/main.cpp:375-454 ------- */
 
 typedef struct roo_engine roo_engine_t;

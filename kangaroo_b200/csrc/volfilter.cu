@@ -16,9 +16,6 @@
 
 namespace roo_b200 {
 
-__device__ __forceinline__ float fmul_ftz(float a, float b) { float r; asm("mul.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float fadd_ftz(float a, float b) { float r; asm("add.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float ffma_ftz(float a, float b, float c) { float r; asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float ex2_ftz(float a) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 constexpr float BIL_LOG2E = 1.4426950216293334961f;   // the constant in the reference's SASS
 

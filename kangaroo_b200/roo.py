@@ -193,6 +193,76 @@ def CostVolMinimumSquarePenaltySubpix(imga: Image, vol: Volume, imgd: Image, max
                                                           lam, theta, _stream(stream)), "CostVolMinimumSquarePenaltySubpix")
 
 
+def ElementwiseMultiply(c: Image, a: Image, b: Image, scalar: float = 1.0, offset: float = 0.0, stream=None) -> None:
+    """roo::ElementwiseMultiply<float,float,float,float>: c = scalar*(a*b) + offset (cu_operations.h:22-23)."""
+    check(lib().roo_elementwise_multiply(C.byref(c.c()), C.byref(a.c()), C.byref(b.c()), scalar, offset, _stream(stream)),
+          "ElementwiseMultiply")
+
+
+def ElementwiseDivision(c: Image, a: Image, b: Image, sa: float = 0.0, sb: float = 0.0, scalar: float = 1.0, offset: float = 0.0,
+                        stream=None) -> None:
+    """roo::ElementwiseDivision<float,...>: c = scalar*(a+sa)/(b+sb) + offset (cu_operations.h:26-27)."""
+    check(lib().roo_elementwise_division(C.byref(c.c()), C.byref(a.c()), C.byref(b.c()), sa, sb, scalar, offset, _stream(stream)),
+          "ElementwiseDivision")
+
+
+def ElementwiseSquare(b: Image, a: Image, scalar: float = 1.0, offset: float = 0.0, stream=None) -> None:
+    """roo::ElementwiseSquare<float,float,float>: b = scalar*a*a + offset (cu_operations.h:30-31)."""
+    check(lib().roo_elementwise_square(C.byref(b.c()), C.byref(a.c()), scalar, offset, _stream(stream)), "ElementwiseSquare")
+
+
+def ElementwiseMultiplyAdd(d: Image, a: Image, b: Image, c: Image, sab: float = 1.0, sc: float = 1.0, offset: float = 0.0,
+                           stream=None) -> None:
+    """roo::ElementwiseMultiplyAdd<float,...>: d = sab*a*b + sc*c + offset (cu_operations.h:34-35)."""
+    check(lib().roo_elementwise_multiply_add(C.byref(d.c()), C.byref(a.c()), C.byref(b.c()), C.byref(c.c()), sab, sc, offset,
+                                             _stream(stream)), "ElementwiseMultiplyAdd")
+
+
+def BoxFilter(out: Image, inp: Image, scratch, rad: int, stream=None) -> None:
+    """roo::BoxFilter<float,float,float>(out, in, scratch, rad) (cu_integral_image.h:26-38).  `scratch` is accepted for the
+    reference's signature and not used."""
+    check(lib().roo_box_filter(C.byref(out.c()), C.byref(inp.c()), rad, _stream(stream)), "BoxFilter")
+
+
+def ComputeMeanVarience(varI: Image, meanII: Image, meanI: Image, I: Image, scratch, rad: int, stream=None) -> None:
+    """roo::ComputeMeanVarience<float,float,float> (cu_integral_image.h:42-54), spelled as the reference spells it."""
+    BoxFilter(meanI, I, scratch, rad, stream)
+    ElementwiseSquare(varI, I, stream=stream)
+    BoxFilter(meanII, varI, scratch, rad, stream)
+    ElementwiseMultiplyAdd(varI, meanI, meanI, meanII, -1.0, stream=stream)
+
+
+def ComputeCovariance(covIP: Image, meanIP: Image, meanP: Image, P: Image, meanI: Image, I: Image, scratch, rad: int,
+                      stream=None) -> None:
+    """roo::ComputeCovariance (cu_integral_image.h:56-68)."""
+    BoxFilter(meanP, P, scratch, rad, stream)
+    ElementwiseMultiply(covIP, I, P, stream=stream)
+    BoxFilter(meanIP, covIP, scratch, rad, stream)
+    ElementwiseMultiplyAdd(covIP, meanI, meanP, meanIP, -1.0, stream=stream)
+
+
+def GuidedFilter(q: Image, covIP: Image, varI: Image, meanP: Image, meanI: Image, I: Image, scratch, tmp1: Image, tmp2: Image,
+                 tmp3: Image, rad: int, eps: float, stream=None) -> None:
+    """roo::GuidedFilter (cu_integral_image.h:72-93): a = cov/(var+eps), b = meanP - a meanI, q = mean(a) I + mean(b)."""
+    a, b, meana, meanb = tmp1, tmp2, tmp3, tmp1
+    ElementwiseDivision(a, covIP, varI, 0.0, eps, stream=stream)
+    BoxFilter(meana, a, scratch, rad, stream)
+    ElementwiseMultiplyAdd(b, a, meanI, meanP, -1.0, stream=stream)
+    BoxFilter(meanb, b, scratch, rad, stream)
+    ElementwiseMultiplyAdd(q, meana, I, meanb, stream=stream)
+
+
+def GuidedFilterVolume(vol: Volume, I: Image, rad: int, eps: float, maxDisp: int, stream=None) -> None:
+    """The applications' loop over the slices of a cost volume (stereo2/main.cpp:392-405: ComputeMeanVarience once, then
+    ComputeCovariance + GuidedFilter per slice, in place) as a handful of launches over all slices."""
+    check(lib().roo_guided_filter_volume(C.byref(vol.c()), C.byref(I.c()), rad, eps, maxDisp, _stream(stream)), "GuidedFilterVolume")
+
+
+def release_scratch() -> None:
+    """Return the scratch the box / guided filters keep between calls to the driver (current device)."""
+    check(lib().roo_release_scratch(), "release_scratch")
+
+
 def FilterDispGrad(dOut: Image, dIn: Image, threshold: float, stream=None) -> None:
     """roo::FilterDispGrad (cu_dense_stereo.h:101-103); dOut may be dIn, as in the applications."""
     check(lib().roo_filter_disp_grad(C.byref(dOut.c()), C.byref(dIn.c()), threshold, _stream(stream)), "FilterDispGrad")

@@ -76,6 +76,9 @@ def lib() -> C.CDLL:
         L.ko_filter_disp_grad.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_float]
         L.ko_bilateral_filter_joint.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
         L.ko_left_right_check_i8.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
+        L.ko_elementwise.argtypes = [C.c_int] + [P(KoImage)] * 4 + [C.c_float] * 4
+        L.ko_box_filter.argtypes = [P(KoImage), P(KoImage), C.c_int]
+        L.ko_guided_filter_volume.argtypes = [P(KoVolume), P(KoImage), C.c_int, C.c_float, C.c_int]
         L.ko_elementwise_scale_bias.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_float, C.c_float]
         L.ko_box_half.argtypes = [P(KoImage), P(KoImage), C.c_int]
         L.ko_disp2depth.argtypes = [P(KoImage), P(KoImage), C.c_float, C.c_float, C.c_float]
@@ -222,6 +225,35 @@ def bilateral_filter_joint(img_in: np.ndarray, guide: np.ndarray, gs: float, gr:
     out = np.zeros_like(img_in)
     lib().ko_bilateral_filter_joint(C.byref(_img(out)), C.byref(_img(img_in)), C.byref(_img(guide)),
                                     IMG_U8 if guide.dtype == np.uint8 else IMG_F32, gs, gr, gc, size)
+    return out
+
+
+EW_MULTIPLY, EW_DIVISION, EW_SQUARE, EW_MULTIPLY_ADD = 0, 1, 2, 3
+
+
+def elementwise(op: int, a: np.ndarray, b=None, c=None, s0: float = 1.0, s1: float = 0.0, s2: float = 1.0, s3: float = 0.0) -> np.ndarray:
+    """cu_operations.cu:91-181 on float images: Multiply s0*(a*b)+s1, Division s2*(a+s0)/(b+s1)+s3, Square (s0*a*a)+s1,
+    MultiplyAdd s0*a*b + s1*c + s2."""
+    a = np.ascontiguousarray(a, np.float32)
+    out = np.zeros_like(a)
+    ib = C.byref(_img(np.ascontiguousarray(b, np.float32))) if b is not None else None
+    ic = C.byref(_img(np.ascontiguousarray(c, np.float32))) if c is not None else None
+    lib().ko_elementwise(op, C.byref(_img(out)), C.byref(_img(a)), ib, ic, s0, s1, s2, s3)
+    return out
+
+
+def box_filter(img_in: np.ndarray, rad: int) -> np.ndarray:
+    img_in = np.ascontiguousarray(img_in, np.float32)
+    out = np.zeros_like(img_in)
+    lib().ko_box_filter(C.byref(_img(out)), C.byref(_img(img_in)), rad)
+    return out
+
+
+def guided_filter_volume(vol: np.ndarray, guide: np.ndarray, rad: int, eps: float, max_disp: int | None = None) -> np.ndarray:
+    """The applications' guided filtering of a (D, h, w) cost volume (stereo2/main.cpp:392-405); returns the filtered copy."""
+    out = np.array(vol, np.float32, order="C", copy=True)
+    guide = np.ascontiguousarray(guide, np.float32)
+    lib().ko_guided_filter_volume(C.byref(_vol(out)), C.byref(_img(guide)), rad, eps, out.shape[0] if max_disp is None else max_disp)
     return out
 
 

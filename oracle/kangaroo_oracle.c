@@ -458,6 +458,130 @@ void ko_bilateral_filter_joint(const ko_image* out, const ko_image* in, const ko
         }
 }
 
+/* ------------------------------------------------- integral-image box / guided filter ---- */
+
+/* src/cu_operations.cu:91-101,117-127,143-153,169-181 for float images, IEEE evaluation in source order (no contraction):
+ * op 0 Multiply   out = s0*(a*b) + s1
+ * op 1 Division   out = s2*(a+s0)/(b+s1) + s3
+ * op 2 Square     out = (s0*a*a) + s1
+ * op 3 MultiplyAdd out = s0*a*b + s1*c + s2 */
+void ko_elementwise(int op, const ko_image* out, const ko_image* a, const ko_image* b, const ko_image* c, float s0, float s1,
+                    float s2, float s3) {
+    const int w = (int)out->w, h = (int)out->h;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float v1 = *(const float*)img_at(a, (size_t)x, (size_t)y, 4);
+            const float v2 = b ? *(const float*)img_at(b, (size_t)x, (size_t)y, 4) : 0.0f;
+            const float v3 = c ? *(const float*)img_at(c, (size_t)x, (size_t)y, 4) : 0.0f;
+            float r;
+            switch (op) {
+            case 0: r = s0 * (v1 * v2) + s1; break;
+            case 1: r = s2 * (v1 + s0) / (v2 + s1) + s3; break;
+            case 2: r = (s0 * v1 * v1) + s1; break;
+            default: r = s0 * v1 * v2 + s1 * v3 + s2; break;
+            }
+            *(float*)img_at(out, (size_t)x, (size_t)y, 4) = r;
+        }
+}
+
+/* src/cu_integral_image.cu:58-107, the work-efficient exclusive scan of one row as the block executes it: an up-sweep
+ * that leaves the sums of aligned power-of-two blocks in place, the root cleared, and a down-sweep that hands every
+ * left child its parent's prefix and every right child prefix + left sum.  temp holds n = nextpow2 floats, n = twice
+ * the block size PrefixSumRows picks (:118-121: the smallest power of two >= ceil(w/2)). */
+static void prefix_sum_tree(float* out, size_t out_stride, const float* in, size_t in_stride, int w, float* temp) {
+    int half = 1;
+    while (half < (w + 1) / 2) half <<= 1;
+    const int n = 2 * half;
+    for (int i = 0; i < n; ++i) temp[i] = i < w ? in[(size_t)i * in_stride] : 0.0f;
+    int offset = 1;
+    for (int d = n >> 1; d > 0; d >>= 1) {
+        for (int t = 0; t < d; ++t) temp[offset * (2 * t + 2) - 1] += temp[offset * (2 * t + 1) - 1];
+        offset *= 2;
+    }
+    temp[n - 1] = 0.0f;
+    for (int d = 1; d < n; d *= 2) {
+        offset >>= 1;
+        for (int t = 0; t < d; ++t) {
+            const int ai = offset * (2 * t + 1) - 1, bi = offset * (2 * t + 2) - 1;
+            const float v = temp[ai];
+            temp[ai] = temp[bi];
+            temp[bi] += v;
+        }
+    }
+    for (int i = 0; i < w; ++i) out[(size_t)i * out_stride] = temp[i];
+}
+
+/* include/kangaroo/cu_integral_image.h:26-38 + src/cu_integral_image.cu:130-157: rows scanned, transposed, scanned
+ * again (= the columns of the row sums), then out(x,y) = (C + A - B - D) / area over the EXCLUSIVE sums at the clamped
+ * corners -- so the window is [minx, maxx) x [miny, maxy) and area = (maxx-minx)*(maxy-miny), both as the reference
+ * has them.  ii: scratch of w*h floats (x-major like the reference's transposed image: ii[x*h + y]). */
+static void box_filter_dense(float* out, const float* in, int w, int h, int rad, float* rows, float* ii) {
+    const int n = 2 * (w > h ? w : h) + 4;
+#pragma omp parallel
+    {
+        float* temp = (float*)malloc(sizeof(float) * 2 * (size_t)n);
+#pragma omp for schedule(static)
+        for (int y = 0; y < h; ++y) prefix_sum_tree(rows + (size_t)y * w, 1, in + (size_t)y * w, 1, w, temp);
+#pragma omp for schedule(static)
+        for (int x = 0; x < w; ++x) prefix_sum_tree(ii + (size_t)x * h, 1, rows + x, (size_t)w, h, temp);
+        free(temp);
+    }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const int minx = x - rad > 0 ? x - rad : 0, maxx = x + rad < w - 1 ? x + rad : w - 1;
+            const int miny = y - rad > 0 ? y - rad : 0, maxy = y + rad < h - 1 ? y + rad : h - 1;
+            const int area = (maxx - minx) * (maxy - miny);
+            const float A = ii[(size_t)minx * h + miny], B = ii[(size_t)maxx * h + miny];
+            const float Cc = ii[(size_t)maxx * h + maxy], D = ii[(size_t)minx * h + maxy];
+            const float sum = Cc + A - B - D;
+            out[(size_t)y * w + x] = sum / (float)area;
+        }
+}
+
+void ko_box_filter(const ko_image* out, const ko_image* in, int rad) {
+    const int w = (int)out->w, h = (int)out->h;
+    float* buf = (float*)calloc(4 * (size_t)w * h, sizeof(float));
+    float *din = buf, *dout = buf + (size_t)w * h, *rows = dout + (size_t)w * h, *ii = rows + (size_t)w * h;
+    for (int y = 0; y < h; ++y) memcpy(din + (size_t)y * w, img_at(in, 0, (size_t)y, 4), 4 * (size_t)w);
+    box_filter_dense(dout, din, w, h, rad, rows, ii);
+    for (int y = 0; y < h; ++y) memcpy(img_at(out, 0, (size_t)y, 4), dout + (size_t)y * w, 4 * (size_t)w);
+    free(buf);
+}
+
+/* applications/stereo2/main.cpp:392-405 on the first maxDisp slices of vol, in place: ComputeMeanVarience once
+ * (cu_integral_image.h:42-54), then per slice ComputeCovariance (:56-68) and GuidedFilter (:72-93); every step in the
+ * reference's order with IEEE arithmetic. */
+void ko_guided_filter_volume(const ko_volume* vol, const ko_image* guide, int rad, float eps, int maxDisp) {
+    const int w = (int)vol->w, h = (int)vol->h;
+    const size_t n = (size_t)w * h;
+    float* buf = (float*)malloc(sizeof(float) * 12 * n);
+    float *I = buf, *meanI = I + n, *varI = meanI + n, *P = varI + n, *meanP = P + n, *t = meanP + n, *meanIP = t + n,
+          *a = meanIP + n, *b = a + n, *meana = b + n, *rows = meana + n, *ii = rows + n;
+    for (int y = 0; y < h; ++y) memcpy(I + (size_t)y * w, img_at(guide, 0, (size_t)y, 4), 4 * (size_t)w);
+    box_filter_dense(meanI, I, w, h, rad, rows, ii);
+    for (size_t i = 0; i < n; ++i) t[i] = (1.0f * I[i] * I[i]) + 0.0f;                         /* ElementwiseSquare */
+    box_filter_dense(varI, t, w, h, rad, rows, ii);                                             /* meanII */
+    for (size_t i = 0; i < n; ++i) varI[i] = -1.0f * meanI[i] * meanI[i] + 1.0f * varI[i] + 0.0f; /* var = meanII - meanI^2 */
+    for (int d = 0; d < maxDisp; ++d) {
+        for (int y = 0; y < h; ++y) memcpy(P + (size_t)y * w, vol_at(vol, 0, (size_t)y, (size_t)d, 4), 4 * (size_t)w);
+        box_filter_dense(meanP, P, w, h, rad, rows, ii);
+        for (size_t i = 0; i < n; ++i) t[i] = 1.0f * (I[i] * P[i]) + 0.0f;                     /* ElementwiseMultiply */
+        box_filter_dense(meanIP, t, w, h, rad, rows, ii);
+        for (size_t i = 0; i < n; ++i) {
+            const float cov = -1.0f * meanI[i] * meanP[i] + 1.0f * meanIP[i] + 0.0f;
+            a[i] = 1.0f * (cov + 0.0f) / (varI[i] + eps) + 0.0f;                               /* Eqn. 5 */
+            b[i] = -1.0f * a[i] * meanI[i] + 1.0f * meanP[i] + 0.0f;                           /* Eqn. 6 */
+        }
+        box_filter_dense(meana, a, w, h, rad, rows, ii);
+        box_filter_dense(t, b, w, h, rad, rows, ii);                                            /* meanb */
+        for (size_t i = 0; i < n; ++i) P[i] = 1.0f * meana[i] * I[i] + 1.0f * t[i] + 0.0f;     /* Eqn. 8 */
+        for (int y = 0; y < h; ++y) memcpy(vol_at(vol, 0, (size_t)y, (size_t)d, 4), P + (size_t)y * w, 4 * (size_t)w);
+    }
+    free(buf);
+}
+
 /* ---------------------------------------------------------------- subpixel refine ---- */
 
 /* patch_score.h:257-298, SANDPatchScore<float,2,ImgAccessRaw> on unsigned char images */

@@ -140,6 +140,15 @@ void ko_filter_disp_grad(const ko_image* out_f32, const ko_image* grad_f32, cons
 /* src/cu_bilateral.cu:110-143, float in/out, guide image of KO_IMG_U8 or KO_IMG_F32; out must not alias in */
 void ko_bilateral_filter_joint(const ko_image* out_f32, const ko_image* in_f32, const ko_image* img, int img_type, float gs,
                                float gr, float gc, int size);
+/* src/cu_operations.cu:91-181, float images: op 0 Multiply s0*(a*b)+s1, 1 Division s2*(a+s0)/(b+s1)+s3, 2 Square (s0*a*a)+s1,
+ * 3 MultiplyAdd s0*a*b + s1*c + s2 (b, c may be NULL where unused) */
+void ko_elementwise(int op, const ko_image* out_f32, const ko_image* a, const ko_image* b, const ko_image* c, float s0, float s1,
+                    float s2, float s3);
+/* include/kangaroo/cu_integral_image.h:26-38, src/cu_integral_image.cu:58-157: box mean through two tree-ordered exclusive
+ * prefix sums; the window is [x-rad, x+rad) x [y-rad, y+rad) clamped, as the reference has it */
+void ko_box_filter(const ko_image* out_f32, const ko_image* in_f32, int rad);
+/* applications/stereo2/main.cpp:392-405 (cu_integral_image.h:42-93): guided filtering of the first maxDisp slices, in place */
+void ko_guided_filter_volume(const ko_volume* vol_f32, const ko_image* guide_f32, int rad, float eps, int maxDisp);
 void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff);
 void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd, int maxDiff);
 

@@ -330,3 +330,38 @@ def create_matlab_lookup_table_h(w: int, h: int, fu, fv, u0, v0, k1, k2, H_on) -
     _ck(lib().kref_create_matlab_lookup_table_h(out.data_ptr(), w * 8, w, h, fu, fv, u0, v0, k1, k2, Hc),
         "CreateMatlabLookupTable(H)")
     return _back(out, np.float32, (h, w, 2))
+
+
+def box_filter(img_in: np.ndarray, rad: int) -> np.ndarray:
+    """roo::BoxFilter<float,float,float> (cu_integral_image.h:26-38) of a dense (h, w) float32 image."""
+    import torch
+    h, w = img_in.shape
+    di = _dev(np.ascontiguousarray(img_in, np.float32))
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    lib().kref_box_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
+    _ck(lib().kref_box_filter(out.data_ptr(), di.data_ptr(), w, h, rad), "BoxFilter")
+    return _back(out, np.float32, (h, w))
+
+
+def guided_filter_volume(vol: np.ndarray, guide: np.ndarray, rad: int, eps: float) -> np.ndarray:
+    """The applications' per-slice ComputeCovariance + GuidedFilter loop (stereo2/main.cpp:392-405) over a dense (D, h, w)
+    float32 volume, guide = (h, w) float32."""
+    D, h, w = vol.shape
+    dv, dg = _dev(np.ascontiguousarray(vol, np.float32)), _dev(np.ascontiguousarray(guide, np.float32))
+    lib().kref_guided_filter_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_float]
+    _ck(lib().kref_guided_filter_volume(dv.data_ptr(), dg.data_ptr(), w, h, D, rad, eps), "GuidedFilter")
+    return _back(dv, np.float32, (D, h, w))
+
+
+def elementwise(op: int, a: np.ndarray, b: np.ndarray | None, c: np.ndarray | None, s0=1.0, s1=0.0, s2=1.0, s3=0.0) -> np.ndarray:
+    """op 0 Multiply(s0 = scalar, s1 = offset), 1 Division(s0 = sa, s1 = sb, s2 = scalar, s3 = offset), 2 Square(s0, s1),
+    3 MultiplyAdd(s0 = sab, s1 = sc, s2 = offset) on dense float32 images (cu_operations.cu:85-190)."""
+    import torch
+    h, w = a.shape
+    da = _dev(np.ascontiguousarray(a, np.float32))
+    db = _dev(np.ascontiguousarray(b, np.float32)) if b is not None else da
+    dc = _dev(np.ascontiguousarray(c, np.float32)) if c is not None else da
+    out = torch.zeros(h * w * 4, dtype=torch.uint8, device="cuda")
+    lib().kref_elementwise.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_size_t] * 2 + [C.c_float] * 4
+    _ck(lib().kref_elementwise(op, out.data_ptr(), da.data_ptr(), db.data_ptr(), dc.data_ptr(), w, h, s0, s1, s2, s3), "Elementwise")
+    return _back(out, np.float32, (h, w))

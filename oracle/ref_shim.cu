@@ -6,7 +6,7 @@
 // (include/kangaroo/cu_census.h, cu_semi_global_matching.h, cu_dense_stereo.h) and
 // forwards plain pointers to the roo:: free functions.  It is compiled together
 // with /root/reference/src/{cu_census,cu_semi_global_matching,cu_dense_stereo,cu_operations,
-// cu_resample,cu_depth_tools,cu_median,cu_lookup_warp}.cu (from where they lie) into oracle/_ref/libkangaroo_ref.so
+// cu_resample,cu_depth_tools,cu_median,cu_lookup_warp,cu_bilateral,cu_integral_image}.cu (from where they lie) into oracle/_ref/libkangaroo_ref.so
 // by oracle/Makefile.
 //
 // The reference kernels launch one thread per pixel of a row/column in ONE block
@@ -23,6 +23,8 @@
 #include <kangaroo/cu_median.h>
 #include <kangaroo/cu_lookup_warp.h>
 #include <kangaroo/cu_bilateral.h>
+#include <kangaroo/cu_integral_image.h>
+#include <vector>
 
 namespace {
 template <typename T>
@@ -39,6 +41,35 @@ int finish() {
     return (int)e;
 }
 bool too_big(size_t w, size_t h) { return w > 1024 || h > 1024; }
+
+// Padded device image for the integral-image operators: BoxFilter (cu_integral_image.h:26-38) borrows its OUTPUT image as
+// storage for the transposed row sums (out.AlignedImage<TSum>(in.h, in.w)), which only fits when
+// align16(4 h) * w <= h * pitch -- hence the slack in the pitch.
+struct PadImg {
+    float* p = nullptr;
+    size_t pitch = 0, w = 0, h = 0;
+    PadImg(size_t w_, size_t h_) : w(w_), h(h_) {
+        pitch = (4 * w + 16 * ((w + h - 1) / h) + 31) / 16 * 16;
+        cudaMalloc((void**)&p, pitch * h);
+        cudaMemset(p, 0, pitch * h);
+    }
+    ~PadImg() { cudaFree(p); }
+    PadImg(const PadImg&) = delete;
+    PadImg& operator=(const PadImg&) = delete;
+    roo::Image<float> im() const { return roo::Image<float>(p, w, h, pitch); }
+    void put(const void* dense) { cudaMemcpy2D(p, pitch, dense, 4 * w, 4 * w, h, cudaMemcpyDeviceToDevice); }
+    void get(void* dense) const { cudaMemcpy2D(dense, 4 * w, p, pitch, 4 * w, h, cudaMemcpyDeviceToDevice); }
+};
+struct ScratchBytes {
+    unsigned char* p = nullptr;
+    size_t n = 0;
+    ScratchBytes(size_t w, size_t h) {
+        n = ((4 * w + 15) / 16 * 16) * h + ((4 * h + 15) / 16 * 16) * w + 256;
+        cudaMalloc((void**)&p, n);
+    }
+    ~ScratchBytes() { cudaFree(p); }
+    roo::Image<unsigned char> im() const { return roo::Image<unsigned char>(p, n, 1, n); }
+};
 }  // namespace
 
 extern "C" {
@@ -249,6 +280,54 @@ int kref_bilateral_joint(void* out, void* in, size_t pitch, void* gimg, size_t g
                          float gr, float gc, unsigned size) {
     if (img_type == 0) roo::BilateralFilter<float, float, unsigned char>(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), img<unsigned char>(gimg, g_pitch, w, h), gs, gr, gc, size);
     else roo::BilateralFilter<float, float, float>(img<float>(out, pitch, w, h), img<float>(in, pitch, w, h), img<float>(gimg, g_pitch, w, h), gs, gr, gc, size);
+    return finish();
+}
+
+// cu_integral_image.h:26-38 (PrefixSumRows -> Transpose -> PrefixSumRows -> BoxFilterIntegralImage); dense w x h float
+// device buffers in and out.  The scan kernel runs one block of nextpow2(w)/2 threads per row: w, h <= 2048.
+int kref_box_filter(void* out, void* in, size_t w, size_t h, int rad) {
+    if (w > 2048 || h > 2048 || w < 2 || h < 2) return -2;
+    PadImg o(w, h), i(w, h);
+    ScratchBytes sc(w, h);
+    i.put(in);
+    roo::BoxFilter<float, float, float>(o.im(), i.im(), sc.im(), rad);
+    const int e = finish();
+    o.get(out);
+    return e ? e : finish();
+}
+
+// The applications' guided filtering of a cost volume (applications/stereo2/main.cpp:392-405): ComputeMeanVarience once
+// per guide image, then ComputeCovariance + GuidedFilter per disparity slice, in place.  v: dense D x h x w floats.
+int kref_guided_filter_volume(void* v, void* guide, size_t w, size_t h, size_t D, int rad, float eps) {
+    if (w > 2048 || h > 2048 || w < 2 || h < 2) return -2;
+    PadImg I(w, h), varI(w, h), meanI(w, h), P(w, h), t0(w, h), t1(w, h), t2(w, h), t3(w, h), t4(w, h);
+    ScratchBytes sc(w, h);
+    I.put(guide);
+    roo::ComputeMeanVarience<float, float, float>(varI.im(), t0.im(), meanI.im(), I.im(), sc.im(), rad);
+    for (size_t d = 0; d < D; ++d) {
+        float* slice = (float*)v + d * w * h;
+        P.put(slice);
+        roo::ComputeCovariance(t0.im(), t2.im(), t1.im(), P.im(), meanI.im(), I.im(), sc.im(), rad);
+        roo::GuidedFilter(P.im(), t0.im(), varI.im(), t1.im(), meanI.im(), I.im(), sc.im(), t2.im(), t3.im(), t4.im(), rad, eps);
+        const int e = finish();
+        if (e) return e;
+        P.get(slice);
+    }
+    return finish();
+}
+
+// cu_operations.cu:85-165,170-190: the float elementwise operators the guided filter is composed of.
+// op: 0 = Multiply (c = s0*(a*b) + s1), 1 = Division (c = s2*(a+s0)/(b+s1) + s3), 2 = Square (c = s0*a*a + s1),
+//     3 = MultiplyAdd (d = s0*a*b + s1*c + s2)
+int kref_elementwise(int op, void* out, void* a, void* b, void* c, size_t w, size_t h, float s0, float s1, float s2, float s3) {
+    const size_t p = 4 * w;
+    switch (op) {
+    case 0: roo::ElementwiseMultiply<float, float, float, float>(img<float>(out, p, w, h), img<float>(a, p, w, h), img<float>(b, p, w, h), s0, s1); break;
+    case 1: roo::ElementwiseDivision<float, float, float, float>(img<float>(out, p, w, h), img<float>(a, p, w, h), img<float>(b, p, w, h), s0, s1, s2, s3); break;
+    case 2: roo::ElementwiseSquare<float, float, float>(img<float>(out, p, w, h), img<float>(a, p, w, h), s0, s1); break;
+    case 3: roo::ElementwiseMultiplyAdd<float, float, float, float, float>(img<float>(out, p, w, h), img<float>(a, p, w, h), img<float>(b, p, w, h), img<float>(c, p, w, h), s0, s1, s2); break;
+    default: return -1;
+    }
     return finish();
 }
 

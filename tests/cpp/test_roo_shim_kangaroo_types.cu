@@ -66,6 +66,22 @@ int main() {
     roo::BilateralFilter<float, float, float>(dispf, depth, img[0], 2.0f, 0.2f, 0.1f, 3);         // stereo2/main.cpp:417 (one slice)
     roo::BilateralFilter<float, float, unsigned char>(dispf, depth, upload, 2.0f, 0.2f, 10.0f, 3);
     roo::BilateralFilterVolume<float>(vol[1], vol[0], img[0], 2.0f, 0.2f, 0.1f, 2, maxdisp);             // the loop at :407-421 in one launch
+    {   // the guided-filter branch of the frame loop, spelled as stereo2/main.cpp:392-405 spells it, and its one-call form
+        roo::Image<unsigned char, roo::TargetDevice, roo::Manage> Scratch(w * sizeof(float), h);          // :186
+        roo::Image<float, roo::TargetDevice, roo::Manage> meanI(w, h), varI(w, h);
+        roo::Image<float, roo::TargetDevice, roo::Manage> temp[] = {{(size_t)w, (size_t)h}, {(size_t)w, (size_t)h}, {(size_t)w, (size_t)h}, {(size_t)w, (size_t)h}, {(size_t)w, (size_t)h}};
+        const int rad = 9;
+        const float eps = 0.01f;
+        roo::Image<float, roo::TargetDevice, roo::Manage>& I = img[0];
+        roo::ComputeMeanVarience<float, float, float>(varI, temp[0], meanI, I, Scratch, rad);       // :396
+        for (int d = 0; d < 2; ++d) {
+            roo::Image<float> P = vol[0].ImageXY(d);
+            roo::ComputeCovariance(temp[0], temp[2], temp[1], P, meanI, I, Scratch, rad);            // :401
+            roo::GuidedFilter(P, temp[0], varI, temp[1], meanI, I, Scratch, temp[2], temp[3], temp[4], rad, eps);   // :402
+        }
+        roo::GuidedFilterVolume(vol[1], I, rad, eps, maxdisp);
+        roo::BoxFilter<float, float, float>(temp[0], img[1], Scratch, 5);                           // :377 (commented out there)
+    }
     roo::LeftRightCheck(dispi8, dispi8r, -1, 0);
     const cudaError_t err = cudaDeviceSynchronize();
     std::printf("%s\n", err == cudaSuccess ? "OK" : cudaGetErrorString(err));

@@ -361,3 +361,135 @@ def test_bilateral_filter_volume_vs_reference_and_oracle(golden):
     with pytest.raises(roo.capi.RooError):
         v = roo.Volume.from_numpy(big)
         roo.BilateralFilterVolume(v, v, roo.Image.from_numpy(guide), 2.0, 0.25, 12.0, 3, 17)   # in place: taps would read filtered values
+
+
+# ---------------------------------------------------------------- integral-image box filter / guided filter
+
+def _img(a, pad=0):
+    return roo.Image.from_numpy(a, pitch=a.shape[1] * a.itemsize + pad)
+
+
+def test_elementwise_float_operators_vs_reference_and_oracle(golden):
+    """ElementwiseMultiply / Division / Square / MultiplyAdd on float images: default mode == the reference kernels bit for
+    bit (their FMUL/FFMA/MUFU.RCP forms), IEEE mode == the oracle's source-order evaluation."""
+    g = golden("guided")
+    a, b, c = g["ew_a"], g["ew_b"], g["ew_c"]
+    h, w = a.shape
+
+    def run():
+        o = {k: roo.Image(w, h, np.float32) for k in ("mul", "div", "sq", "mad", "mad2")}
+        roo.ElementwiseMultiply(o["mul"], _img(a), _img(b, 12), 1.7, -0.3)
+        roo.ElementwiseDivision(o["div"], _img(a), _img(b), 0.25, 0.01, 1.3, 0.5)
+        roo.ElementwiseSquare(o["sq"], _img(a, 4), 0.9, 0.1)
+        roo.ElementwiseMultiplyAdd(o["mad"], _img(a), _img(b), _img(c), -1.0, 1.0, 0.0)
+        roo.ElementwiseMultiplyAdd(o["mad2"], _img(a), _img(b), _img(c, 8), 0.7, -1.1, 0.2)
+        return {k: v.numpy() for k, v in o.items()}
+
+    got = run()
+    for k in got:
+        assert same_bits(got[k], g[f"ew_{k}"]), k
+    roo.set_ieee_division(True)
+    got = run()
+    f = np.float32
+    want = {"mul": ko.elementwise(ko.EW_MULTIPLY, a, b, None, f(1.7), f(-0.3)), "div": ko.elementwise(ko.EW_DIVISION, a, b, None, 0.25, f(0.01), f(1.3), 0.5),
+            "sq": ko.elementwise(ko.EW_SQUARE, a, None, None, f(0.9), f(0.1)), "mad": ko.elementwise(ko.EW_MULTIPLY_ADD, a, b, c, -1.0, 1.0, 0.0),
+            "mad2": ko.elementwise(ko.EW_MULTIPLY_ADD, a, b, c, f(0.7), f(-1.1), f(0.2))}
+    for k in got:
+        assert same_bits(got[k], want[k]), k
+
+
+def test_box_filter_vs_reference_and_oracle(golden):
+    """BoxFilter<float,float,float>: bit-identical to the reference's PrefixSumRows/Transpose/PrefixSumRows/BoxFilterIntegralImage
+    chain at sizes either side of its power-of-two scan padding and of this library's 256-element / 8-row steps; IEEE mode
+    bit-identical to the oracle, which executes the reference's tree literally."""
+    g = golden("guided")
+    for nm in "abcde":
+        src, rad = g[f"box_in_{nm}"], int(g[f"box_rad_{nm}"])
+        h, w = src.shape
+        out = roo.Image(w, h, np.float32)
+        roo.BoxFilter(out, _img(src, 20 if nm in "ac" else 0), None, rad)
+        assert same_float(out.numpy(), g[f"box_out_{nm}"]), nm
+        inplace = _img(src)
+        roo.BoxFilter(inplace, inplace, None, rad)
+        assert same_float(inplace.numpy(), g[f"box_out_{nm}"]), nm
+    roo.set_ieee_division(True)
+    rng = np.random.default_rng(5)
+    for (h, w, rad) in ((37, 70, 3), (9, 255, 2), (8, 256, 4), (17, 257, 30), (129, 513, 7), (300, 31, 11), (2, 2, 1), (65, 1100, 5)):
+        src = (rng.random((h, w), dtype=np.float32) * 4 - 1).astype(np.float32)
+        out = roo.Image(w, h, np.float32)
+        roo.BoxFilter(out, _img(src), None, rad)
+        assert same_float(out.numpy(), ko.box_filter(src, rad)), (h, w, rad)
+
+
+def test_box_filter_beyond_the_reference_size_limit():
+    """The reference scans a row with one block of w/2 threads (w, h <= 2048); here the same summation order continues to
+    any size.  3000 x 2100 against the oracle (IEEE mode), and the defining property on a constant image (default mode):
+    exact sums of small integers, so every interior mean is exactly 1."""
+    rng = np.random.default_rng(9)
+    src = rng.integers(0, 4, (2100, 3000)).astype(np.float32)
+    roo.set_ieee_division(True)
+    out = roo.Image(3000, 2100, np.float32)
+    roo.BoxFilter(out, _img(src), None, 12)
+    assert same_float(out.numpy(), ko.box_filter(src, 12))
+    roo.set_ieee_division(False)
+    ones = np.ones((2100, 3000), np.float32)
+    roo.BoxFilter(out, _img(ones), None, 12)
+    assert np.abs(out.numpy() - 1.0).max() <= 2e-7        # sum / area through MUFU.RCP: within an ulp of 1
+
+
+def _guided_sequence(vol, guide, rad, eps):
+    """applications/stereo2/main.cpp:392-405 spelled with the operators, one slice at a time"""
+    D, h, w = vol.shape
+    I = _img(guide)
+    varI, meanI, P = (roo.Image(w, h, np.float32) for _ in range(3))
+    t = [roo.Image(w, h, np.float32) for _ in range(5)]
+    roo.ComputeMeanVarience(varI, t[0], meanI, I, None, rad)
+    out = np.empty_like(vol)
+    for d in range(D):
+        P = _img(vol[d])
+        roo.ComputeCovariance(t[0], t[2], t[1], P, meanI, I, None, rad)
+        roo.GuidedFilter(P, t[0], varI, t[1], meanI, I, None, t[2], t[3], t[4], rad, eps)
+        out[d] = P.numpy()
+    return out
+
+
+def test_guided_filter_volume_vs_reference_sequence_and_oracle(golden):
+    """The whole-volume guided filter == the reference's per-slice ComputeCovariance + GuidedFilter calls bit for bit (default
+    mode), == the same sequence spelled with this library's operators, == the oracle in IEEE mode.  The oracle itself is
+    only within ~1e-3 of the reference here (var_I and cov_Ip are differences of nearly equal means, so one ulp of
+    MUFU.RCP vs IEEE division is amplified) -- which is why the pin for the default mode is the reference output."""
+    g = golden("guided")
+    vol, guide = g["gf_vol"], g["gf_guide"]
+    D, h, w = vol.shape
+    for nm in ("r4", "r9", "r1"):
+        rad, eps = int(g[f"gf_par_{nm}"][0]), float(g[f"gf_par_{nm}"][1])
+        v = roo.Volume.from_numpy(vol)
+        roo.GuidedFilterVolume(v, _img(guide, 16), rad, eps, D)
+        assert same_float(v.numpy(), g[f"gf_out_{nm}"]), nm
+        assert same_float(_guided_sequence(vol, guide, rad, eps), g[f"gf_out_{nm}"]), nm
+    # maxDisp < depth leaves the remaining slices alone
+    v = roo.Volume.from_numpy(vol)
+    roo.GuidedFilterVolume(v, _img(guide), 4, 1e-4, D - 2)
+    assert same_float(v.numpy()[:D - 2], g["gf_out_r4"][:D - 2]) and same_bits(v.numpy()[D - 2:], vol[D - 2:])
+    roo.set_ieee_division(True)
+    for nm in ("r4", "r9"):
+        rad, eps = int(g[f"gf_par_{nm}"][0]), float(g[f"gf_par_{nm}"][1])
+        v = roo.Volume.from_numpy(vol)
+        roo.GuidedFilterVolume(v, _img(guide), rad, eps, D)
+        assert same_float(v.numpy(), ko.guided_filter_volume(vol, guide, rad, np.float32(eps)))
+    with pytest.raises(roo.capi.RooError):
+        roo.GuidedFilterVolume(roo.Volume.from_numpy(vol), _img(guide[:-1]), 4, 1e-4, D)
+
+
+def test_guided_filter_volume_chunks_and_camera_size():
+    """640 x 480 x 64 (the applications' default working size) in IEEE mode against the oracle -- more rows than one CTA's
+    warps, several 256-element steps per row, and a volume with padded row / slice pitches."""
+    rng = np.random.default_rng(33)
+    D, h, w = 12, 480, 640
+    vol = (rng.integers(0, 64, (D, h, w)) / np.float32(64)).astype(np.float32)
+    yy, xx = np.mgrid[0:h, 0:w]
+    guide = (np.clip(30 + 0.3 * xx + 80 * (yy > 200) + rng.normal(0, 5, (h, w)), 0, 255) / 255).astype(np.float32)
+    roo.set_ieee_division(True)
+    v = roo.Volume.from_numpy(vol)
+    roo.GuidedFilterVolume(v, _img(guide), 9, 1e-3, D)
+    assert same_float(v.numpy(), ko.guided_filter_volume(vol, guide, 9, np.float32(1e-3)))

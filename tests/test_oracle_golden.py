@@ -449,3 +449,37 @@ def test_kat_bilateral_filter():
     out = ko.bilateral_filter_joint(step, gstep, 2.0, 10.0, 5.0, 3)                                    # wide range kernel: only the guide protects the edge
     assert abs(out[4, 4] - 0.25) < 1e-3 and abs(out[4, 5] - 0.75) < 1e-3
     assert abs(ko.bilateral_filter_joint(step, guide, 2.0, 10.0, 5.0, 3)[4, 4] - 0.25) > 0.05          # without the guide edge it blurs
+
+
+def test_box_filter_and_elementwise_oracle_vs_reference_golden(golden):
+    """The oracle's literal restatement of the reference scan tree (cu_integral_image.cu:58-107) against outputs of the
+    reference kernels: the only difference left is sum * MUFU.RCP(area) vs IEEE division -- one ulp."""
+    g = golden("guided")
+    for nm in "abcde":
+        o = ko.box_filter(g[f"box_in_{nm}"], int(g[f"box_rad_{nm}"]))
+        r = g[f"box_out_{nm}"]
+        assert np.array_equal(np.isfinite(o), np.isfinite(r))
+        fin = np.isfinite(r)
+        assert (np.abs(o[fin] - r[fin]) <= 2.5e-7 * np.abs(r[fin])).all(), nm
+    a, b, c = g["ew_a"], g["ew_b"], g["ew_c"]
+    f = np.float32
+    for nm, o in {"ew_mul": ko.elementwise(ko.EW_MULTIPLY, a, b, None, f(1.7), f(-0.3)),
+                  "ew_div": ko.elementwise(ko.EW_DIVISION, a, b, None, 0.25, f(0.01), f(1.3), 0.5),
+                  "ew_sq": ko.elementwise(ko.EW_SQUARE, a, None, None, f(0.9), f(0.1)),
+                  "ew_mad": ko.elementwise(ko.EW_MULTIPLY_ADD, a, b, c, -1.0, 1.0, 0.0),
+                  "ew_mad2": ko.elementwise(ko.EW_MULTIPLY_ADD, a, b, c, f(0.7), f(-1.1), f(0.2))}.items():
+        assert (np.abs(o - g[nm]) <= 1e-5 * np.maximum(np.abs(g[nm]), 1e-2)).all(), nm     # FFMA contraction vs two roundings
+
+
+def test_guided_filter_oracle_vs_reference_golden(golden):
+    """stereo2/main.cpp:392-405 on a small volume.  var_I = mean_II - mean_I^2 and cov_Ip cancel, so the one-ulp differences
+    between the reference's fast-math forms and IEEE are amplified: the oracle is within 1e-4 absolute for radii >= 4 and
+    1e-3 at radius 1 (window of one pixel: var_I ~ 0, a = cov / eps).  Bit-exact pins: the GPU tests (reference golden in
+    the default mode, this oracle in IEEE mode)."""
+    g = golden("guided")
+    for nm, tol in (("r4", 1e-4), ("r9", 1e-4), ("r1", 1e-3)):
+        rad, eps = int(g[f"gf_par_{nm}"][0]), np.float32(g[f"gf_par_{nm}"][1])
+        o = ko.guided_filter_volume(g["gf_vol"], g["gf_guide"], rad, eps)
+        r = g[f"gf_out_{nm}"]
+        assert np.isfinite(o).all() and np.isfinite(r).all()
+        assert np.abs(o - r).max() <= tol, (nm, float(np.abs(o - r).max()))

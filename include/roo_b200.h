@@ -209,12 +209,12 @@ int roo_elementwise_multiply_add(const roo_image_t* d_f32, const roo_image_t* a_
 /* roo::BoxFilter<float,float,float>(out, in, scratch, rad) (cu_integral_image.h:26-38): box mean through two exclusive prefix
  * sums in the reference's tree order and its four-corner lookup (window [x-rad, x+rad) x [y-rad, y+rad), clamped; divisor =
  * that window's area) -- bit-identical to the reference kernels.  No scratch image (stream-ordered internal scratch), any
- * w <= 262144 and h <= 65536 (the reference: w, h <= 2048); out may be in. */
+ * w <= 16384 and h <= 65536 (the reference: w, h <= 2048); out may be in. */
 int roo_box_filter(const roo_image_t* out_f32, const roo_image_t* in_f32, int rad, void* stream);
 
 /* The applications' guided filtering of a cost volume (stereo2/main.cpp:392-405): ComputeMeanVarience(I) once, then per slice
  * ComputeCovariance + GuidedFilter (cu_integral_image.h:42-93), in place on the first maxDisp slices -- here 3 launches for
- * the guide image + 6 per chunk of slices (one chunk unless 4 fp32 copies of the chunk exceed 2 GiB) instead of 37 per
+ * the guide image + 5 per chunk of slices (one chunk unless 4 fp32 copies of the chunk exceed 2 GiB) instead of 37 per
  * slice.  Same results as that sequence of reference calls, bit for bit. */
 int roo_guided_filter_volume(const roo_volume_t* vol_f32, const roo_image_t* guide_f32, int rad, float eps, int maxDisp, void* stream);
 /* Both take their scratch stream-ordered from a memory pool of this library that keeps it between calls (4 fp32 copies of

@@ -12,11 +12,12 @@
 // of i from the most significant down (down-sweep).  That order does not need the tree's storage: a pairwise-summation
 // stack (one partial sum per level, a binary counter) holds exactly those block sums when element i arrives.  So here
 //   * scan_rows_kernel: one warp per image row, 256 elements per step (8 per lane in registers, five shuffle levels),
-//     the levels above 256 on the per-warp stack -- any width, coalesced, one read and one write;
+//     the levels above 256 on the per-warp stack -- any width, coalesced; P and I*P (I and I*I) come from one read, and a, b
+//     are computed on the fly from the integral images of P and I*P, never written;
 //   * scan_cols_kernel: one thread per column streaming down the rows, eight rows per step, in place -- this replaces
 //     Transpose + the second PrefixSumRows (the transposed image is never written);
 //   * box_epilogue_kernel: the four-corner lookup fused with the elementwise algebra that follows it in the guided filter;
-// and the whole volume goes through 6 launches per chunk of slices (all slices at c2's size) instead of 21 per slice.
+// and the whole volume goes through 5 launches per chunk of slices (all slices at c2's size) instead of 37 per slice.
 // Results are bit-identical to the reference kernels (tests/golden/guided.npz) in the default fp mode -- every operation
 // is the reference's -use_fast_math SASS form (FADD/FMUL/FFMA.FTZ, MUFU.RCP) -- and to the CPU oracle in IEEE mode.
 #include "common.cuh"
@@ -124,70 +125,141 @@ __device__ __forceinline__ void stack_push(float (&st)[LEVELS], unsigned n, floa
 }
 
 // ---- pass 1: exclusive prefix sums along the rows ---------------------------------------------------------------------
-// What a row of plane z is made of: the guided filter scans P and I*P (or I and I*I) in one launch.
-enum RowSrcMode { SRC_PLANES = 0, SRC_P_AND_IP = 1, SRC_I_AND_II = 2 };
-struct RowSrc {
-    int mode;
-    Vol<float> p;     // SRC_PLANES: planes z0.. ; SRC_P_AND_IP: the S slices starting at z0
-    Img<float> g;     // guide image
-    int z0, S;
-};
 struct Planes {       // dense fp32 scratch [plane][y][x], rows padded to a multiple of 8 elements (16-byte aligned)
     float* ptr;
     size_t pitch, plane;   // elements
     __device__ __forceinline__ float* row(int y, int z) const { return ptr + (size_t)z * plane + (size_t)y * pitch; }
 };
 
-constexpr int SCAN_ROW_WARPS = 8, SCAN_ROW_LEVELS = 10;   // 256 << 10 elements per row at most
-
+// ---- pass 3: four-corner lookup + the algebra that follows it ----------------------------------------------------------
+// cu_integral_image.cu:130-157.  SASS: I2FP area; MUFU.RCP; FADD.FTZ (C + A); FADD.FTZ -B; FADD.FTZ -D; FMUL.FTZ sum * rcp.
+// The sums are exclusive, so the window is [minx, maxx) x [miny, maxy) and area = (maxx - minx) * (maxy - miny).
+struct BoxWin { int o_a, o_b, o_c, o_d; float area; };   // element offsets inside a plane
+__device__ __forceinline__ BoxWin box_window(int x, int y, int w, int h, int rad, size_t pitch) {
+    const int minx = max(0, x - rad), maxx = min(w - 1, x + rad), miny = max(0, y - rad), maxy = min(h - 1, y + rad);
+    BoxWin b;
+    b.o_a = (int)(miny * pitch) + minx;
+    b.o_b = (int)(miny * pitch) + maxx;
+    b.o_c = (int)(maxy * pitch) + maxx;
+    b.o_d = (int)(maxy * pitch) + minx;
+    b.area = (float)((maxx - minx) * (maxy - miny));
+    return b;
+}
 template <bool IEEE>
-__global__ void __launch_bounds__(SCAN_ROW_WARPS * 32)
-scan_rows_kernel(RowSrc src, Planes dst, int w, int h, int nz) {
+__device__ __forceinline__ float box_mean(const float* __restrict__ ii, const BoxWin& b, float rcp_area) {
+    const float sum = gadd<IEEE>(gadd<IEEE>(gadd<IEEE>(ii[b.o_c], ii[b.o_a]), -ii[b.o_b]), -ii[b.o_d]);
+    return IEEE ? __fdiv_rn(sum, b.area) : fmul_ftz(sum, rcp_area);
+}
+
+// What the rows a warp scans are made of.  The pair modes read their input once and scan two planes (z and S + z):
+//   ROWS_PLANE   one plane of p                                         (BoxFilter)
+//   ROWS_I_II    I and I*I of the guide image                           (ComputeMeanVarience, cu_integral_image.h:45-50)
+//   ROWS_P_IP    P and I*P of slice z0 + z                              (ComputeCovariance, :59-64)
+//   ROWS_A_B     a = cov_Ip / (var_I + eps) and b = mean_p - a mean_I, computed on the fly from the integral images of P and
+//                I*P (the four-corner lookups of ComputeCovariance and the first half of GuidedFilter, :59-86): a and b are
+//                never written, only their row sums
+enum RowMode { ROWS_PLANE = 0, ROWS_I_II = 1, ROWS_P_IP = 2, ROWS_A_B = 3 };
+struct RowArgs {
+    Vol<float> p;
+    Img<float> g, meanI, varI;
+    Planes ii;            // ROWS_A_B: integral images of P (plane z) and I*P (plane S + z)
+    Planes dst;
+    int w, h, nz, z0, S, rad;
+    float eps;
+};
+
+constexpr int SCAN_ROW_WARPS = 8, SCAN_ROW_LEVELS = 6;    // 256 << 6 = 16384 elements per row at most
+
+template <bool IEEE, int MODE>
+__global__ void __launch_bounds__(SCAN_ROW_WARPS * 32, 4)
+scan_rows_kernel(RowArgs a) {
+    constexpr int NV = MODE == ROWS_PLANE ? 1 : 2;
     const int lane = threadIdx.x & 31;
     const long long rid = (long long)blockIdx.x * SCAN_ROW_WARPS + (threadIdx.x >> 5);
-    if (rid >= (long long)h * nz) return;
-    const int y = (int)(rid % h), z = (int)(rid / h);
-    const float *p0 = nullptr, *p1 = nullptr;    // value = p1 ? op(p0, p1) : p0
-    if (src.mode == SRC_PLANES) p0 = src.p.row(y, src.z0 + z);
-    else if (src.mode == SRC_P_AND_IP) { p0 = src.p.row(y, src.z0 + (z < src.S ? z : z - src.S)); if (z >= src.S) p1 = src.g.row(y); }
-    else { p0 = src.g.row(y); if (z) p1 = p0; }
-    const bool square = src.mode == SRC_I_AND_II;
-    float* drow = dst.row(y, z);
-    float st[SCAN_ROW_LEVELS];
+    if (rid >= (long long)a.h * a.nz) return;
+    const int y = (int)(rid % a.h), z = (int)(rid / a.h), w = a.w;
+    const float* prow = MODE == ROWS_I_II ? a.g.row(y) : (MODE == ROWS_A_B ? nullptr : a.p.row(y, a.z0 + z));
+    const float* grow = a.g.row(y);
+    const int miny = max(0, y - a.rad), maxy = min(a.h - 1, y + a.rad);
+    float st[NV][SCAN_ROW_LEVELS];
 #pragma unroll
-    for (int b = 0; b < SCAN_ROW_LEVELS; ++b) st[b] = 0.0f;
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int b = 0; b < SCAN_ROW_LEVELS; ++b) st[k][b] = 0.0f;
     const int nseg = (w + 255) >> 8;
     for (int seg = 0; seg < nseg; ++seg) {
         const int x0 = (seg << 8) + lane * 8;
-        float v[8];
+        float v[NV][8];
+        if (MODE == ROWS_A_B) {
+            // lookups with the lanes on consecutive pixels (coalesced corners), then through shared memory to 8 per lane
+            __shared__ __align__(16) float sh[SCAN_ROW_WARPS][2][256];
+            float(*mine)[256] = sh[threadIdx.x >> 5];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float e = 0.0f;
-            if (x0 + j < w) {
-                e = p0[x0 + j];
-                // ElementwiseSquare(II, I) / ElementwiseMultiply(IP, I, P) with scalar 1, offset 0 (cu_integral_image.h:49,63)
-                if (p1) e = square ? ew_square<IEEE>(e, 1.0f, 0.0f) : ew_multiply<IEEE>(p1[x0 + j], e, 1.0f, 0.0f);
+            for (int j = 0; j < 8; ++j) {
+                const int x = (seg << 8) + j * 32 + lane;
+                float e0 = 0.0f, e1 = 0.0f;
+                if (x < w) {
+                    const int minx = max(0, x - a.rad), maxx = min(w - 1, x + a.rad);
+                    BoxWin b;
+                    b.o_a = (int)(miny * a.ii.pitch) + minx; b.o_b = (int)(miny * a.ii.pitch) + maxx;
+                    b.o_c = (int)(maxy * a.ii.pitch) + maxx; b.o_d = (int)(maxy * a.ii.pitch) + minx;
+                    b.area = (float)((maxx - minx) * (maxy - miny));
+                    const float rcp_area = IEEE ? 0.0f : rcp_approx_ftz(b.area);
+                    const float* ii0 = a.ii.ptr + (size_t)z * a.ii.plane;
+                    const float mP = box_mean<IEEE>(ii0, b, rcp_area), mIP = box_mean<IEEE>(ii0 + (size_t)a.S * a.ii.plane, b, rcp_area);
+                    const float mI = a.meanI(x, y);
+                    const float cov = ew_multiply_add<IEEE>(mI, mP, mIP, -1.0f, 1.0f, 0.0f);
+                    e0 = ew_division<IEEE>(cov, a.varI(x, y), 0.0f, a.eps, 1.0f, 0.0f);          // Eqn. 5
+                    e1 = ew_multiply_add<IEEE>(e0, mI, mP, -1.0f, 1.0f, 0.0f);                   // Eqn. 6
+                }
+                mine[0][j * 32 + lane] = e0;
+                mine[1][j * 32 + lane] = e1;
             }
-            v[j] = e;
-        }
-        float t1[4], t2[2], sib[5];
-        float cur = tree8_sum<IEEE>(v, t1, t2);
+            __syncwarp();
 #pragma unroll
-        for (int b = 0; b < 5; ++b) {
-            sib[b] = __shfl_xor_sync(0xffffffffu, cur, 1 << b);
-            cur = gadd<IEEE>(cur, sib[b]);      // a+b == b+a bit for bit: both lanes of a pair hold the same block sum
-        }
-        float base = stack_prefix<IEEE, SCAN_ROW_LEVELS>(st, (unsigned)seg);
+            for (int k = 0; k < 2; ++k) {
+                const float4 lo = *reinterpret_cast<const float4*>(&mine[k][lane * 8]), hi = *reinterpret_cast<const float4*>(&mine[k][lane * 8 + 4]);
+                v[k ? NV - 1 : 0][0] = lo.x; v[k ? NV - 1 : 0][1] = lo.y; v[k ? NV - 1 : 0][2] = lo.z; v[k ? NV - 1 : 0][3] = lo.w;
+                v[k ? NV - 1 : 0][4] = hi.x; v[k ? NV - 1 : 0][5] = hi.y; v[k ? NV - 1 : 0][6] = hi.z; v[k ? NV - 1 : 0][7] = hi.w;
+            }
+            __syncwarp();
+        } else {
 #pragma unroll
-        for (int b = 4; b >= 0; --b)
-            if ((lane >> b) & 1) base = gadd<IEEE>(base, sib[b]);
-        float o[8];
-        tree8_prefix<IEEE>(base, v, t1, t2, o);
-        if (x0 < (int)dst.pitch) {             // rows are padded to 8: whole vectors, the tail past w is never read
-            *reinterpret_cast<float4*>(drow + x0) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(drow + x0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            for (int j = 0; j < 8; ++j) {
+                const int x = x0 + j;
+                float e0 = 0.0f, e1 = 0.0f;
+                if (x < w) {
+                    e0 = prow[x];
+                    // ElementwiseSquare(II, I) / ElementwiseMultiply(IP, I, P) with scalar 1, offset 0
+                    if (MODE == ROWS_I_II) e1 = ew_square<IEEE>(e0, 1.0f, 0.0f);
+                    if (MODE == ROWS_P_IP) e1 = ew_multiply<IEEE>(grow[x], e0, 1.0f, 0.0f);
+                }
+                v[0][j] = e0;
+                if (NV == 2) v[NV - 1][j] = e1;
+            }
         }
-        stack_push<IEEE, SCAN_ROW_LEVELS>(st, (unsigned)seg, cur);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float t1[4], t2[2], sib[5];
+            float cur = tree8_sum<IEEE>(v[k], t1, t2);
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                sib[b] = __shfl_xor_sync(0xffffffffu, cur, 1 << b);
+                cur = gadd<IEEE>(cur, sib[b]);      // a+b == b+a bit for bit: both lanes of a pair hold the same block sum
+            }
+            float base = stack_prefix<IEEE, SCAN_ROW_LEVELS>(st[k], (unsigned)seg);
+#pragma unroll
+            for (int b = 4; b >= 0; --b)
+                if ((lane >> b) & 1) base = gadd<IEEE>(base, sib[b]);
+            float o[8];
+            tree8_prefix<IEEE>(base, v[k], t1, t2, o);
+            if (x0 < (int)a.dst.pitch) {           // rows are padded to 8: whole vectors, the tail past w is never read
+                float* drow = a.dst.row(y, k ? a.S + z : z);
+                *reinterpret_cast<float4*>(drow + x0) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(drow + x0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            stack_push<IEEE, SCAN_ROW_LEVELS>(st[k], (unsigned)seg, cur);
+        }
     }
 }
 
@@ -219,64 +291,50 @@ scan_cols_kernel(Planes io, int w, int h) {
     }
 }
 
-// ---- pass 3: four-corner lookup + the algebra that follows it ----------------------------------------------------------
-// cu_integral_image.cu:130-157.  SASS: I2FP area; MUFU.RCP; FADD.FTZ (C + A); FADD.FTZ -B; FADD.FTZ -D; FMUL.FTZ sum * rcp.
-// The sums are exclusive, so the window is [minx, maxx) x [miny, maxy) and area = (maxx - minx) * (maxy - miny).
-struct BoxWin { int o_a, o_b, o_c, o_d; float area; };   // element offsets inside a plane
-__device__ __forceinline__ BoxWin box_window(int x, int y, int w, int h, int rad, size_t pitch) {
-    const int minx = max(0, x - rad), maxx = min(w - 1, x + rad), miny = max(0, y - rad), maxy = min(h - 1, y + rad);
-    BoxWin b;
-    b.o_a = (int)(miny * pitch) + minx;
-    b.o_b = (int)(miny * pitch) + maxx;
-    b.o_c = (int)(maxy * pitch) + maxx;
-    b.o_d = (int)(maxy * pitch) + minx;
-    b.area = (float)((maxx - minx) * (maxy - miny));
-    return b;
-}
-template <bool IEEE>
-__device__ __forceinline__ float box_mean(const float* __restrict__ ii, const BoxWin& b, float rcp_area) {
-    const float sum = gadd<IEEE>(gadd<IEEE>(gadd<IEEE>(ii[b.o_c], ii[b.o_a]), -ii[b.o_b]), -ii[b.o_d]);
-    return IEEE ? __fdiv_rn(sum, b.area) : fmul_ftz(sum, rcp_area);
-}
-
-enum BoxEpi { BEPI_MEAN = 0, BEPI_MEANVAR = 1, BEPI_AB = 2, BEPI_Q = 3 };
+enum BoxEpi { BEPI_MEAN = 0, BEPI_MEANVAR = 1, BEPI_Q = 2 };
 struct BoxEpiArgs {
     Planes ii;            // integral images of this pass
-    Planes ab;            // BEPI_AB: destination planes (a: z, b: S + z)
     Vol<float> vol;       // BEPI_MEAN: destination planes from z0; BEPI_Q: the cost volume (slice z0 + z)
     Img<float> guide, meanI, varI;
     int w, h, rad, z0, S;
     float eps;
 };
 
+constexpr int BEPI_ZPT = 4;   // slices per thread: one window, 8 (16) independent corner loads per slice in flight
+
 template <int EPI, bool IEEE>
 __global__ void __launch_bounds__(128)
-box_epilogue_kernel(BoxEpiArgs a) {
-    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+box_epilogue_kernel(BoxEpiArgs a, int nz) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
     if (x >= a.w) return;
     const BoxWin b = box_window(x, y, a.w, a.h, a.rad, a.ii.pitch);
     const float rcp_area = IEEE ? 0.0f : rcp_approx_ftz(b.area);
-    const float* ii0 = a.ii.ptr + (size_t)z * a.ii.plane;
-    if (EPI == BEPI_MEAN) {
-        a.vol(x, y, a.z0 + z) = box_mean<IEEE>(ii0, b, rcp_area);
-    } else if (EPI == BEPI_MEANVAR) {
+    if (EPI == BEPI_MEANVAR) {
         // ComputeMeanVarience (cu_integral_image.h:42-54): var_I = mean_II - mean_I * mean_I
-        const float mI = box_mean<IEEE>(ii0, b, rcp_area), mII = box_mean<IEEE>(ii0 + a.ii.plane, b, rcp_area);
+        const float mI = box_mean<IEEE>(a.ii.ptr, b, rcp_area), mII = box_mean<IEEE>(a.ii.ptr + a.ii.plane, b, rcp_area);
         a.meanI(x, y) = mI;
         a.varI(x, y) = ew_multiply_add<IEEE>(mI, mI, mII, -1.0f, 1.0f, 0.0f);
-    } else if (EPI == BEPI_AB) {
-        // ComputeCovariance (:56-68) and the first half of GuidedFilter (:79-86)
-        const float mP = box_mean<IEEE>(ii0, b, rcp_area), mIP = box_mean<IEEE>(ii0 + (size_t)a.S * a.ii.plane, b, rcp_area);
-        const float mI = a.meanI(x, y);
-        const float cov = ew_multiply_add<IEEE>(mI, mP, mIP, -1.0f, 1.0f, 0.0f);
-        const float ca = ew_division<IEEE>(cov, a.varI(x, y), 0.0f, a.eps, 1.0f, 0.0f);      // Eqn. 5
-        const float cb = ew_multiply_add<IEEE>(ca, mI, mP, -1.0f, 1.0f, 0.0f);               // Eqn. 6
-        a.ab.row(y, z)[x] = ca;
-        a.ab.row(y, a.S + z)[x] = cb;
-    } else {
-        // GuidedFilter (:88-92): q = mean_a * I + mean_b                                      Eqn. 8
-        const float ma = box_mean<IEEE>(ii0, b, rcp_area), mb = box_mean<IEEE>(ii0 + (size_t)a.S * a.ii.plane, b, rcp_area);
-        a.vol(x, y, a.z0 + z) = ew_multiply_add<IEEE>(ma, a.guide(x, y), mb, 1.0f, 1.0f, 0.0f);
+        return;
+    }
+    const float g = EPI == BEPI_Q ? a.guide(x, y) : 0.0f;
+    float q[BEPI_ZPT];
+#pragma unroll
+    for (int k = 0; k < BEPI_ZPT; ++k) {
+        const int z = blockIdx.z * BEPI_ZPT + k;
+        if (z < nz) {
+            const float* ii0 = a.ii.ptr + (size_t)z * a.ii.plane;
+            if (EPI == BEPI_MEAN) q[k] = box_mean<IEEE>(ii0, b, rcp_area);
+            else {
+                // GuidedFilter (:88-92): q = mean_a * I + mean_b                                  Eqn. 8
+                const float ma = box_mean<IEEE>(ii0, b, rcp_area), mb = box_mean<IEEE>(ii0 + (size_t)a.S * a.ii.plane, b, rcp_area);
+                q[k] = ew_multiply_add<IEEE>(ma, g, mb, 1.0f, 1.0f, 0.0f);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BEPI_ZPT; ++k) {
+        const int z = blockIdx.z * BEPI_ZPT + k;
+        if (z < nz) a.vol(x, y, a.z0 + z) = q[k];
     }
 }
 
@@ -317,17 +375,18 @@ struct AsyncBuf {
 
 static size_t plane_pitch(size_t w) { return (w + 7) / 8 * 8; }
 
-template <bool IEEE>
-static int scan_planes(const RowSrc& src, const Planes& pl, int w, int h, int nz, cudaStream_t st) {
-    scan_rows_kernel<IEEE><<<cdiv((long long)h * nz, SCAN_ROW_WARPS), SCAN_ROW_WARPS * 32, 0, st>>>(src, pl, w, h, nz);
-    scan_cols_kernel<IEEE><<<dim3(cdiv(w, 128), nz), 128, 0, st>>>(pl, w, h);
+// rows (pass 1), then columns in place (pass 2): `planes` integral images in a.dst
+template <bool IEEE, int MODE>
+static int scan_planes(const RowArgs& a, int planes, cudaStream_t st) {
+    scan_rows_kernel<IEEE, MODE><<<cdiv((long long)a.h * a.nz, SCAN_ROW_WARPS), SCAN_ROW_WARPS * 32, 0, st>>>(a);
+    scan_cols_kernel<IEEE><<<dim3(cdiv(a.w, 128), planes), 128, 0, st>>>(a.dst, a.w, a.h);
     count_launch(2);
     return launch_status();
 }
 
 template <int EPI, bool IEEE>
 static int box_epilogue(const BoxEpiArgs& a, int nz, cudaStream_t st) {
-    box_epilogue_kernel<EPI, IEEE><<<dim3(cdiv(a.w, 128), a.h, nz), 128, 0, st>>>(a);
+    box_epilogue_kernel<EPI, IEEE><<<dim3(cdiv(a.w, 128), a.h, cdiv(nz, BEPI_ZPT)), 128, 0, st>>>(a, nz);
     count_launch();
     return launch_status();
 }
@@ -340,12 +399,13 @@ static int box_filter_impl(const roo_image_t& out, const roo_image_t& in, int ra
     AsyncBuf buf(st);
     const size_t pitch = plane_pitch(w);
     if (buf.alloc(pitch * h * sizeof(float))) { cudaGetLastError(); return ROO_ERR_OUT_OF_MEMORY; }
-    const Planes pl{(float*)buf.p, pitch, pitch * h};
-    RowSrc src{SRC_PLANES, Vol<float>(as_volume(in)), Img<float>(in), 0, 1};
-    int rc = scan_planes<IEEE>(src, pl, w, h, 1, st);
+    RowArgs r{};
+    r.p = Vol<float>(as_volume(in)); r.g = Img<float>(in); r.dst = Planes{(float*)buf.p, pitch, pitch * h};
+    r.w = w; r.h = h; r.nz = 1; r.z0 = 0; r.S = 1; r.rad = rad;
+    int rc = scan_planes<IEEE, ROWS_PLANE>(r, 1, st);
     if (rc) return rc;
     BoxEpiArgs a{};
-    a.ii = pl; a.vol = Vol<float>(as_volume(out)); a.w = w; a.h = h; a.rad = rad; a.z0 = 0; a.S = 1;
+    a.ii = r.dst; a.vol = Vol<float>(as_volume(out)); a.w = w; a.h = h; a.rad = rad; a.z0 = 0; a.S = 1;
     return box_epilogue<BEPI_MEAN, IEEE>(a, 1, st);
 }
 
@@ -359,32 +419,32 @@ static int guided_filter_impl(const roo_volume_t& vol, const roo_image_t& guide,
     int S = (int)(GF_SCRATCH_BYTES / (4 * plane * sizeof(float)));
     S = S < 1 ? 1 : (S > nd ? nd : S);
     AsyncBuf buf(st);
-    // [2S planes: integral images | 2S planes: a, b and their integral images | meanI | varI]
+    // [2S planes: integral images of P, I*P | 2S planes: integral images of a, b | meanI | varI]
     if (buf.alloc((4 * (size_t)S + 2) * plane * sizeof(float))) { cudaGetLastError(); return ROO_ERR_OUT_OF_MEMORY; }
     float* base = (float*)buf.p;
     const Planes A{base, pitch, plane}, B{base + 2 * (size_t)S * plane, pitch, plane};
     const roo_image_t meanI{pitch * sizeof(float), base + 4 * (size_t)S * plane, (size_t)w, (size_t)h};
     const roo_image_t varI{pitch * sizeof(float), base + (4 * (size_t)S + 1) * plane, (size_t)w, (size_t)h};
 
+    RowArgs r{};
+    r.p = Vol<float>(vol); r.g = Img<float>(guide); r.meanI = Img<float>(meanI); r.varI = Img<float>(varI);
+    r.w = w; r.h = h; r.rad = rad; r.eps = eps;
     BoxEpiArgs a{};
     a.vol = Vol<float>(vol); a.guide = Img<float>(guide); a.meanI = Img<float>(meanI); a.varI = Img<float>(varI);
     a.w = w; a.h = h; a.rad = rad; a.eps = eps;
     int rc;
     // guide statistics: box(I), box(I*I) -> mean_I, var_I
-    RowSrc src{SRC_I_AND_II, Vol<float>(vol), Img<float>(guide), 0, 1};
-    if ((rc = scan_planes<IEEE>(src, A, w, h, 2, st))) return rc;
+    r.dst = A; r.nz = 1; r.z0 = 0; r.S = 1;
+    if ((rc = scan_planes<IEEE, ROWS_I_II>(r, 2, st))) return rc;
     a.ii = A; a.S = 1;
     if ((rc = box_epilogue<BEPI_MEANVAR, IEEE>(a, 1, st))) return rc;
     for (int z0 = 0; z0 < nd; z0 += S) {
         const int s = nd - z0 < S ? nd - z0 : S;
-        src = RowSrc{SRC_P_AND_IP, Vol<float>(vol), Img<float>(guide), z0, s};
-        if ((rc = scan_planes<IEEE>(src, A, w, h, 2 * s, st))) return rc;
-        a.ii = A; a.ab = B; a.z0 = z0; a.S = s;
-        if ((rc = box_epilogue<BEPI_AB, IEEE>(a, s, st))) return rc;
-        roo_volume_t bv{pitch * sizeof(float), B.ptr, (size_t)w, (size_t)h, plane * sizeof(float), (size_t)(2 * s)};
-        src = RowSrc{SRC_PLANES, Vol<float>(bv), Img<float>(guide), 0, 2 * s};
-        if ((rc = scan_planes<IEEE>(src, B, w, h, 2 * s, st))) return rc;     // in place: a row is read whole before it is written
-        a.ii = B;
+        r.dst = A; r.nz = s; r.z0 = z0; r.S = s;
+        if ((rc = scan_planes<IEEE, ROWS_P_IP>(r, 2 * s, st))) return rc;
+        r.ii = A; r.dst = B;
+        if ((rc = scan_planes<IEEE, ROWS_A_B>(r, 2 * s, st))) return rc;
+        a.ii = B; a.z0 = z0; a.S = s;
         if ((rc = box_epilogue<BEPI_Q, IEEE>(a, s, st))) return rc;
     }
     return ROO_OK;

@@ -70,7 +70,10 @@ enum roo_tuning_knob { ROO_TUNE_HSWEEP = 0,
                        ROO_TUNE_INSWEEP_COST = 1,
                        /* roo_split_engine: CTAs per SM of a sweep that crosses strips (0 = as many as fit; default 3).  A
                         * small number makes the grid run in waves, so a strip hands its first scanlines on early */
-                       ROO_TUNE_STRIP_CTAS_PER_SM = 2 };
+                       ROO_TUNE_STRIP_CTAS_PER_SM = 2,
+                       /* roo_guided_filter_volume: scratch budget in MiB (default 2048); the slices go through in chunks
+                        * of budget / (4 fp32 planes) -- a small value exercises the chunk loop on small volumes */
+                       ROO_TUNE_GUIDED_SCRATCH_MIB = 3 };
 int roo_set_tuning(int knob, int value);
 
 /* ---- granular operators: one per reference launcher -------------------------------------- */

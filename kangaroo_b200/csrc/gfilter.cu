@@ -409,14 +409,14 @@ static int box_filter_impl(const roo_image_t& out, const roo_image_t& in, int ra
     return box_epilogue<BEPI_MEAN, IEEE>(a, 1, st);
 }
 
-// Scratch budget of the volume filter: 4 planes per slice in flight.
-constexpr size_t GF_SCRATCH_BYTES = (size_t)2 << 30;
+// Scratch budget of the volume filter (MiB; ROO_TUNE_GUIDED_SCRATCH_MIB): 4 planes per slice in flight.
+std::atomic<int> g_guided_scratch_mib{2048};
 
 template <bool IEEE>
 static int guided_filter_impl(const roo_volume_t& vol, const roo_image_t& guide, int rad, float eps, int nd, cudaStream_t st) {
     const int w = (int)vol.w, h = (int)vol.h;
     const size_t pitch = plane_pitch(w), plane = pitch * h;
-    int S = (int)(GF_SCRATCH_BYTES / (4 * plane * sizeof(float)));
+    int S = (int)(((size_t)g_guided_scratch_mib.load() << 20) / (4 * plane * sizeof(float)));
     S = S < 1 ? 1 : (S > nd ? nd : S);
     AsyncBuf buf(st);
     // [2S planes: integral images of P, I*P | 2S planes: integral images of a, b | meanI | varI]

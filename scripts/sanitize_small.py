@@ -73,5 +73,14 @@ for strips in (2, 3):
     out = torch.empty((60, 150), dtype=torch.float32).pin_memory()
     se.run_host(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory(), out)
     se.close()
+rng = np.random.default_rng(3)
+for (w, h, D, rad) in ((70, 37, 3, 3), (300, 21, 2, 9), (13, 260, 2, 40)):
+    gv = roo.Volume.from_numpy(rng.random((D, h, w), dtype=np.float32))
+    gi = roo.Image.from_numpy(rng.random((h, w), dtype=np.float32))
+    roo.GuidedFilterVolume(gv, gi, rad, 1e-3, D)
+    bo = roo.Image(w, h, np.float32)
+    roo.BoxFilter(bo, gi, None, rad)
+    roo.ElementwiseMultiplyAdd(bo, gi, gi, bo, -1.0)
+    roo.ElementwiseDivision(bo, gi, bo, 0.0, 1e-3)
 torch.cuda.synchronize()
 print("done")

@@ -492,4 +492,14 @@ def test_guided_filter_volume_chunks_and_camera_size():
     roo.set_ieee_division(True)
     v = roo.Volume.from_numpy(vol)
     roo.GuidedFilterVolume(v, _img(guide), 9, 1e-3, D)
-    assert same_float(v.numpy(), ko.guided_filter_volume(vol, guide, 9, np.float32(1e-3)))
+    want = ko.guided_filter_volume(vol, guide, 9, np.float32(1e-3))
+    assert same_float(v.numpy(), want)
+    # a scratch budget of 24 MiB = chunks of 5 slices (4 planes of 1.23 MB per slice): 5 + 5 + 1 slices of the first 11
+    roo.set_tuning(roo.capi.TUNE_GUIDED_SCRATCH_MIB, 24)
+    try:
+        v = roo.Volume.from_numpy(vol)
+        roo.GuidedFilterVolume(v, _img(guide), 9, 1e-3, 11)
+        assert same_float(v.numpy()[:11], want[:11]) and same_bits(v.numpy()[11], vol[11])
+    finally:
+        roo.set_tuning(roo.capi.TUNE_GUIDED_SCRATCH_MIB, 2048)
+        roo.release_scratch()

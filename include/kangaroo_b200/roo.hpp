@@ -192,6 +192,16 @@ inline void BilateralFilterVolume(Volume<float> vOut, Volume<float> vIn, const I
     b200::done(roo_bilateral_filter_volume(&o, &i2, &g, b200::imgtype<Ti2>::v, gs, gr, gc, size, maxDisp, b200::stream_slot()),
                "BilateralFilterVolume");
 }
+// ---- cu_dense_stereo.h:24-28 (instantiated for <unsigned char, unsigned char> and <char, unsigned char>, cu_dense_stereo.cu:405-406)
+template <typename TDisp, typename TImg>
+inline void DenseStereo(Image<TDisp> dDisp, const Image<TImg> dCamLeft, const Image<TImg> dCamRight, TDisp maxDisp, float acceptThresh,
+                        int score_rad) {
+    static_assert(std::is_same<TImg, unsigned char>::value && (std::is_same<TDisp, unsigned char>::value || std::is_same<TDisp, char>::value),
+                  "DenseStereo<{unsigned char, char}, unsigned char>");
+    auto d = b200::c(dDisp), l = b200::c(dCamLeft), r = b200::c(dCamRight);
+    b200::done(roo_dense_stereo(&d, std::is_same<TDisp, char>::value ? 1 : 0, &l, &r, (int)maxDisp, acceptThresh, score_rad,
+                                b200::stream_slot()), "DenseStereo");
+}
 // ---- cu_operations.h:22-35, the float instantiations the guided filter is composed of
 template <typename Tout, typename Tin1, typename Tin2, typename Tup>
 inline void ElementwiseMultiply(Image<Tout> c, Image<Tin1> a, Image<Tin2> b, Tup scalar = 1, Tup offset = 0) {

@@ -196,6 +196,15 @@ int roo_bilateral_filter_joint(const roo_image_t* out_f32, const roo_image_t* in
 int roo_bilateral_filter_volume(const roo_volume_t* out_f32, const roo_volume_t* in_f32, const roo_image_t* img, int img_type,
                                 float gs, float gr, float gc, unsigned size, int maxDisp, void* stream);
 
+/* roo::DenseStereo<TDisp, unsigned char>(dDisp, dCamLeft, dCamRight, maxDisp, acceptThresh, score_rad) -- the direct block
+ * matcher (cu_dense_stereo.h:24-28; cu_dense_stereo.cu:209-253,376-406).  disp_signed: 0 = TDisp unsigned char, 1 = char
+ * (negative maxDisp searches the other way).  score_rad 0 = squared pixel difference, 1..7 = SANDPatchScore<float,rad>.
+ * Pixels within 2 rad + 1 of the border and rejected matches get 0.  maxDisp 255 (127 for char) hangs the reference (its
+ * candidate counter wraps) and returns ROO_ERR_UNSUPPORTED here; any width (the reference: w <= 1024).  Candidates that
+ * reach left of the image read the bytes preceding the row, as the reference's raw access does. */
+int roo_dense_stereo(const roo_image_t* disp_8, int disp_signed, const roo_image_t* left_u8, const roo_image_t* right_u8, int maxDisp,
+                     float acceptThresh, int score_rad, void* stream);
+
 /* ---- integral-image box filter and guided filter (gfilter.cu) ------------------------------ */
 
 /* roo::ElementwiseMultiply / Division / Square / MultiplyAdd for float images (cu_operations.h:22-35; cu_operations.cu:85-190):

@@ -75,6 +75,7 @@ SYMBOLS = {
     "roo_box_filter": (C.c_int, [_IMG, _IMG, C.c_int, _S]),
     "roo_guided_filter_volume": (C.c_int, [_VOL, _IMG, C.c_int, C.c_float, C.c_int, _S]),
     "roo_release_scratch": (C.c_int, []),
+    "roo_dense_stereo": (C.c_int, [_IMG, C.c_int, _IMG, _IMG, C.c_int, C.c_float, C.c_int, _S]),
     "roo_bilateral_filter_volume": (C.c_int, [_VOL, _VOL, _IMG, C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint, C.c_int, _S]),
     "roo_dense_stereo_subpixel_refine": (C.c_int, [_IMG, _IMG, _IMG, _IMG, _S]),
     "roo_left_right_check_f32": (C.c_int, [_IMG, _IMG, C.c_float, C.c_float, _S]),

@@ -258,6 +258,14 @@ def GuidedFilterVolume(vol: Volume, I: Image, rad: int, eps: float, maxDisp: int
     check(lib().roo_guided_filter_volume(C.byref(vol.c()), C.byref(I.c()), rad, eps, maxDisp, _stream(stream)), "GuidedFilterVolume")
 
 
+def DenseStereo(dDisp: Image, dCamLeft: Image, dCamRight: Image, maxDisp: int, acceptThresh: float, score_rad: int, stream=None) -> None:
+    """roo::DenseStereo<{unsigned char, char}, unsigned char> (cu_dense_stereo.h:24-28): TDisp follows dDisp's dtype."""
+    if dDisp.dtype not in (np.uint8, np.int8):
+        raise TypeError("DenseStereo: disparity image must be uint8 or int8")
+    check(lib().roo_dense_stereo(C.byref(dDisp.c()), 1 if dDisp.dtype == np.int8 else 0, C.byref(dCamLeft.c()), C.byref(dCamRight.c()),
+                                 int(maxDisp), acceptThresh, int(score_rad), _stream(stream)), "DenseStereo")
+
+
 def release_scratch() -> None:
     """Return the scratch the box / guided filters keep between calls to the driver (current device)."""
     check(lib().roo_release_scratch(), "release_scratch")

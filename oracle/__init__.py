@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         L.ko_filter_disp_grad.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_float]
         L.ko_bilateral_filter_joint.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
         L.ko_left_right_check_i8.argtypes = [P(KoImage), P(KoImage), C.c_int, C.c_int]
+        L.ko_dense_stereo.argtypes = [P(KoImage), P(KoImage), P(KoImage), C.c_int, C.c_int, C.c_float, C.c_int]
         L.ko_elementwise.argtypes = [C.c_int] + [P(KoImage)] * 4 + [C.c_float] * 4
         L.ko_box_filter.argtypes = [P(KoImage), P(KoImage), C.c_int]
         L.ko_guided_filter_volume.argtypes = [P(KoVolume), P(KoImage), C.c_int, C.c_float, C.c_int]
@@ -225,6 +226,14 @@ def bilateral_filter_joint(img_in: np.ndarray, guide: np.ndarray, gs: float, gr:
     out = np.zeros_like(img_in)
     lib().ko_bilateral_filter_joint(C.byref(_img(out)), C.byref(_img(img_in)), C.byref(_img(guide)),
                                     IMG_U8 if guide.dtype == np.uint8 else IMG_F32, gs, gr, gc, size)
+    return out
+
+
+def dense_stereo(left: np.ndarray, right: np.ndarray, max_disp: int, accept_thresh: float, score_rad: int, signed: bool = False) -> np.ndarray:
+    """roo::DenseStereo<{unsigned char, char}, unsigned char> on tightly packed (h, w) uint8 images."""
+    left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+    out = np.zeros(left.shape, np.int8 if signed else np.uint8)
+    lib().ko_dense_stereo(C.byref(_img(out)), C.byref(_img(left)), C.byref(_img(right)), 1 if signed else 0, max_disp, accept_thresh, score_rad)
     return out
 
 

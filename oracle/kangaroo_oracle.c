@@ -582,6 +582,69 @@ void ko_guided_filter_volume(const ko_volume* vol, const ko_image* guide, int ra
     free(buf);
 }
 
+/* ---------------------------------------------------------------- direct block matcher ---- */
+
+/* patch_score.h:81-100 (rad 0: squared difference of the two pixels) and :257-298 (SANDPatchScore<float,rad,ImgAccessRaw>):
+ * raw access -- a column index left of the image addresses the bytes that precede the row, as img(x,y) = row(y)[x] does. */
+static float dense_score(const ko_image* i1, int x1, int y1, const ko_image* i2, int x2, int y2, int rad) {
+    if (rad == 0) {
+        const float diff = (float)((int)*(const uint8_t*)(img_at(i1, 0, (size_t)y1, 1) + x1) - (int)*(const uint8_t*)(img_at(i2, 0, (size_t)y2, 1) + x2));
+        return diff * diff;
+    }
+    const int area = (2 * rad + 1) * (2 * rad + 1);
+    float sum1 = 0.0f, sum2 = 0.0f, sad = 0.0f;
+    for (int r = -rad; r <= rad; ++r)
+        for (int c = -rad; c <= rad; ++c) {
+            sum1 += (float)*(const uint8_t*)(img_at(i1, 0, (size_t)(y1 + r), 1) + (x1 + c));
+            sum2 += (float)*(const uint8_t*)(img_at(i2, 0, (size_t)(y2 + r), 1) + (x2 + c));
+        }
+    const float mean1 = sum1 / (float)area, mean2 = sum2 / (float)area;
+    for (int r = -rad; r <= rad; ++r)
+        for (int c = -rad; c <= rad; ++c) {
+            const float a = (float)*(const uint8_t*)(img_at(i1, 0, (size_t)(y1 + r), 1) + (x1 + c));
+            const float b = (float)*(const uint8_t*)(img_at(i2, 0, (size_t)(y2 + r), 1) + (x2 + c));
+            sad += fabsf((a - mean1) - (b - mean2));
+        }
+    return sad;
+}
+
+/* src/cu_dense_stereo.cu:209-253 (KernDenseStereo<TD, unsigned char, Score>, dispStep 1), TD = unsigned char (is_signed 0) or
+ * char.  Border of Score::width = 2 rad + 1 pixels and every rejected pixel get InvalidValue<TD> = 0.  Candidates run from
+ * max(min(maxDisp,0), -((w - width) - x)) to min(max(0,maxDisp), x + width); best and second best by strict / non-strict
+ * comparison in candidate order; a best whose runner-up is more than one disparity away is dropped when
+ * (second - best) / best < acceptThresh. */
+void ko_dense_stereo(const ko_image* disp, const ko_image* left, const ko_image* right, int is_signed, int maxDispVal, float acceptThresh,
+                     int score_rad) {
+    (void)is_signed;   /* both instantiations store the same low byte; unsigned maxDisp is never negative */
+    const int w = (int)left->w, h = (int)left->h, width = 2 * score_rad + 1;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int bestDisp = 0;
+            if (width <= x && x < w - width && width <= y && y < h - width) {
+                float bestScore = 1e36f, sndBestScore = 1e37f;
+                int sndBestDisp = 0;
+                int minDisp = maxDispVal < 0 ? maxDispVal : 0, maxDisp = maxDispVal > 0 ? maxDispVal : 0;
+                if (minDisp < -((w - width) - x)) minDisp = -((w - width) - x);
+                if (maxDisp > x + width) maxDisp = x + width;
+                for (int c = minDisp; c <= maxDisp; ++c) {
+                    const float score = dense_score(left, x, y, right, x - c, y, score_rad);
+                    if (score < bestScore) {
+                        sndBestDisp = bestDisp; sndBestScore = bestScore;
+                        bestDisp = c; bestScore = score;
+                    } else if (score <= sndBestScore) {
+                        sndBestDisp = c; sndBestScore = score;
+                    }
+                }
+                if (abs(bestDisp - sndBestDisp) > 1) {
+                    const float cd = (sndBestScore - bestScore) / bestScore;
+                    if (cd < acceptThresh) bestDisp = 0;
+                }
+            }
+            *(int8_t*)img_at(disp, (size_t)x, (size_t)y, 1) = (int8_t)bestDisp;
+        }
+}
+
 /* ---------------------------------------------------------------- subpixel refine ---- */
 
 /* patch_score.h:257-298, SANDPatchScore<float,2,ImgAccessRaw> on unsigned char images */

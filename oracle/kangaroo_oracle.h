@@ -149,6 +149,9 @@ void ko_elementwise(int op, const ko_image* out_f32, const ko_image* a, const ko
 void ko_box_filter(const ko_image* out_f32, const ko_image* in_f32, int rad);
 /* applications/stereo2/main.cpp:392-405 (cu_integral_image.h:42-93): guided filtering of the first maxDisp slices, in place */
 void ko_guided_filter_volume(const ko_volume* vol_f32, const ko_image* guide_f32, int rad, float eps, int maxDisp);
+/* src/cu_dense_stereo.cu:209-253,376-406: DenseStereo<{unsigned char, char}, unsigned char>, score_rad 0..7 */
+void ko_dense_stereo(const ko_image* disp_8, const ko_image* left_u8, const ko_image* right_u8, int is_signed, int maxDisp,
+                     float acceptThresh, int score_rad);
 void ko_left_right_check_f32(const ko_image* dispL, const ko_image* dispR, float sd, float maxDiff);
 void ko_left_right_check_i8(const ko_image* dispL, const ko_image* dispR, int sd, int maxDiff);
 

@@ -365,3 +365,17 @@ def elementwise(op: int, a: np.ndarray, b: np.ndarray | None, c: np.ndarray | No
     lib().kref_elementwise.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_size_t] * 2 + [C.c_float] * 4
     _ck(lib().kref_elementwise(op, out.data_ptr(), da.data_ptr(), db.data_ptr(), dc.data_ptr(), w, h, s0, s1, s2, s3), "Elementwise")
     return _back(out, np.float32, (h, w))
+
+
+def dense_stereo(left: np.ndarray, right: np.ndarray, max_disp: int, accept_thresh: float, score_rad: int, signed: bool = False) -> np.ndarray:
+    """roo::DenseStereo<{unsigned char, char}, unsigned char> (cu_dense_stereo.cu:209-253,376-406) on dense (h, w) uint8 images.
+    Candidates left of the image read the bytes that precede the row (raw access): the previous row's tail in these tightly
+    packed buffers -- inside the allocation, since the kernel only scores rows y >= 2 rad + 1."""
+    import torch
+    h, w = left.shape
+    dl, dr = _dev(np.ascontiguousarray(left, np.uint8)), _dev(np.ascontiguousarray(right, np.uint8))
+    out = torch.zeros(h * w, dtype=torch.uint8, device="cuda")
+    lib().kref_dense_stereo.argtypes = [C.c_void_p] * 3 + [C.c_size_t] * 2 + [C.c_int, C.c_int, C.c_float, C.c_int]
+    _ck(lib().kref_dense_stereo(out.data_ptr(), dl.data_ptr(), dr.data_ptr(), w, h, 1 if signed else 0, max_disp, accept_thresh, score_rad),
+        "DenseStereo")
+    return _back(out, np.int8 if signed else np.uint8, (h, w))

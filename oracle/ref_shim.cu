@@ -331,6 +331,23 @@ int kref_elementwise(int op, void* out, void* a, void* b, void* c, size_t w, siz
     return finish();
 }
 
+// cu_dense_stereo.cu:209-253,376-406: the direct block matcher.  disp_type 0 = unsigned char, 1 = char disparities; dense
+// w x h images.  One block of w threads per row: w <= 1024.  maxDisp == 255 (127 for char) never terminates in the
+// reference (the candidate counter wraps before it exceeds the bound) and is refused here.
+int kref_dense_stereo(void* disp, void* l, void* r, size_t w, size_t h, int disp_type, int maxDisp, float acceptThresh, int score_rad) {
+    if (w > 1024 || score_rad < 0 || score_rad > 7) return -2;
+    if (disp_type == 0) {
+        if (maxDisp < 0 || maxDisp >= 255) return -2;
+        roo::DenseStereo<unsigned char, unsigned char>(img<unsigned char>(disp, w, w, h), img<unsigned char>(l, w, w, h), img<unsigned char>(r, w, w, h),
+                                                       (unsigned char)maxDisp, acceptThresh, score_rad);
+    } else {
+        if (maxDisp <= -128 || maxDisp >= 127) return -2;
+        roo::DenseStereo<char, unsigned char>(img<char>(disp, w, w, h), img<unsigned char>(l, w, w, h), img<unsigned char>(r, w, w, h), (char)maxDisp,
+                                              acceptThresh, score_rad);
+    }
+    return finish();
+}
+
 int kref_create_matlab_lookup_table(void* lookup, size_t pitch, size_t w, size_t h, float fu, float fv, float u0, float v0,
                                     float k1, float k2) {
     roo::CreateMatlabLookupTable(img<float2>(lookup, pitch, w, h), fu, fv, u0, v0, k1, k2);

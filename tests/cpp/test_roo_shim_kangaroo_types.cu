@@ -82,6 +82,8 @@ int main() {
         roo::GuidedFilterVolume(vol[1], I, rad, eps, maxdisp);
         roo::BoxFilter<float, float, float>(temp[0], img[1], Scratch, 5);                           // :377 (commented out there)
     }
+    roo::DenseStereo<unsigned char, unsigned char>(disp_c, upload, upload, (unsigned char)maxdisp, 0.05f, 2);   // cu_dense_stereo.cu:405
+    roo::DenseStereo<char, unsigned char>(dispi8, upload, upload, (char)-40, 0.05f, 0);                          // :406
     roo::LeftRightCheck(dispi8, dispi8r, -1, 0);
     const cudaError_t err = cudaDeviceSynchronize();
     std::printf("%s\n", err == cudaSuccess ? "OK" : cudaGetErrorString(err));

@@ -503,3 +503,49 @@ def test_guided_filter_volume_chunks_and_camera_size():
     finally:
         roo.set_tuning(roo.capi.TUNE_GUIDED_SCRATCH_MIB, 2048)
         roo.release_scratch()
+
+
+# ---------------------------------------------------------------- direct block matcher (cu_dense_stereo.h:24-28)
+
+def _dense(a, b, md, th, rad, signed):
+    h, w = a.shape
+    d = roo.Image(w, h, np.int8 if signed else np.uint8)
+    # tightly packed, like the golden's and the oracle's arrays: what lies left of a row is the previous row's tail
+    roo.DenseStereo(d, roo.Image.from_numpy(a, pitch=w), roo.Image.from_numpy(b, pitch=w), md, th, rad)
+    return d.numpy()
+
+
+def test_dense_stereo_vs_reference_and_oracle(golden):
+    """DenseStereo<{unsigned char, char}, unsigned char> for every score radius, both search directions and several acceptance
+    thresholds: bit-identical to the reference kernel (default mode, tightly packed images like the golden's -- candidates left
+    of the image read the previous row's tail, as the reference's raw access does) and to the oracle in IEEE mode."""
+    g = golden("dense")
+    L, R = g["left"], g["right"]
+    names = [k[4:] for k in g.files if k.startswith("out_")]
+    assert len(names) == 13
+    for nm in names:
+        md, th, rad, signed, swap = g[f"par_{nm}"]
+        a, b = (R, L) if swap else (L, R)
+        got = _dense(a, b, int(md), float(th), int(rad), bool(signed))
+        assert got.dtype == g[f"out_{nm}"].dtype and np.array_equal(got, g[f"out_{nm}"]), nm
+    roo.set_ieee_division(True)
+    for nm in names:
+        md, th, rad, signed, swap = g[f"par_{nm}"]
+        a, b = (R, L) if swap else (L, R)
+        assert np.array_equal(_dense(a, b, int(md), float(th), int(rad), bool(signed)),
+                              ko.dense_stereo(a, b, int(md), np.float32(th), int(rad), bool(signed))), nm
+
+
+def test_dense_stereo_wide_image_and_argument_checks():
+    """1500 pixels wide (the reference's one-block-per-row launch stops at 1024), several CTAs per row, maximum search range;
+    maxDisp values at which the reference never terminates are refused."""
+    from kangaroo_b200.synth import stereo_pair
+    L, R, _ = stereo_pair(1500, 40, 200, config=5)
+    roo.set_ieee_division(True)
+    assert np.array_equal(_dense(L, R, 254, 0.05, 2, False), ko.dense_stereo(L, R, 254, np.float32(0.05), 2, False))
+    assert np.array_equal(_dense(R, L, -128, 0.05, 1, True), ko.dense_stereo(R, L, -128, np.float32(0.05), 1, True))
+    for md, signed in ((255, False), (127, True), (-1, False)):
+        with pytest.raises(roo.capi.RooError):
+            _dense(L, R, md, 0.05, 2, signed)
+    with pytest.raises(roo.capi.RooError):
+        _dense(L, R, 40, 0.05, 8, False)

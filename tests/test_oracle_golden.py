@@ -483,3 +483,21 @@ def test_guided_filter_oracle_vs_reference_golden(golden):
         r = g[f"gf_out_{nm}"]
         assert np.isfinite(o).all() and np.isfinite(r).all()
         assert np.abs(o - r).max() <= tol, (nm, float(np.abs(o - r).max()))
+
+
+def test_dense_stereo_oracle_vs_reference_golden(golden):
+    """KernDenseStereo restated (cu_dense_stereo.cu:209-253) against the reference kernel for all eight score radii, both
+    search directions: identical except where the reference's approximate divisions (patch mean, acceptance ratio) flip a
+    comparison -- at most 6 of 12800 pixels per case, none for most."""
+    g = golden("dense")
+    L, R = g["left"], g["right"]
+    worst = 0
+    for k in g.files:
+        if not k.startswith("out_"):
+            continue
+        md, th, rad, signed, swap = g["par_" + k[4:]]
+        a, b = (R, L) if swap else (L, R)
+        o = ko.dense_stereo(a, b, int(md), np.float32(th), int(rad), bool(signed))
+        assert o.dtype == g[k].dtype
+        worst = max(worst, int((o != g[k]).sum()))
+    assert worst <= 6

@@ -164,10 +164,10 @@ int roo_costvol_from_stereo_truncated_abs_and_grad(const roo_volume_t* vol_f32, 
                                                    void* stream);
 
 /* roo::MedianFilterRejectNegative5x5 / 7x7 / 9x9 (cu_median.h:19-32; cu_median.cu:160-350), size in {5,7,9}: NaN unless
- * fewer than maxbad (and not all) samples of the clamp-to-edge window are non-finite, else the median of the valid
- * samples.  Bit-identical to the reference for windows without invalid samples; with invalid samples the reference
- * returns a comparator-order-dependent near-median, this returns the true median of the valid
- * ones.  `out` may alias `in` (both reference applications call it in place, where the reference itself races):
+ * fewer than maxbad (and not all) samples of the clamp-to-edge window are non-finite, else element (size^2 + bad)/2 of the
+ * window after the reference's exchange network: the exact median for windows without invalid samples, and with them the
+ * same comparator-order-dependent near-median the reference returns -- bit-identical to the reference
+ * kernels for every input.  `out` may alias `in` (both reference applications call it in place, where the reference itself races):
  * an overlapping call filters into a stream-ordered temporary and copies back, i.e. gives the out-of-place result. */
 int roo_median_filter_reject_negative(const roo_image_t* out_f32, const roo_image_t* in_f32, int size, int maxbad,
                                       void* stream);

@@ -1,19 +1,23 @@
 // MedianFilterRejectNegative{5x5,7x7,9x9} (src/cu_median.cu:160-350) -- the step between winner-takes-all and the
 // left-right check in both applications (stereo2/main.cpp:438-444).  SURVEY.md section 8f, N1.
 //
-// Semantics (out of place): window = clamp-to-edge neighbourhood, bad = number of non-finite samples, output NaN
-// unless bad < maxbad && bad < size^2, else the median of the valid samples: sorted valid samples, element
-// (size^2 + bad)/2 - bad.  For windows without invalid samples this is bit-identical to the reference (its exchange
-// network then returns the exact median); with invalid samples the reference's result depends on its comparator
-// order (fminf/fmaxf overwrite NaNs with copies of their partners) and is NOT reproduced -- see oracle header and
-// tests/golden/median.npz.  Calling it in place (as the applications do) races in the reference; here in == out is
-// refused.
+// Semantics = the reference's, for every input: window = clamp-to-edge neighbourhood gathered column-major
+// (v[(dX + r) * size + (dY + r)]), bad = number of non-finite samples, output NaN unless bad < maxbad && bad < size^2,
+// else v[(size^2 + bad)/2] after the reference's exchange network s2(a,b): a = min(a,b), b = max(a_old,b) has run over the
+// raw samples.  min/max ignore a NaN operand, so an invalid sample is overwritten by a copy of its partner: for windows
+// without invalid samples the result is the exact median, with them it is the sample the partially sorted array holds at
+// that index -- which depends on the comparator sequence.  That sequence is not transcribed but GENERATED at compile
+// time: it is the bitonic sorting network for n = size^2 inputs (for every block size k = 2, 4, ..: a flip stage pairing
+// i with i ^ (k-1), then half-cleaners pairing i with i + j for j = k/4 .. 1), comparators that would reach past input
+// n-1 dropped, and every comparator that cannot influence outputs n/2 .. n-1 removed (the median index never lies below
+// n/2) -- 155 / 439 / 968 compare-exchanges for 25 / 49 / 81, the reference's sequence comparator for comparator
+// (tests/test_oracle_golden.py checks that against the reference file when it is present; tests/golden/median.npz pins the
+// outputs, windows with invalid samples included).  Calling the filter in place (as the applications do) races in the
+// reference; here an overlapping call goes through a temporary.
 //
 // Kernel: a 32x8 tile (+ apron) staged in shared memory with clamp-to-edge; every thread keeps its size^2 samples in
-// registers as order-preserving integer keys (invalid samples = the largest key) and sorts them with Batcher's
-// odd-even merge sort, generated at compile time for exactly size^2 inputs (140 / 394 / 864 compare-exchanges of two
-// integer min/max instructions each) -- a network of this file's own making, exact for any input; the wanted rank
-// (size^2 + bad)/2 - bad is then picked with a select chain.
+// registers -- every register index of the network is a template constant -- and exchanges with min.ftz / max.ftz (the
+// reference build's FMNMX.FTZ); the wanted index (size^2 + bad)/2 is then picked with a select chain.
 #include <utility>
 
 #include "common.cuh"
@@ -23,40 +27,55 @@ namespace roo_b200 {
 
 constexpr int MED_TX = 32, MED_TY = 8;
 
-__device__ __forceinline__ unsigned float_key(float f) {   // monotonic: a < b  <=>  key(a) < key(b)
-    const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_float(unsigned k) {
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-// Batcher's odd-even merge sort for exactly K inputs, built at compile time: the comparators that would touch the
-// virtual +inf padding up to the next power of two are dropped (140 / 394 / 864 compare-exchanges for 25 / 49 / 81).
-template <int K> struct SortNet { int a[1024]; int b[1024]; int n; };
+// The reference's exchange network for exactly K inputs (see the header), built at compile time.
+template <int K> struct SortNet { unsigned char a[1024]; unsigned char b[1024]; int n; };
 template <int K> __host__ __device__ constexpr SortNet<K> make_sort_net() {
+    unsigned char ca[2048] = {}, cb[2048] = {};
+    bool keep[2048] = {};
+    int stage_end[64] = {};
+    int N = 1, total = 0, nstage = 0;
+    while (N < K) N <<= 1;
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int i = 0; i < N; ++i) {
+            const int l = i ^ (k - 1);
+            if (l > i && l < K) { ca[total] = (unsigned char)i; cb[total] = (unsigned char)l; ++total; }
+        }
+        stage_end[nstage++] = total;
+        for (int j = k >> 2; j >= 1; j >>= 1) {
+            for (int i = 0; i < N; ++i)
+                if (!(i & j) && i + j < K) { ca[total] = (unsigned char)i; cb[total] = (unsigned char)(i + j); ++total; }
+            stage_end[nstage++] = total;
+        }
+    }
+    bool need[128] = {};
+    for (int i = K / 2; i < K; ++i) need[i] = true;
+    for (int s = nstage - 1; s >= 0; --s) {             // dead-comparator elimination, last stage first
+        const int lo = s ? stage_end[s - 1] : 0, hi = stage_end[s];
+        for (int c = lo; c < hi; ++c) keep[c] = need[ca[c]] || need[cb[c]];
+        for (int c = lo; c < hi; ++c)
+            if (keep[c]) { need[ca[c]] = true; need[cb[c]] = true; }
+    }
     SortNet<K> r{};
     int n = 0;
-    for (int p = 1; p < K; p <<= 1)
-        for (int k = p; k >= 1; k >>= 1)
-            for (int j = k % p; j + k < K; j += 2 * k)
-                for (int i = 0; i < k; ++i)
-                    if (i + j + k < K && (i + j) / (2 * p) == (i + j + k) / (2 * p)) { r.a[n] = i + j; r.b[n] = i + j + k; ++n; }
+    for (int c = 0; c < total; ++c)
+        if (keep[c]) { r.a[n] = ca[c]; r.b[n] = cb[c]; ++n; }
     r.n = n;
     return r;
 }
 template <int K> struct SortNetOf { static constexpr SortNet<K> net = make_sort_net<K>(); };
+static_assert(SortNetOf<25>::net.n == 155 && SortNetOf<49>::net.n == 439 && SortNetOf<81>::net.n == 968, "comparator counts of cu_median.cu");
 
+// s2(a, b) of cu_median.cu:15-16 on FMNMX.FTZ: a NaN operand is ignored, -0 < +0
 template <int A, int B, int K>
-__device__ __forceinline__ void compare_exchange(unsigned (&key)[K]) {
-    const unsigned x = key[A], y = key[B];
-    key[A] = min(x, y);
-    key[B] = max(x, y);
+__device__ __forceinline__ void compare_exchange(float (&v)[K]) {
+    const float x = v[A], y = v[B];
+    asm("min.ftz.f32 %0, %1, %2;" : "=f"(v[A]) : "f"(x), "f"(y));
+    asm("max.ftz.f32 %0, %1, %2;" : "=f"(v[B]) : "f"(x), "f"(y));
 }
-// every register index is a template constant, so the keys never leave registers
+// every register index is a template constant, so the samples never leave registers
 template <int K, int... I>
-__device__ __forceinline__ void sort_keys(unsigned (&key)[K], std::integer_sequence<int, I...>) {
-    (compare_exchange<SortNetOf<K>::net.a[I], SortNetOf<K>::net.b[I], K>(key), ...);
+__device__ __forceinline__ void run_network(float (&v)[K], std::integer_sequence<int, I...>) {
+    (compare_exchange<SortNetOf<K>::net.a[I], SortNetOf<K>::net.b[I], K>(v), ...);
 }
 
 template <int SIZE>
@@ -74,25 +93,23 @@ median_reject_kernel(Img<float> out, Img<float> in, int maxbad, size_t out_batch
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= out.w || y >= out.h) return;
-    unsigned key[K];
+    float v[K];
     int bad = 0;
 #pragma unroll
-    for (int dy = 0; dy < SIZE; ++dy)
+    for (int dx = 0; dx < SIZE; ++dx)
 #pragma unroll
-        for (int dx = 0; dx < SIZE; ++dx) {
-            const float v = tile[threadIdx.y + dy][threadIdx.x + dx];
-            const bool ok = isfinite(v);            // InvalidValue<float>::IsValid (InvalidValue.h:18-47)
-            bad += ok ? 0 : 1;
-            key[dy * SIZE + dx] = ok ? float_key(v) : 0xffffffffu;   // invalid samples sort last
+        for (int dy = 0; dy < SIZE; ++dy) {
+            const float s = tile[threadIdx.y + dy][threadIdx.x + dx];
+            bad += isfinite(s) ? 0 : 1;             // InvalidValue<float>::IsValid (InvalidValue.h:18-47)
+            v[dx * SIZE + dy] = s;                  // the reference's column-major gather order
         }
     float r = __int_as_float(0x7fffffff);
     if (bad < maxbad && bad < K) {
-        sort_keys<K>(key, std::make_integer_sequence<int, SortNetOf<K>::net.n>{});
-        const int rank = (K + bad) / 2 - bad;        // valid samples sorted ascending, invalid ones last
-        unsigned sel = key[K / 2];
+        run_network<K>(v, std::make_integer_sequence<int, SortNetOf<K>::net.n>{});
+        const int idx = (K + bad) / 2;
+        r = v[K / 2];
 #pragma unroll
-        for (int i = 0; i < K / 2; ++i) sel = (i == rank) ? key[i] : sel;
-        r = key_float(sel);
+        for (int i = K / 2 + 1; i < K; ++i) r = (i == idx) ? v[i] : r;
     }
     out(x, y) = r;
 }

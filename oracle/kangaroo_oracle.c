@@ -866,32 +866,100 @@ void ko_warp(const ko_image* out, const ko_image* in, const ko_image* lookup) {
 
 /* ---------------------------------------------------------------- median (N1) ---- */
 
-static int cmp_float(const void* a, const void* b) {
-    const float x = *(const float*)a, y = *(const float*)b;
-    return (x > y) - (x < y);
+/* CUDA's min/max on floats (FMNMX): a NaN operand is ignored -- the other operand is returned -- and -0 < +0. */
+static float fmnmx_min(float a, float b) {
+    if (isnan(a)) return b;
+    if (isnan(b)) return a;
+    if (a == b) return signbit(a) ? a : b;
+    return a < b ? a : b;
+}
+static float fmnmx_max(float a, float b) {
+    if (isnan(a)) return b;
+    if (isnan(b)) return a;
+    if (a == b) return signbit(a) ? b : a;
+    return a > b ? a : b;
 }
 
-/* cu_median.cu:160-207 (5x5), :217-273 (7x7), :283-342 (9x9): gather with GetWithClampedRange, count invalid
- * samples, output the median of the valid ones (see the header for the exact relation to the reference). */
+/* The exchange network of cu_median.cu:177-199 / :240-263 / :306-333, generated instead of transcribed.  It is the bitonic
+ * sorting network for n inputs -- for every block size k = 2, 4, .. a "flip" stage pairing i with i ^ (k-1), then
+ * half-cleaners pairing i with i + j for j = k/4 .. 1 -- with the comparators that would reach past input n-1 dropped, and
+ * then every comparator that cannot influence outputs n/2 .. n-1 removed (the reference's "only top half are guaranteed
+ * valid": the median index (n + bad)/2 never lies below n/2).  tests/test_oracle_golden.py checks the generated sequence
+ * against the reference file when /root/reference is present: 155 / 439 / 968 comparators for 25 / 49 / 81, same order. */
+typedef struct { unsigned char a, b; } ko_cmp;
+static int median_network(int n, ko_cmp* net) {
+    static ko_cmp all[4096];
+    static int stage_end[64];
+    int N = 1, total = 0, nstage = 0;
+    while (N < n) N <<= 1;
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int i = 0; i < N; ++i) {
+            const int l = i ^ (k - 1);
+            if (l > i && l < n) { all[total].a = (unsigned char)i; all[total].b = (unsigned char)l; ++total; }
+        }
+        stage_end[nstage++] = total;
+        for (int j = k >> 2; j >= 1; j >>= 1) {
+            for (int i = 0; i < N; ++i)
+                if (!(i & j) && i + j < n) { all[total].a = (unsigned char)i; all[total].b = (unsigned char)(i + j); ++total; }
+            stage_end[nstage++] = total;
+        }
+    }
+    static unsigned char keep[4096];
+    unsigned char need[128] = {0};
+    for (int i = n / 2; i < n; ++i) need[i] = 1;
+    for (int s = nstage - 1; s >= 0; --s) {
+        const int lo = s ? stage_end[s - 1] : 0, hi = stage_end[s];
+        for (int c = lo; c < hi; ++c) keep[c] = need[all[c].a] || need[all[c].b];
+        for (int c = lo; c < hi; ++c)
+            if (keep[c]) { need[all[c].a] = 1; need[all[c].b] = 1; }
+    }
+    int m = 0;
+    for (int c = 0; c < total; ++c)
+        if (keep[c]) net[m++] = all[c];
+    return m;
+}
+int ko_median_network(int size, unsigned char* pairs) {   /* for the tests: 2 bytes per comparator, returns the count */
+    static ko_cmp net[4096];
+    const int m = median_network(size * size, net);
+    for (int c = 0; c < m; ++c) { pairs[2 * c] = net[c].a; pairs[2 * c + 1] = net[c].b; }
+    return m;
+}
+
+/* cu_median.cu:160-207 (5x5), :217-273 (7x7), :283-342 (9x9): gather with GetWithClampedRange in the reference's order
+ * (v[(dX + r) * size + (dY + r)], column-major), count the invalid samples (InvalidValue<float>::IsValid = isfinite), run the
+ * exchange network s2(a,b): a = min(a,b), b = max(a_old,b) on the raw samples -- min/max ignore NaNs, so a NaN is
+ * overwritten by a copy of its partner -- and return v[(size^2 + bad)/2].  Without invalid samples that is the exact
+ * median; with them it is whatever the network leaves at that index, reproduced here exactly. */
 void ko_median_filter_reject_negative(const ko_image* out, const ko_image* in, int size, int maxbad) {
     const int w = (int)out->w, h = (int)out->h, krad = size / 2, kpix = size * size;
+    static ko_cmp nets[3][1024];
+    static int nnet[3];
+    const int slot = size == 5 ? 0 : (size == 7 ? 1 : 2);
+#pragma omp critical(ko_median_net)
+    if (!nnet[slot]) nnet[slot] = median_network(kpix, nets[slot]);
+    const ko_cmp* net = nets[slot];
+    const int m = nnet[slot];
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
             float v[81];
-            int n = 0;
+            int bad = 0;
             for (int dx = -krad; dx <= krad; ++dx)
                 for (int dy = -krad; dy <= krad; ++dy) {
                     const int xx = x + dx < 0 ? 0 : (x + dx > w - 1 ? w - 1 : x + dx);
                     const int yy = y + dy < 0 ? 0 : (y + dy > h - 1 ? h - 1 : y + dy);
                     const float s = *(const float*)img_at(in, (size_t)xx, (size_t)yy, 4);
-                    if (isfinite(s)) v[n++] = s;
+                    v[(dx + krad) * size + (dy + krad)] = s;
+                    if (!isfinite(s)) ++bad;
                 }
-            const int bad = kpix - n;
             float r = NAN;
             if (bad < maxbad && bad < kpix) {
-                qsort(v, (size_t)n, sizeof(float), cmp_float);
-                r = v[(kpix + bad) / 2 - bad];
+                for (int c = 0; c < m; ++c) {
+                    const float a = v[net[c].a], b = v[net[c].b];
+                    v[net[c].a] = fmnmx_min(a, b);
+                    v[net[c].b] = fmnmx_max(a, b);
+                }
+                r = v[(kpix + bad) / 2];
             }
             *(float*)img_at(out, (size_t)x, (size_t)y, 4) = r;
         }

@@ -123,12 +123,13 @@ void ko_warp(const ko_image* out_u8, const ko_image* in_u8, const ko_image* look
 /* src/cu_median.cu:160-350 (MedianFilterRejectNegative5x5 / 7x7 / 9x9), OUT OF PLACE.  size in {5,7,9}.
  * Window = clamp-to-edge neighbourhood (Image.h:298-303); bad = number of non-finite samples
  * (InvalidValue<float>::IsValid = isfinite, InvalidValue.h:18-47); out = NaN unless bad < maxbad && bad < size^2.
- * For windows WITHOUT invalid samples the reference's exchange network returns the exact median v[size^2/2] and so
- * does this.  With invalid samples the reference returns v[(size^2+bad)/2] of a PARTIALLY sorted array in which
- * fminf/fmaxf have overwritten NaNs with copies of their partners -- a near-median sample that depends on the
- * comparator order; this restatement returns what the code says it means ("select median, ignoring bad values"):
- * the valid samples sorted, element (size^2+bad)/2 - bad.  tests/golden/median.npz pins both facts. */
+ * The window is gathered in the reference's order, run through its exchange network (the bitonic network for size^2 inputs
+ * with dead comparators removed, generated in kangaroo_oracle.c, on min/max that ignore NaNs) and v[(size^2+bad)/2] is
+ * returned: the exact median for windows without invalid samples, and for windows with them exactly the sample the
+ * reference's partially sorted array holds there.  tests/golden/median.npz pins both, bit for bit. */
 void ko_median_filter_reject_negative(const ko_image* out_f32, const ko_image* in_f32, int size, int maxbad);
+/* the generated comparator sequence (2 bytes per comparator into pairs, capacity >= 2048 bytes); returns the count */
+int ko_median_network(int size, unsigned char* pairs);
 
 /* src/cu_dense_stereo.cu:512-546 */
 /* src/cu_dense_stereo.cu:122-174; mask (optional, u8): 1 where the reference reads slice vol.d (Q7) */

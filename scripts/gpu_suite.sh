@@ -1,0 +1,6 @@
+#!/bin/bash
+# whole GPU suite + front/back-end operator timings
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/r2_gpu_tests.log
+cat gpurun_out/r2_gpu_tests.log
+timeout 300 python scripts/bench_frontback.py > gpurun_out/frontback_bench.log 2>&1; tail -3 gpurun_out/frontback_bench.log | cut -c1-600

@@ -177,15 +177,18 @@ def test_median_reject_negative_vs_reference_and_oracle(golden, size):
     # no invalid samples: bit-identical to the reference kernels
     assert same_bits(median(g["clean"], size, 100), g[f"clean_{size}_mb100"])
     assert np.isnan(median(g["clean"], size, 0)).all()
-    # invalid samples: same valid/NaN pattern as the reference, values = median of the valid samples (oracle)
+    # invalid samples (NaN and inf): the reference's exchange network overwrites a NaN with a copy of its partner, so what
+    # ends up at index (size^2 + bad)/2 depends on the comparator sequence -- which is generated, not transcribed, and
+    # reproduces the reference kernels bit for bit
     for mb in (1, 4, 100):
         out = median(g["dirty"], size, mb, pitch=64 * 4 + 16)
-        assert np.array_equal(np.isnan(out), np.isnan(g[f"dirty_{size}_mb{mb}"]))
+        assert same_float(out, g[f"dirty_{size}_mb{mb}"])
         assert same_float(out, ko.median_filter_reject_negative(g["dirty"], size, mb))
-    # full-size frame with ties, negatives and holes; odd size so that the last tiles are partial
+    # full-size frame with ties, negatives, infinities and holes; odd size so that the last tiles are partial
     rng = np.random.default_rng(size)
     big = np.round(rng.normal(40, 20, (375, 1242)), 1).astype(np.float32)
     big[rng.random(big.shape) < 0.03] = np.nan
+    big[rng.random(big.shape) < 0.002] = np.inf
     assert same_float(median(big, size, 10), ko.median_filter_reject_negative(big, size, 10))
 
 

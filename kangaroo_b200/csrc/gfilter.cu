@@ -21,6 +21,7 @@
 // Results are bit-identical to the reference kernels (tests/golden/guided.npz) in the default fp mode -- every operation
 // is the reference's -use_fast_math SASS form (FADD/FMUL/FFMA.FTZ, MUFU.RCP) -- and to the CPU oracle in IEEE mode.
 #include "common.cuh"
+#include "ftz.cuh"
 #include "kernels.cuh"
 
 #include <mutex>

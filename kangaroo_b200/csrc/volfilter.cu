@@ -12,6 +12,7 @@
 //   d = p - q, cw likewise on the guide image, w = cw * (sw * rw), sumw = w + sumw, sum = FFMA(q, w, sum),
 //   out = sumw == 0 ? p : sum * MUFU.RCP(sumw) (div.approx.ftz); every operation flushes denormals (.ftz).
 #include "common.cuh"
+#include "ftz.cuh"
 #include "kernels.cuh"
 
 namespace roo_b200 {

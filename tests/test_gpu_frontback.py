@@ -552,3 +552,37 @@ def test_dense_stereo_wide_image_and_argument_checks():
             _dense(L, R, md, 0.05, 2, signed)
     with pytest.raises(roo.capi.RooError):
         _dense(L, R, 40, 0.05, 8, False)
+
+
+def test_application_guided_filter_path_operator_chain():
+    """The filter branch of the application's frame loop spelled with the operators (stereo2/main.cpp:376-432):
+    ElementwiseScaleBias -> Census (ulong4) -> CensusStereoVolume<float> -> guided filtering of the volume -> SemiGlobalMatching
+    -> CostVolMinimumSubpix, in IEEE mode against the same chain of oracle functions, bit for bit."""
+    from kangaroo_b200.synth import stereo_pair
+    w, h, D, rad, eps = 160, 96, 32, 5, 1e-3
+    L8, R8, _ = stereo_pair(w, h, D, config=4)
+    roo.set_ieee_division(True)
+    img = []
+    for raw in (L8, R8):
+        f = roo.Image(w, h, np.float32)
+        roo.ElementwiseScaleBias(f, roo.Image.from_numpy(raw), 1.0 / 255.0)
+        img.append(f)
+    cen = [roo.Image(w, h, roo.ULONG4) for _ in range(2)]
+    for c, f in zip(cen, img):
+        roo.Census(c, f)
+    vol, volh, disp = roo.Volume(w, h, D, np.float32), roo.Volume(w, h, D, np.float32), roo.Image(w, h, np.float32)
+    roo.CensusStereoVolume(vol, cen[0], cen[1], D, -1.0)
+    roo.GuidedFilterVolume(vol, img[0], rad, eps, D)
+    roo.SemiGlobalMatching(volh, vol, img[0], D, 0.01, 0.02, True, True, True)
+    roo.CostVolMinimumSubpix(disp, volh, D, -1.0)
+    # the oracle chain
+    fl, fr = (ko.elementwise_scale_bias(a, np.float32(1.0 / 255.0)) for a in (L8, R8))
+    assert same_bits(img[0].numpy(), fl)
+    ovol = ko.census_stereo_volume(ko.census(fl, ko.WIN_16x16), ko.census(fr, ko.WIN_16x16), D, -1.0)
+    ovol = ko.guided_filter_volume(ovol, fl, rad, np.float32(eps))
+    assert same_float(vol.numpy(), ovol)
+    ovolh = ko.sgm(ovol, fl, D, 0.01, 0.02, True, True, True)
+    assert same_float(volh.numpy(), ovolh)
+    odisp, mask = ko.costvol_minimum_subpix(ovolh, D, -1.0)
+    got = disp.numpy()
+    assert same_float(got[mask == 0], odisp[mask == 0])

@@ -417,7 +417,8 @@ def test_box_filter_vs_reference_and_oracle(golden):
         assert same_float(inplace.numpy(), g[f"box_out_{nm}"]), nm
     roo.set_ieee_division(True)
     rng = np.random.default_rng(5)
-    for (h, w, rad) in ((37, 70, 3), (9, 255, 2), (8, 256, 4), (17, 257, 30), (129, 513, 7), (300, 31, 11), (2, 2, 1), (65, 1100, 5)):
+    for (h, w, rad) in ((37, 70, 3), (9, 255, 2), (8, 256, 4), (17, 257, 30), (129, 513, 7), (300, 31, 11), (2, 2, 1), (65, 1100, 5),
+                        (1, 5, 1), (5, 1, 2), (3, 3, 0)):    # degenerate windows: area 0 -> 0/0, NaN in both
         src = (rng.random((h, w), dtype=np.float32) * 4 - 1).astype(np.float32)
         out = roo.Image(w, h, np.float32)
         roo.BoxFilter(out, _img(src), None, rad)

@@ -103,6 +103,45 @@ int main() {
         if (bad) return 1;
     }
 
+    // the alternative aggregation of the applications (stereo2/main.cpp:392-405) and the direct matcher: the one-call guided
+    // filter equals the reference's per-slice sequence spelled with the operators, bit for bit; DenseStereo finds the
+    // constant disparity of this pair
+    {
+        auto imgf = alloc_image<float>(w, h), meanI = alloc_image<float>(w, h), varI = alloc_image<float>(w, h);
+        roo::Image<float> t[5];
+        for (auto& i : t) i = alloc_image<float>(w, h);
+        roo::Image<unsigned char> scratch = alloc_image<unsigned char>(16, 1);       // part of the signature, unused
+        roo::ElementwiseScaleBias<float, unsigned char, float>(imgf, imgL, 1.0f / 255.0f);
+        roo::CensusStereoVolume<float, unsigned long>(volC, cenL, cenR, D, -1);
+        CK(cudaMemcpy(volH.ptr, volC.ptr, volC.img_pitch * D, cudaMemcpyDeviceToDevice));
+        const int rad = 4;
+        const float eps = 1e-3f;
+        roo::GuidedFilterVolume(volH, imgf, rad, eps, D);
+        roo::ComputeMeanVarience<float, float, float>(varI, t[0], meanI, imgf, scratch, rad);
+        for (int d = 0; d < D; ++d) {
+            roo::Image<float> P = volC.ImageXY(d);
+            roo::ComputeCovariance(t[0], t[2], t[1], P, meanI, imgf, scratch, rad);
+            roo::GuidedFilter(P, t[0], varI, t[1], meanI, imgf, scratch, t[2], t[3], t[4], rad, eps);
+        }
+        CK(cudaDeviceSynchronize());
+        std::vector<float> a((size_t)w * h * D), b((size_t)w * h * D);
+        CK(cudaMemcpy2D(a.data(), w * 4, volH.ptr, volH.pitch, w * 4, (size_t)h * D, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2D(b.data(), w * 4, volC.ptr, volC.pitch, w * 4, (size_t)h * D, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (size_t i = 0; i < a.size(); ++i)
+            if (std::memcmp(&a[i], &b[i], 4) != 0 && !(a[i] != a[i] && b[i] != b[i])) ++bad;
+        auto dd = alloc_image<unsigned char>(w, h);
+        roo::DenseStereo<unsigned char, unsigned char>(dd, imgL, imgR, (unsigned char)D, 0.0f, 2);
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned char> dh(w * h);
+        CK(cudaMemcpy2D(dh.data(), w, dd.ptr, dd.pitch, w, h, cudaMemcpyDeviceToHost));
+        int hit = 0, all = 0;
+        for (int y = 8; y < h - 8; ++y)
+            for (int x = D + 8; x < w - 24; ++x) { ++all; hit += dh[y * w + x] == 9; }
+        std::printf("shim: guided filter volume vs operator sequence %d mismatches; DenseStereo %d / %d at the true disparity\n", bad, hit, all);
+        if (bad || hit < all * 0.95) return 1;
+    }
+
     // invalid arguments raise under ROO_B200_THROW
     bool threw = false;
     try { roo::CensusStereoVolume<float, unsigned long>(volC, cenL, cenR, D, 0.5f); } catch (const std::exception&) { threw = true; }

@@ -330,11 +330,14 @@ def main():
             tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             if tr.get("csrc_sha256") != csrc_hash():
                 traffic_note = "kernel sources changed since the ncu capture (profiles/r2_traffic.json): traffic not reported"
-            elif dom and wl in tr.get("workloads", {}):
-                ent = tr["workloads"][wl]["passes"]
+            elif args.materialised_cost or args.generic_hsweep:
+                traffic_note = "no ncu capture for this development configuration"
+            elif dom and (wl + ("@16x16" if args.window == "16x16" else "")) in tr.get("workloads", {}):
+                key = wl + ("@16x16" if args.window == "16x16" else "")      # the capture of this census window
+                ent = tr["workloads"][key]["passes"]
                 if dom["pass"] < len(ent):
-                    traffic = ent[dom["pass"]]["dram_bytes"] * B / tr["workloads"][wl]["pairs_per_launch"]
-                    traffic_note = f"ncu dram__bytes_read+write, {tr['workloads'][wl]['source']}"
+                    traffic = ent[dom["pass"]]["dram_bytes"] * B / tr["workloads"][key]["pairs_per_launch"]
+                    traffic_note = f"ncu dram__bytes_read+write, {tr['workloads'][key]['source']}"
         except Exception:
             pass
         agg_ms = sum(q["ms"] for q in passes)

@@ -73,7 +73,10 @@ enum roo_tuning_knob { ROO_TUNE_HSWEEP = 0,
                        ROO_TUNE_STRIP_CTAS_PER_SM = 2,
                        /* roo_guided_filter_volume: scratch budget in MiB (default 2048); the slices go through in chunks
                         * of budget / (4 fp32 planes) -- a small value exercises the chunk loop on small volumes */
-                       ROO_TUNE_GUIDED_SCRATCH_MIB = 3 };
+                       ROO_TUNE_GUIDED_SCRATCH_MIB = 3,
+                       /* 1 (default): a launch of ONE pair at 256 disparities runs its fused vertical passes with 12 warps x 2
+                        * columns per band instead of 8 x 3 (more warps per SM while a band waits for its predecessor) */
+                       ROO_TUNE_SOLO_GEOMETRY = 4 };
 int roo_set_tuning(int knob, int value);
 
 /* ---- granular operators: one per reference launcher -------------------------------------- */

@@ -16,7 +16,7 @@ WORDS = {WIN_9x7: 1, WIN_11x11: 2, WIN_16x16: 4}
 IMG_U8, IMG_F32 = 0, 1
 POPC32_COMPAT, POPC64 = 0, 1
 FP_DEFAULT, FP_REFERENCE, FP_IEEE = 0, 1, 2
-TUNE_HSWEEP, TUNE_INSWEEP_COST, TUNE_STRIP_CTAS_PER_SM, TUNE_GUIDED_SCRATCH_MIB = 0, 1, 2, 3
+TUNE_HSWEEP, TUNE_INSWEEP_COST, TUNE_STRIP_CTAS_PER_SM, TUNE_GUIDED_SCRATCH_MIB, TUNE_SOLO_GEOMETRY = 0, 1, 2, 3, 4
 VOL_U16, VOL_F32, VOL_I32, VOL_U32, VOL_U8, VOL_ELEM = 0, 1, 2, 3, 4, 5
 DISP_I8, DISP_F32 = 0, 1
 PROF_KINDS = ("census", "cost", "sweep", "wta", "lrcheck", "vgroup") + tuple(f"pass{i}" for i in range(8))

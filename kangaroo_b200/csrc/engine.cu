@@ -591,6 +591,7 @@ extern "C" int roo_set_tuning(int knob, int value) {
         case ROO_TUNE_HSWEEP: g_use_hsweep.store(value ? 1 : 0); return ROO_OK;
         case ROO_TUNE_INSWEEP_COST: g_insweep_cost.store(value ? 1 : 0); return ROO_OK;
         case ROO_TUNE_STRIP_CTAS_PER_SM: g_strip_ctas_per_sm.store(value < 0 ? 0 : value); return ROO_OK;
+        case ROO_TUNE_SOLO_GEOMETRY: g_solo_geometry.store(value ? 1 : 0); return ROO_OK;
         case ROO_TUNE_GUIDED_SCRATCH_MIB: g_guided_scratch_mib.store(value < 1 ? 1 : value); return ROO_OK;
         default: return ROO_ERR_INVALID_ARGUMENT;
     }

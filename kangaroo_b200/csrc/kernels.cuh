@@ -59,6 +59,8 @@ extern std::atomic<int> g_use_hsweep;
 extern std::atomic<int> g_insweep_cost;
 // split engine: CTAs per SM of a strip-crossing sweep (0 = as many as fit); fewer = waves = earlier hand-offs
 extern std::atomic<int> g_strip_ctas_per_sm;
+// sgm_fused.cu: 1 = a single pair at 256 disparities runs 12 warps x 2 columns per band (development knob)
+extern std::atomic<int> g_solo_geometry;
 // gfilter.cu: scratch budget of roo_guided_filter_volume in MiB
 extern std::atomic<int> g_guided_scratch_mib;
 int launch_image_to_f32(float* dst, const void* src, size_t pitch, size_t src_pair, int img_type, int w, int h,

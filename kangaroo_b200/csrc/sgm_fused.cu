@@ -54,7 +54,15 @@ __host__ __device__ constexpr int vg_pfs(int DPL, int CE) {
 #ifndef VG_NWW8
 #define VG_NWW8 8
 #endif
-__host__ __device__ constexpr int vg_ncw(int DPL) { return DPL >= 8 ? VG_NCW8 : VG_NCW; }
+// a single pair at 256 disparities (BASELINE config 5) has no second pair to fill the time a band waits for its
+// predecessor: 12 warps x 2 columns (same 24-column bands, more warps per SM) instead of 8 x 3 -- geometry class 3
+#ifndef VG_NCW8_SOLO
+#define VG_NCW8_SOLO 2
+#endif
+#ifndef VG_NWW8_SOLO
+#define VG_NWW8_SOLO 12
+#endif
+__host__ __device__ constexpr int vg_ncw(int DPL, int cls = 0) { return DPL >= 8 ? (cls == 3 ? VG_NCW8_SOLO : VG_NCW8) : VG_NCW; }
 // 12 warps x 4 columns: 13 warps of <= 152 registers fill the register file, and ring + prefetch stages fill
 // the 227 KB of shared memory (measured on B200 at 128 disparities: 8 warps 6.6 ms, 10: 6.5 ms, 12: 6.1 ms per 16 pairs)
 #ifndef VG_NWW
@@ -78,11 +86,13 @@ __host__ __device__ constexpr int vg_min_ctas(int DPL, int cost, bool first, int
 #ifndef VG_NWW8_CEN
 #define VG_NWW8_CEN VG_NWW8
 #endif
-// geometry class of a launch: 0 = cost read from a volume, 1 = in-sweep cost, 2 = in-sweep cost and write-only first pass
+// geometry class of a launch: 0 = cost read from a volume, 1 = in-sweep cost, 2 = in-sweep cost and write-only first pass,
+// 3 = in-sweep cost, one pair per launch at 256 disparities
 __host__ __device__ constexpr int vg_nww(int DPL, int cls = 0) {
-    return DPL >= 8 ? (cls == 2 ? VG_NWW8_FC : (cls == 1 ? VG_NWW8_CEN : VG_NWW8)) : (cls == 2 ? VG_NWW_FC : VG_NWW);
+    return DPL >= 8 ? (cls == 3 ? VG_NWW8_SOLO : (cls == 2 ? VG_NWW8_FC : (cls == 1 ? VG_NWW8_CEN : VG_NWW8)))
+                    : (cls == 2 ? VG_NWW_FC : VG_NWW);
 }
-inline int vg_cols_of_dp(int DP, int cls = 0) { return vg_ncw(DP / 32) * vg_nww(DP / 32, cls); }
+inline int vg_cols_of_dp(int DP, int cls = 0) { return vg_ncw(DP / 32, cls) * vg_nww(DP / 32, cls); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -684,10 +694,21 @@ sgm_vgroup_kernel(const VGroupArgs a) {
 #endif
 }
 
+std::atomic<int> g_solo_geometry{1};
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else n = 148;
+    }
+    return n;
+}
+
 // scratch sizing: the geometry with the narrower bands (more bands)
 int vgroup_bands(int w, int h, int DP) {
     int nc = vg_cols_of_dp(DP, 0);
-    for (int cls = 1; cls <= 2; ++cls) nc = vg_cols_of_dp(DP, cls) < nc ? vg_cols_of_dp(DP, cls) : nc;
+    for (int cls = 1; cls <= 3; ++cls) nc = vg_cols_of_dp(DP, cls) < nc ? vg_cols_of_dp(DP, cls) : nc;
     return cdiv(w + h - 1, nc);
 }
 size_t vgroup_edge_floats(int w, int h, int DP) { return (size_t)vgroup_bands(w, h, DP) * h * (3 * (size_t)DP + 8); }
@@ -703,7 +724,7 @@ constexpr size_t vg_smem_bytes() {
 
 template <int DPL, int COST, bool FIRST, int CLS>
 static int vgroup_launch3(VGroupArgs a, cudaStream_t st) {
-    constexpr int NWW = vg_nww(DPL, CLS), NCW = vg_ncw(DPL);
+    constexpr int NWW = vg_nww(DPL, CLS), NCW = vg_ncw(DPL, CLS);
     a.n_bands = cdiv(a.w + a.h - 1, NWW * NCW);
     constexpr size_t smem = vg_smem_bytes<DPL, COST, FIRST, NWW, NCW>();
     static_assert(smem <= 227 * 1024, "vertical-group kernel: shared memory budget of one sm_100 CTA exceeded");
@@ -727,6 +748,12 @@ static int vgroup_launch3(VGroupArgs a, cudaStream_t st) {
 template <int DPL, int COST>
 static int vgroup_launch2(const VGroupArgs& a, bool first, cudaStream_t st) {
     constexpr int CEN_CLS = COST == COST_CEN32 ? 1 : 0;
+    if constexpr (DPL >= 8 && COST == COST_CEN32) {
+        // measured on B200 (profiles/r2_solo_geometry.json): 3840x2160 (250 bands) 16.95 -> 16.2 ms per pair, but 1920x1080
+        // (125 bands, all resident at once) 5.93 -> 6.30 ms: only when the bands do not all fit on the SMs
+        if (a.batch == 1 && g_solo_geometry.load(std::memory_order_relaxed) && cdiv(a.w + a.h - 1, vg_cols_of_dp(32 * DPL, 3)) > sm_count())
+            return first ? vgroup_launch3<DPL, COST, true, 3>(a, st) : vgroup_launch3<DPL, COST, false, 3>(a, st);
+    }
     if (!first) return vgroup_launch3<DPL, COST, false, CEN_CLS>(a, st);
     if constexpr (COST == COST_CEN32 && vg_nww(DPL, 2) != vg_nww(DPL, 1)) return vgroup_launch3<DPL, COST, true, 2>(a, st);
     else return vgroup_launch3<DPL, COST, true, CEN_CLS>(a, st);

@@ -172,7 +172,7 @@ def run_reference(args, wl):
            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    _emit(_REAL_STDOUT, json.dumps(out))
 
 
 def main():
@@ -392,12 +392,30 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                    "sample": f"{reps} whole {w}x{h}x{D} pair(s), {paths}-path, {dt:.2f} s each "
                                              f"on {cores} threads (after 1 warm-up pair)"}
-        print(json.dumps(out), flush=True)
+        _emit(_REAL_STDOUT, json.dumps(out))
     eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when the
+    first communicator is created), so everything that goes to fd 1 during the run is sent to stderr and the JSON line is
+    written to the real stdout at the end."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_fd: int, line: str) -> None:
+    sys.stdout.flush()
+    os.write(real_fd, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _json_only_stdout()
     main()
